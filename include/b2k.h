@@ -1,0 +1,156 @@
+/* b2k.h -- C ABI of libb2k.so: the B200-native replacement for the numeric backend behind
+ * PyEMMA's k-means / assign / regspace / minRMSD hot path.
+ *
+ * What it replaces (reference @ 3327f28, paths relative to /root/reference):
+ *   the per-metric pybind11 module that
+ *     pyemma/coordinates/clustering/src/clustering_module.cpp:38-43
+ *   builds with deeptime::clustering::registerClusteringImplementation<Metric>(m)
+ *   (functions: assign, kmeans.cluster, kmeans.cluster_loop, kmeans.cost_function,
+ *   kmeans.init_centers_kmpp, regspace.cluster, compute_metric) and that is called from
+ *     clustering/kmeans.py:254-258      (KMeans.fit -> init_centers_kmpp + cluster_loop)
+ *     clustering/interface.py:164-165   (ClusterModel.transform -> assign)
+ *     clustering/regspace.py:150        (RegularSpace.partial_fit -> regspace.cluster)
+ *     clustering/tests/test_kmeans.py:250,304 (compute_metric, init_centers_kmpp)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy / C++ types cross this boundary.
+ *   - frames X: float32, C-contiguous (n, d); centers: float32 (k, d); labels: int32.
+ *   - the caller allocates every input and output buffer; the library never frees caller
+ *     memory.  Opaque handles own streams and scratch; explicit create / destroy.
+ *   - every function returns an int status (B2K_OK == 0); b2k_last_error() gives the text.
+ *   - b2k_*      : HOST pointers (pageable or pinned); the library stages chunks through its
+ *                  own pinned buffers onto CUDA streams (the reference's chunk hand-off,
+ *                  coordinates/data/_base/datasource.py:405-410, kmeans.py:326-338).
+ *   - b2k_dev_*  : DEVICE pointers (cudaMalloc / torch.Tensor.data_ptr()); work is enqueued
+ *                  on the context stream; results are complete after b2k_ctx_sync() unless a
+ *                  host out-parameter is written (then the call synchronises itself).
+ *   - there is NO CPU fallback: every entry point fails with B2K_ERR_CUDA when no sm_100
+ *     device is usable.
+ */
+#ifndef B2K_H
+#define B2K_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes -> Python exceptions raised by the reference for the same condition */
+#define B2K_OK 0
+#define B2K_ERR_INVALID_ARG 2   /* std::invalid_argument -> ValueError (dim mismatch, k>n; tests/test_assign.py:183-197) */
+#define B2K_ERR_DIM_NOT_MULT3 3 /* std::range_error (clustering_module.cpp:12-14) */
+#define B2K_ERR_MAX_CENTERS 4   /* MaxCentersReachedException (regspace.py:153-163); centers so far are valid */
+#define B2K_ERR_CUDA 5          /* CUDA runtime/driver error or no usable device */
+#define B2K_ERR_NOMEM 6         /* device or pinned allocation failed (kmeans.py:187-192 MemoryError) */
+#define B2K_ERR_NONFINITE 7     /* NaN/inf in input (InvalidDataInStreamException, datasource.py:1067-1075) */
+
+#define B2K_METRIC_EUCLIDEAN 0
+#define B2K_METRIC_MINRMSD 1
+
+/* ordered-sum mode of k-means++ (DESIGN.md "k-means++"): */
+#define B2K_KMPP_SERIAL 0  /* fp32 sums in frame order: bit-faithful to the reference at n_jobs=1 */
+#define B2K_KMPP_BLOCKED 1 /* balanced-tree sums + tree descent: parallel, deterministic */
+
+/* assignment engine selection (b2k_ctx_set_option "assign_engine") */
+#define B2K_ENGINE_AUTO 0
+#define B2K_ENGINE_DIRECT 1 /* exact fp32 CUDA-core kernel only */
+#define B2K_ENGINE_SCREEN 2 /* tcgen05 screen + exact verify (euclidean only) */
+
+typedef struct b2k_ctx b2k_ctx;
+typedef struct b2k_lloyd b2k_lloyd;
+typedef struct b2k_regspace b2k_regspace;
+typedef void (*b2k_callback)(void* user);
+
+const char* b2k_last_error(void);
+int b2k_version(void);
+/* number of kernels launched by this library in this process so far (bench.py "gpu_launches") */
+int64_t b2k_launch_count(void);
+
+/* ---- context ---------------------------------------------------------------------------- */
+int b2k_ctx_create(int device, b2k_ctx** out);
+int b2k_ctx_destroy(b2k_ctx* ctx);
+/* use an external cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream */
+int b2k_ctx_set_stream(b2k_ctx* ctx, void* cuda_stream);
+int b2k_ctx_sync(b2k_ctx* ctx);
+/* options: "assign_engine" (B2K_ENGINE_*), "screen_terms" (1|3, 0=auto), "stage_bytes" (pinned
+ * staging buffer size per slot) */
+int b2k_ctx_set_option(b2k_ctx* ctx, const char* name, int64_t value);
+int b2k_ctx_get_stat(b2k_ctx* ctx, const char* name, double* value);
+
+/* ---- compute_metric  (clustering_module.cpp:41-43) -------------------------------------- */
+int b2k_compute_metric(b2k_ctx* ctx, const float* x, const float* y, int64_t d, int metric, float* out);
+
+/* ---- assign  (deeptime assign_chunk_to_centers; interface.py:164-165) ------------------- */
+/* labels[i] = first argmin_j sqrt(dist2(x_i, c_j)); -1 when no distance is < FLT_MAX */
+int b2k_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* centers, int32_t k, int metric,
+               int32_t* labels);
+int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, const float* dcenters, int32_t k,
+                   int metric, int32_t* dlabels, float* dmindist_or_null);
+
+/* ---- k-means  (deeptime kmeans.cluster / cost_function / cluster_loop; kmeans.py:254-258) */
+/* one Lloyd step: labels from `centers`, new centers = member mean (empty cluster keeps the old) */
+int b2k_kmeans_cluster(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* centers, int32_t k,
+                       int metric, float* new_centers, int32_t* labels);
+int b2k_kmeans_cost(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* centers, int32_t k,
+                    const int32_t* labels, int metric, float* cost);
+/* do { step; cost; rel=|cost-prev|/cost; converged if rel<=tol else callback } while (it<max_iter && !conv)
+ * code: 0 converged, 1 not; inertias[0..iters) */
+int b2k_kmeans_cluster_loop(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, float* centers_io, int32_t k,
+                            int metric, int32_t max_iter, float tolerance, b2k_callback cb, void* user, int* code,
+                            int* iters, float* inertias, int32_t inertias_cap);
+/* k-means++ (test_kmeans.py:304: init_centers_kmpp(data,k,random_seed,n_threads,callback)); seed<0 = entropy */
+int b2k_kmeans_init_centers_kmpp(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, int32_t k, int metric,
+                                 int64_t seed, int scan_mode, b2k_callback cb, void* user, float* centers_out,
+                                 int64_t* chosen_or_null);
+
+/* device-resident Lloyd session: the frames of ONE shard stay in HBM across iterations.
+ * Multi-GPU: every rank owns a session over its shard; `acc` is the exchange buffer that the
+ * caller all-reduces (sum, int64) between accumulate and finalize -- layout
+ *   acc[0 .. k*d)   fixed-point coordinate sums (value * 2^qbits, exact integer adds)
+ *   acc[k*d .. k*d+k) member counts
+ *   acc[k*d+k]      fixed-point cost
+ * so results are independent of the number of ranks and of any reduction order. */
+int b2k_dev_lloyd_create(b2k_ctx* ctx, const float* dX, int64_t n_local, int32_t d, int32_t k, int metric,
+                         int64_t n_total, float absmax_global, b2k_lloyd** out);
+int b2k_dev_lloyd_destroy(b2k_lloyd* s);
+int64_t b2k_dev_lloyd_acc_len(const b2k_lloyd* s);
+/* labels (n_local) <- argmin vs dcenters (Lloyd tie/NaN semantics); acc <- local sums+counts (cost slot zeroed) */
+int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dcenters, int32_t* dlabels, int64_t* dacc);
+/* new centers from (all-reduced) acc; count==0 keeps old */
+int b2k_dev_lloyd_finalize(b2k_lloyd* s, const int64_t* dacc, const float* dcenters_old, float* dcenters_new);
+/* acc[k*d+k] <- local fixed-point sum of compute(x_i, new_centers[label_i])^2 */
+int b2k_dev_lloyd_cost(b2k_lloyd* s, const float* dcenters_new, const int32_t* dlabels, int64_t* dacc);
+/* host-side decode of the (all-reduced) cost slot */
+double b2k_dev_lloyd_decode_cost(const b2k_lloyd* s, int64_t cost_fixed);
+/* max |x| over a device array (for absmax_global; all-reduce(max) it across ranks) */
+int b2k_dev_absmax(b2k_ctx* ctx, const float* dX, int64_t count, float* out_host);
+/* 1 if every value is finite */
+int b2k_dev_all_finite(b2k_ctx* ctx, const float* dX, int64_t count, int* out_host);
+
+/* cluster_loop over device-resident frames of ONE GPU (no exchange); dlabels_or_null receives the labels of the last step */
+int b2k_dev_kmeans_cluster_loop(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, float* dcenters_io, int32_t k,
+                                int metric, int32_t max_iter, float tolerance, b2k_callback cb, void* user, int* code,
+                                int* iters, float* inertias, int32_t inertias_cap, int32_t* dlabels_or_null);
+
+int b2k_dev_kmeans_init_centers_kmpp(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, int32_t k, int metric,
+                                     int64_t seed, int scan_mode, b2k_callback cb, void* user, float* dcenters_out,
+                                     int64_t* chosen_host_or_null);
+
+/* ---- regspace  (deeptime regspace.cluster; regspace.py:144-151) -------------------------- */
+int b2k_regspace_create(b2k_ctx* ctx, int32_t d, float dmin, int64_t max_centers, int metric, b2k_regspace** out);
+int b2k_regspace_destroy(b2k_regspace* r);
+/* feed the next chunk (frames in order).  B2K_ERR_MAX_CENTERS when a frame would be center
+ * max_centers+1: the handle then holds exactly max_centers centers and ignores further chunks. */
+int b2k_regspace_partial_fit(b2k_regspace* r, const float* X, int64_t n);
+int b2k_dev_regspace_partial_fit(b2k_regspace* r, const float* dX, int64_t n);
+int64_t b2k_regspace_n_centers(const b2k_regspace* r);
+int b2k_regspace_get_centers(b2k_regspace* r, float* centers_out /* n_centers*d */);
+/* one-shot convenience with the reference's signature shape */
+int b2k_regspace_cluster(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, float* centers_io,
+                         int64_t* n_centers_io, float dmin, int64_t max_centers, int metric);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2K_H */

@@ -78,7 +78,7 @@ def _metric(m):
 
 def _check(rc):
     if rc == 3:
-        raise IndexError("RMSDMetric is only implemented for input data with a dimension divisible by 3.")
+        raise ValueError("RMSDMetric is only implemented for input data with a dimension divisible by 3.")
     if rc == 2:
         raise ValueError("invalid argument")
     if rc not in (0, 4):

@@ -1,0 +1,8 @@
+"""pyemma_b200 -- B200-native k-means / Voronoi-assignment engine behind PyEMMA's clustering API.
+
+Only the hot path named in BASELINE.json is implemented: k-means++ init,
+Lloyd iterations, assign / dtrajs, cluster_regspace and metric='minRMSD'.  The arithmetic lives in
+hand-written sm_100a CUDA kernels behind the C ABI of include/b2k.h (libb2k.so, loaded with
+ctypes); there is no CPU fallback.
+"""
+__version__ = "0.1.0"

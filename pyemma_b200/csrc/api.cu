@@ -1,0 +1,677 @@
+// api.cu -- extern "C" entry points of libb2k (see include/b2k.h for what each one replaces).
+#include "common.cuh"
+#include "kernels.h"
+#include <cstdarg>
+#include <algorithm>
+
+namespace b2k {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int kmpp_run(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int metric, int64_t seed, int scan_mode,
+             b2k_callback cb, void* user, float* dcenters_out, int64_t* chosen_host);
+
+struct DevMem {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~DevMem() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        if (p && bytes <= cap) return B2K_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cap = bytes ? bytes : 16;
+        if (cudaMalloc(&p, cap) != cudaSuccess) {
+            p = nullptr;
+            cap = 0;
+            cudaGetLastError();
+            return set_error(B2K_ERR_NOMEM, "cudaMalloc(%zu bytes) failed", bytes);
+        }
+        return B2K_OK;
+    }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+static bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int ensure_pinned(b2k_ctx* ctx, size_t in_bytes, size_t out_bytes) {
+    if (in_bytes > ctx->pinned_cap) {
+        for (int s = 0; s < 2; ++s) {
+            if (ctx->pinned[s]) cudaFreeHost(ctx->pinned[s]);
+            ctx->pinned[s] = nullptr;
+            CUDA_TRY(cudaMallocHost(&ctx->pinned[s], in_bytes));
+        }
+        ctx->pinned_cap = in_bytes;
+    }
+    if (out_bytes > ctx->pinned_out_cap) {
+        for (int s = 0; s < 2; ++s) {
+            if (ctx->pinned_out[s]) cudaFreeHost(ctx->pinned_out[s]);
+            ctx->pinned_out[s] = nullptr;
+            CUDA_TRY(cudaMallocHost(&ctx->pinned_out[s], out_bytes));
+        }
+        ctx->pinned_out_cap = out_bytes;
+    }
+    return B2K_OK;
+}
+
+// Copy a host array to the device in chunks: pageable sources bounce through the two pinned
+// staging slots (memcpy of chunk c+1 overlaps the DMA of chunk c); pinned sources DMA directly.
+int upload_host(b2k_ctx* ctx, const void* src, void* dst, size_t bytes) {
+    if (bytes == 0) return B2K_OK;
+    if (host_ptr_is_pinned(src)) {
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return B2K_OK;
+    }
+    const size_t chunk = std::min(bytes, ctx->stage_bytes);
+    B2K_TRY(ensure_pinned(ctx, chunk, 0));
+    size_t off = 0;
+    int c = 0;
+    while (off < bytes) {
+        const int s = c & 1;
+        const size_t len = std::min(chunk, bytes - off);
+        CUDA_TRY(cudaEventSynchronize(ctx->ev_done[s]));
+        std::memcpy(ctx->pinned[s], (const char*)src + off, len);
+        CUDA_TRY(cudaMemcpyAsync((char*)dst + off, ctx->pinned[s], len, cudaMemcpyHostToDevice, ctx->copy_stream[s]));
+        CUDA_TRY(cudaEventRecord(ctx->ev_done[s], ctx->copy_stream[s]));
+        off += len;
+        ++c;
+    }
+    for (int s = 0; s < 2; ++s) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_done[s], 0));
+    return B2K_OK;
+}
+
+static int check_metric_dim(int metric, int d) {
+    if (metric != B2K_METRIC_EUCLIDEAN && metric != B2K_METRIC_MINRMSD)
+        return set_error(B2K_ERR_INVALID_ARG, "unknown metric id %d", metric);
+    if (metric == B2K_METRIC_MINRMSD && d % 3)
+        return set_error(B2K_ERR_DIM_NOT_MULT3,
+                         "RMSDMetric is only implemented for input data with a dimension divisible by 3.");
+    return B2K_OK;
+}
+
+// ---- metric-generic primitives -----------------------------------------------------------------
+// centers prepared for a metric (minRMSD: centered copies + traces, owned here)
+struct PreparedCenters {
+    const float* C = nullptr;  // what the kernels read (euclid: the caller's; rmsd: centered copy)
+    float* Gb = nullptr;
+    DevMem mem_c, mem_g;
+    int prepare(b2k_ctx* ctx, const float* dC, int k, int d, int metric) {
+        if (metric == B2K_METRIC_MINRMSD) {
+            B2K_TRY(mem_c.alloc((size_t)k * d * 4));
+            B2K_TRY(mem_g.alloc((size_t)k * 4));
+            B2K_TRY(launch_rmsd_center(ctx, dC, k, d, mem_c.as<float>(), mem_g.as<float>()));
+            C = mem_c.as<float>();
+            Gb = mem_g.as<float>();
+        } else {
+            C = dC;
+        }
+        return B2K_OK;
+    }
+};
+
+static int assign_any(b2k_ctx* ctx, const float* dX, const float* Ga, int64_t n, int d, const PreparedCenters& pc,
+                      int k, int metric, int32_t* labels, float* mind, int lloyd) {
+    if (metric == B2K_METRIC_MINRMSD) return launch_rmsd_assign(ctx, dX, Ga, n, d, pc.C, pc.Gb, k, labels, mind, lloyd);
+    return launch_assign_exact(ctx, dX, n, d, pc.C, k, labels, mind, lloyd);
+}
+
+}  // namespace b2k
+
+using namespace b2k;
+
+int b2k_ctx::ensure_scratch(size_t bytes) {
+    if (bytes <= scratch_cap) return B2K_OK;
+    if (scratch) cudaFree(scratch);
+    scratch = nullptr;
+    scratch_cap = 0;
+    CUDA_TRY(cudaMalloc(&scratch, bytes));
+    scratch_cap = bytes;
+    return B2K_OK;
+}
+
+// =================================================================================================
+B2K_API const char* b2k_last_error(void) { return g_last_error.c_str(); }
+B2K_API int b2k_version(void) { return 100; }
+B2K_API int64_t b2k_launch_count(void) { return g_launches.load(); }
+
+B2K_API int b2k_ctx_create(int device, b2k_ctx** out) {
+    if (!out) return set_error(B2K_ERR_INVALID_ARG, "ctx_create: null out");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return set_error(B2K_ERR_CUDA, "no CUDA device available: libb2k has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return set_error(B2K_ERR_INVALID_ARG, "device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_error(B2K_ERR_CUDA, "device %d is sm_%d%d; libb2k is built for sm_100a only", device, prop.major,
+                         prop.minor);
+    b2k_ctx* c = new b2k_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    for (int s = 0; s < 2; ++s) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream[s], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[s], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[s], cudaEventDisableTiming));
+    }
+    *out = c;
+    return B2K_OK;
+}
+
+B2K_API int b2k_ctx_destroy(b2k_ctx* c) {
+    if (!c) return B2K_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int s = 0; s < 2; ++s) {
+        if (c->pinned[s]) cudaFreeHost(c->pinned[s]);
+        if (c->pinned_out[s]) cudaFreeHost(c->pinned_out[s]);
+        if (c->copy_stream[s]) cudaStreamDestroy(c->copy_stream[s]);
+        if (c->ev_h2d[s]) cudaEventDestroy(c->ev_h2d[s]);
+        if (c->ev_done[s]) cudaEventDestroy(c->ev_done[s]);
+    }
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return B2K_OK;
+}
+
+B2K_API int b2k_ctx_set_stream(b2k_ctx* c, void* cuda_stream) {
+    if (!c) return set_error(B2K_ERR_INVALID_ARG, "null ctx");
+    if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+    else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    return B2K_OK;
+}
+
+B2K_API int b2k_ctx_sync(b2k_ctx* c) {
+    if (!c) return set_error(B2K_ERR_INVALID_ARG, "null ctx");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B2K_OK;
+}
+
+B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
+    if (!c || !name) return set_error(B2K_ERR_INVALID_ARG, "null argument");
+    if (!strcmp(name, "assign_engine")) c->engine = (int)value;
+    else if (!strcmp(name, "screen_terms")) c->screen_terms = (int)value;
+    else if (!strcmp(name, "stage_bytes")) c->stage_bytes = (size_t)std::max<int64_t>(value, 1 << 16);
+    else return set_error(B2K_ERR_INVALID_ARG, "unknown option '%s'", name);
+    return B2K_OK;
+}
+
+B2K_API int b2k_ctx_get_stat(b2k_ctx* c, const char* name, double* value) {
+    if (!c || !name || !value) return set_error(B2K_ERR_INVALID_ARG, "null argument");
+    if (!strcmp(name, "screen_cand_chunks")) *value = c->stat_cand_chunks;
+    else if (!strcmp(name, "screen_fallback_frames")) *value = c->stat_fallback_frames;
+    else if (!strcmp(name, "screen_frames")) *value = c->stat_screen_frames;
+    else if (!strcmp(name, "sm_count")) *value = c->sm_count;
+    else return set_error(B2K_ERR_INVALID_ARG, "unknown stat '%s'", name);
+    return B2K_OK;
+}
+
+// ---- compute_metric ---------------------------------------------------------------------------
+B2K_API int b2k_compute_metric(b2k_ctx* ctx, const float* x, const float* y, int64_t d, int metric, float* out) {
+    if (!ctx || !x || !y || !out || d < 1) return set_error(B2K_ERR_INVALID_ARG, "compute_metric: bad arguments");
+    B2K_TRY(check_metric_dim(metric, (int)d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    DevMem buf;
+    B2K_TRY(buf.alloc((size_t)(2 * d + 8) * 4 + 64));
+    float* dx = buf.as<float>();
+    float* dy = dx + d;
+    float* dres = dy + d;
+    CUDA_TRY(cudaMemcpyAsync(dx, x, d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(dy, y, d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (metric == B2K_METRIC_MINRMSD) {
+        DevMem t;
+        B2K_TRY(t.alloc((size_t)(d + 8) * 4));
+        float* yc = t.as<float>();
+        float* g = dres + 1;
+        B2K_TRY(launch_rmsd_center(ctx, dx, 1, (int)d, nullptr, g));          // Ga
+        B2K_TRY(launch_rmsd_center(ctx, dy, 1, (int)d, yc, g + 1));           // centered y, Gb
+        B2K_TRY(launch_rmsd_dist_rows(ctx, dx, g, 1, (int)d, yc, g + 1, 1, dres));
+        CUDA_TRY(cudaMemcpyAsync(out, dres, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return B2K_OK;
+    }
+    B2K_TRY(launch_dist_rows(ctx, dx, 1, (int)d, dy, 1, dres));
+    CUDA_TRY(cudaMemcpyAsync(out, dres, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B2K_OK;
+}
+
+// ---- assign -----------------------------------------------------------------------------------
+B2K_API int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, const float* dC, int32_t k,
+                           int metric, int32_t* dlabels, float* dmind) {
+    if (!ctx || n < 0 || d < 1 || k < 1 || (n > 0 && (!dX || !dlabels)) || !dC)
+        return set_error(B2K_ERR_INVALID_ARG, "assign: bad arguments (n=%lld d=%d k=%d)", (long long)n, d, k);
+    B2K_TRY(check_metric_dim(metric, d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n == 0) return B2K_OK;
+    PreparedCenters pc;
+    B2K_TRY(pc.prepare(ctx, dC, k, d, metric));
+    DevMem ga;
+    if (metric == B2K_METRIC_MINRMSD) {
+        B2K_TRY(ga.alloc((size_t)n * 4));
+        B2K_TRY(launch_rmsd_center(ctx, dX, n, d, nullptr, ga.as<float>()));
+    } else if (ctx->engine != B2K_ENGINE_DIRECT && screen_supported(ctx, d, k, n)) {
+        ScreenPlan* plan = nullptr;
+        B2K_TRY(screen_plan_create(ctx, n, d, k, &plan));
+        int rc = screen_prepare_frames(plan, dX, n);
+        if (rc == B2K_OK) rc = screen_assign(plan, dX, n, dC, dlabels, dmind, 0);
+        if (rc == B2K_OK) { cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = set_error(B2K_ERR_CUDA, "%s", cudaGetErrorString(e)); }
+        screen_plan_destroy(plan);
+        return rc;
+    }
+    B2K_TRY(assign_any(ctx, dX, ga.as<float>(), n, d, pc, k, metric, dlabels, dmind, 0));
+    if (pc.mem_c.p || ga.p) CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // temporaries die with this frame
+    return B2K_OK;
+}
+
+// Host frames are streamed chunk by chunk: H2D of chunk c+1 (copy stream) overlaps the kernels of
+// chunk c (compute stream) and the D2H of chunk c-1's labels.
+B2K_API int b2k_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* centers, int32_t k,
+                       int metric, int32_t* labels) {
+    if (!ctx || n < 0 || d < 1 || k < 1 || (n > 0 && (!X || !labels)) || !centers)
+        return set_error(B2K_ERR_INVALID_ARG, "assign: bad arguments (n=%lld d=%d k=%d)", (long long)n, d, k);
+    B2K_TRY(check_metric_dim(metric, d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n == 0) return B2K_OK;
+    cudaStream_t st = ctx->stream;
+    DevMem dC;
+    B2K_TRY(dC.alloc((size_t)k * d * 4));
+    CUDA_TRY(cudaMemcpyAsync(dC.p, centers, (size_t)k * d * 4, cudaMemcpyHostToDevice, st));
+    PreparedCenters pc;
+    B2K_TRY(pc.prepare(ctx, dC.as<float>(), k, d, metric));
+
+    const int64_t row_bytes = (int64_t)d * 4;
+    int64_t cf = std::max<int64_t>(1, (int64_t)ctx->stage_bytes / row_bytes);
+    cf = std::min(cf, n);
+    const bool in_pinned = host_ptr_is_pinned(X), out_pinned = host_ptr_is_pinned(labels);
+    B2K_TRY(ensure_pinned(ctx, in_pinned ? 0 : (size_t)cf * row_bytes, out_pinned ? 0 : (size_t)cf * 4));
+    DevMem dX[2], dL[2], dG[2];
+    for (int s = 0; s < 2; ++s) {
+        B2K_TRY(dX[s].alloc((size_t)cf * row_bytes));
+        B2K_TRY(dL[s].alloc((size_t)cf * 4));
+        if (metric == B2K_METRIC_MINRMSD) B2K_TRY(dG[s].alloc((size_t)cf * 4));
+    }
+    const bool use_screen = metric == B2K_METRIC_EUCLIDEAN && ctx->engine != B2K_ENGINE_DIRECT &&
+                            screen_supported(ctx, d, k, cf);
+    ScreenPlan* plan = nullptr;
+    if (use_screen) B2K_TRY(screen_plan_create(ctx, cf, d, k, &plan));
+    cudaEvent_t ev_k[2];
+    for (int s = 0; s < 2; ++s) CUDA_TRY(cudaEventCreateWithFlags(&ev_k[s], cudaEventDisableTiming));
+    int64_t pend_off[2] = {-1, -1}, pend_len[2] = {0, 0};
+    int rc = B2K_OK;
+    int c = 0;
+    for (int64_t off = 0; off < n && rc == B2K_OK; off += cf, ++c) {
+        const int s = c & 1;
+        const int64_t len = std::min(cf, n - off);
+        // slot free? (its previous D2H finished) -> hand the previous labels of this slot to the caller
+        cudaEventSynchronize(ctx->ev_done[s]);
+        if (pend_off[s] >= 0 && !out_pinned)
+            std::memcpy(labels + pend_off[s], ctx->pinned_out[s], (size_t)pend_len[s] * 4);
+        pend_off[s] = -1;
+        const void* src = X + off * d;
+        if (!in_pinned) { std::memcpy(ctx->pinned[s], src, (size_t)len * row_bytes); src = ctx->pinned[s]; }
+        cudaMemcpyAsync(dX[s].p, src, (size_t)len * row_bytes, cudaMemcpyHostToDevice, ctx->copy_stream[s]);
+        cudaEventRecord(ctx->ev_h2d[s], ctx->copy_stream[s]);
+        cudaStreamWaitEvent(st, ctx->ev_h2d[s], 0);
+        if (use_screen) {
+            rc = screen_prepare_frames(plan, dX[s].as<float>(), len);
+            if (rc == B2K_OK) rc = screen_assign(plan, dX[s].as<float>(), len, dC.as<float>(), dL[s].as<int32_t>(), nullptr, 0);
+        } else {
+            if (metric == B2K_METRIC_MINRMSD)
+                rc = launch_rmsd_center(ctx, dX[s].as<float>(), len, d, nullptr, dG[s].as<float>());
+            if (rc == B2K_OK)
+                rc = assign_any(ctx, dX[s].as<float>(), dG[s].as<float>(), len, d, pc, k, metric, dL[s].as<int32_t>(),
+                                nullptr, 0);
+        }
+        cudaEventRecord(ev_k[s], st);
+        cudaStreamWaitEvent(ctx->copy_stream[s], ev_k[s], 0);
+        void* dst = out_pinned ? (void*)(labels + off) : ctx->pinned_out[s];
+        cudaMemcpyAsync(dst, dL[s].p, (size_t)len * 4, cudaMemcpyDeviceToHost, ctx->copy_stream[s]);
+        cudaEventRecord(ctx->ev_done[s], ctx->copy_stream[s]);
+        pend_off[s] = off;
+        pend_len[s] = len;
+    }
+    for (int s = 0; s < 2; ++s) {
+        cudaEventSynchronize(ctx->ev_done[s]);
+        if (pend_off[s] >= 0 && !out_pinned)
+            std::memcpy(labels + pend_off[s], ctx->pinned_out[s], (size_t)pend_len[s] * 4);
+        cudaEventDestroy(ev_k[s]);
+    }
+    cudaStreamSynchronize(st);
+    if (plan) screen_plan_destroy(plan);
+    if (rc != B2K_OK) return rc;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(B2K_ERR_CUDA, "assign: %s", cudaGetErrorString(e));
+    return B2K_OK;
+}
+
+// ---- Lloyd session ----------------------------------------------------------------------------
+struct b2k_lloyd {
+    b2k_ctx* ctx = nullptr;
+    const float* dX = nullptr;
+    int64_t n = 0, n_total = 0;
+    int d = 0, k = 0, metric = 0;
+    int q_sum = 0, q_cost = 0;
+    double scale_sum = 1, scale_cost = 1;
+    DevMem l, Ga;
+    PreparedCenters pc;
+    ScreenPlan* plan = nullptr;
+};
+
+static int ceil_log2_d(double v) {
+    if (!(v > 0)) return 0;
+    int e;
+    const double m = std::frexp(v, &e);  // v = m * 2^e, m in [0.5,1)
+    return (m == 0.5) ? e - 1 : e;
+}
+
+B2K_API int b2k_dev_lloyd_create(b2k_ctx* ctx, const float* dX, int64_t n_local, int32_t d, int32_t k, int metric,
+                                 int64_t n_total, float absmax_global, b2k_lloyd** out) {
+    if (!ctx || !out || n_local < 0 || d < 1 || k < 1 || n_total < n_local || (n_local > 0 && !dX))
+        return set_error(B2K_ERR_INVALID_ARG, "lloyd_create: bad arguments");
+    if (!std::isfinite(absmax_global))
+        return set_error(B2K_ERR_NONFINITE, "lloyd_create: data contains NaN or inf");
+    B2K_TRY(check_metric_dim(metric, d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    b2k_lloyd* s = new b2k_lloyd();
+    s->ctx = ctx; s->dX = dX; s->n = n_local; s->n_total = n_total; s->d = d; s->k = k; s->metric = metric;
+    // fixed point: |x| <= 2^eM, n_total <= 2^eN  =>  |sum| * 2^q < 2^62
+    const int eM = ceil_log2_d((double)absmax_global);
+    const int eN = ceil_log2_d((double)std::max<int64_t>(n_total, 1)) + 1;
+    s->q_sum = 62 - eN - eM;
+    // cost terms l^2 <= d * (2M)^2 (1+eps)
+    s->q_cost = 61 - eN - (2 * (eM + 1) + ceil_log2_d((double)d));
+    s->scale_sum = std::ldexp(1.0, s->q_sum);
+    s->scale_cost = std::ldexp(1.0, s->q_cost);
+    int rc = s->l.alloc((size_t)std::max<int64_t>(n_local, 1) * 4);
+    if (rc == B2K_OK && metric == B2K_METRIC_MINRMSD) {
+        rc = s->Ga.alloc((size_t)std::max<int64_t>(n_local, 1) * 4);
+        if (rc == B2K_OK) rc = launch_rmsd_center(ctx, dX, n_local, d, nullptr, s->Ga.as<float>());
+    }
+    if (rc == B2K_OK && metric == B2K_METRIC_EUCLIDEAN && ctx->engine != B2K_ENGINE_DIRECT &&
+        screen_supported(ctx, d, k, n_local)) {
+        rc = screen_plan_create(ctx, n_local, d, k, &s->plan);
+        if (rc == B2K_OK) rc = screen_prepare_frames(s->plan, dX, n_local);
+    }
+    if (rc != B2K_OK) { b2k_dev_lloyd_destroy(s); return rc; }
+    *out = s;
+    return B2K_OK;
+}
+
+B2K_API int b2k_dev_lloyd_destroy(b2k_lloyd* s) {
+    if (!s) return B2K_OK;
+    cudaStreamSynchronize(s->ctx->stream);
+    if (s->plan) screen_plan_destroy(s->plan);
+    delete s;
+    return B2K_OK;
+}
+
+B2K_API int64_t b2k_dev_lloyd_acc_len(const b2k_lloyd* s) { return s ? (int64_t)s->k * s->d + s->k + 1 : 0; }
+
+B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32_t* dlabels, int64_t* dacc) {
+    if (!s || !dC || !dacc || (s->n > 0 && !dlabels)) return set_error(B2K_ERR_INVALID_ARG, "lloyd step: null argument");
+    b2k_ctx* ctx = s->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemsetAsync(dacc, 0, (size_t)b2k_dev_lloyd_acc_len(s) * 8, ctx->stream));
+    if (s->n == 0) return B2K_OK;
+    if (s->plan) {
+        B2K_TRY(screen_assign(s->plan, s->dX, s->n, dC, dlabels, nullptr, 1));
+    } else {
+        B2K_TRY(s->pc.prepare(ctx, dC, s->k, s->d, s->metric));
+        B2K_TRY(assign_any(ctx, s->dX, s->Ga.as<float>(), s->n, s->d, s->pc, s->k, s->metric, dlabels, nullptr, 1));
+    }
+    return launch_accumulate(ctx, s->dX, s->n, s->d, s->k, dlabels, s->scale_sum, dacc);
+}
+
+B2K_API int b2k_dev_lloyd_finalize(b2k_lloyd* s, const int64_t* dacc, const float* dC_old, float* dC_new) {
+    if (!s || !dacc || !dC_old || !dC_new) return set_error(B2K_ERR_INVALID_ARG, "lloyd finalize: null argument");
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    return launch_finalize(s->ctx, dacc, s->k, s->d, std::ldexp(1.0, -s->q_sum), dC_old, dC_new);
+}
+
+B2K_API int b2k_dev_lloyd_cost(b2k_lloyd* s, const float* dC_new, const int32_t* dlabels, int64_t* dacc) {
+    if (!s || !dC_new || !dacc) return set_error(B2K_ERR_INVALID_ARG, "lloyd cost: null argument");
+    b2k_ctx* ctx = s->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int64_t* slot = dacc + (int64_t)s->k * s->d + s->k;
+    CUDA_TRY(cudaMemsetAsync(slot, 0, 8, ctx->stream));
+    if (s->n == 0) return B2K_OK;
+    if (s->metric == B2K_METRIC_MINRMSD) {
+        B2K_TRY(s->pc.prepare(ctx, dC_new, s->k, s->d, s->metric));
+        B2K_TRY(launch_rmsd_labeled_dist(ctx, s->dX, s->Ga.as<float>(), s->n, s->d, s->pc.C, s->pc.Gb, dlabels,
+                                         s->l.as<float>()));
+    } else {
+        B2K_TRY(launch_labeled_dist(ctx, s->dX, s->n, s->d, dC_new, dlabels, s->l.as<float>()));
+    }
+    return launch_cost_reduce(ctx, s->l.as<float>(), s->n, s->scale_cost, slot);
+}
+
+B2K_API double b2k_dev_lloyd_decode_cost(const b2k_lloyd* s, int64_t cost_fixed) {
+    return s ? std::ldexp((double)cost_fixed, -s->q_cost) : 0.0;
+}
+
+B2K_API int b2k_dev_absmax(b2k_ctx* ctx, const float* dX, int64_t count, float* out_host) {
+    if (!ctx || !out_host) return set_error(B2K_ERR_INVALID_ARG, "absmax: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    B2K_TRY(ctx->ensure_scratch(64));
+    CUDA_TRY(cudaMemsetAsync(ctx->scratch, 0, 4, ctx->stream));
+    B2K_TRY(launch_absmax(ctx, dX, count, (float*)ctx->scratch));
+    CUDA_TRY(cudaMemcpyAsync(out_host, ctx->scratch, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B2K_OK;
+}
+
+B2K_API int b2k_dev_all_finite(b2k_ctx* ctx, const float* dX, int64_t count, int* out_host) {
+    if (!ctx || !out_host) return set_error(B2K_ERR_INVALID_ARG, "all_finite: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    B2K_TRY(ctx->ensure_scratch(64));
+    const int one = 1;
+    CUDA_TRY(cudaMemcpyAsync(ctx->scratch, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
+    B2K_TRY(launch_all_finite(ctx, dX, count, (int*)ctx->scratch));
+    CUDA_TRY(cudaMemcpyAsync(out_host, ctx->scratch, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B2K_OK;
+}
+
+// single-GPU cluster_loop over device-resident frames (the per-iteration exchange is a no-op)
+static int dev_cluster_loop(b2k_ctx* ctx, const float* dX, int64_t n, int d, float* dC_io, int k, int metric,
+                            int max_iter, float tol, b2k_callback cb, void* user, int* code, int* iters,
+                            float* inertias, int cap, int32_t* dlabels_opt) {
+    float absmax = 0.f;
+    B2K_TRY(b2k_dev_absmax(ctx, dX, n * d, &absmax));
+    b2k_lloyd* s = nullptr;
+    B2K_TRY(b2k_dev_lloyd_create(ctx, dX, n, d, k, metric, n, absmax, &s));
+    DevMem acc, cnew, lab;
+    int rc = acc.alloc((size_t)b2k_dev_lloyd_acc_len(s) * 8);
+    if (rc == B2K_OK) rc = cnew.alloc((size_t)k * d * 4);
+    if (rc == B2K_OK && !dlabels_opt) rc = lab.alloc((size_t)std::max<int64_t>(n, 1) * 4);
+    int32_t* dl = dlabels_opt ? dlabels_opt : lab.as<int32_t>();
+    float* cur = dC_io;
+    float* nxt = cnew.as<float>();
+    int it = 0;
+    bool converged = false;
+    float prev = 0.f;
+    while (rc == B2K_OK) {
+        rc = b2k_dev_lloyd_assign_accumulate(s, cur, dl, acc.as<int64_t>());
+        if (rc == B2K_OK) rc = b2k_dev_lloyd_finalize(s, acc.as<int64_t>(), cur, nxt);
+        if (rc == B2K_OK) rc = b2k_dev_lloyd_cost(s, nxt, dl, acc.as<int64_t>());
+        if (rc != B2K_OK) break;
+        int64_t cf = 0;
+        cudaMemcpyAsync(&cf, acc.as<int64_t>() + (int64_t)k * d + k, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { rc = set_error(B2K_ERR_CUDA, "cluster_loop: %s", cudaGetErrorString(e)); break; }
+        std::swap(cur, nxt);
+        const float cost = (float)b2k_dev_lloyd_decode_cost(s, cf);
+        if (it < cap && inertias) inertias[it] = cost;
+        const float rel = (cost != 0.0f) ? std::fabs(cost - prev) / cost : 0.f;
+        prev = cost;
+        if (rel <= tol) converged = true;
+        else if (cb) cb(user);
+        it += 1;
+        if (!(it < max_iter && !converged)) break;
+    }
+    if (rc == B2K_OK && cur != dC_io) {
+        cudaMemcpyAsync(dC_io, cur, (size_t)k * d * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    b2k_dev_lloyd_destroy(s);
+    if (rc != B2K_OK) return rc;
+    *code = converged ? 0 : 1;
+    *iters = it;
+    return B2K_OK;
+}
+
+B2K_API int b2k_dev_kmeans_cluster_loop(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, float* dC_io, int32_t k,
+                                        int metric, int32_t max_iter, float tol, b2k_callback cb, void* user,
+                                        int* code, int* iters, float* inertias, int32_t cap, int32_t* dlabels_opt) {
+    if (!ctx || !dX || !dC_io || !code || !iters || n < 1 || d < 1 || k < 1)
+        return set_error(B2K_ERR_INVALID_ARG, "cluster_loop: bad arguments");
+    B2K_TRY(check_metric_dim(metric, d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return dev_cluster_loop(ctx, dX, n, d, dC_io, k, metric, max_iter, tol, cb, user, code, iters, inertias, cap,
+                            dlabels_opt);
+}
+
+// ---- host-pointer k-means entry points ----------------------------------------------------------
+struct HostFrames {  // frames of a host array made resident in HBM
+    DevMem mem;
+    int load(b2k_ctx* ctx, const float* X, int64_t n, int d) {
+        B2K_TRY(mem.alloc((size_t)n * d * 4));
+        return upload_host(ctx, X, mem.p, (size_t)n * d * 4);
+    }
+};
+
+B2K_API int b2k_kmeans_cluster(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* centers, int32_t k,
+                               int metric, float* new_centers, int32_t* labels) {
+    if (!ctx || !X || !centers || !new_centers || !labels || n < 1 || d < 1 || k < 1)
+        return set_error(B2K_ERR_INVALID_ARG, "kmeans_cluster: bad arguments");
+    B2K_TRY(check_metric_dim(metric, d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    HostFrames F;
+    B2K_TRY(F.load(ctx, X, n, d));
+    DevMem dC, dN, dL, acc;
+    B2K_TRY(dC.alloc((size_t)k * d * 4));
+    B2K_TRY(dN.alloc((size_t)k * d * 4));
+    B2K_TRY(dL.alloc((size_t)n * 4));
+    CUDA_TRY(cudaMemcpyAsync(dC.p, centers, (size_t)k * d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    float absmax = 0.f;
+    B2K_TRY(b2k_dev_absmax(ctx, F.mem.as<float>(), n * d, &absmax));
+    b2k_lloyd* s = nullptr;
+    B2K_TRY(b2k_dev_lloyd_create(ctx, F.mem.as<float>(), n, d, k, metric, n, absmax, &s));
+    int rc = acc.alloc((size_t)b2k_dev_lloyd_acc_len(s) * 8);
+    if (rc == B2K_OK) rc = b2k_dev_lloyd_assign_accumulate(s, dC.as<float>(), dL.as<int32_t>(), acc.as<int64_t>());
+    if (rc == B2K_OK) rc = b2k_dev_lloyd_finalize(s, acc.as<int64_t>(), dC.as<float>(), dN.as<float>());
+    if (rc == B2K_OK) {
+        cudaMemcpyAsync(new_centers, dN.p, (size_t)k * d * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(labels, dL.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = set_error(B2K_ERR_CUDA, "kmeans_cluster: %s", cudaGetErrorString(e));
+    }
+    b2k_dev_lloyd_destroy(s);
+    return rc;
+}
+
+B2K_API int b2k_kmeans_cost(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* centers, int32_t k,
+                            const int32_t* labels, int metric, float* cost) {
+    if (!ctx || !X || !centers || !labels || !cost || n < 1 || d < 1 || k < 1)
+        return set_error(B2K_ERR_INVALID_ARG, "kmeans_cost: bad arguments");
+    B2K_TRY(check_metric_dim(metric, d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    HostFrames F;
+    B2K_TRY(F.load(ctx, X, n, d));
+    DevMem dC, dL, acc;
+    B2K_TRY(dC.alloc((size_t)k * d * 4));
+    B2K_TRY(dL.alloc((size_t)n * 4));
+    CUDA_TRY(cudaMemcpyAsync(dC.p, centers, (size_t)k * d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(dL.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    float absmax = 0.f;
+    B2K_TRY(b2k_dev_absmax(ctx, F.mem.as<float>(), n * d, &absmax));
+    // the cost fixed-point scale must also cover the centers
+    float cmax = 0.f;
+    B2K_TRY(b2k_dev_absmax(ctx, dC.as<float>(), (int64_t)k * d, &cmax));
+    b2k_lloyd* s = nullptr;
+    const int saved_engine = ctx->engine;
+    ctx->engine = B2K_ENGINE_DIRECT;  // no screen operands needed for a cost evaluation
+    int rc = b2k_dev_lloyd_create(ctx, F.mem.as<float>(), n, d, k, metric, n, std::max(absmax, cmax), &s);
+    ctx->engine = saved_engine;
+    if (rc != B2K_OK) return rc;
+    rc = acc.alloc((size_t)b2k_dev_lloyd_acc_len(s) * 8);
+    if (rc == B2K_OK) rc = b2k_dev_lloyd_cost(s, dC.as<float>(), dL.as<int32_t>(), acc.as<int64_t>());
+    if (rc == B2K_OK) {
+        int64_t cf = 0;
+        cudaMemcpyAsync(&cf, acc.as<int64_t>() + (int64_t)k * d + k, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = set_error(B2K_ERR_CUDA, "kmeans_cost: %s", cudaGetErrorString(e));
+        else *cost = (float)b2k_dev_lloyd_decode_cost(s, cf);
+    }
+    b2k_dev_lloyd_destroy(s);
+    return rc;
+}
+
+B2K_API int b2k_kmeans_cluster_loop(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, float* centers_io, int32_t k,
+                                    int metric, int32_t max_iter, float tolerance, b2k_callback cb, void* user,
+                                    int* code, int* iters, float* inertias, int32_t inertias_cap) {
+    if (!ctx || !X || !centers_io || !code || !iters || n < 1 || d < 1 || k < 1)
+        return set_error(B2K_ERR_INVALID_ARG, "cluster_loop: bad arguments");
+    B2K_TRY(check_metric_dim(metric, d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    HostFrames F;
+    B2K_TRY(F.load(ctx, X, n, d));
+    DevMem dC;
+    B2K_TRY(dC.alloc((size_t)k * d * 4));
+    CUDA_TRY(cudaMemcpyAsync(dC.p, centers_io, (size_t)k * d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    B2K_TRY(dev_cluster_loop(ctx, F.mem.as<float>(), n, d, dC.as<float>(), k, metric, max_iter, tolerance, cb, user,
+                             code, iters, inertias, inertias_cap, nullptr));
+    CUDA_TRY(cudaMemcpyAsync(centers_io, dC.p, (size_t)k * d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B2K_OK;
+}
+
+B2K_API int b2k_dev_kmeans_init_centers_kmpp(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, int32_t k,
+                                             int metric, int64_t seed, int scan_mode, b2k_callback cb, void* user,
+                                             float* dcenters_out, int64_t* chosen_host) {
+    if (!ctx || !dX || !dcenters_out || n < 1 || d < 1)
+        return set_error(B2K_ERR_INVALID_ARG, "init_centers_kmpp: bad arguments");
+    B2K_TRY(check_metric_dim(metric, d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return kmpp_run(ctx, dX, n, d, k, metric, seed, scan_mode, cb, user, dcenters_out, chosen_host);
+}
+
+B2K_API int b2k_kmeans_init_centers_kmpp(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, int32_t k, int metric,
+                                         int64_t seed, int scan_mode, b2k_callback cb, void* user,
+                                         float* centers_out, int64_t* chosen_or_null) {
+    if (!ctx || !X || !centers_out || n < 1 || d < 1)
+        return set_error(B2K_ERR_INVALID_ARG, "init_centers_kmpp: bad arguments");
+    if (k < 1 || k > n) return set_error(B2K_ERR_INVALID_ARG, "k-means++: need 1 <= k <= n (k=%d, n=%lld)", k, (long long)n);
+    B2K_TRY(check_metric_dim(metric, d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    HostFrames F;
+    B2K_TRY(F.load(ctx, X, n, d));
+    DevMem dC;
+    B2K_TRY(dC.alloc((size_t)k * d * 4));
+    B2K_TRY(kmpp_run(ctx, F.mem.as<float>(), n, d, k, metric, seed, scan_mode, cb, user, dC.as<float>(), chosen_or_null));
+    CUDA_TRY(cudaMemcpyAsync(centers_out, dC.p, (size_t)k * d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B2K_OK;
+}
+

@@ -1,0 +1,129 @@
+// common.cuh -- shared host/device helpers of libb2k (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <atomic>
+#include "../../include/b2k.h"
+
+#define B2K_API extern "C" __attribute__((visibility("default")))
+
+namespace b2k {
+
+// ---- error plumbing ------------------------------------------------------------------------
+extern thread_local std::string g_last_error;
+extern std::atomic<long long> g_launches;
+int set_error(int code, const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return b2k::set_error(_e == cudaErrorMemoryAllocation ? B2K_ERR_NOMEM : B2K_ERR_CUDA, \
+                                  "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,        \
+                                  cudaGetErrorString(_e));                                      \
+    } while (0)
+#define B2K_TRY(expr)                  \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != B2K_OK) return _rc; \
+    } while (0)
+#define LAUNCH_CHECK()                 \
+    do {                               \
+        b2k::g_launches.fetch_add(1);  \
+        CUDA_TRY(cudaGetLastError());  \
+    } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace b2k
+
+// ---- context -------------------------------------------------------------------------------
+struct b2k_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // pinned staging slots for the host-pointer entry points
+    void* pinned[2] = {nullptr, nullptr};
+    void* pinned_out[2] = {nullptr, nullptr};
+    size_t stage_bytes = size_t(64) << 20;
+    size_t pinned_cap = 0, pinned_out_cap = 0;
+    // options
+    int engine = B2K_ENGINE_AUTO;
+    int screen_terms = 0;
+    // stats of the last screen call
+    double stat_cand_chunks = 0, stat_fallback_frames = 0, stat_screen_frames = 0;
+    // generic device scratch (grown on demand)
+    void* scratch = nullptr;
+    size_t scratch_cap = 0;
+    int ensure_scratch(size_t bytes);
+};
+
+// ---- device helpers: the exact fp32 arithmetic of the reference path -------------------------
+namespace b2k {
+
+// Euclidean squared distance in the pinned reference order:
+// 4 interleaved lane accumulators over i<4*(d/4), the d%4 tail into lane 0, ((a0+a1)+a2)+a3.
+// __f*_rn intrinsics are never contracted into FMA by nvcc.
+struct Lanes4 {
+    float a0, a1, a2, a3;
+    __device__ __forceinline__ void init() { a0 = a1 = a2 = a3 = 0.f; }
+    __device__ __forceinline__ void add4(float x0, float x1, float x2, float x3, float c0, float c1, float c2,
+                                          float c3) {
+        float t0 = __fsub_rn(x0, c0), t1 = __fsub_rn(x1, c1), t2 = __fsub_rn(x2, c2), t3 = __fsub_rn(x3, c3);
+        a0 = __fadd_rn(a0, __fmul_rn(t0, t0));
+        a1 = __fadd_rn(a1, __fmul_rn(t1, t1));
+        a2 = __fadd_rn(a2, __fmul_rn(t2, t2));
+        a3 = __fadd_rn(a3, __fmul_rn(t3, t3));
+    }
+    __device__ __forceinline__ void tail(float x, float c) {
+        float t = __fsub_rn(x, c);
+        a0 = __fadd_rn(a0, __fmul_rn(t, t));
+    }
+    __device__ __forceinline__ float result() const {
+        return __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);  // (0+a0)==a0 exactly
+    }
+};
+
+// generic-pointer version (global or shared), any d
+__device__ __forceinline__ float euclid_sq_exact(const float* __restrict__ x, const float* __restrict__ c, int d) {
+    Lanes4 L;
+    L.init();
+    const int d4 = d & ~3;
+    for (int i = 0; i < d4; i += 4) L.add4(x[i], x[i + 1], x[i + 2], x[i + 3], c[i], c[i + 1], c[i + 2], c[i + 3]);
+    for (int i = d4; i < d; ++i) L.tail(x[i], c[i]);
+    return L.result();
+}
+
+// "first minimum AFTER the sqrt" bookkeeping on squared values.
+// The reference compares dj = sqrt(s_j) with strict '<' scanning j upwards.  sqrt is monotone,
+// so s_c >= best_s can never win; s_c < best_s wins unless both round to the same sqrt, which
+// needs s_c >= best_s*(1-2^-20) (two floats closer than that can share a correctly rounded sqrt).
+struct ArgMin {
+    float s;    // squared distance of the current winner (+inf: none yet)
+    int32_t j;  // its index (-1: none)
+    __device__ __forceinline__ void init() { s = __int_as_float(0x7f800000); j = -1; }
+    // candidate with index larger than every index seen so far by THIS scanner
+    __device__ __forceinline__ void offer(float sc, int32_t jc) {
+        if (sc < s) {
+            if (sc < s * 0.99999905f || __fsqrt_rn(sc) < __fsqrt_rn(s)) { s = sc; j = jc; }
+        }
+    }
+    // order-free merge of two partial winners: lexicographic (sqrt(s), j)
+    __device__ __forceinline__ void merge(float so, int32_t jo) {
+        if (jo < 0) return;
+        if (j < 0) { s = so; j = jo; return; }
+        const float ra = __fsqrt_rn(s), rb = __fsqrt_rn(so);
+        if (rb < ra || (rb == ra && jo < j)) { s = so; j = jo; }
+    }
+};
+
+}  // namespace b2k

@@ -1,0 +1,266 @@
+// exact.cu -- exact fp32 CUDA-core kernels of the Euclidean path (K1 of SURVEY 2.2).
+//
+// Every distance here is evaluated in the pinned operation order of the reference build
+// (common.cuh Lanes4 / SURVEY Appendix B.1) so that the argmin is bit-identical to the
+// reference's `argmin_j sqrt(sum)` with lowest-index tie break (deeptime
+// assign_chunk_to_centers, call site pyemma/coordinates/clustering/interface.py:164-165).
+//
+//   assign_small_kernel<D>  d <= 16: frame in registers, centers broadcast from smem.
+//   tile_kernel<MODE>       any d: a tile of FB frames is staged coalesced into padded
+//                           smem, 128 threads = FB frames x G center groups, 4 centers
+//                           register-tiled per thread.  MODE_ARGMIN -> labels (+min dist),
+//                           MODE_ALL -> all distances out[j][i] (k-means++ candidates,
+//                           regspace steps).
+//   labeled_dist_kernel     l_i = sqrt(dist2(x_i, C[label_i])) (cost function).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b2k {
+
+// -------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) assign_small_kernel(const float* __restrict__ X, int64_t n,
+                                                           const float* __restrict__ C, int k, int kt,
+                                                           int32_t* __restrict__ labels, float* __restrict__ mind,
+                                                           int lloyd) {
+    extern __shared__ __align__(16) float cs[];
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool valid = i < n;
+    float x[D];
+    if (valid) {
+#pragma unroll
+        for (int e = 0; e < D; ++e) x[e] = __ldg(X + i * D + e);
+    }
+    ArgMin am;
+    am.init();
+    for (int j0 = 0; j0 < k; j0 += kt) {
+        const int kk = min(kt, k - j0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < kk * D; t += 256) cs[t] = __ldg(C + (int64_t)j0 * D + t);
+        __syncthreads();
+        if (valid) {
+#pragma unroll 4
+            for (int j = 0; j < kk; ++j) {
+                const float* c = cs + j * D;
+                Lanes4 L;
+                L.init();
+#pragma unroll
+                for (int e = 0; e + 3 < D; e += 4)
+                    L.add4(x[e], x[e + 1], x[e + 2], x[e + 3], c[e], c[e + 1], c[e + 2], c[e + 3]);
+#pragma unroll
+                for (int e = D & ~3; e < D; ++e) L.tail(x[e], c[e]);
+                am.offer(D < 4 ? L.a0 : L.result(), j0 + j);
+            }
+        }
+    }
+    if (valid) {
+        labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
+        if (mind) mind[i] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+struct TileCfg {
+    int FB, G, KT, ds, xstride;
+    size_t smem;
+};
+
+static TileCfg tile_cfg(int d, int k, size_t smem_budget) {
+    TileCfg c;
+    c.ds = (d + 3) & ~3;
+    c.xstride = ((c.ds / 4) % 2 == 0) ? c.ds + 4 : c.ds + 8;
+    int FB = 128;
+    // X tile may use at most ~60% of the budget
+    while (FB > 4 && (size_t)FB * c.xstride * 4 > smem_budget * 6 / 10) FB >>= 1;
+    c.FB = FB;
+    c.G = 128 / FB;
+    size_t left = smem_budget - (size_t)FB * c.xstride * 4 - 128 * 8;
+    int KT = (int)(left / ((size_t)c.ds * 4));
+    KT = (KT / (4 * c.G)) * (4 * c.G);
+    int kmax = (int)cdiv(k, 4 * c.G) * 4 * c.G;
+    if (KT > kmax) KT = kmax;
+    if (KT < 4 * c.G) KT = 4 * c.G;
+    c.KT = KT;
+    c.smem = (size_t)FB * c.xstride * 4 + (size_t)KT * c.ds * 4 + 128 * 8;
+    return c;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) tile_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                   const float* __restrict__ C, int k, TileCfg cfg,
+                                                   int32_t* __restrict__ labels, float* __restrict__ out,
+                                                   int lloyd) {
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;
+    float* cs = sm + (size_t)cfg.FB * cfg.xstride;
+    float* red_s = cs + (size_t)cfg.KT * cfg.ds;
+    int32_t* red_j = (int32_t*)(red_s + 128);
+    const int tid = threadIdx.x;
+    const int f = tid % cfg.FB, g = tid / cfg.FB;
+    const int64_t base = (int64_t)blockIdx.x * cfg.FB;
+    const int nf = (int)min((int64_t)cfg.FB, n - base);
+    const int d4 = d & ~3;
+
+    // stage the frame tile (coalesced over the flattened tile)
+    {
+        const float* src = X + base * d;
+        const int total = nf * d;
+        for (int t = tid; t < total; t += 128) {
+            const int r = t / d, c = t - r * d;
+            xs[(size_t)r * cfg.xstride + c] = __ldg(src + t);
+        }
+    }
+    ArgMin am;
+    am.init();
+    const float* xrow = xs + (size_t)f * cfg.xstride;
+    const bool valid = f < nf;
+
+    for (int j0 = 0; j0 < k; j0 += cfg.KT) {
+        const int kk = min(cfg.KT, k - j0);
+        __syncthreads();
+        {
+            const float* src = C + (int64_t)j0 * d;
+            const int total = kk * d;
+            for (int t = tid; t < total; t += 128) {
+                const int r = t / d, c = t - r * d;
+                cs[(size_t)r * cfg.ds + c] = __ldg(src + t);
+            }
+        }
+        __syncthreads();
+        if (!valid) continue;
+        for (int jj = g; jj < kk; jj += 4 * cfg.G) {
+            // 4 centers jj, jj+G, jj+2G, jj+3G (clamped duplicates are discarded below)
+            const float* cr[4];
+            int jx[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                jx[c] = jj + c * cfg.G;
+                cr[c] = cs + (size_t)min(jx[c], kk - 1) * cfg.ds;
+            }
+            Lanes4 L[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) L[c].init();
+            for (int e = 0; e < d4; e += 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(xrow + e);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 cv = *reinterpret_cast<const float4*>(cr[c] + e);
+                    L[c].add4(xv.x, xv.y, xv.z, xv.w, cv.x, cv.y, cv.z, cv.w);
+                }
+            }
+            for (int e = d4; e < d; ++e) {
+                const float xv = xrow[e];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) L[c].tail(xv, cr[c][e]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (jx[c] < kk) {
+                    const float s = L[c].result();
+                    if (MODE == MODE_ARGMIN) am.offer(s, j0 + jx[c]);
+                    else out[(int64_t)(j0 + jx[c]) * n + base + f] = __fsqrt_rn(s);
+                }
+            }
+        }
+    }
+    if (MODE == MODE_ARGMIN) {
+        if (cfg.G > 1) {
+            __syncthreads();
+            red_s[tid] = am.s;
+            red_j[tid] = am.j;
+            __syncthreads();
+            if (g == 0) {
+                for (int gg = 1; gg < cfg.G; ++gg) am.merge(red_s[gg * cfg.FB + f], red_j[gg * cfg.FB + f]);
+            }
+        }
+        if (g == 0 && valid) {
+            labels[base + f] = (lloyd && am.j < 0) ? 0 : am.j;
+            if (out) out[base + f] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// l_i = sqrt(dist2(x_i, C[label_i]))  -- thread per frame, rows streamed from global/L1.
+__global__ void __launch_bounds__(256) labeled_dist_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                           const float* __restrict__ C,
+                                                           const int32_t* __restrict__ labels,
+                                                           float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int32_t a = labels[i];
+    out[i] = __fsqrt_rn(euclid_sq_exact(X + i * d, C + (int64_t)a * d, d));
+}
+
+// -------------------------------------------------------------------------------------------
+template <int D>
+static int launch_small(b2k_ctx* ctx, const float* X, int64_t n, const float* C, int k, int32_t* labels, float* mind,
+                        int lloyd) {
+    const size_t budget = 96 * 1024;
+    int kt = (int)std::min<int64_t>(k, budget / (D * 4));
+    const size_t smem = (size_t)kt * D * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(assign_small_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)budget));
+        attr_set = true;
+    }
+    const int64_t blocks = cdiv(n, 256);
+    assign_small_kernel<D><<<(unsigned)blocks, 256, smem, ctx->stream>>>(X, n, C, k, kt, labels, mind, lloyd);
+    LAUNCH_CHECK();
+    return B2K_OK;
+}
+
+int launch_assign_exact(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels,
+                        float* mind, int lloyd) {
+    if (n <= 0) return B2K_OK;
+    if (k <= 0) return set_error(B2K_ERR_INVALID_ARG, "assign: no centers");
+    switch (d) {
+#define CASE(D) case D: return launch_small<D>(ctx, X, n, C, k, labels, mind, lloyd);
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+        CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
+#undef CASE
+        default: break;
+    }
+    return launch_tile(ctx, X, n, d, C, k, labels, mind, lloyd, MODE_ARGMIN);
+}
+
+int launch_tile(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels, float* out,
+                int lloyd, int mode) {
+    if (n <= 0 || k <= 0) return B2K_OK;
+    const size_t budget = std::min<size_t>(ctx->smem_optin, 200 * 1024);
+    TileCfg cfg = tile_cfg(d, k, budget);
+    if (cfg.smem > ctx->smem_optin)
+        return set_error(B2K_ERR_INVALID_ARG, "dimension %d too large for the exact tile kernel", d);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(tile_kernel<MODE_ARGMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)ctx->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(tile_kernel<MODE_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)ctx->smem_optin));
+        attr_set = true;
+    }
+    const int64_t blocks = cdiv(n, cfg.FB);
+    if (mode == MODE_ARGMIN)
+        tile_kernel<MODE_ARGMIN><<<(unsigned)blocks, 128, cfg.smem, ctx->stream>>>(X, n, d, C, k, cfg, labels, out,
+                                                                                    lloyd);
+    else
+        tile_kernel<MODE_ALL><<<(unsigned)blocks, 128, cfg.smem, ctx->stream>>>(X, n, d, C, k, cfg, labels, out,
+                                                                                 lloyd);
+    LAUNCH_CHECK();
+    return B2K_OK;
+}
+
+int launch_dist_rows(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out) {
+    return launch_tile(ctx, X, n, d, rows, m, nullptr, out, 0, MODE_ALL);
+}
+
+int launch_labeled_dist(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, const int32_t* labels,
+                        float* out) {
+    if (n <= 0) return B2K_OK;
+    labeled_dist_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(X, n, d, C, labels, out);
+    LAUNCH_CHECK();
+    return B2K_OK;
+}
+
+}  // namespace b2k

@@ -1,0 +1,59 @@
+// kernels.h -- internal launcher prototypes shared by the libb2k translation units.
+#pragma once
+#include "common.cuh"
+
+namespace b2k {
+
+enum { MODE_ARGMIN = 0, MODE_ALL = 1 };
+
+// ---- exact.cu (Euclidean, exact fp32 reference order) -------------------------------------
+int launch_assign_exact(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels,
+                        float* mind, int lloyd);
+int launch_tile(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels, float* out,
+                int lloyd, int mode);
+// out[j][i] = sqrt(dist2(x_i, rows_j)), j < m
+int launch_dist_rows(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out);
+int launch_labeled_dist(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, const int32_t* labels,
+                        float* out);
+
+// ---- rmsd.cu (minRMSD / QCP) ----------------------------------------------------------------
+// centered copies + traces of m structures (rows of `src`, optionally gathered by idx)
+int launch_rmsd_center(b2k_ctx* ctx, const float* src, int64_t m, int d, float* centered_or_null, float* traces);
+int launch_rmsd_assign(b2k_ctx* ctx, const float* X, const float* Ga, int64_t n, int d, const float* Cc,
+                       const float* Gb, int k, int32_t* labels, float* mind, int lloyd);
+int launch_rmsd_dist_rows(b2k_ctx* ctx, const float* X, const float* Ga, int64_t n, int d, const float* Rc,
+                          const float* Gb, int m, float* out);
+int launch_rmsd_labeled_dist(b2k_ctx* ctx, const float* X, const float* Ga, int64_t n, int d, const float* Cc,
+                             const float* Gb, const int32_t* labels, float* out);
+
+// ---- metric-generic front (api.cu) ----------------------------------------------------------
+struct MetricData {  // per-dataset auxiliary data of a metric (minRMSD: traces of the centered frames)
+    int metric = 0;
+    float* Ga = nullptr;  // device, n floats (minRMSD only)
+};
+
+// ---- api.cu ----------------------------------------------------------------------------------
+// host array -> device (pageable sources bounce through the pinned staging slots)
+int upload_host(b2k_ctx* ctx, const void* src, void* dst, size_t bytes);
+
+// ---- lloyd.cu -------------------------------------------------------------------------------
+int launch_accumulate(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, const int32_t* labels, double scale,
+                      int64_t* acc);
+int launch_finalize(b2k_ctx* ctx, const int64_t* acc, int k, int d, double inv_scale, const float* old_centers,
+                    float* new_centers);
+int launch_cost_reduce(b2k_ctx* ctx, const float* l, int64_t n, double scale, int64_t* acc_slot);
+int launch_absmax(b2k_ctx* ctx, const float* X, int64_t count, float* d_out /* device, 1 float, pre-zeroed */);
+int launch_all_finite(b2k_ctx* ctx, const float* X, int64_t count, int* d_flag /* device, pre-set to 1 */);
+
+// ---- screen.cu (tcgen05 distance screen + exact verify) -------------------------------------
+struct ScreenPlan;
+int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** out);
+void screen_plan_destroy(ScreenPlan* p);
+// (re)build the frame operand for n frames at dX (done once per dataset / chunk)
+int screen_prepare_frames(ScreenPlan* p, const float* dX, int64_t n);
+// labels for the prepared frames against dcenters
+int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dcenters, int32_t* labels, float* mind,
+                  int lloyd);
+bool screen_supported(const b2k_ctx* ctx, int d, int k, int64_t n);
+
+}  // namespace b2k

@@ -1,0 +1,536 @@
+// kmpp.cu -- k-means++ seeding (K4 of SURVEY 2.2).
+//
+// Replaces deeptime kmeans.init_centers_kmpp(data, k, random_seed, n_threads, callback)
+// (signature evidenced by pyemma/coordinates/clustering/tests/test_kmeans.py:304; invoked
+// from KMeans.fit, call site pyemma/coordinates/clustering/kmeans.py:254-255).
+//
+// Algorithm: first center uniform; D2[i] = compute(x_i,c0)^2; every round
+// draws n_trials = 2 + floor(ln k) thresholds r_j = dist_sum * u_j, picks candidate_j as the
+// first frame whose running D2 prefix reaches r_j, evaluates each candidate's potential
+// sum_i min(D2[i], compute(x_i, cand_j)^2), keeps the best, updates D2.
+//
+// The RNG stream does not depend on the data, so the host precomputes every u_j
+// (own mt19937 + the libstdc++ uniform_int mapping, restated below) and the device never waits
+// for a random number.  Distances are the exact fp32 reference-order kernels (exact.cu / rmsd.cu).
+//
+// Ordered sums.  The reference's prefix scan, potentials and dist_sum bookkeeping are fp32 sums
+// in frame order, so their bits depend on that order:
+//   B2K_KMPP_SERIAL  reproduces that order exactly (one warp walks the array; bit-faithful to the
+//                    reference at n_jobs=1; inherently latency-bound: 1 dependent FADD per frame)
+//   B2K_KMPP_BLOCKED every sum is the balanced binary tree over aligned power-of-two index blocks,
+//                    dist_sum is the tree root, and candidates are found by descending the tree
+//                    (left if r <= sum(left) else r -= sum(left)).  Deterministic, parallel, and
+//                    defined identically in oracle/oracle.cpp so parity stays bit-exact.
+#include "common.cuh"
+#include "kernels.h"
+#include <random>
+
+namespace b2k {
+
+// ---- host RNG: mt19937 + libstdc++ uniform_int_distribution (Lemire) + (T)g()/(T)g.max() -----
+struct MT19937 {
+    uint32_t mt[624];
+    int idx;
+    explicit MT19937(uint32_t seed) {
+        mt[0] = seed;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    uint32_t next() {
+        if (idx >= 624) {
+            for (int i = 0; i < 624; ++i) {
+                const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+                mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    // uniform integer in [0, range) for range <= 2^32 (libstdc++ _S_nd<uint64_t> on a 32-bit URBG)
+    uint64_t below(uint64_t range) {
+        if (range == (uint64_t(1) << 32)) return next();
+        const uint32_t r32 = (uint32_t)range;
+        uint64_t product = (uint64_t)next() * r32;
+        uint32_t low = (uint32_t)product;
+        if (low < r32) {
+            const uint32_t threshold = (0u - r32) % r32;
+            while (low < threshold) {
+                product = (uint64_t)next() * r32;
+                low = (uint32_t)product;
+            }
+        }
+        return product >> 32;
+    }
+    float unit() { return (float)next() / (float)0xffffffffu; }
+};
+
+// ---- device state --------------------------------------------------------------------------
+#define KMPP_MAX_TRIALS 24
+struct KmppState {
+    float dist_sum;
+    int n_cand;
+    long long cand[KMPP_MAX_TRIALS];  // -1 = none
+    float rands[KMPP_MAX_TRIALS];
+    float pot[KMPP_MAX_TRIALS];
+    long long best;  // frame index of the accepted center
+    int jbest;       // which candidate (-1: fallback "first non-taken frame")
+    float delta_sum;
+};
+
+__global__ void kmpp_square_init_kernel(const float* __restrict__ v, int64_t n, int64_t first, float* __restrict__ D,
+                                        unsigned char* __restrict__ taken) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = v[i];
+    D[i] = (i == first) ? 0.f : __fmul_rn(x, x);
+    taken[i] = (i == first) ? 1 : 0;
+}
+
+// cd[j][i] <- contribution of frame i to candidate j's potential (0 for taken / self / no candidate)
+__global__ void kmpp_contrib_kernel(float* __restrict__ cd, int64_t n, int m, const float* __restrict__ D,
+                                    const unsigned char* __restrict__ taken, const KmppState* __restrict__ st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool tk = taken[i] != 0;
+    const float di = D[i];
+    for (int j = 0; j < m; ++j) {
+        const long long c = st->cand[j];
+        float out = 0.f;
+        if (!tk && c >= 0 && c != i) {
+            const float v = cd[(int64_t)j * n + i];
+            const float dd = __fmul_rn(v, v);
+            out = (dd < di) ? dd : di;
+        }
+        cd[(int64_t)j * n + i] = out;
+    }
+}
+
+// gather candidate rows (missing candidates -> row of frame 0, ignored later)
+__global__ void kmpp_gather_kernel(const float* __restrict__ X, int d, const KmppState* __restrict__ st, int m,
+                                   float* __restrict__ rows) {
+    const int j = blockIdx.x;
+    long long c = st->cand[j];
+    if (c < 0) c = 0;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) rows[(int64_t)j * d + e] = X[c * d + e];
+}
+
+// D[i] <- min(D[i], d2(x_i,best)) using the stored contributions; delta[i] <- change (serial mode)
+__global__ void kmpp_update_kernel(float* __restrict__ D, const unsigned char* __restrict__ taken, int64_t n,
+                                   const float* __restrict__ src /* cd[jbest] or fresh distances (sqrt'd) */,
+                                   int src_is_sqrt, float* __restrict__ delta) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float dl = 0.f;
+    if (!taken[i]) {
+        float dd = src[i];
+        if (src_is_sqrt) dd = __fmul_rn(dd, dd);
+        const float old = D[i];
+        if (dd < old) { dl = __fsub_rn(dd, old); D[i] = dd; }
+    }
+    if (delta) delta[i] = dl;
+}
+
+// ---- SERIAL ordered sums: one warp, values fetched coalesced, summed in frame order ------------
+// prefix scan + candidate pick (reference: `sum += D2[i]; if (sum >= r_j && cand_j == none) cand_j = i`)
+__global__ void __launch_bounds__(32) kmpp_serial_scan_kernel(const float* __restrict__ D,
+                                                              const unsigned char* __restrict__ taken, int64_t n,
+                                                              KmppState* st, const float* __restrict__ u, int m) {
+    const int lane = threadIdx.x;
+    __shared__ float r[KMPP_MAX_TRIALS];
+    __shared__ long long cand[KMPP_MAX_TRIALS];
+    if (lane < m) {
+        r[lane] = __fmul_rn(st->dist_sum, u[lane]);
+        cand[lane] = -1;
+    }
+    __syncwarp();
+    float pending = 3.402823466e+38f;  // smallest unmet threshold
+    int unmet = m;
+    unsigned found_mask = 0;  // warp-uniform: which thresholds already have their candidate
+    for (int j = 0; j < m; ++j) pending = fminf(pending, r[j]);
+    float sum = 0.f;
+    for (int64_t i0 = 0; i0 < n && unmet > 0; i0 += 32) {
+        const int64_t i = i0 + lane;
+        float v = 0.f;
+        bool act = false;
+        if (i < n && !taken[i]) { v = D[i]; act = true; }
+        const unsigned actmask = __ballot_sync(0xffffffffu, act);
+        for (int t = 0; t < 32; ++t) {
+            const float vt = __shfl_sync(0xffffffffu, v, t);
+            if (!((actmask >> t) & 1u)) continue;
+            sum = __fadd_rn(sum, vt);
+            if (sum >= pending) {
+                pending = 3.402823466e+38f;
+                unmet = 0;
+                for (int j = 0; j < m; ++j) {
+                    if (!((found_mask >> j) & 1u)) {
+                        if (sum >= r[j]) { found_mask |= 1u << j; if (lane == 0) cand[j] = i0 + t; }
+                        else { pending = fminf(pending, r[j]); ++unmet; }
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < m) {
+        st->cand[lane] = cand[lane];
+        st->rands[lane] = r[lane];
+    }
+    if (lane == 0) st->n_cand = m;
+}
+
+// out[j] = ((..(0 + a[j][0]) + a[j][1]) + ...) fp32 in index order.  The block stages tiles of
+// all m arrays coalesced into smem; thread j then walks row j sequentially (one dependent FADD
+// per element -- the reference's order allows nothing faster).
+#define KSUM_TI 256
+__global__ void __launch_bounds__(256) kmpp_serial_sum_kernel(const float* __restrict__ a, int64_t n, int m,
+                                                              float* __restrict__ out) {
+    __shared__ float tile[KMPP_MAX_TRIALS][KSUM_TI + 1];
+    const int tid = threadIdx.x;
+    float s = 0.f;
+    for (int64_t i0 = 0; i0 < n; i0 += KSUM_TI) {
+        const int len = (int)min((int64_t)KSUM_TI, n - i0);
+        for (int j = 0; j < m; ++j)
+            if (tid < len) tile[j][tid] = a[(int64_t)j * n + i0 + tid];
+        __syncthreads();
+        if (tid < m) {
+#pragma unroll 8
+            for (int t = 0; t < len; ++t) s = __fadd_rn(s, tile[tid][t]);
+        }
+        __syncthreads();
+    }
+    if (tid < m) out[tid] = s;
+}
+
+// initial dist_sum: ordered sum of D over non-taken frames (D[first]==0 so no mask needed)
+__global__ void kmpp_set_dist_sum_kernel(KmppState* st, const float* __restrict__ s) { st->dist_sum = s[0]; }
+
+// ---- BLOCKED ordered sums: balanced tree, levels stored every 5 heights ----------------------
+// in: len values (level h0; masked by `taken` when given).  out5[t] = tree sum of 32, out10[b] of 1024.
+__global__ void __launch_bounds__(1024) tree_up_kernel(const float* __restrict__ in, int64_t len, int64_t in_stride,
+                                                       const unsigned char* __restrict__ taken,
+                                                       float* __restrict__ out5, int64_t out5_stride,
+                                                       float* __restrict__ out10, int64_t out10_stride) {
+    __shared__ float ws[32];
+    const int j = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    float v = 0.f;
+    if (i < len) {
+        v = in[(int64_t)j * in_stride + i];
+        if (taken && taken[i]) v = 0.f;
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        ws[w] = v;
+        const int64_t t5 = (int64_t)blockIdx.x * 32 + w;
+        if (out5 && t5 * 32 < len) out5[(int64_t)j * out5_stride + t5] = v;
+    }
+    __syncthreads();
+    if (w == 0) {
+        float s = ws[threadIdx.x];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+        if (threadIdx.x == 0) out10[(int64_t)j * out10_stride + blockIdx.x] = s;
+    }
+}
+
+struct TreeLevels {
+    const float* lv[7];  // heights 0,5,...,30
+    long long len[7];
+    int H;  // height of the root: 2^H = pow2_ceil(n)
+};
+
+__device__ float tree_node_sum(const TreeLevels& T, const unsigned char* taken, int h, long long t) {
+    const int b = h / 5, r = h - 5 * b;
+    const int cnt = 1 << r;
+    float vals[16];
+    for (int q = 0; q < cnt; ++q) {
+        const long long idx = t * cnt + q;
+        float v = 0.f;
+        if (idx < T.len[b]) {
+            v = T.lv[b][idx];
+            if (b == 0 && taken && taken[idx]) v = 0.f;
+        }
+        vals[q] = v;
+    }
+    for (int s = 1; s < cnt; s <<= 1)
+        for (int q = 0; q < cnt; q += 2 * s) vals[q] = __fadd_rn(vals[q], vals[q + s]);
+    return vals[0];
+}
+
+__global__ void kmpp_tree_pick_kernel(TreeLevels T, const unsigned char* __restrict__ taken, int64_t n,
+                                      KmppState* st, const float* __restrict__ u, int m) {
+    __shared__ float root;
+    if (threadIdx.x == 0) {
+        root = tree_node_sum(T, taken, T.H, 0);
+        st->dist_sum = root;
+        st->n_cand = m;
+    }
+    __syncthreads();
+    const int j = threadIdx.x;
+    if (j >= m) return;
+    float r = __fmul_rn(root, u[j]);
+    st->rands[j] = r;
+    long long node = 0;
+    for (int h = T.H; h > 0; --h) {
+        const float left = tree_node_sum(T, taken, h - 1, 2 * node);
+        if (r <= left) node = 2 * node;
+        else { r = __fsub_rn(r, left); node = 2 * node + 1; }
+    }
+    st->cand[j] = (node < n && !taken[node]) ? node : -1;
+}
+
+// roots of m trees: the first stored level (height 10, 20 or 30) that has a single entry IS the
+// root (the levels above the true height only add zeros, and v + 0 == v exactly)
+__global__ void kmpp_tree_roots_kernel(const float* __restrict__ lv, int64_t stride, int m, float* __restrict__ out) {
+    const int j = threadIdx.x;
+    if (j < m) out[j] = lv[(int64_t)j * stride];
+}
+
+// ---- selection -----------------------------------------------------------------------------
+__global__ void kmpp_select_kernel(KmppState* st, const float* __restrict__ pots, int m,
+                                   const unsigned char* __restrict__ taken, int64_t n) {
+    if (threadIdx.x != 0) return;
+    long long best = -1;
+    int jbest = -1;
+    float bp = 3.402823466e+38f;
+    for (int j = 0; j < m; ++j) {
+        st->pot[j] = pots[j];
+        if (st->cand[j] >= 0 && pots[j] < bp) { bp = pots[j]; best = st->cand[j]; jbest = j; }
+    }
+    st->best = best;
+    st->jbest = jbest;
+}
+
+__global__ void kmpp_first_free_kernel(const unsigned char* __restrict__ taken, int64_t n, long long* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !taken[i]) atomicMin((unsigned long long*)out, (unsigned long long)i);
+}
+
+__global__ void kmpp_commit_kernel(KmppState* st, long long best, const float* __restrict__ X, int d,
+                                   const float* __restrict__ D, unsigned char* __restrict__ taken,
+                                   float* __restrict__ center_out) {
+    for (int e = threadIdx.x; e < d; e += blockDim.x) center_out[e] = X[best * d + e];
+    if (threadIdx.x == 0) {
+        taken[best] = 1;
+        st->dist_sum = __fsub_rn(st->dist_sum, D[best]);
+    }
+}
+
+__global__ void kmpp_add_delta_kernel(KmppState* st, const float* __restrict__ s) {
+    st->dist_sum = __fadd_rn(st->dist_sum, s[0]);
+}
+
+// ---- driver ----------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();
+            return set_error(B2K_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
+        }
+        return B2K_OK;
+    }
+    template <class T> T* as() { return (T*)p; }
+};
+
+static int pow2_height(int64_t n) { int h = 0; while ((int64_t(1) << h) < n) ++h; return h; }
+
+int kmpp_run(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int metric, int64_t seed, int scan_mode,
+             b2k_callback cb, void* user, float* dcenters_out, int64_t* chosen_host) {
+    if (k < 1 || k > n) return set_error(B2K_ERR_INVALID_ARG, "k-means++: need 1 <= k <= n (k=%d, n=%lld)", k, (long long)n);
+    if (metric == B2K_METRIC_MINRMSD && d % 3) return set_error(B2K_ERR_DIM_NOT_MULT3, "RMSDMetric is only implemented for input data with a dimension divisible by 3.");
+    const int m = 2 + (int)std::log((double)k);
+    if (m > KMPP_MAX_TRIALS) return set_error(B2K_ERR_INVALID_ARG, "k too large");
+    cudaStream_t st = ctx->stream;
+
+    // RNG stream (data independent)
+    uint32_t s32;
+    if (seed < 0) { std::random_device rd; s32 = rd(); } else s32 = (uint32_t)seed;
+    MT19937 gen(s32);
+    const int64_t first = (int64_t)gen.below((uint64_t)n);
+    std::vector<float> u((size_t)(k > 1 ? (k - 1) : 1) * m);
+    for (size_t t = 0; t < (size_t)(k - 1) * m; ++t) u[t] = gen.unit();
+
+    DevBuf bD, bTaken, bCd, bDelta, bRows, bRowsC, bGb, bGa, bU, bState, bPots, bFree, bL5, bL10, bL15, bL20, bL25, bL30,
+        bP5, bP10, bP15, bP20, bP25, bP30;
+    B2K_TRY(bD.alloc(n * 4));
+    B2K_TRY(bTaken.alloc(n));
+    B2K_TRY(bCd.alloc((size_t)m * n * 4));
+    B2K_TRY(bRows.alloc((size_t)m * d * 4));
+    B2K_TRY(bU.alloc(u.size() * 4));
+    B2K_TRY(bState.alloc(sizeof(KmppState)));
+    B2K_TRY(bPots.alloc(KMPP_MAX_TRIALS * 4));
+    B2K_TRY(bFree.alloc(8));
+    float* D = bD.as<float>();
+    unsigned char* taken = bTaken.as<unsigned char>();
+    float* cd = bCd.as<float>();
+    float* rows = bRows.as<float>();
+    KmppState* S = bState.as<KmppState>();
+    float* pots = bPots.as<float>();
+    CUDA_TRY(cudaMemcpyAsync(bU.p, u.data(), u.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(S, 0, sizeof(KmppState), st));
+
+    float* Ga = nullptr;
+    if (metric == B2K_METRIC_MINRMSD) {
+        B2K_TRY(bGa.alloc(n * 4));
+        B2K_TRY(bRowsC.alloc((size_t)m * d * 4));
+        B2K_TRY(bGb.alloc(m * 4));
+        Ga = bGa.as<float>();
+        B2K_TRY(launch_rmsd_center(ctx, dX, n, d, nullptr, Ga));
+    }
+    auto dist_rows = [&](const float* R, int mm, float* out) -> int {
+        if (metric == B2K_METRIC_MINRMSD) {
+            B2K_TRY(launch_rmsd_center(ctx, R, mm, d, bRowsC.as<float>(), bGb.as<float>()));
+            return launch_rmsd_dist_rows(ctx, dX, Ga, n, d, bRowsC.as<float>(), bGb.as<float>(), mm, out);
+        }
+        return launch_dist_rows(ctx, dX, n, d, R, mm, out);
+    };
+
+    // tree levels (blocked mode)
+    const int H = pow2_height(n);
+    const int64_t n5 = cdiv(n, 32), n10 = cdiv(n, 1024), n15 = cdiv(n10, 32), n20 = cdiv(n10, 1024),
+                  n25 = cdiv(n20, 32), n30 = cdiv(n20, 1024);
+    if (scan_mode == B2K_KMPP_BLOCKED) {
+        B2K_TRY(bL5.alloc(n5 * 4)); B2K_TRY(bL10.alloc(n10 * 4)); B2K_TRY(bL15.alloc(n15 * 4));
+        B2K_TRY(bL20.alloc(n20 * 4)); B2K_TRY(bL25.alloc(n25 * 4)); B2K_TRY(bL30.alloc(n30 * 4));
+        B2K_TRY(bP10.alloc((size_t)m * n10 * 4)); B2K_TRY(bP20.alloc((size_t)m * n20 * 4));
+        B2K_TRY(bP30.alloc((size_t)m * n30 * 4));
+    } else {
+        B2K_TRY(bDelta.alloc(n * 4));
+    }
+    // build the stored levels of mm trees over `in` (stride n), return top stored level info
+    auto tree_build = [&](const float* in, int mm, const unsigned char* mask, float* l5, float* l10, float* l15,
+                          float* l20, float* l25, float* l30) -> int {
+        tree_up_kernel<<<dim3((unsigned)n10, mm), 1024, 0, st>>>(in, n, n, mask, l5, n5, l10, n10);
+        LAUNCH_CHECK();
+        if (H > 10) {
+            tree_up_kernel<<<dim3((unsigned)n20, mm), 1024, 0, st>>>(l10, n10, n10, nullptr, l15, n15, l20, n20);
+            LAUNCH_CHECK();
+        }
+        if (H > 20) {
+            tree_up_kernel<<<dim3((unsigned)n30, mm), 1024, 0, st>>>(l20, n20, n20, nullptr, l25, n25, l30, n30);
+            LAUNCH_CHECK();
+        }
+        return B2K_OK;
+    };
+    auto tree_roots = [&](float* l10, float* l20, float* l30, int mm, float* out) -> int {
+        if (H > 30) return set_error(B2K_ERR_INVALID_ARG, "n too large");
+        const float* lv = H <= 10 ? l10 : (H <= 20 ? l20 : l30);
+        const int64_t stride = H <= 10 ? n10 : (H <= 20 ? n20 : n30);
+        kmpp_tree_roots_kernel<<<1, 32, 0, st>>>(lv, stride, mm, out);
+        LAUNCH_CHECK();
+        return B2K_OK;
+    };
+
+    // ---- first center ----
+    std::vector<int64_t> chosen((size_t)k, -1);
+    chosen[0] = first;
+    CUDA_TRY(cudaMemcpyAsync(dcenters_out, dX + first * d, (size_t)d * 4, cudaMemcpyDeviceToDevice, st));
+    if (cb) { CUDA_TRY(cudaStreamSynchronize(st)); cb(user); }
+    if (k == 1) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (chosen_host) chosen_host[0] = first;
+        return B2K_OK;
+    }
+    B2K_TRY(dist_rows(dcenters_out, 1, cd));
+    kmpp_square_init_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cd, n, first, D, taken);
+    LAUNCH_CHECK();
+    if (scan_mode == B2K_KMPP_SERIAL) {
+        kmpp_serial_sum_kernel<<<1, 256, 0, st>>>(D, n, 1, pots);
+        LAUNCH_CHECK();
+        kmpp_set_dist_sum_kernel<<<1, 1, 0, st>>>(S, pots);
+        LAUNCH_CHECK();
+    }
+
+    TreeLevels T;
+    T.H = H;
+    T.lv[0] = D; T.len[0] = n;
+    T.lv[1] = bL5.as<float>(); T.len[1] = n5;
+    T.lv[2] = bL10.as<float>(); T.len[2] = n10;
+    T.lv[3] = bL15.as<float>(); T.len[3] = n15;
+    T.lv[4] = bL20.as<float>(); T.len[4] = n20;
+    T.lv[5] = bL25.as<float>(); T.len[5] = n25;
+    T.lv[6] = bL30.as<float>(); T.len[6] = n30;
+
+    KmppState hs;
+    for (int found = 1; found < k; ++found) {
+        const float* ur = bU.as<float>() + (size_t)(found - 1) * m;
+        // candidates
+        if (scan_mode == B2K_KMPP_SERIAL) {
+            kmpp_serial_scan_kernel<<<1, 32, 0, st>>>(D, taken, n, S, ur, m);
+            LAUNCH_CHECK();
+        } else {
+            B2K_TRY(tree_build(D, 1, taken, bL5.as<float>(), bL10.as<float>(), bL15.as<float>(), bL20.as<float>(),
+                               bL25.as<float>(), bL30.as<float>()));
+            kmpp_tree_pick_kernel<<<1, 32, 0, st>>>(T, taken, n, S, ur, m);
+            LAUNCH_CHECK();
+        }
+        kmpp_gather_kernel<<<m, 128, 0, st>>>(dX, d, S, m, rows);
+        LAUNCH_CHECK();
+        B2K_TRY(dist_rows(rows, m, cd));
+        kmpp_contrib_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cd, n, m, D, taken, S);
+        LAUNCH_CHECK();
+        // potentials
+        if (scan_mode == B2K_KMPP_SERIAL) {
+            kmpp_serial_sum_kernel<<<1, 256, 0, st>>>(cd, n, m, pots);
+            LAUNCH_CHECK();
+        } else {
+            B2K_TRY(tree_build(cd, m, nullptr, nullptr, bP10.as<float>(), nullptr, bP20.as<float>(), nullptr,
+                               bP30.as<float>()));
+            B2K_TRY(tree_roots(bP10.as<float>(), bP20.as<float>(), bP30.as<float>(), m, pots));
+        }
+        kmpp_select_kernel<<<1, 32, 0, st>>>(S, pots, m, taken, n);
+        LAUNCH_CHECK();
+        CUDA_TRY(cudaMemcpyAsync(&hs, S, sizeof(KmppState), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        long long best = hs.best;
+        int jbest = hs.jbest;
+        if (best < 0) {  // "if for some reason we did not find a best candidate, take the next available point"
+            long long init = 0x7fffffffffffffffll;
+            CUDA_TRY(cudaMemcpyAsync(bFree.p, &init, 8, cudaMemcpyHostToDevice, st));
+            kmpp_first_free_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(taken, n, bFree.as<long long>());
+            LAUNCH_CHECK();
+            CUDA_TRY(cudaMemcpyAsync(&best, bFree.p, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (best == init) break;
+            jbest = -1;
+        }
+        chosen[found] = best;
+        kmpp_commit_kernel<<<1, 128, 0, st>>>(S, best, dX, d, D, taken, dcenters_out + (size_t)found * d);
+        LAUNCH_CHECK();
+        if (cb) cb(user);
+        if (found + 1 < k) {
+            float* delta = scan_mode == B2K_KMPP_SERIAL ? bDelta.as<float>() : nullptr;
+            if (jbest >= 0) {
+                kmpp_update_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(D, taken, n, cd + (size_t)jbest * n, 0, delta);
+                LAUNCH_CHECK();
+            } else {
+                B2K_TRY(dist_rows(dcenters_out + (size_t)found * d, 1, cd));
+                kmpp_update_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(D, taken, n, cd, 1, delta);
+                LAUNCH_CHECK();
+            }
+            if (scan_mode == B2K_KMPP_SERIAL) {
+                kmpp_serial_sum_kernel<<<1, 256, 0, st>>>(delta, n, 1, pots);
+                LAUNCH_CHECK();
+                kmpp_add_delta_kernel<<<1, 1, 0, st>>>(S, pots);
+                LAUNCH_CHECK();
+            }
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (chosen_host) std::memcpy(chosen_host, chosen.data(), sizeof(int64_t) * k);
+    for (int i = 0; i < k; ++i)
+        if (chosen[i] < 0) return set_error(B2K_ERR_INVALID_ARG, "k-means++ could not find %d centers", k);
+    return B2K_OK;
+}
+
+}  // namespace b2k

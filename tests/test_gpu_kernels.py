@@ -1,0 +1,174 @@
+"""GPU parity of the C-ABI entry points against the CPU oracle (bit-exact for labels / indices).
+
+Every call goes through libb2k.so's extern "C" functions via ctypes (pyemma_b200/_lib.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def blobs(rng, n, d, nb, spread=5.0, sigma=1.0):
+    cen = rng.uniform(-spread, spread, size=(nb, d))
+    lab = rng.randint(0, nb, size=n)
+    return (cen[lab] + sigma * rng.randn(n, d)).astype(np.float32)
+
+
+ASSIGN_SHAPES = [(1000, 1, 7), (5000, 2, 100), (3000, 3, 33), (2000, 4, 64), (2000, 5, 17), (4000, 10, 1000),
+                 (1500, 16, 300), (1000, 17, 50), (1200, 45, 15), (900, 64, 200), (700, 130, 40), (300, 256, 500),
+                 (257, 300, 9), (100, 1027, 5)]
+
+
+@pytest.mark.parametrize("n,d,k", ASSIGN_SHAPES)
+def test_assign_bit_exact(b2k, oracle, n, d, k):
+    rng = np.random.RandomState(n + d + k)
+    X = blobs(rng, n, d, 8)
+    C = X[rng.choice(n, k, replace=k > n)].copy()
+    C[: k // 2] += 0.01 * rng.randn(k // 2, d).astype(np.float32)
+    ref = oracle.assign(X, C, n_threads=4)
+    got = b2k.assign(X, C)
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_assign_ties_lowest_index(b2k, oracle):
+    rng = np.random.RandomState(3)
+    X = rng.randn(500, 6).astype(np.float32)
+    C = np.repeat(rng.randn(10, 6).astype(np.float32), 3, axis=0)  # every center three times
+    ref = oracle.assign(X, C)
+    got = b2k.assign(X, C)
+    np.testing.assert_array_equal(got, ref)
+    assert (got % 3 == 0).all()
+
+
+def test_assign_sqrt_merge_ties(b2k, oracle):
+    # centers that differ in the last bits: squared distances differ but sqrt may merge them
+    rng = np.random.RandomState(4)
+    base = rng.randn(1, 3).astype(np.float32)
+    C = np.repeat(base, 64, axis=0)
+    C[:, 0] = np.nextafter(C[:, 0], np.float32(10), dtype=np.float32) if False else C[:, 0]
+    for j in range(64):
+        C[j, 0] = np.float32(base[0, 0]) + np.float32(j % 5) * np.spacing(np.float32(base[0, 0]))
+    X = (base + rng.randn(4000, 3).astype(np.float32) * 3).astype(np.float32)
+    np.testing.assert_array_equal(b2k.assign(X, C), oracle.assign(X, C))
+
+
+def test_assign_chunked_streaming(b2k, oracle):
+    rng = np.random.RandomState(5)
+    X = blobs(rng, 50000, 7, 10)
+    C = X[:50].copy()
+    ctx = b2k.context()
+    ctx.set_option("stage_bytes", 1 << 16)  # many chunks through the pinned double buffer
+    try:
+        got = b2k.assign(X, C)
+    finally:
+        ctx.set_option("stage_bytes", 64 << 20)
+    np.testing.assert_array_equal(got, oracle.assign(X, C, n_threads=4))
+
+
+def test_assign_minrmsd(b2k, oracle):
+    rng = np.random.RandomState(123)
+    for n_atoms, n, k in [(15, 500, 15), (3, 300, 5), (30, 400, 40), (301, 64, 7)]:
+        X = rng.uniform(-50, 50, size=(n, 3 * n_atoms)).astype(np.float32)
+        C = X[rng.choice(n, k, replace=False)] + rng.randn(k, 3 * n_atoms).astype(np.float32)
+        np.testing.assert_array_equal(b2k.assign(X, C, "minRMSD"), oracle.assign(X, C, "minRMSD", n_threads=4))
+
+
+def test_compute_metric(b2k, oracle):
+    rng = np.random.RandomState(9)
+    for na in (3, 15, 16, 300):
+        x = rng.uniform(size=3 * na).astype(np.float32)
+        y = rng.uniform(size=3 * na).astype(np.float32)
+        assert b2k.compute_metric(x, y, "minRMSD").tobytes() == oracle.compute_metric(x, y, "minRMSD").tobytes()
+        assert b2k.compute_metric(x, y).tobytes() == oracle.compute_metric(x, y).tobytes()
+    with pytest.raises(ValueError):
+        b2k.compute_metric(np.zeros(10, np.float32), np.zeros(10, np.float32), "minRMSD")
+
+
+@pytest.mark.parametrize("n,d,k,metric", [(20000, 2, 100, "euclidean"), (5000, 10, 50, "euclidean"),
+                                          (3000, 64, 20, "euclidean"), (600, 45, 8, "minRMSD")])
+def test_lloyd_step_and_cost(b2k, oracle, n, d, k, metric):
+    rng = np.random.RandomState(d)
+    X = blobs(rng, n, d, 6)
+    C0 = X[rng.choice(n, k, replace=False)].copy()
+    refC, refL = oracle.kmeans_cluster(X, C0, metric, n_threads=4, acc="f64")
+    gotC, gotL = b2k.kmeans_cluster(X, C0, metric)
+    np.testing.assert_array_equal(gotL, refL)
+    # GPU sums are exact fixed point -> equal to the fp64 oracle up to 1 ulp of the final rounding
+    np.testing.assert_allclose(gotC, refC, rtol=2e-7, atol=1e-7 * np.abs(X).max())
+    # fp32-sequential reference sums (what the reference does): within the stated 1e-5
+    refC32, _ = oracle.kmeans_cluster(X, C0, metric, acc="f32seq")
+    assert np.abs(gotC - refC32).max() <= 1e-5 * np.abs(refC32).max()
+    c_ref = oracle.cost(X, refC, refL, metric, acc="f64")
+    c_got = b2k.kmeans_cost(X, refC, refL, metric)
+    assert abs(float(c_got) - float(c_ref)) <= 2e-7 * float(c_ref)
+
+
+def test_cluster_loop_matches_oracle(b2k, oracle):
+    rng = np.random.RandomState(11)
+    X = blobs(rng, 30000, 2, 3, spread=2.0, sigma=0.4)
+    C0 = oracle.kmpp_init(X, 100, 42)
+    calls = []
+    cen, code, it, inert = b2k.kmeans_cluster_loop(X, C0, 10, 1e-5, callback=lambda: calls.append(1))
+    rcen, rcode, rit, rinert = oracle.cluster_loop(X, C0, 10, 1e-5, acc="f32seq")
+    assert (code, it) == (rcode, rit)
+    assert len(calls) == it - (1 if code == 0 else 0)
+    np.testing.assert_allclose(inert, rinert, rtol=1e-5)
+    assert np.abs(cen - rcen).max() <= 1e-5 * np.abs(rcen).max()
+    # labels under the final centers are bit-exact when both sides use the same centers
+    np.testing.assert_array_equal(b2k.assign(X, rcen), oracle.assign(X, rcen, n_threads=4))
+
+
+def test_cluster_loop_converges_trivial(b2k, oracle):
+    # reference known-answer test (tests/test_kmeans.py:411-426): 4 constant blobs -> exact centers
+    X = np.concatenate([np.full((100, 3), v, np.float32) for v in (30, 60, 90, 120)])
+    C0 = np.array([[29] * 3, [61] * 3, [88] * 3, [125] * 3], np.float32)
+    cen, code, it, inert = b2k.kmeans_cluster_loop(X, C0, 10, 1e-5)
+    assert code == 0
+    np.testing.assert_array_equal(np.sort(cen[:, 0]), [30, 60, 90, 120])
+
+
+@pytest.mark.parametrize("scan", ["serial", "blocked"])
+@pytest.mark.parametrize("n,d,k,metric", [(3000, 2, 20, "euclidean"), (1500, 10, 40, "euclidean"),
+                                          (1100, 70, 12, "euclidean"), (300, 45, 6, "minRMSD")])
+def test_kmpp_bit_exact(b2k, oracle, scan, n, d, k, metric):
+    rng = np.random.RandomState(n)
+    X = blobs(rng, n, d, 5)
+    calls = []
+    ref, ridx = oracle.kmpp_init(X, k, 42, metric, scan=scan, return_indices=True)
+    got, gidx = b2k.kmeans_init_centers_kmpp(X, k, 42, metric, scan=scan, return_indices=True,
+                                             callback=lambda: calls.append(1))
+    np.testing.assert_array_equal(gidx, ridx)
+    np.testing.assert_array_equal(got, ref)
+    assert len(calls) == k
+
+
+def test_kmpp_k_larger_than_n(b2k):
+    with pytest.raises(ValueError):
+        b2k.kmeans_init_centers_kmpp(np.zeros((5, 2), np.float32), 6, 1)
+
+
+@pytest.mark.parametrize("metric,d", [("euclidean", 2), ("euclidean", 20), ("minRMSD", 30)])
+def test_regspace_bit_exact(b2k, oracle, metric, d):
+    rng = np.random.RandomState(d)
+    X = (rng.randn(6000, d) * 2).astype(np.float32)
+    dmin = {2: 0.7, 20: 9.0, 30: 2.0}[d]
+    ref, ridx, rfull = oracle.regspace(X, dmin, 1000, metric, n_threads=4)
+    h = b2k.RegspaceHandle(d, dmin, 1000, metric)
+    for a in range(0, len(X), 1700):  # several chunks
+        h.partial_fit(X[a:a + 1700])
+    got = h.centers()
+    h.close()
+    assert not rfull
+    assert len(got) == len(ref) > 3
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_regspace_max_centers(b2k, oracle):
+    rng = np.random.RandomState(0)
+    X = (rng.randn(5000, 3) * 3).astype(np.float32)
+    ref, ridx, rfull = oracle.regspace(X, 0.5, 37, "euclidean")
+    assert rfull and len(ref) == 37
+    h = b2k.RegspaceHandle(3, 0.5, 37)
+    with pytest.raises(b2k.MaxCentersReachedException):
+        h.partial_fit(X)
+    np.testing.assert_array_equal(h.centers(), ref)
+    h.close()
