@@ -6,3 +6,6 @@ hand-written sm_100a CUDA kernels behind the C ABI of include/b2k.h (libb2k.so, 
 ctypes); there is no CPU fallback.
 """
 __version__ = "0.1.0"
+
+from .api import assign_to_centers, cluster_kmeans, cluster_regspace  # noqa: E402,F401
+from .clustering import AssignCenters, KmeansClustering, RegularSpaceClustering  # noqa: E402,F401

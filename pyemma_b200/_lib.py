@@ -211,9 +211,10 @@ def _check_2d(X, centers):
 
 
 def assign(X, centers, metric="euclidean", ctx=None, out=None):
-    ctx = ctx or context()
     X, centers = _f32c(X), _f32c(centers)
     _check_2d(X, centers)
+    metric_id(metric)
+    ctx = ctx or context()
     n, d = X.shape
     labels = out if out is not None else np.empty(n, np.int32)
     check(ctx.lib.b2k_assign(ctx.handle, _ptr(X), n, d, _ptr(centers), centers.shape[0], metric_id(metric),
@@ -222,9 +223,9 @@ def assign(X, centers, metric="euclidean", ctx=None, out=None):
 
 
 def kmeans_cluster(X, centers, metric="euclidean", ctx=None):
-    ctx = ctx or context()
     X, centers = _f32c(X), _f32c(centers)
     _check_2d(X, centers)
+    ctx = ctx or context()
     n, d = X.shape
     newc = np.empty_like(centers)
     labels = np.empty(n, np.int32)

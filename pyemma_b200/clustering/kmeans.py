@@ -1,0 +1,272 @@
+"""KmeansClustering on the B200 backend.
+
+Mirrors pyemma/coordinates/clustering/kmeans.py:48-339 (reference @ 3327f28): same constructor
+parameters, fixed_seed semantics (:146-164), n_clusters default min(sqrt(N), 5000) (:294-297),
+resume via clustercenters= / keep_data (:103-109, 205-207, 269-284), 'uniform' picks (:304-324).
+
+What changes:
+  * the gathered "in-memory" frame array lives in HBM (staging.gather_frames) instead of host RAM;
+  * deeptime KMeans.fit (kmeans.py:254-255) -> libb2k: k-means++ (b2k_dev_kmeans_init_centers_kmpp)
+    and Lloyd iterations driven through the device session API (assign+accumulate / finalize / cost);
+  * frames shard over the ranks of an initialised torch.distributed job; per iteration ONE int64
+    buffer [k*d sums | k counts] and one cost word are all-reduced (NCCL).  Sums are exact fixed
+    point, so centers and inertias are bit-identical for any number of GPUs.
+"""
+import ctypes as C
+import math
+import random
+
+import numpy as np
+import torch
+
+from .. import _lib, staging
+from .interface import AbstractClustering
+
+__all__ = ["KmeansClustering"]
+
+
+class KmeansClustering(AbstractClustering):
+    def __init__(self, n_clusters, max_iter=5, metric="euclidean", tolerance=1e-5, init_strategy="kmeans++",
+                 fixed_seed=False, oom_strategy="memmap", stride=1, n_jobs=None, skip=0, clustercenters=None,
+                 keep_data=False, kmpp_scan="auto"):
+        super().__init__(metric=metric, n_jobs=n_jobs)
+        if clustercenters is None:
+            clustercenters = []
+        self._in_memory_chunks_set = False
+        self._converged = False
+        self.initial_centers_ = None
+        self.inertias_ = np.zeros(0, np.float32)
+        self.set_params(n_clusters=n_clusters, max_iter=max_iter, tolerance=tolerance, init_strategy=init_strategy,
+                        oom_strategy=oom_strategy, fixed_seed=fixed_seed, stride=stride, skip=skip,
+                        clustercenters=clustercenters, keep_data=keep_data, kmpp_scan=kmpp_scan)
+
+    # ---- parameters ---------------------------------------------------------------------------
+    @property
+    def init_strategy(self):
+        return self._init_strategy
+
+    @init_strategy.setter
+    def init_strategy(self, value):
+        valid = ("kmeans++", "uniform")
+        if value not in valid:
+            raise ValueError("invalid parameter '{}' for init_strategy. Should be one of {}".format(value, valid))
+        self._init_strategy = value
+
+    @property
+    def fixed_seed(self):
+        """seed for the random choice of initial centers (kmeans.py:141-164)"""
+        return self._fixed_seed
+
+    @fixed_seed.setter
+    def fixed_seed(self, val):
+        if isinstance(val, (bool, np.bool_)) or val is None:
+            self._fixed_seed = 42 if val else random.randint(0, 2 ** 32 - 1)
+        elif isinstance(val, (int, np.integer)):
+            if val < 0 or val > 2 ** 32 - 1:
+                self.logger.warning("seed has to be positive (or smaller than 2**32-1). Seed will be chosen randomly.")
+                self.fixed_seed = False
+            else:
+                self._fixed_seed = int(val)
+        else:
+            raise ValueError("fixed seed has to be bool or integer")
+
+    @property
+    def converged(self):
+        return self._converged
+
+    def describe(self):
+        return "[Kmeans, k=%i, inp_dim=%i]" % (self.n_clusters, self.data_producer.dimension())
+
+    def _check_resume_iteration(self):
+        return self.clustercenters is not None and self.clustercenters.size != 0
+
+    # ---- estimation ---------------------------------------------------------------------------
+    def _gather(self, iterable):
+        """kmeans.py:286-312 + 326-338, with the array in HBM."""
+        stride = self.stride if self.stride else 1
+        rank, ws = staging.world()
+        if (self._in_memory_chunks_set and getattr(self, "_dev_frames", None) is not None
+                and self._dev_n_total == int(np.sum(iterable.trajectory_lengths(stride=stride, skip=self.skip)))):
+            self.logger.debug("re-use in memory data.")
+            return
+        if self._check_resume_iteration() and not self._in_memory_chunks_set and not self.keep_data:
+            self.logger.warning('Resuming kmeans iteration without the setting "keep_data=True", will re-create'
+                                " the linear in-memory data. This is inefficient! Consider setting keep_data=True,"
+                                " when you intend to resume the kmeans iteration.")
+        lengths = iterable.trajectory_lengths(stride=stride, skip=self.skip)
+        total = int(np.sum(lengths))
+        need = total * iterable.dimension() * 4 // ws
+        free, _tot = torch.cuda.mem_get_info(staging.device())
+        if need > free * 0.9:
+            # kmeans.py:181-200 falls back to a host memmap; there is no slower tier below HBM here
+            self.logger.warning("K-means failed to load all the data (%d bytes required, %d available) into HBM. "
+                                "Consider using a larger stride or more GPUs.", need, free)
+            raise MemoryError()
+        X, n_total, lo = staging.gather_frames(iterable, stride=stride, skip=self.skip, chunksize=self.chunksize,
+                                               rank=rank, world_size=ws)
+        self._dev_frames, self._dev_n_total, self._dev_lo = X, n_total, lo
+        self._in_memory_chunks_set = True
+
+    def _uniform_picks(self, iterable):
+        """PyEMMA's own 'uniform' picks (kmeans.py:304-324): per trajectory ceil(len/total*k) random frame
+        indices drawn with python `random` under random_seed(fixed_seed); the first n_clusters picked frames
+        in iteration order become initial_centers_."""
+        stride = self.stride if self.stride else 1
+        lengths = [int(l) for l in iterable.trajectory_lengths(stride=stride, skip=self.skip)]
+        total = sum(lengths)
+        state = random.getstate()
+        random.seed(self.fixed_seed)
+        try:
+            picks = {i: set(random.sample(list(range(0, L)), int(math.ceil((L / float(total)) * self.n_clusters))))
+                     for i, L in enumerate(lengths)}
+        finally:
+            random.setstate(state)
+        rows = []
+        with iterable.iterator(stride=stride, skip=self.skip, chunk=self.chunksize, return_trajindex=True) as it:
+            for itraj, X in it:
+                for l in range(len(X)):
+                    if len(rows) < self.n_clusters and it.pos + l in picks[itraj]:
+                        rows.append(np.asarray(X[l], dtype=np.float32))
+        return np.array(rows, dtype=np.float32).reshape(-1, iterable.dimension())
+
+    def _estimate(self, iterable, **kw):
+        stride = self.stride if self.stride else 1
+        lengths = iterable.trajectory_lengths(stride=stride, skip=self.skip)
+        total_length = int(np.sum(lengths))
+        if not self.n_clusters:
+            self.n_clusters = min(int(math.sqrt(total_length)), 5000)
+            self.logger.info("The number of cluster centers was not specified, "
+                             "using min(sqrt(N), 5000)=%s as n_clusters." % self.n_clusters)
+        resume = self._check_resume_iteration()
+        if resume and len(self.clustercenters) != self.n_clusters:
+            raise RuntimeError("Passed clustercenters do not match n_clusters: {} vs. {}".format(
+                len(self.clustercenters), self.n_clusters))
+        if not resume and self.init_strategy == "uniform":
+            self.initial_centers_ = self._uniform_picks(iterable)
+        self._gather(iterable)
+        X = self._dev_frames
+        n_local, d = X.shape
+        k = int(self.n_clusters)
+        if k > total_length:
+            raise ValueError("n_clusters=%d larger than the number of frames %d" % (k, total_length))
+        rank, ws = staging.world()
+        ctx = _lib.context()
+        dev = X.device
+        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        metric = _lib.metric_id(self.metric)
+        lib = ctx.lib
+
+        # ---- initial centers ----
+        if resume:
+            centers = torch.from_numpy(np.array(self.clustercenters, dtype=np.float32)).to(dev)
+        elif self.init_strategy == "uniform":
+            # deeptime draws its own uniform picks: data[RandomState(seed).randint(0,N,k)]
+            idx = np.random.RandomState(self.fixed_seed).randint(0, total_length, size=k)
+            centers = self._rows_by_global_index(idx, d, dev)
+        else:
+            if ws > 1:
+                raise NotImplementedError("k-means++ over sharded frames is not implemented yet: pass "
+                                          "clustercenters= or use init_strategy='uniform' in multi-GPU runs")
+            scan = self.kmpp_scan
+            if scan == "auto":
+                scan = "serial" if total_length <= 20000 else "blocked"
+            centers = torch.empty((k, d), dtype=torch.float32, device=dev)
+            cb = self._callback(lambda: None) if self.show_progress else _lib.CALLBACK(0)
+            _lib.check(lib.b2k_dev_kmeans_init_centers_kmpp(
+                ctx.handle, C.c_void_p(X.data_ptr()), n_local, d, k, metric, int(self.fixed_seed),
+                _lib.KMPP_SERIAL if scan == "serial" else _lib.KMPP_BLOCKED, cb, None,
+                C.c_void_p(centers.data_ptr()), None))
+            self.initial_centers_ = centers.cpu().numpy()
+        if resume:
+            self.initial_centers_ = np.array(self.clustercenters, dtype=np.float32)
+
+        # ---- Lloyd iterations (deeptime cluster_loop semantics) ----
+        try:
+            centers, converged, inertias = self._lloyd(ctx, X, centers, k, metric, total_length, rank, ws)
+            self.clustercenters = centers.cpu().numpy()
+            self._converged = converged
+            self.inertias_ = np.asarray(inertias, dtype=np.float32)
+        finally:
+            # kmeans.py:269-284: drop the big array unless the user keeps it for a resume
+            if not self.keep_data or self._converged:
+                self._dev_frames = None
+                self._in_memory_chunks_set = False
+        if self._converged:
+            self.logger.debug("Cluster centers converged after %i steps.", len(self.inertias_))
+        else:
+            self.logger.warning("Algorithm did not reach convergence criterion"
+                                " of %g in %i iterations. Consider increasing max_iter.",
+                                self.tolerance, self.max_iter)
+        return self
+
+    def _callback(self, fn):
+        cb = _lib.CALLBACK(lambda _u: fn())
+        self._dev_cb_keepalive = cb
+        return cb
+
+    def _rows_by_global_index(self, idx, d, dev):
+        """rows of the (sharded) frame array by global frame index, replicated on every rank"""
+        import torch.distributed as dist
+        rank, ws = staging.world()
+        lo = self._dev_lo
+        n_local = self._dev_frames.shape[0]
+        idx_t = torch.as_tensor(idx, dtype=torch.int64, device=dev)
+        rows = torch.zeros((len(idx), d), dtype=torch.float32, device=dev)
+        mine = (idx_t >= lo) & (idx_t < lo + n_local)
+        if mine.any():
+            rows[mine] = self._dev_frames[idx_t[mine] - lo]
+        if ws > 1:
+            dist.all_reduce(rows)  # every row is non-zero on exactly one rank
+        return rows
+
+    def _lloyd(self, ctx, X, centers, k, metric, n_total, rank, ws):
+        import torch.distributed as dist
+        lib = ctx.lib
+        dev = X.device
+        n_local, d = X.shape
+        absmax = C.c_float(0)
+        _lib.check(lib.b2k_dev_absmax(ctx.handle, C.c_void_p(X.data_ptr()), n_local * d, C.byref(absmax)))
+        am = torch.tensor([absmax.value, float(centers.abs().max())], dtype=torch.float32, device=dev)
+        if ws > 1:
+            dist.all_reduce(am, op=dist.ReduceOp.MAX)
+        absmax_g = float(am.max())
+        if not math.isfinite(absmax_g):
+            raise _lib.InvalidDataInStreamException("Found invalid values (NaN/inf) in the input frames")
+        sess = C.c_void_p()
+        _lib.check(lib.b2k_dev_lloyd_create(ctx.handle, C.c_void_p(X.data_ptr()), n_local, d, k, metric, n_total,
+                                            C.c_float(absmax_g), C.byref(sess)))
+        try:
+            acc_len = int(lib.b2k_dev_lloyd_acc_len(sess))
+            acc = torch.zeros(acc_len, dtype=torch.int64, device=dev)
+            labels = torch.empty(max(n_local, 1), dtype=torch.int32, device=dev)
+            cur = centers.contiguous().clone()
+            nxt = torch.empty_like(cur)
+            it, converged, prev = 0, False, np.float32(0)
+            inertias = []
+            tol = np.float32(self.tolerance)
+            while True:
+                _lib.check(lib.b2k_dev_lloyd_assign_accumulate(sess, C.c_void_p(cur.data_ptr()),
+                                                               C.c_void_p(labels.data_ptr()),
+                                                               C.c_void_p(acc.data_ptr())))
+                if ws > 1:
+                    dist.all_reduce(acc[:acc_len - 1])
+                _lib.check(lib.b2k_dev_lloyd_finalize(sess, C.c_void_p(acc.data_ptr()), C.c_void_p(cur.data_ptr()),
+                                                      C.c_void_p(nxt.data_ptr())))
+                _lib.check(lib.b2k_dev_lloyd_cost(sess, C.c_void_p(nxt.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                                  C.c_void_p(acc.data_ptr())))
+                if ws > 1:
+                    dist.all_reduce(acc[acc_len - 1:])
+                cost = np.float32(lib.b2k_dev_lloyd_decode_cost(sess, int(acc[acc_len - 1].item())))
+                cur, nxt = nxt, cur
+                inertias.append(cost)
+                rel = np.float32(abs(cost - prev) / cost) if cost != 0 else np.float32(0)
+                prev = cost
+                if rel <= tol:
+                    converged = True
+                it += 1
+                if not (it < self.max_iter and not converged):
+                    break
+            self._dev_last_labels = labels[:n_local]
+            return cur, converged, inertias
+        finally:
+            lib.b2k_dev_lloyd_destroy(sess)

@@ -1,0 +1,229 @@
+"""GPU: the estimator API (cluster_kmeans / cluster_regspace / assign_to_centers) -- the reference's own
+clustering tests restated (pyemma/coordinates/clustering/tests/*.py), plus oracle parity end to end."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import pyemma_b200 as coor
+from pyemma_b200.data import DataInMemory
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def make_blobs(rng, n, centers, std):
+    X = np.concatenate([c + std * rng.randn(n // len(centers), len(c)) for c in centers])
+    return X.astype(np.float32)
+
+
+# ---- test_kmeans.py ---------------------------------------------------------------------------------
+def test_kmeans_api_and_dtraj_dtype():
+    X = np.random.RandomState(0).randn(5000, 3)
+    km = coor.cluster_kmeans(X, k=10)
+    assert km.dtrajs[0].dtype == km.output_type()          # test_kmeans.py:48
+    assert km.clustercenters.shape == (10, 3) and km.clustercenters.dtype == np.float32
+    assert len(km.dtrajs) == 1 and len(km.dtrajs[0]) == 5000
+    assert km.dimension() == 1 and "Kmeans" in km.describe()
+
+
+@pytest.mark.parametrize("init_strategy", ["uniform", "kmeans++"])
+@pytest.mark.parametrize("fixed_seed", [True, 463498])
+def test_kmeans_seed_determinism(init_strategy, fixed_seed):
+    # test_kmeans.py:75-102
+    rng = np.random.RandomState(1)
+    X = make_blobs(rng, 3000, [[-2, -2], [2, 2], [-2, 2]], 0.4)
+    a = coor.cluster_kmeans(X, k=10, init_strategy=init_strategy, fixed_seed=fixed_seed, max_iter=20, n_jobs=1)
+    b = coor.cluster_kmeans(X, k=10, init_strategy=init_strategy, fixed_seed=fixed_seed, max_iter=20, n_jobs=1)
+    np.testing.assert_array_equal(a.initial_centers_, b.initial_centers_)
+    np.testing.assert_array_equal(a.clustercenters, b.clustercenters)  # deterministic: exact fixed-point sums
+    np.testing.assert_array_equal(a.dtrajs[0], b.dtrajs[0])
+
+
+def test_kmeans_known_answers():
+    cube = np.array([[1, 1, 1], [1, 1, -1], [1, -1, -1], [-1, -1, -1], [-1, 1, 1], [-1, -1, 1], [-1, 1, -1],
+                     [1, -1, 1]], np.float32)
+    km = coor.cluster_kmeans(cube, k=1)                      # test_kmeans.py:154-166
+    np.testing.assert_equal(km.clustercenters.squeeze(), [0, 0, 0])
+    X = cube.copy()
+    X[0, 1] = 1.5
+    km = coor.cluster_kmeans(X, k=2, clustercenters=np.array([[2, 0, 0], [-2, 0, 0]]), max_iter=500, n_jobs=1)
+    assert np.all(np.abs(km.clustercenters) <= 1)           # test_kmeans.py:168-179
+    T = np.zeros((40000, 4))
+    for i, v in enumerate((30.0, 60.0, 90.0, 120.0)):
+        T[i * 10000:(i + 1) * 10000] = v
+    cl = coor.cluster_kmeans(T, k=4)                         # test_kmeans.py:411-426
+    assert sorted(cl.clustercenters[:, 0].tolist()) == [30.0, 60.0, 90.0, 120.0]
+
+
+def test_kmeans_minrmsd_assignment_manual_argmin(b2k):
+    # test_kmeans.py:235-252
+    data = np.random.RandomState(123).uniform(-50, 50, size=(500, 3 * 15))
+    km = coor.cluster_kmeans([data], 15, metric="minRMSD", max_iter=0, fixed_seed=32, init_strategy="kmeans++",
+                             n_jobs=1)
+    km2 = coor.cluster_kmeans([data], 15, metric="minRMSD", max_iter=0, fixed_seed=32, init_strategy="kmeans++",
+                              n_jobs=1)
+    np.testing.assert_array_equal(km.dtrajs[0], km2.dtrajs[0])
+    np.testing.assert_array_equal(km.clustercenters, km2.clustercenters)
+    assert km.metric == "minRMSD"
+    manual = [int(np.argmin([b2k.compute_metric(f, c, "minRMSD") for c in km.clustercenters])) for f in data[:60]]
+    np.testing.assert_array_equal(manual, km.dtrajs[0][:60])
+
+
+def test_kmeans_skip_stride_resume_keep_data():
+    X = np.random.RandomState(2).rand(100, 3)
+    assert len(coor.cluster_kmeans(X, k=3, skip=42).dtrajs[0]) == 100 - 42   # test_kmeans.py:318-320
+    rng = np.random.RandomState(3)
+    Y = make_blobs(rng, 6000, [[0, 0], [5, 5], [-5, 5]], 0.5)
+    init = np.array([[1, 1], [4, 4], [-4, 4]], np.float32)
+    cl = coor.cluster_kmeans(Y, clustercenters=init, k=3, max_iter=1, keep_data=True, tolerance=0)
+    assert not cl.converged and cl._dev_frames is not None   # test_kmeans.py:401-409
+    d1 = np.abs(cl.clustercenters - [[0, 0], [5, 5], [-5, 5]]).max()
+    cl.estimate(Y, clustercenters=cl.clustercenters, max_iter=50, tolerance=1e-7)
+    assert cl.converged and cl._dev_frames is None           # freed on convergence (test_kmeans.py:390-399)
+    assert np.abs(cl.clustercenters - [[0, 0], [5, 5], [-5, 5]]).max() <= d1   # resume improves (:357-374)
+    st = coor.cluster_kmeans(Y, k=3, stride=7, fixed_seed=True)
+    assert len(st.dtrajs[0]) == 6000  # dtrajs are assigned at stride 1
+    assert coor.cluster_kmeans(Y, k=None, max_iter=1).n_clusters == min(int(np.sqrt(6000)), 5000)
+
+
+def test_kmeans_rejects_nan():
+    X = np.random.RandomState(0).rand(100, 2)
+    X[17, 1] = np.nan
+    with pytest.raises(Exception, match="invalid"):
+        coor.cluster_kmeans(X, k=3)
+
+
+# ---- oracle parity end to end (cfg1 shape at reduced N, golden fixture) ------------------------------------
+def test_cfg1_golden_end_to_end(oracle):
+    g = np.load(os.path.join(GOLD, "cfg1_small.npz"))
+    X = g["X"]
+    km = coor.cluster_kmeans(X, k=100, max_iter=10, fixed_seed=42, kmpp_scan="serial")
+    c0 = oracle.kmpp_init(X, 100, 42)
+    np.testing.assert_array_equal(km.initial_centers_, c0)                 # k-means++ bit-exact (serial scan)
+    assert (int(not km.converged), len(km.inertias_)) == (int(g["code"]), int(g["iters"]))  # iteration count
+    np.testing.assert_allclose(km.inertias_, g["inertias_f64"], rtol=2e-6)
+    assert np.abs(km.clustercenters - g["centers_f64"]).max() <= 1e-5 * np.abs(g["centers_f64"]).max()
+    np.testing.assert_allclose(km.inertias_, g["inertias_f32seq"], rtol=1e-4)
+    # dtrajs bit-exact given the same centers
+    np.testing.assert_array_equal(km.dtrajs[0], oracle.assign(X, km.clustercenters, n_threads=4))
+    np.testing.assert_array_equal(coor.assign_to_centers(X, g["centers_f32seq"])[0], g["dtraj"])
+    kb = coor.cluster_kmeans(X, k=100, max_iter=1, fixed_seed=42, kmpp_scan="blocked")
+    np.testing.assert_array_equal(kb.initial_centers_, X[g["kmpp_blocked_idx"]])
+
+
+def test_golden_minrmsd_and_cfg2(oracle, b2k):
+    g = np.load(os.path.join(GOLD, "minrmsd_small.npz"))
+    np.testing.assert_array_equal(coor.assign_to_centers(g["X"], g["C"], metric="minRMSD")[0], g["dtraj"])
+    g = np.load(os.path.join(GOLD, "cfg2_small.npz"))
+    np.testing.assert_array_equal(coor.assign_to_centers(g["X"], g["C"])[0], g["dtraj"])
+    newc, lab = b2k.kmeans_cluster(g["X"], g["C"])
+    np.testing.assert_array_equal(lab, g["dtraj"])
+    assert np.abs(newc - g["newC_f32seq"]).max() <= 1e-5 * np.abs(g["newC_f32seq"]).max()
+    np.testing.assert_allclose(newc, g["newC_f64"], rtol=3e-7, atol=1e-7)
+
+
+# ---- test_assign.py -----------------------------------------------------------------------------------
+def test_assign_to_centers_reference_cases():
+    rng = np.random.RandomState(0)
+    centers = np.array([[0, 0, 0], [10, 0, 0], [0, 10, 0], [0, 0, 10], [10, 10, 10]], np.float32)
+    X = np.concatenate([c + 0.1 * rng.randn(1000, 3) for c in centers])
+    ass = coor.assign_to_centers(X, centers, return_dtrajs=False)
+    assert len(ass.dtrajs) == 1 and ass.dtrajs[0].dtype == ass.output_type()
+    assert (ass.dtrajs[0] == np.arange(5000) // 1000).all()                # test_assign.py:102-109
+    np.testing.assert_array_equal(ass.transform(X), ass.get_output()[0])    # :137-143
+    dtr = coor.assign_to_centers(data=X, centers=centers)
+    np.testing.assert_array_equal(dtr[0], ass.dtrajs[0])
+    with pytest.raises(ValueError):                                          # :183-197
+        coor.assign_to_centers(X, centers[:, :2])
+    with pytest.raises(ValueError):
+        ass.assign(X, stride=2)
+    # chunked / list input / stride
+    two = coor.assign_to_centers([X[:1234], X[1234:]], centers, chunksize=100)
+    np.testing.assert_array_equal(np.concatenate(two), ass.dtrajs[0])
+    np.testing.assert_array_equal(ass.assign(stride=3)[0], ass.dtrajs[0][::3] if False else (np.arange(5000) // 1000)[::3])
+
+
+def test_assign_from_file(tmp_path):
+    c = np.random.RandomState(1).randn(6, 4)
+    X = np.random.RandomState(2).randn(300, 4)
+    np.save(tmp_path / "c.npy", c)
+    np.savetxt(tmp_path / "c.dat", c)
+    a = coor.assign_to_centers(X, str(tmp_path / "c.npy"))[0]
+    b = coor.assign_to_centers(X, str(tmp_path / "c.dat"))[0]
+    np.testing.assert_array_equal(a, coor.assign_to_centers(X, c)[0])
+    assert (a == b).mean() > 0.99
+
+
+# ---- test_regspace.py / test_cluster_samples.py --------------------------------------------------------------
+def test_regspace_reference_cases(oracle):
+    trajs = [[0, 1, 2], [3, 4, 5], [6, 7, 8], [0, 1, 2], [3, 4, 5], [6, 7, 8]]
+    cl = coor.cluster_regspace(data=trajs, dmin=.5)           # test_cluster_samples.py:41-60
+    np.testing.assert_array_equal(cl.clustercenters.ravel(), np.arange(9))
+    assert cl.n_clusters == 9
+    ref = [[[0, 0], [3, 0]], [[0, 1], [3, 1]], [[0, 2], [3, 2]], [[1, 0], [4, 0]], [[1, 1], [4, 1]],
+           [[1, 2], [4, 2]], [[2, 0], [5, 0]], [[2, 1], [5, 1]], [[2, 2], [5, 2]]]
+    for cc in range(cl.n_clusters):
+        np.testing.assert_array_equal(cl.index_clusters[cc], ref[cc])
+    for ii, s in enumerate(cl.sample_indexes_by_cluster(np.arange(cl.n_clusters), 10)):
+        assert all(cl.dtrajs[a][b] == ii for a, b in s)
+
+    rng = np.random.RandomState(0)
+    src = DataInMemory([rng.rand(1000, 3), rng.rand(700, 3)], chunksize=250)
+    rs = coor.RegularSpaceClustering(dmin=0.3)
+    rs.estimate(src)
+    X = np.concatenate([t for t in src.data]).astype(np.float32)
+    ref_c, _, _ = oracle.regspace(X, 0.3, 1000)
+    np.testing.assert_array_equal(rs.clustercenters, ref_c)
+    assert len(np.unique(np.concatenate(rs.dtrajs))) == len(rs.clustercenters)   # test_regspace.py:77-89
+    assert coor.cluster_regspace(rng.rand(500), dmin=0.1).clustercenters.shape[1] == 1   # 1-D input (:96-98)
+    for metric in ("euclidean", "minRMSD"):                      # :107-115, :137-141
+        a = coor.cluster_regspace(src, dmin=0.3, metric=metric, n_jobs=1)
+        b = coor.cluster_regspace(src, dmin=0.3, metric=metric, n_jobs=2)
+        np.testing.assert_equal(a.clustercenters, b.clustercenters)
+        np.testing.assert_array_equal(a.clustercenters, oracle.regspace(X, 0.3, 1000, metric)[0])
+
+
+def test_regspace_max_centers_warns_once():
+    # test_regspace.py:117-135
+    rng = np.random.RandomState(1)
+    src = DataInMemory([rng.rand(1000, 3)], chunksize=300)
+    rs = coor.RegularSpaceClustering(dmin=1e-8, max_centers=50)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        rs.estimate(src)
+        assert len(w) == 1
+    assert len(rs.clustercenters) == 50 and not rs.converged
+    out = rs.get_output()
+    assert len(out) == rs.number_of_trajectories() and len(out[0]) == rs.trajectory_lengths()[0]
+
+
+# ---- test_cluster.py: generic estimator contract ---------------------------------------------------------------
+@pytest.mark.parametrize("make", [lambda X: coor.cluster_kmeans(X, k=100, max_iter=3),
+                                  lambda X: coor.cluster_regspace(X, dmin=0.5)])
+def test_generic_contract(make):
+    rng = np.random.RandomState(5)
+    X = [rng.randn(1500, 3), rng.randn(800, 3)]
+    cl = make(X)
+    assert isinstance(cl.chunksize, int)
+    assert cl.clustercenters.shape[1] == 3 and cl.clustercenters.shape[0] == cl.n_clusters
+    assert cl.dimension() == 1
+    assert [len(d) for d in cl.dtrajs] == [1500, 800] and all(d.dtype == np.int32 for d in cl.dtrajs)
+    out = cl.get_output()
+    assert all(o.shape == (n, 1) and o.dtype == np.int32 for o, n in zip(out, (1500, 800)))
+    for itraj, chunk in cl.iterator(chunk=400):
+        assert chunk.shape[1] == 1 and chunk.dtype == np.int32 and len(chunk) <= 400
+    np.testing.assert_array_equal(cl.transform(X[0]), out[0])
+    assert isinstance(cl.describe(), str)
+
+
+def test_save_dtrajs(tmp_path):
+    X = np.random.RandomState(0).randn(200, 2)
+    cl = coor.cluster_kmeans([X, X[:50]], k=5, max_iter=2)
+    cl.save_dtrajs(prefix="pre", output_dir=str(tmp_path))
+    np.testing.assert_array_equal(np.loadtxt(tmp_path / "pre_0.dtraj", dtype=int), cl.dtrajs[0])
+    cl.save_dtrajs(prefix="pre", output_dir=str(tmp_path), output_format="npy", extension=".npy")
+    np.testing.assert_array_equal(np.load(tmp_path / "pre_1.npy"), cl.dtrajs[1])
+    with pytest.raises(EnvironmentError):
+        cl.save_dtrajs(prefix="pre", output_dir=str(tmp_path))

@@ -108,11 +108,18 @@ def test_cluster_loop_matches_oracle(b2k, oracle):
     C0 = oracle.kmpp_init(X, 100, 42)
     calls = []
     cen, code, it, inert = b2k.kmeans_cluster_loop(X, C0, 10, 1e-5, callback=lambda: calls.append(1))
-    rcen, rcode, rit, rinert = oracle.cluster_loop(X, C0, 10, 1e-5, acc="f32seq")
-    assert (code, it) == (rcode, rit)
     assert len(calls) == it - (1 if code == 0 else 0)
-    np.testing.assert_allclose(inert, rinert, rtol=1e-5)
+    # free-running vs the oracle with fp64 sums (the GPU sums are exact fixed point): same trajectory
+    rcen, rcode, rit, rinert = oracle.cluster_loop(X, C0, 10, 1e-5, acc="f64")
+    assert (code, it) == (rcode, rit)
+    np.testing.assert_allclose(inert, rinert, rtol=2e-6)
     assert np.abs(cen - rcen).max() <= 1e-5 * np.abs(rcen).max()
+    # free-running vs the reference-faithful fp32-sequential sums: same iteration count and inertias; the
+    # centers drift apart by label flips of boundary frames (chaotic), so they are compared per step
+    # with identical inputs in test_lloyd_step_and_cost instead.
+    scen, scode, sit, sinert = oracle.cluster_loop(X, C0, 10, 1e-5, acc="f32seq")
+    assert (code, it) == (scode, sit)
+    np.testing.assert_allclose(inert, sinert, rtol=1e-4)
     # labels under the final centers are bit-exact when both sides use the same centers
     np.testing.assert_array_equal(b2k.assign(X, rcen), oracle.assign(X, rcen, n_threads=4))
 
