@@ -70,11 +70,13 @@ int64_t b2k_launch_count(void);
 /* ---- context ---------------------------------------------------------------------------- */
 int b2k_ctx_create(int device, b2k_ctx** out);
 int b2k_ctx_destroy(b2k_ctx* ctx);
-/* use an external cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream */
+/* run on an external cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream).  The handle is used
+ * as is: NULL is CUDA's legacy default stream.  b2k_ctx_set_option(ctx, "own_stream", 1) goes back to a
+ * private non-blocking stream (the state after b2k_ctx_create). */
 int b2k_ctx_set_stream(b2k_ctx* ctx, void* cuda_stream);
 int b2k_ctx_sync(b2k_ctx* ctx);
 /* options: "assign_engine" (B2K_ENGINE_*), "screen_terms" (1|3, 0=auto), "stage_bytes" (pinned
- * staging buffer size per slot) */
+ * staging buffer size per slot), "own_stream" */
 int b2k_ctx_set_option(b2k_ctx* ctx, const char* name, int64_t value);
 int b2k_ctx_get_stat(b2k_ctx* ctx, const char* name, double* value);
 

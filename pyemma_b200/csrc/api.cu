@@ -195,9 +195,10 @@ B2K_API int b2k_ctx_destroy(b2k_ctx* c) {
 
 B2K_API int b2k_ctx_set_stream(b2k_ctx* c, void* cuda_stream) {
     if (!c) return set_error(B2K_ERR_INVALID_ARG, "null ctx");
+    // the handle is used as is: NULL is CUDA's legacy default stream (what torch uses unless told otherwise)
     if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
-    if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
-    else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
     return B2K_OK;
 }
 
@@ -212,6 +213,12 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "assign_engine")) c->engine = (int)value;
     else if (!strcmp(name, "screen_terms")) c->screen_terms = (int)value;
     else if (!strcmp(name, "stage_bytes")) c->stage_bytes = (size_t)std::max<int64_t>(value, 1 << 16);
+    else if (!strcmp(name, "own_stream")) {
+        if (!c->own_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            c->own_stream = true;
+        }
+    }
     else return set_error(B2K_ERR_INVALID_ARG, "unknown option '%s'", name);
     return B2K_OK;
 }
@@ -275,7 +282,8 @@ B2K_API int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, 
         B2K_TRY(screen_plan_create(ctx, n, d, k, &plan));
         int rc = screen_prepare_frames(plan, dX, n);
         if (rc == B2K_OK) rc = screen_assign(plan, dX, n, dC, dlabels, dmind, 0);
-        if (rc == B2K_OK) { cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = set_error(B2K_ERR_CUDA, "%s", cudaGetErrorString(e)); }
+        if (rc == B2K_OK) rc = screen_read_stats(plan, &ctx->stat_cand_chunks, &ctx->stat_fallback_frames);
+        ctx->stat_screen_frames = (double)n;
         screen_plan_destroy(plan);
         return rc;
     }

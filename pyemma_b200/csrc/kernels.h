@@ -54,6 +54,7 @@ int screen_prepare_frames(ScreenPlan* p, const float* dX, int64_t n);
 // labels for the prepared frames against dcenters
 int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dcenters, int32_t* labels, float* mind,
                   int lloyd);
+int screen_read_stats(ScreenPlan* p, double* cand_chunks, double* fallback_frames);
 bool screen_supported(const b2k_ctx* ctx, int d, int k, int64_t n);
 
 }  // namespace b2k

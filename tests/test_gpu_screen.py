@@ -1,0 +1,94 @@
+"""GPU: the tcgen05 screen + exact verify path must give the oracle's labels bit for bit."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def blobs(rng, n, d, nb, spread=5.0, sigma=1.0):
+    cen = rng.uniform(-spread, spread, size=(nb, d))
+    lab = rng.randint(0, nb, size=n)
+    return (cen[lab] + sigma * rng.randn(n, d)).astype(np.float32)
+
+
+@pytest.fixture()
+def screen_ctx(b2k):
+    ctx = b2k.context()
+    ctx.set_option("assign_engine", b2k.ENGINE_SCREEN)
+    yield ctx
+    ctx.set_option("assign_engine", b2k.ENGINE_AUTO)
+    ctx.set_option("screen_terms", 0)
+
+
+SHAPES = [(5000, 2, 100, 0), (20000, 10, 1000, 1), (20000, 10, 1000, 3), (4096, 3, 257, 0), (3000, 16, 300, 0),
+          (6000, 17, 513, 0), (5000, 64, 2000, 3), (5000, 64, 2000, 1), (2500, 256, 1000, 3), (1000, 300, 64, 0),
+          (129, 5, 40, 0)]
+
+
+@pytest.mark.parametrize("n,d,k,terms", SHAPES)
+def test_screen_assign_bit_exact(b2k, oracle, screen_ctx, n, d, k, terms):
+    rng = np.random.RandomState(n + 7 * d + k)
+    X = blobs(rng, n, d, 12)
+    C = X[rng.choice(n, k, replace=k > n)].copy()
+    C[: k // 2] += (0.05 * rng.randn(k // 2, d)).astype(np.float32)  # near-duplicates: small gaps
+    screen_ctx.set_option("screen_terms", terms)
+    ref = oracle.assign(X, C, n_threads=8)
+    got = b2k.assign(X, C)
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_screen_offset_data_and_ties(b2k, oracle, screen_ctx):
+    # large common offset (centering must cope), exact duplicates of centers (lowest index wins)
+    rng = np.random.RandomState(3)
+    X = (blobs(rng, 8000, 12, 6, spread=2.0, sigma=0.3) + 1000.0).astype(np.float32)
+    base = X[rng.choice(8000, 150, replace=False)]
+    C = np.concatenate([base, base, base[:50]]).astype(np.float32)
+    ref = oracle.assign(X, C, n_threads=8)
+    got = b2k.assign(X, C)
+    np.testing.assert_array_equal(got, ref)
+    assert got.max() < 150
+
+
+def test_screen_outliers_and_constant_data(b2k, oracle, screen_ctx):
+    rng = np.random.RandomState(4)
+    X = blobs(rng, 6000, 8, 5)
+    X[100] *= 1e4  # far outlier changes the scale
+    X[200] = 0
+    C = X[rng.choice(6000, 300, replace=False)].copy()
+    np.testing.assert_array_equal(b2k.assign(X, C), oracle.assign(X, C, n_threads=8))
+    Z = np.full((5000, 4), 3.25, np.float32)
+    Cz = np.full((130, 4), 3.25, np.float32)
+    np.testing.assert_array_equal(b2k.assign(Z, Cz), oracle.assign(Z, Cz))
+
+
+def test_screen_lloyd_matches_direct(b2k, oracle, screen_ctx):
+    rng = np.random.RandomState(5)
+    X = blobs(rng, 30000, 10, 20, spread=3.0, sigma=0.8)
+    C0 = X[rng.choice(30000, 500, replace=False)].copy()
+    cen_s, code_s, it_s, in_s = b2k.kmeans_cluster_loop(X, C0, 6, 0.0)
+    screen_ctx.set_option("assign_engine", b2k.ENGINE_DIRECT)
+    cen_d, code_d, it_d, in_d = b2k.kmeans_cluster_loop(X, C0, 6, 0.0)
+    np.testing.assert_array_equal(cen_s, cen_d)      # same labels -> identical exact sums
+    np.testing.assert_array_equal(in_s, in_d)
+    rc, rcode, rit, rin = oracle.cluster_loop(X, C0, 6, 0.0, n_threads=8, acc="f64")
+    assert np.abs(cen_s - rc).max() <= 1e-5 * np.abs(rc).max()
+
+
+def test_screen_candidate_statistics(b2k, screen_ctx):
+    import ctypes as C
+    import torch
+    rng = np.random.RandomState(6)
+    X = blobs(rng, 100000, 10, 20, spread=3.0, sigma=0.8)
+    Cn = X[rng.choice(100000, 1000, replace=False)].copy()
+    dev = torch.device("cuda", screen_ctx.device)
+    dX, dC = torch.from_numpy(X).to(dev), torch.from_numpy(Cn).to(dev)
+    lab = torch.empty(len(X), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    b2k.check(screen_ctx.lib.b2k_dev_assign(screen_ctx.handle, C.c_void_p(dX.data_ptr()), len(X), 10,
+                                            C.c_void_p(dC.data_ptr()), 1000, 0, C.c_void_p(lab.data_ptr()), None))
+    frames = screen_ctx.get_stat("screen_frames")
+    assert frames == len(X)
+    chunks = screen_ctx.get_stat("screen_cand_chunks") / frames
+    fb = screen_ctx.get_stat("screen_fallback_frames") / frames
+    print("candidate chunks per frame %.3f, fallback fraction %.5f" % (chunks, fb))
+    assert chunks < 3.0 and fb < 0.01
