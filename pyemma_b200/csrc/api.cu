@@ -187,6 +187,7 @@ B2K_API int b2k_ctx_destroy(b2k_ctx* c) {
         if (c->ev_h2d[s]) cudaEventDestroy(c->ev_h2d[s]);
         if (c->ev_done[s]) cudaEventDestroy(c->ev_done[s]);
     }
+    screen_plan_release_cached(c);
     if (c->scratch) cudaFree(c->scratch);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -225,6 +226,10 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
 
 B2K_API int b2k_ctx_get_stat(b2k_ctx* c, const char* name, double* value) {
     if (!c || !name || !value) return set_error(B2K_ERR_INVALID_ARG, "null argument");
+    if (c->stat_pending && c->assign_plan && !strncmp(name, "screen_", 7)) {  // stats of the last device assign, read lazily
+        B2K_TRY(screen_read_stats(static_cast<ScreenPlan*>(c->assign_plan), &c->stat_cand_chunks, &c->stat_fallback_frames));
+        c->stat_pending = false;
+    }
     if (!strcmp(name, "screen_cand_chunks")) *value = c->stat_cand_chunks;
     else if (!strcmp(name, "screen_fallback_frames")) *value = c->stat_fallback_frames;
     else if (!strcmp(name, "screen_frames")) *value = c->stat_screen_frames;
@@ -279,12 +284,11 @@ B2K_API int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, 
         B2K_TRY(launch_rmsd_center(ctx, dX, n, d, nullptr, ga.as<float>()));
     } else if (ctx->engine != B2K_ENGINE_DIRECT && screen_supported(ctx, d, k, n)) {
         ScreenPlan* plan = nullptr;
-        B2K_TRY(screen_plan_create(ctx, n, d, k, &plan));
+        B2K_TRY(screen_plan_acquire(ctx, n, d, k, &plan));
         int rc = screen_prepare_frames(plan, dX, n);
         if (rc == B2K_OK) rc = screen_assign(plan, dX, n, dC, dlabels, dmind, 0);
-        if (rc == B2K_OK) rc = screen_read_stats(plan, &ctx->stat_cand_chunks, &ctx->stat_fallback_frames);
         ctx->stat_screen_frames = (double)n;
-        screen_plan_destroy(plan);
+        ctx->stat_pending = rc == B2K_OK;
         return rc;
     }
     B2K_TRY(assign_any(ctx, dX, ga.as<float>(), n, d, pc, k, metric, dlabels, dmind, 0));
@@ -322,7 +326,7 @@ B2K_API int b2k_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const
     const bool use_screen = metric == B2K_METRIC_EUCLIDEAN && ctx->engine != B2K_ENGINE_DIRECT &&
                             screen_supported(ctx, d, k, cf);
     ScreenPlan* plan = nullptr;
-    if (use_screen) B2K_TRY(screen_plan_create(ctx, cf, d, k, &plan));
+    if (use_screen) B2K_TRY(screen_plan_acquire(ctx, cf, d, k, &plan));
     cudaEvent_t ev_k[2];
     for (int s = 0; s < 2; ++s) CUDA_TRY(cudaEventCreateWithFlags(&ev_k[s], cudaEventDisableTiming));
     int64_t pend_off[2] = {-1, -1}, pend_len[2] = {0, 0};
@@ -366,7 +370,10 @@ B2K_API int b2k_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const
         cudaEventDestroy(ev_k[s]);
     }
     cudaStreamSynchronize(st);
-    if (plan) screen_plan_destroy(plan);
+    if (use_screen) {  // candidate statistics of the LAST chunk are readable through b2k_ctx_get_stat
+        ctx->stat_screen_frames = (double)(n - (int64_t)(c - 1) * cf);
+        ctx->stat_pending = rc == B2K_OK;
+    }
     if (rc != B2K_OK) return rc;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(B2K_ERR_CUDA, "assign: %s", cudaGetErrorString(e));

@@ -61,6 +61,10 @@ struct b2k_ctx {
     int screen_terms = 0;
     // stats of the last screen call
     double stat_cand_chunks = 0, stat_fallback_frames = 0, stat_screen_frames = 0;
+    bool stat_pending = false;
+    // screen plan of the last b2k_assign / b2k_dev_assign call, kept so that chunked assignment does not
+    // reallocate the operand buffers for every chunk (owned here, freed by b2k_ctx_destroy)
+    void* assign_plan = nullptr;
     // generic device scratch (grown on demand)
     void* scratch = nullptr;
     size_t scratch_cap = 0;

@@ -49,6 +49,9 @@ int launch_all_finite(b2k_ctx* ctx, const float* X, int64_t count, int* d_flag /
 struct ScreenPlan;
 int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** out);
 void screen_plan_destroy(ScreenPlan* p);
+// plan cached in the context for one-shot / chunked assignment (reused while d, k match and n fits)
+int screen_plan_acquire(b2k_ctx* ctx, int64_t n, int d, int k, ScreenPlan** out);
+void screen_plan_release_cached(b2k_ctx* ctx);
 // (re)build the frame operand for n frames at dX (done once per dataset / chunk)
 int screen_prepare_frames(ScreenPlan* p, const float* dX, int64_t n);
 // labels for the prepared frames against dcenters

@@ -7,13 +7,21 @@
 //
 //  1. screen   acc[i][j] = x~_i . c~_j - |c~_j|^2/2   (maximising acc == minimising the distance)
 //              as ONE fp16 GEMM on the 5th-gen tensor cores: tcgen05.mma, operands staged by TMA
-//              (SWIZZLE_128B), fp32 accumulators in TMEM.  x~ = (x-mu)*sigma is centred/scaled so it
-//              fits fp16; precision comes from splitting each fp32 value into hi+lo fp16 parts and
-//              concatenating along K:   A' = [x_hi | x_hi | x_lo | 1 1 1],  B' = [c_hi | c_lo | c_hi |
-//              -b1 -b2 -b3]  (terms=3; terms=1 keeps only the hi parts), b = |c~|^2/2 split in 3.
-//              The N x k score matrix is never written: 4 epilogue warps read the accumulators with
-//              tcgen05.ld, keep a running row maximum (FMNMX3) and remember every 32-column chunk
-//              whose maximum is within a rigorous error margin of it.
+//              (SWIZZLE_128B), fp32 accumulators in TMEM.  x~ = (x-mu)*sigma is centred/scaled (power of
+//              two, max |.| <= 2048) so it fits fp16; precision comes from splitting each fp32 value into
+//              hi+lo fp16 parts and concatenating along K (terms=3; terms=1 keeps only the first segment):
+//                 A' = [ x_hi*2^-5 | x_lo*2^5  | x_hi | 2^8  2^-3  2^-14 ]
+//                 B' = [ c_lo*2^5  | c_hi*2^-5 | c_hi | -b1  -b2   -b3   ],  b = |c~|^2/2 = b1*2^8+b2*2^-3+b3*2^-14
+//              (small cross terms first: while they accumulate the partial sums stay ~2^-11 of the final
+//              magnitude, so only the K=16 steps that touch the hi.hi segment or the bias contribute to the
+//              accumulation-error bound)
+//              The power-of-two factors keep the lo parts out of the fp16 subnormal range, and every value
+//              below 2^-14 is flushed to zero HERE (measured: tcgen05.mma kind::f16 does not honour fp16
+//              subnormals), so the flush error is part of the margin instead of a silent loss.
+//              The N x k score matrix is never written: 8 epilogue warps read the accumulators with
+//              tcgen05.ld (software-pipelined), keep a running row maximum (FMNMX3) and remember every
+//              32-column chunk -- with a 4-bit mask of its 8-column groups -- whose maximum is within a
+//              rigorous error margin of it.
 //  2. verify   the (few) surviving chunks are re-evaluated per frame with the exact reference-order
 //              fp32 kernel arithmetic (common.cuh) -> the argmin matches the reference exactly.
 //              Frames whose candidate list overflows fall back to a full exact scan.
@@ -36,13 +44,14 @@ static constexpr int TILE_M = 128;    // frames per CTA tile (UMMA M)
 static constexpr int TILE_N = 256;    // centers per accumulator stage (UMMA N)
 static constexpr int BLOCK_K = 64;    // fp16 elements per k-block (one 128-byte swizzle row)
 static constexpr int STAGES = 4;
-static constexpr int CHUNK = 32;      // columns per candidate chunk
-static constexpr int LIST_CAP = 16;   // running candidate chunks remembered per frame
-static constexpr int CAND_CAP = 4;    // candidate chunks handed to the verify kernel per frame
+static constexpr int CHUNK = 32;      // columns per candidate chunk (one tcgen05.ld.32x32b.x32)
+static constexpr int GROUP = 8;       // columns per candidate group: a chunk entry carries a 4-bit group mask
+static constexpr int LIST_CAP = 16;   // running candidate chunks remembered per frame and column half
+static constexpr int CAND_CAP = 8;    // candidate chunks handed to the verify kernel per frame
+static constexpr uint32_t ID_MASK = 0x0fffffffu;  // candidate entry: chunk id | group mask << 28
 static constexpr int A_BYTES = TILE_M * BLOCK_K * 2;
 static constexpr int B_BYTES = TILE_N * BLOCK_K * 2;
 static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-static constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue
 
 struct ScreenParams {  // device resident; written by the prep kernels, read by everything else
     float sigma;       // power-of-two scale
@@ -63,7 +72,7 @@ struct ScreenPlan {
     float* X2 = nullptr;       // [n_pad] |x~|^2
     float* mu = nullptr;       // [d]
     ScreenParams* params = nullptr;
-    uint16_t* cand = nullptr;  // [n_pad][CAND_CAP]
+    uint32_t* cand = nullptr;  // [n_pad][CAND_CAP]  chunk id | group mask << 28
     uint8_t* ncand = nullptr;  // [n_pad]  (255: overflow -> exact fallback)
     CUtensorMap tmA, tmB;
     int64_t prepared_n = -1;
@@ -121,15 +130,23 @@ __global__ void __launch_bounds__(256) screen_maxnorm_kernel(const float* __rest
     if ((threadIdx.x & 31) == 0) atomicMax((int*)out, __float_as_int(m));
 }
 
+// fp16 image of v with everything below the smallest NORMAL fp16 flushed to zero
+__device__ __forceinline__ float h16_ftz(float v) {
+    const float f = __half2float(__float2half_rn(v));
+    return fabsf(f) < 6.103515625e-5f ? 0.f : f;
+}
+static constexpr float SCALE_TARGET = 2048.f;  // max |x~|, |c~| after scaling (power of two keeps hi/lo splits exact)
+static constexpr float CMAX_LIMIT = 4096.f;    // centers may drift this far before the operands are declared unusable
+
 __global__ void screen_sigma_kernel(ScreenParams* p) {
     const float mx = sqrtf(fmaxf(p->xmax2_raw, p->cmax2_raw));
     float sigma = 1.f;
     int valid = 1;
     if (!(mx < 3.0e38f)) valid = 0;
     else if (mx > 0.f) {
-        // largest power of two with mx*sigma <= 200  (=> |x~|,|c~| <= 200 < 256, |c~|^2/2 <= 2e4 < 65504)
+        // largest power of two with mx*sigma <= SCALE_TARGET
         int e;
-        frexpf(200.f / fmaxf(mx, 1e-30f), &e);  // 200/mx = f*2^e, f in [0.5,1)  -> 2^(e-1) <= 200/mx
+        frexpf(SCALE_TARGET / fmaxf(mx, 1e-30f), &e);  // target/mx = f*2^e, f in [0.5,1)  -> 2^(e-1) <= target/mx
         e -= 1;
         if (e > 100) e = 100;
         if (e < -100) { e = -100; valid = 0; }
@@ -139,37 +156,63 @@ __global__ void screen_sigma_kernel(ScreenParams* p) {
     p->valid = valid;
 }
 
-// A' rows: [x_hi | (x_hi | x_lo) | 1 1 1 | 0..]; X2[i] = |x~_i|^2; rows >= n are zero
+// A' rows (layout in the file header); rows >= n are zero.  One thread owns one 16-byte piece (8 fp16) of
+// the row and keeps that piece for every row it visits, so the column -> (segment, dimension) decode and the
+// mu values are loop invariant; stores are fully coalesced, the fp32 frame values come through L1.
 __global__ void __launch_bounds__(256) screen_frames_kernel(const float* __restrict__ X, int64_t n, int64_t n_pad,
                                                             int d, int terms, int Kp,
                                                             const float* __restrict__ mu,
                                                             const ScreenParams* __restrict__ prm,
-                                                            __half2* __restrict__ A) {
-    const int half_cols = Kp >> 1;
-    const int64_t total = n_pad * half_cols;
+                                                            uint4* __restrict__ A) {
+    const int pieces = Kp >> 3;
+    const int rows_per_pass = 256 / pieces;  // pieces <= 256 (Kp <= 2048) is checked by the plan
+    const int piece = threadIdx.x % pieces, rloc = threadIdx.x / pieces;
+    if (rloc >= rows_per_pass) return;
     const float sigma = prm->sigma;
     const int ones0 = terms * d;
-    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
-        const int64_t i = t / half_cols;
-        const int c0 = (int)(t - i * half_cols) * 2;
-        float v[2];
+    int seg[8], dim[8];
+    float muv[8], cst[8];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int c = c0 + q;
-            float out = 0.f;
-            if (i < n) {
-                if (c < ones0) {
-                    const int seg = c / d, e = c - seg * d;
-                    const float xt = __fmul_rn(__fsub_rn(X[i * d + e], mu[e]), sigma);
-                    const float hi = __half2float(__float2half_rn(xt));
-                    out = (seg == 2) ? __fsub_rn(xt, hi) : hi;  // rounded to fp16 below
-                } else if (c < ones0 + 3) {
-                    out = 1.f;
-                }
+    for (int q = 0; q < 8; ++q) {
+        const int c = piece * 8 + q;
+        seg[q] = -1;
+        dim[q] = 0;
+        muv[q] = 0.f;
+        cst[q] = 0.f;
+        if (c < ones0) {
+            const int ps = (c >= 2 * d) ? 2 : (c >= d ? 1 : 0);  // physical segment; the hi.hi products come LAST
+            seg[q] = (terms == 3) ? (ps == 2 ? 0 : ps + 1) : 0;
+            dim[q] = c - ps * d;
+            muv[q] = __ldg(mu + dim[q]);
+        } else if (c < ones0 + 3) {
+            cst[q] = (c == ones0) ? 256.f : (c == ones0 + 1 ? 0.125f : 6.103515625e-5f);
+        }
+    }
+    for (int64_t i = (int64_t)blockIdx.x * rows_per_pass + rloc; i < n_pad; i += (int64_t)gridDim.x * rows_per_pass) {
+        float v[8];
+        const bool live = i < n;
+        const float* xrow = X + i * d;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (live && seg[q] >= 0) ? __ldg(xrow + dim[q]) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float out = live ? cst[q] : 0.f;
+            if (seg[q] >= 0) {
+                const float xt = __fmul_rn(__fsub_rn(v[q], muv[q]), sigma);
+                const float hi = h16_ftz(xt);
+                out = seg[q] == 0 ? hi : (seg[q] == 1 ? h16_ftz(hi * 0.03125f) : h16_ftz(__fsub_rn(xt, hi) * 32.f));
+                if (!live) out = 0.f;
             }
             v[q] = out;
         }
-        A[t] = __floats2half2_rn(v[0], v[1]);
+        __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+        __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&h0);
+        o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2);
+        o.w = *reinterpret_cast<uint32_t*>(&h3);
+        A[i * pieces + piece] = o;
     }
 }
 
@@ -207,20 +250,25 @@ __global__ void __launch_bounds__(128) screen_centers_kernel(const float* __rest
     for (int e = 0; e < d; ++e) {
         const float ct = __fmul_rn(__fsub_rn(C[(int64_t)j * d + e], mu[e]), sigma);
         s += ct * ct;
-        const __half hi = __float2half_rn(ct);
-        const __half lo = __float2half_rn(__fsub_rn(ct, __half2float(hi)));
-        row[e] = hi;
-        if (terms == 3) { row[d + e] = lo; row[2 * d + e] = hi; }
+        const float hi = h16_ftz(ct);
+        if (terms == 3) {
+            row[e] = __float2half_rn(h16_ftz(__fsub_rn(ct, hi) * 32.f));
+            row[d + e] = __float2half_rn(h16_ftz(hi * 0.03125f));
+            row[2 * d + e] = __float2half_rn(hi);
+        } else {
+            row[e] = __float2half_rn(hi);
+        }
     }
+    // b = b1*2^8 + b2*2^-3 + b3*2^-14 (+ residual <= 2^-28 + 2^-33 b); every step below is exact in fp32
     const float b = 0.5f * s;
-    const __half b1 = __float2half_rn(b);
-    const float r1 = __fsub_rn(b, __half2float(b1));
-    const __half b2 = __float2half_rn(r1);
-    const float r2 = __fsub_rn(r1, __half2float(b2));
-    const __half b3 = __float2half_rn(r2);
-    row[ones0] = __hneg(b1);
-    row[ones0 + 1] = __hneg(b2);
-    row[ones0 + 2] = __hneg(b3);
+    const float b1 = h16_ftz(b * 0.00390625f);
+    const float r1 = __fsub_rn(b, b1 * 256.f);
+    const float b2 = h16_ftz(r1 * 8.f);
+    const float r2 = __fsub_rn(r1, b2 * 0.125f);
+    const float b3 = h16_ftz(r2 * 16384.f);
+    row[ones0] = __float2half_rn(-b1);
+    row[ones0 + 1] = __float2half_rn(-b2);
+    row[ones0 + 2] = __float2half_rn(-b3);
     for (int c = ones0 + 3; c < Kp; ++c) row[c] = __float2half_rn(0.f);
     atomicMax((int*)&prm->cmax2_now, __float_as_int(s));
 }
@@ -229,7 +277,7 @@ __global__ void screen_finish_centers_kernel(ScreenParams* p, int d) {
     // upper bound of max |c~| (the fp32 evaluation above is within (d+2) ulp)
     const float c2 = p->cmax2_now * (1.f + (d + 4) * 1.2e-7f);
     p->cmax = sqrtf(c2) * 1.000001f;
-    if (!(p->cmax <= 256.f)) p->valid = 0;  // centers moved outside the scaled range
+    if (!(p->cmax <= CMAX_LIMIT)) p->valid = 0;  // centers moved outside the scaled range
 }
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -302,6 +350,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the registers of an earlier tcgen05.ld are defined only after the wait: tie every later use to this point
+__device__ __forceinline__ void tmem_ld_fence(float (&v)[32]) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 8)
+        asm volatile("" : "+f"(v[e]), "+f"(v[e + 1]), "+f"(v[e + 2]), "+f"(v[e + 3]), "+f"(v[e + 4]), "+f"(v[e + 5]),
+                          "+f"(v[e + 6]), "+f"(v[e + 7])::"memory");
+}
 
 // ---- margin ----------------------------------------------------------------------------------------------------
 struct Margin {
@@ -314,9 +369,15 @@ struct Margin {
         const float R = X + C;
         const float d1 = 2.1f * u * R * R;
         const float erep = (terms == 3) ? 3.01f * 2.3841858e-7f : (2.f * 4.8828125e-4f + 2.4e-7f) * 1.01f;
-        const float eacc = (float)(nk16 * 17) * 1.1920929e-7f;
-        const float d2 = erep * X * C + 3.01e-8f * sqrtf((float)d) * R + eacc * (1.01f * X * C + 0.5f * C * C) +
-                         (gam + 1.2e-10f) * 0.5f * C * C;
+        // K=16 steps whose addends/partial sums are of full magnitude: from the step that holds the first
+        // hi.hi column (2d for terms=3, 0 for terms=1) to the end; the earlier ones see sums <= 2^-10 X C
+        const int nk_lo = (terms == 3) ? (2 * d) / 16 : 0;
+        const float eacc = ((float)((nk16 - nk_lo) * 17) + (float)(nk_lo * 17) * 9.8e-4f) * 1.1920929e-7f;
+        // values flushed to zero by the operand builder: per element <= (2^-19+2^-20)(|x_e|+|c_e|) with the
+        // scaled lo segments (terms=3), <= 2^-14 (|x_e|+|c_e|) with the hi segment alone (terms=1)
+        const float eflush = (terms == 3) ? 2.9e-6f : 6.2e-5f;
+        const float d2 = erep * X * C + eflush * sqrtf((float)d) * R + eacc * (1.01f * X * C + 0.5f * C * C) +
+                         (gam + 1.2e-10f) * 0.5f * C * C + 4e-9f;
         a = (2.f * d2 + d1) * 1.01f;
         r = 0.5f * rho * 1.01f;
         x2 = x2_;
@@ -333,59 +394,140 @@ struct GemmArgs {
     int n_kblocks;      // Kp / 64
     int nk16;           // K=16 MMA steps that carry data
     int d, terms;
+    int resident;       // 1: the whole center operand B' stays in shared memory, only frame tiles stream
+    int n_stages;       // pipeline stages
+    int stage_bytes;    // resident: n_kblocks*A_BYTES (a frame tile, full K); streaming: A_BYTES+B_BYTES (one k-block)
+    int bres_bytes;     // resident: bytes of B' in shared memory
     const float* X2;
     const ScreenParams* prm;
-    uint16_t* cand;
+    uint32_t* cand;
     uint8_t* ncand;
 };
+
+static constexpr int MAX_STAGES = 8;
+static constexpr int EPI_WARPS = 8;                    // 2 column halves x 4 TMEM lane quarters
+static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-9 epilogue
+static constexpr int HALF_CHUNKS = TILE_N / CHUNK / 2;  // chunks of one accumulator stage handled by one epilogue warp
+
+// small shared-memory block behind the operand tiles
+struct GemmSmemTail {
+    uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2], bfull_bar;
+    uint32_t tmem_slot, pad[3];
+    uint32_t list_id[2][LIST_CAP][TILE_M];
+    float list_v[2][LIST_CAP][TILE_M];
+    float half_m[2][TILE_M];
+    uint32_t out_n[2][TILE_M];              // kept entries of each half (CAND_CAP+1: too many)
+    uint32_t out_id[2][CAND_CAP][TILE_M];
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// running candidate bookkeeping of one epilogue thread (one frame, one column half)
+struct RowScan {
+    float m, thr;
+    int cnt;
+    bool overflow;
+    __device__ __forceinline__ void init() {
+        m = __int_as_float(0xff800000);
+        thr = m;
+        cnt = 0;
+        overflow = false;
+    }
+};
+
+__device__ __forceinline__ void scan_chunk(const float (&v)[32], uint32_t chunk_id, RowScan& rs, const Margin& mg,
+                                           uint32_t* lid, float* lv /* this thread's column of the list arrays */) {
+    float gm[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float* w = v + q * GROUP;
+        gm[q] = fmaxf(fmaxf(fmaxf(fmaxf(w[0], w[1]), w[2]), fmaxf(fmaxf(w[3], w[4]), w[5])), fmaxf(w[6], w[7]));
+    }
+    const float cm = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), gm[3]);
+    if (cm > rs.m) { rs.m = cm; rs.thr = mg.threshold(cm); }
+    if (cm >= rs.thr) {
+        // groups below the CURRENT threshold can never pass the final (higher) one
+        const uint32_t mask = (gm[0] >= rs.thr ? 1u : 0u) | (gm[1] >= rs.thr ? 2u : 0u) | (gm[2] >= rs.thr ? 4u : 0u) |
+                              (gm[3] >= rs.thr ? 8u : 0u);
+        if (rs.cnt == LIST_CAP) {  // compact: drop entries the risen threshold has already excluded
+            int w = 0;
+            for (int t = 0; t < LIST_CAP; ++t) {
+                const float tv = lv[t * TILE_M];
+                if (tv >= rs.thr) { lv[w * TILE_M] = tv; lid[w * TILE_M] = lid[t * TILE_M]; ++w; }
+            }
+            rs.cnt = w;
+        }
+        if (rs.cnt < LIST_CAP) {
+            lid[rs.cnt * TILE_M] = chunk_id | (mask << 28);
+            lv[rs.cnt * TILE_M] = cm;
+            ++rs.cnt;
+        } else {
+            rs.overflow = true;
+        }
+    }
+}
 
 // ---- the screen kernel ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* tiles = smem;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    uint32_t* list_id = tmem_slot + 4;                                   // [LIST_CAP][128]
-    float* list_v = reinterpret_cast<float*>(list_id + LIST_CAP * 128);  // [LIST_CAP][128]
+    uint8_t* bres = smem;                       // resident B' (bres_bytes, multiple of 1024)
+    uint8_t* tiles = smem + g.bres_bytes;       // n_stages * stage_bytes
+    GemmSmemTail* T = reinterpret_cast<GemmSmemTail*>(tiles + (size_t)g.n_stages * g.stage_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < g.n_stages; ++s) { mbar_init(&T->full_bar[s], 1); mbar_init(&T->empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&T->tfull_bar[s], 1); mbar_init(&T->tempty_bar[s], EPI_WARPS); }
+        mbar_init(&T->bfull_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T->tmem_slot)),
                      "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = T->tmem_slot;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-                for (int nt = 0; nt < g.n_ntiles; ++nt) {
-                    for (int kb = 0; kb < g.n_kblocks; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* sa = tiles + stage * STAGE_BYTES;
-                        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, tile * TILE_M);
-                        tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, nt * TILE_N);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (g.resident) {
+                mbar_expect_tx(&T->bfull_bar, (uint32_t)g.bres_bytes);
+                for (int nt = 0; nt < g.n_ntiles; ++nt)
+                    for (int kb = 0; kb < g.n_kblocks; ++kb)
+                        tma_load_2d(bres + (size_t)(nt * g.n_kblocks + kb) * B_BYTES, &tmB, &T->bfull_bar, kb * BLOCK_K,
+                                    nt * TILE_N);
+                for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+                    mbar_wait(&T->empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = tiles + (size_t)stage * g.stage_bytes;
+                    mbar_expect_tx(&T->full_bar[stage], (uint32_t)g.stage_bytes);
+                    for (int kb = 0; kb < g.n_kblocks; ++kb)
+                        tma_load_2d(sa + (size_t)kb * A_BYTES, &tmA, &T->full_bar[stage], kb * BLOCK_K, tile * TILE_M);
+                    if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+                }
+            } else {
+                for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+                    for (int nt = 0; nt < g.n_ntiles; ++nt) {
+                        for (int kb = 0; kb < g.n_kblocks; ++kb) {
+                            mbar_wait(&T->empty_bar[stage], phase ^ 1);
+                            uint8_t* sa = tiles + (size_t)stage * g.stage_bytes;
+                            mbar_expect_tx(&T->full_bar[stage], STAGE_BYTES);
+                            tma_load_2d(sa, &tmA, &T->full_bar[stage], kb * BLOCK_K, tile * TILE_M);
+                            tma_load_2d(sa + A_BYTES, &tmB, &T->full_bar[stage], kb * BLOCK_K, nt * TILE_N);
+                            if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+                        }
                     }
                 }
             }
@@ -399,37 +541,60 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
+            if (g.resident) {
+                mbar_wait(&T->bfull_bar, 0);
+                tc_fence_after();
+            }
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+                if (g.resident) {
+                    mbar_wait(&T->full_bar[stage], phase);
+                    tc_fence_after();
+                }
                 for (int nt = 0; nt < g.n_ntiles; ++nt, ++it) {
                     const uint32_t acc = it & 1u, accphase = (it >> 1) & 1u;
-                    mbar_wait(&tempty_bar[acc], accphase ^ 1);
+                    mbar_wait(&T->tempty_bar[acc], accphase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * TILE_N;
                     for (int kb = 0; kb < g.n_kblocks; ++kb) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
+                        uint32_t sa, sb;
+                        if (g.resident) {
+                            sa = smem_u32(tiles + (size_t)stage * g.stage_bytes + (size_t)kb * A_BYTES);
+                            sb = smem_u32(bres + (size_t)(nt * g.n_kblocks + kb) * B_BYTES);
+                        } else {
+                            mbar_wait(&T->full_bar[stage], phase);
+                            tc_fence_after();
+                            sa = smem_u32(tiles + (size_t)stage * g.stage_bytes);
+                            sb = sa + A_BYTES;
+                        }
                         const uint64_t adesc = make_smem_desc(sa);
-                        const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+                        const uint64_t bdesc = make_smem_desc(sb);
                         const int ksteps = min(BLOCK_K / 16, g.nk16 - kb * (BLOCK_K / 16));
                         for (int ks = 0; ks < ksteps; ++ks) {
                             // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
                             tc_mma_f16(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc,
                                        (kb | ks) != 0 ? 1u : 0u);
                         }
-                        tc_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (!g.resident) {
+                            tc_commit(&T->empty_bar[stage]);  // smem slot free once these MMAs retire
+                            if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+                        }
                     }
-                    tc_commit(&tfull_bar[acc]);  // accumulator stage complete
+                    tc_commit(&T->tfull_bar[acc]);  // accumulator stage complete
+                }
+                if (g.resident) {
+                    tc_commit(&T->empty_bar[stage]);  // frame tile consumed by every center tile
+                    if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else {
-        // ===== epilogue: 4 warps, one frame (TMEM lane) per thread =====
+        // ===== epilogue: 8 warps = 2 column halves x 4 TMEM lane quarters, one frame (TMEM lane) per thread =====
         const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int h = (warp - 2) >> 2;       // column half of every accumulator stage
         const int row = q * 32 + lane;       // row inside the frame tile
-        const int et = row;                  // list slot
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * (TILE_N / 2));
+        uint32_t* lid = &T->list_id[h][0][row];
+        float* lv = &T->list_v[h][0][row];
         uint32_t it = 0;
         const float C = g.prm->cmax;
         const int valid_ops = g.prm->valid;
@@ -438,53 +603,80 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const float x2 = (grow < g.n) ? g.X2[grow] : 0.f;
             Margin mg;
             mg.init(x2, C, g.d, g.nk16, g.terms);
-            float m = __int_as_float(0xff800000);  // -inf
-            float thr = m;
-            int cnt = 0;
-            for (int nt = 0; nt < g.n_ntiles; ++nt, ++it) {
+            RowScan rs;
+            rs.init();
+            float va[32], vb[32];
+            {
                 const uint32_t acc = it & 1u, accphase = (it >> 1) & 1u;
-                mbar_wait(&tfull_bar[acc], accphase);
+                mbar_wait(&T->tfull_bar[acc], accphase);
                 tc_fence_after();
-                const uint32_t taddr = lane_addr + acc * TILE_N;
-#pragma unroll 1
-                for (int c = 0; c < TILE_N / CHUNK; ++c) {
-                    float v[32];
-                    tmem_ld32(taddr + c * CHUNK, v);
-                    tmem_ld_wait();
-                    float cm = fmaxf(fmaxf(v[0], v[1]), v[2]);
-#pragma unroll
-                    for (int e = 3; e + 1 < 32; e += 2) cm = fmaxf(fmaxf(cm, v[e]), v[e + 1]);
-                    cm = fmaxf(cm, v[31]);
-                    if (cm > m) { m = cm; thr = mg.threshold(m); }
-                    if (cm >= thr) {
-                        if (cnt < LIST_CAP) {
-                            list_id[cnt * 128 + et] = (uint32_t)(nt * (TILE_N / CHUNK) + c);
-                            list_v[cnt * 128 + et] = cm;
-                        }
-                        ++cnt;
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                tmem_ld32(lane_addr + acc * TILE_N, va);
             }
-            // final filter against the final maximum
-            if (grow < g.n) {
-                uint32_t ids[CAND_CAP] = {0, 0, 0, 0};
+            for (int nt = 0; nt < g.n_ntiles; ++nt, ++it) {
+                const uint32_t acc = it & 1u;
+                const uint32_t taddr = lane_addr + acc * TILE_N;
+                const uint32_t cbase = (uint32_t)(nt * (TILE_N / CHUNK) + h * HALF_CHUNKS);
+#pragma unroll
+                for (int c = 0; c < HALF_CHUNKS; ++c) {
+                    tmem_ld_wait();
+                    if (c & 1) tmem_ld_fence(vb);
+                    else tmem_ld_fence(va);
+                    if (c + 1 < HALF_CHUNKS) {
+                        if (c & 1) tmem_ld32(taddr + (c + 1) * CHUNK, va);
+                        else tmem_ld32(taddr + (c + 1) * CHUNK, vb);
+                    } else {
+                        // every load of this accumulator stage has landed: hand it back to the MMA warp,
+                        // then start on the next stage while the last chunk is being scanned
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&T->tempty_bar[acc]);
+                        if (nt + 1 < g.n_ntiles) {
+                            const uint32_t nacc = (it + 1) & 1u, nphase = ((it + 1) >> 1) & 1u;
+                            mbar_wait(&T->tfull_bar[nacc], nphase);
+                            tc_fence_after();
+                            tmem_ld32(lane_addr + nacc * TILE_N, va);  // HALF_CHUNKS is even: chunk 0 always lands in va
+                        }
+                    }
+                    if (c & 1) scan_chunk(vb, cbase + c, rs, mg, lid, lv);
+                    else scan_chunk(va, cbase + c, rs, mg, lid, lv);
+                }
+            }
+            // ---- merge the two column halves of this frame ----
+            T->half_m[h][row] = rs.m;
+            named_bar_sync(1, EPI_WARPS * 32);
+            const float m = fmaxf(T->half_m[0][row], T->half_m[1][row]);
+            const float thr = mg.threshold(m);
+            {
                 int kept = 0;
-                bool overflow = (cnt > LIST_CAP) || !(m > -3.0e38f) || !valid_ops || !(x2 < 3.0e38f);
-                const int lim = cnt < LIST_CAP ? cnt : LIST_CAP;
-                for (int t = 0; t < lim; ++t) {
-                    if (list_v[t * 128 + et] >= thr) {
-                        if (kept < CAND_CAP) ids[kept] = list_id[t * 128 + et];
+                for (int t = 0; t < rs.cnt; ++t) {
+                    if (lv[t * TILE_M] >= thr) {
+                        if (kept < CAND_CAP) T->out_id[h][kept][row] = lid[t * TILE_M];
                         ++kept;
                     }
                 }
-                if (kept > CAND_CAP || kept == 0) overflow = true;
-                uint2 packed;
-                packed.x = (ids[0] & 0xffffu) | (ids[1] << 16);
-                packed.y = (ids[2] & 0xffffu) | (ids[3] << 16);
-                *reinterpret_cast<uint2*>(g.cand + grow * CAND_CAP) = packed;
+                if (rs.overflow || kept > CAND_CAP) kept = CAND_CAP + 1;
+                T->out_n[h][row] = (uint32_t)kept;
+            }
+            named_bar_sync(2, EPI_WARPS * 32);
+            if (h == 0 && grow < g.n) {
+                const int n0 = (int)T->out_n[0][row], n1 = (int)T->out_n[1][row];
+                uint32_t ids[CAND_CAP] = {0, 0, 0, 0, 0, 0, 0, 0};
+                int kept = n0 + n1;
+                bool overflow = n0 > CAND_CAP || n1 > CAND_CAP || kept > CAND_CAP || kept == 0 || !(m > -3.0e38f) ||
+                                !valid_ops || !(x2 < 3.0e38f);
+                if (!overflow) {
+                    // each half's list is ascending; the verify scan needs ONE ascending list (lowest index wins ties)
+                    int a = 0, b = 0;
+                    for (int w = 0; w < kept; ++w) {
+                        const uint32_t ia = a < n0 ? T->out_id[0][a][row] : 0xffffffffu;
+                        const uint32_t ib = b < n1 ? T->out_id[1][b][row] : 0xffffffffu;
+                        if (a < n0 && (b >= n1 || (ia & ID_MASK) < (ib & ID_MASK))) { ids[w] = ia; ++a; }
+                        else { ids[w] = ib; ++b; }
+                    }
+                }
+                uint4* cout = reinterpret_cast<uint4*>(g.cand + grow * CAND_CAP);
+                cout[0] = make_uint4(ids[0], ids[1], ids[2], ids[3]);
+                if (kept > 4 && !overflow) cout[1] = make_uint4(ids[4], ids[5], ids[6], ids[7]);
                 g.ncand[grow] = overflow ? (uint8_t)255 : (uint8_t)kept;
             }
         }
@@ -497,80 +689,269 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
-// ---- verify: exact reference-order evaluation of the surviving chunks ----------------------------------------------
-template <int DREG>
-__global__ void __launch_bounds__(128) screen_verify_kernel(const float* __restrict__ X, int64_t n, int d,
-                                                            const float* __restrict__ Cn, int k,
-                                                            const uint16_t* __restrict__ cand,
-                                                            const uint8_t* __restrict__ ncand,
-                                                            int32_t* __restrict__ labels, float* __restrict__ mind,
-                                                            int lloyd, ScreenParams* prm) {
-    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    unsigned long long my_chunks = 0, my_fb = 0;
-    if (i < n) {
-        const float* xg = X + i * d;
-        float xr[DREG > 0 ? DREG : 1];
-        if (DREG > 0) {
-#pragma unroll
-            for (int e = 0; e < DREG; ++e) xr[e] = e < d ? xg[e] : 0.f;
-        }
-        ArgMin am;
-        am.init();
-        const int nc = ncand[i];
-        const int n_chunks_all = (k + CHUNK - 1) / CHUNK;
-        const int loops = nc == 255 ? n_chunks_all : nc;
-        const uint2 pk = *reinterpret_cast<const uint2*>(cand + i * CAND_CAP);
-        for (int t = 0; t < loops; ++t) {
-            int ch;
-            if (nc == 255) ch = t;
-            else ch = (t == 0) ? (pk.x & 0xffff) : (t == 1) ? (pk.x >> 16) : (t == 2) ? (pk.y & 0xffff) : (pk.y >> 16);
-            const int j0 = ch * CHUNK, j1 = min(j0 + CHUNK, k);
-            for (int j = j0; j < j1; ++j) {
-                const float* c = Cn + (int64_t)j * d;
-                float s;
-                if (DREG > 0) {
-                    Lanes4 L;
-                    L.init();
-                    const int d4 = d & ~3;
-#pragma unroll
-                    for (int e = 0; e < DREG; e += 4)
-                        if (e < d4) L.add4(xr[e], xr[e + 1], xr[e + 2], xr[e + 3], c[e], c[e + 1], c[e + 2], c[e + 3]);
-#pragma unroll
-                    for (int e = 0; e < DREG; ++e)
-                        if (e >= d4 && e < d) L.tail(xr[e], c[e]);
-                    s = L.result();
-                } else {
-                    s = euclid_sq_exact(xg, c, d);
-                }
-                am.offer(s, j);
-            }
-        }
-        labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
-        if (mind) mind[i] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
-        my_chunks = (nc == 255) ? 0 : nc;
-        my_fb = (nc == 255) ? 1 : 0;
-    }
-    // statistics (warp aggregated)
+// ---- verify: exact reference-order evaluation of the surviving 8-center groups --------------------------------------
+// Every distance is ONE thread's sequential 4-lane sum in the reference order (common.cuh), so the work is
+// spread over (frame, center) pairs, never over the dimensions of one pair.
+
+__device__ __forceinline__ void verify_stats(unsigned long long groups, unsigned long long fb, ScreenParams* prm) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        my_chunks += __shfl_xor_sync(0xffffffffu, my_chunks, o);
-        my_fb += __shfl_xor_sync(0xffffffffu, my_fb, o);
+        groups += __shfl_xor_sync(0xffffffffu, groups, o);
+        fb += __shfl_xor_sync(0xffffffffu, fb, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (my_chunks) atomicAdd(&prm->cand_chunks, my_chunks);
-        if (my_fb) atomicAdd(&prm->fallback_frames, my_fb);
+        if (groups) atomicAdd(&prm->cand_chunks, groups);
+        if (fb) atomicAdd(&prm->fallback_frames, fb);
     }
 }
 
+// d <= 16: 8 lanes per frame (4 frames per warp), lane `sub` evaluates center `sub` of every candidate group
+// with the frame in registers; the center table sits in shared memory when it fits (row stride rs = 4 mod 8
+// floats: the 8 rows of a group then cover all 32 banks, so a 16-byte load per lane is conflict free).
+template <int DREG>
+__global__ void __launch_bounds__(256) screen_verify_small_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                                  const float* __restrict__ Cn, int k,
+                                                                  const uint32_t* __restrict__ cand,
+                                                                  const uint8_t* __restrict__ ncand,
+                                                                  int32_t* __restrict__ labels,
+                                                                  float* __restrict__ mind, int lloyd,
+                                                                  ScreenParams* prm, int use_smem, int rs) {
+    extern __shared__ __align__(16) float ctab[];
+    if (use_smem) {
+        for (int t = threadIdx.x; t < k * rs; t += 256) {
+            const int r = t / rs, c = t - r * rs;
+            ctab[t] = c < d ? __ldg(Cn + (int64_t)r * d + c) : 0.f;
+        }
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, sub = lane & 7, slot = lane >> 3;
+    const int d4 = d & ~3;
+    const int n_groups_all = (k + GROUP - 1) / GROUP;
+    unsigned long long my_groups = 0, my_fb = 0;
+    const int64_t warp_global = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * 256) >> 5;
+    for (int64_t base = warp_global * 4; base < n; base += n_warps * 4) {
+        const int64_t i = base + slot;
+        const bool live = i < n;
+        float xr[DREG];
+#pragma unroll
+        for (int e = 0; e < DREG; ++e) xr[e] = (live && e < d) ? __ldg(X + i * d + e) : 0.f;
+        const int nc = live ? (int)ncand[i] : 0;
+        uint32_t ent[CAND_CAP];
+        {
+            const uint4* cp = reinterpret_cast<const uint4*>(cand + (live ? i : 0) * CAND_CAP);
+            const uint4 p0 = cp[0];
+            uint4 p1 = make_uint4(0, 0, 0, 0);
+            if (nc > 4 && nc != 255) p1 = cp[1];
+            ent[0] = p0.x; ent[1] = p0.y; ent[2] = p0.z; ent[3] = p0.w;
+            ent[4] = p1.x; ent[5] = p1.y; ent[6] = p1.z; ent[7] = p1.w;
+        }
+        ArgMin am;
+        am.init();
+        auto eval_group = [&](int g) {
+            const int j = g * GROUP + sub;
+            if (j < k) {
+                Lanes4 L;
+                L.init();
+                if (use_smem) {
+                    const float4* c4 = reinterpret_cast<const float4*>(ctab + (size_t)j * rs);
+#pragma unroll
+                    for (int e = 0; e < DREG; e += 4) {
+                        if (e < d4) {
+                            const float4 cv = c4[e >> 2];
+                            L.add4(xr[e], xr[e + 1], xr[e + 2], xr[e + 3], cv.x, cv.y, cv.z, cv.w);
+                        }
+                    }
+                    if (d4 < d) {
+                        const float4 cv = c4[d4 >> 2];
+                        const float ct[3] = {cv.x, cv.y, cv.z};
+#pragma unroll
+                        for (int e = 0; e < DREG; ++e)
+                            if (e >= d4 && e < d) L.tail(xr[e], ct[e & 3]);
+                    }
+                } else {
+                    const float* c = Cn + (int64_t)j * d;
+#pragma unroll
+                    for (int e = 0; e < DREG; e += 4)
+                        if (e < d4)
+                            L.add4(xr[e], xr[e + 1], xr[e + 2], xr[e + 3], __ldg(c + e), __ldg(c + e + 1), __ldg(c + e + 2),
+                                   __ldg(c + e + 3));
+#pragma unroll
+                    for (int e = 0; e < DREG; ++e)
+                        if (e >= d4 && e < d) L.tail(xr[e], __ldg(c + e));
+                }
+                am.offer(L.result(), j);  // a lane meets its centers in ascending order
+            }
+        };
+        if (nc == 255) {  // the screen could not bound this frame: exact scan of every center
+            for (int g = 0; g < n_groups_all; ++g) eval_group(g);
+            if (sub == 0) my_fb += 1;
+        } else {
+#pragma unroll
+            for (int t = 0; t < CAND_CAP; ++t) {
+                if (t < nc) {
+                    const int g0 = (int)(ent[t] & ID_MASK) * (CHUNK / GROUP);
+                    uint32_t mask = ent[t] >> 28;
+                    while (mask) {
+                        const int q = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        eval_group(g0 + q);
+                        if (sub == 0) my_groups += 1;
+                    }
+                }
+            }
+        }
+        // combine the 8 lanes of the frame: lexicographic (sqrt(s), j), order free
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const float so = __shfl_xor_sync(0xffffffffu, am.s, o);
+            const int32_t jo = __shfl_xor_sync(0xffffffffu, am.j, o);
+            am.merge(so, jo);
+        }
+        if (live && sub == 0) {
+            labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
+            if (mind) mind[i] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
+        }
+    }
+    verify_stats(my_groups, my_fb, prm);
+}
+
+// d > 16: one warp per frame.  The 8 rows of a candidate group (contiguous in memory) are copied coalesced into
+// a per-warp shared-memory buffer (row stride rsb, rsb/4 odd: conflict free below); lane (c = lane/4, l = lane%4)
+// then owns accumulator lane l of center c -- elements l, l+4, l+8, ... in order, the d%4 tail into lane 0 --
+// exactly the reference's four interleaved partial sums, finished as ((a0+a1)+a2)+a3 by lane (c,0).
+__global__ void __launch_bounds__(256) screen_verify_big_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                                const float* __restrict__ Cn, int k,
+                                                                const uint32_t* __restrict__ cand,
+                                                                const uint8_t* __restrict__ ncand,
+                                                                int32_t* __restrict__ labels,
+                                                                float* __restrict__ mind, int lloyd,
+                                                                ScreenParams* prm, int rsb, int warps_per_cta) {
+    extern __shared__ __align__(16) float vsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp >= warps_per_cta) return;
+    const int dpad = (d + 3) & ~3;
+    float* xb = vsm + (size_t)warp * (dpad + (size_t)GROUP * rsb);  // frame row
+    float* cb = xb + dpad;                                          // 8 center rows
+    const int c = lane >> 2, l = lane & 3;
+    const int d4 = d & ~3;
+    const int n_groups_all = (k + GROUP - 1) / GROUP;
+    const bool vec4 = (d & 3) == 0;
+    unsigned long long my_groups = 0, my_fb = 0;
+    for (int64_t i = (int64_t)blockIdx.x * warps_per_cta + warp; i < n; i += (int64_t)gridDim.x * warps_per_cta) {
+        __syncwarp();
+        if (vec4) {
+            const float4* src = reinterpret_cast<const float4*>(X + i * d);
+            for (int t = lane; t < (d >> 2); t += 32) reinterpret_cast<float4*>(xb)[t] = __ldg(src + t);
+        } else {
+            for (int t = lane; t < d; t += 32) xb[t] = __ldg(X + i * d + t);
+        }
+        const int nc = ncand[i];
+        uint32_t my_ent = 0;
+        if (nc != 255 && lane < nc) my_ent = cand[i * CAND_CAP + lane];
+        ArgMin am;
+        am.init();
+        auto eval_group = [&](int g) {
+            const int jb = g * GROUP;
+            const int rows = min(GROUP, k - jb);
+            __syncwarp();
+            if (vec4) {
+                const float4* src = reinterpret_cast<const float4*>(Cn + (int64_t)jb * d);
+                const int per_row = d >> 2;
+                for (int t = lane; t < rows * per_row; t += 32) {
+                    const int r = t / per_row, q = t - r * per_row;
+                    *reinterpret_cast<float4*>(cb + (size_t)r * rsb + 4 * q) = __ldg(src + t);
+                }
+            } else {
+                const float* src = Cn + (int64_t)jb * d;
+                for (int t = lane; t < rows * d; t += 32) {
+                    const int r = t / d, q = t - r * d;
+                    cb[(size_t)r * rsb + q] = __ldg(src + t);
+                }
+            }
+            __syncwarp();
+            const float* crow = cb + (size_t)c * rsb;
+            float a = 0.f;
+            if (c < rows) {
+#pragma unroll 4
+                for (int e = l; e < d4; e += 4) {
+                    const float t = __fsub_rn(xb[e], crow[e]);
+                    a = __fadd_rn(a, __fmul_rn(t, t));
+                }
+                if (l == 0) {
+                    for (int e = d4; e < d; ++e) {
+                        const float t = __fsub_rn(xb[e], crow[e]);
+                        a = __fadd_rn(a, __fmul_rn(t, t));
+                    }
+                }
+            }
+            const float a1 = __shfl_down_sync(0xffffffffu, a, 1);
+            const float a2 = __shfl_down_sync(0xffffffffu, a, 2);
+            const float a3 = __shfl_down_sync(0xffffffffu, a, 3);
+            if (l == 0 && c < rows) am.offer(__fadd_rn(__fadd_rn(__fadd_rn(a, a1), a2), a3), jb + c);
+        };
+        if (nc == 255) {
+            for (int g = 0; g < n_groups_all; ++g) eval_group(g);
+            if (lane == 0) my_fb += 1;
+        } else {
+            for (int t = 0; t < nc; ++t) {
+                const uint32_t ent = __shfl_sync(0xffffffffu, my_ent, t);
+                const int g0 = (int)(ent & ID_MASK) * (CHUNK / GROUP);
+                uint32_t mask = ent >> 28;
+                while (mask) {
+                    const int q = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    eval_group(g0 + q);
+                    if (lane == 0) my_groups += 1;
+                }
+            }
+        }
+        // lanes (c,0) hold per-center-slot winners: combine slots (xor 4, 8, 16)
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            const float so = __shfl_xor_sync(0xffffffffu, am.s, o);
+            const int32_t jo = __shfl_xor_sync(0xffffffffu, am.j, o);
+            am.merge(so, jo);
+        }
+        if (lane == 0) {
+            labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
+            if (mind) mind[i] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
+        }
+    }
+    verify_stats(my_groups, my_fb, prm);
+}
+
 // ---- plan -------------------------------------------------------------------------------------------------------------
-static size_t gemm_smem_bytes() {
-    return 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + (size_t)LIST_CAP * 128 * 8;
+// shared-memory plan of the screen kernel for a (k_pad, Kp) operand pair
+struct GemmSmemPlan {
+    int resident, n_stages, stage_bytes, bres_bytes;
+    size_t total;
+};
+static GemmSmemPlan gemm_smem_plan(int k_pad, int Kp, size_t smem_optin) {
+    GemmSmemPlan sp;
+    const size_t tail = sizeof(GemmSmemTail) + 1024 /* alignment slack */;
+    const size_t b_all = (size_t)k_pad * Kp * 2;            // multiple of B_BYTES
+    const size_t a_full = (size_t)(Kp / BLOCK_K) * A_BYTES;  // one frame tile, full K
+    if (b_all + 2 * a_full + tail <= smem_optin) {
+        sp.resident = 1;
+        sp.bres_bytes = (int)b_all;
+        sp.stage_bytes = (int)a_full;
+        sp.n_stages = (int)std::min<size_t>(MAX_STAGES, (smem_optin - tail - b_all) / a_full);
+        if (sp.n_stages > 4) sp.n_stages = 4;
+    } else {
+        sp.resident = 0;
+        sp.bres_bytes = 0;
+        sp.stage_bytes = STAGE_BYTES;
+        sp.n_stages = (int)std::min<size_t>(MAX_STAGES, (smem_optin - tail) / STAGE_BYTES);
+    }
+    sp.total = tail + (size_t)sp.bres_bytes + (size_t)sp.n_stages * sp.stage_bytes;
+    return sp;
 }
 
 bool screen_supported(const b2k_ctx* ctx, int d, int k, int64_t n) {
     if (ctx->engine == B2K_ENGINE_DIRECT) return false;
-    if (d < 1 || d > 1300 || k < 2 || k > 65535 * CHUNK) return false;
-    if (gemm_smem_bytes() > ctx->smem_optin) return false;
+    if (d < 1 || 3 * d + 3 > 2048 || k < 2 || k > (1 << 27)) return false;
+    if (sizeof(GemmSmemTail) + 1024 + 2 * (size_t)STAGE_BYTES > ctx->smem_optin) return false;
     if (ctx->engine == B2K_ENGINE_SCREEN) return true;
     // auto: the screen pays off once a frame meets enough center coordinates
     return k >= 128 && (int64_t)k * d >= 2048 && n >= 4096;
@@ -592,7 +973,7 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     p->d = d;
     p->k = k;
     p->k_pad = (int)(cdiv(k, TILE_N) * TILE_N);
-    p->terms = ctx->screen_terms == 1 ? 1 : (ctx->screen_terms == 3 ? 3 : (d <= 16 ? 1 : 3));
+    p->terms = ctx->screen_terms == 1 ? 1 : 3;  // hi-only operands leave too many candidates
     p->Kc = p->terms * d + 3;
     p->Kp = (int)(cdiv(p->Kc, BLOCK_K) * BLOCK_K);
     p->nk16 = (int)cdiv(p->Kc, 16);
@@ -601,7 +982,7 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     if (e == cudaSuccess) e = cudaMalloc(&p->X2, (size_t)p->n_pad * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->mu, (size_t)d * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->params, sizeof(ScreenParams));
-    if (e == cudaSuccess) e = cudaMalloc(&p->cand, (size_t)p->n_pad * CAND_CAP * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&p->cand, (size_t)p->n_pad * CAND_CAP * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->ncand, (size_t)p->n_pad);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -614,12 +995,32 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t ae = cudaFuncSetAttribute(screen_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)gemm_smem_bytes());
+                                              (int)ctx->smem_optin);
         if (ae != cudaSuccess) { screen_plan_destroy(p); return set_error(B2K_ERR_CUDA, "screen smem attr: %s", cudaGetErrorString(ae)); }
         attr_set = true;
     }
     *out = p;
     return B2K_OK;
+}
+
+int screen_plan_acquire(b2k_ctx* ctx, int64_t n, int d, int k, ScreenPlan** out) {
+    ScreenPlan* c = static_cast<ScreenPlan*>(ctx->assign_plan);
+    const int terms = ctx->screen_terms == 1 ? 1 : 3;
+    if (c && c->d == d && c->k == k && c->terms == terms && n <= c->n_cap) {
+        c->prepared_n = -1;
+        *out = c;
+        return B2K_OK;
+    }
+    screen_plan_release_cached(ctx);
+    B2K_TRY(screen_plan_create(ctx, n, d, k, &c));
+    ctx->assign_plan = c;
+    *out = c;
+    return B2K_OK;
+}
+
+void screen_plan_release_cached(b2k_ctx* ctx) {
+    if (ctx->assign_plan) screen_plan_destroy(static_cast<ScreenPlan*>(ctx->assign_plan));
+    ctx->assign_plan = nullptr;
 }
 
 static unsigned capped_grid(b2k_ctx* ctx, int64_t items, int per_block) {
@@ -643,8 +1044,8 @@ int screen_prepare_frames_with_centers(ScreenPlan* p, const float* dX, int64_t n
     screen_sigma_kernel<<<1, 1, 0, st>>>(p->params);
     LAUNCH_CHECK();
     const int64_t n_pad_now = cdiv(n, TILE_M) * TILE_M;
-    screen_frames_kernel<<<capped_grid(ctx, n_pad_now * (p->Kp / 2), 256), 256, 0, st>>>(
-        dX, n, n_pad_now, p->d, p->terms, p->Kp, p->mu, p->params, reinterpret_cast<__half2*>(p->A));
+    screen_frames_kernel<<<capped_grid(ctx, n_pad_now, 256 / (p->Kp / 8)), 256, 0, st>>>(
+        dX, n, n_pad_now, p->d, p->terms, p->Kp, p->mu, p->params, reinterpret_cast<uint4*>(p->A));
     LAUNCH_CHECK();
     screen_x2_kernel<<<(unsigned)cdiv(n_pad_now, 256), 256, 0, st>>>(dX, n, n_pad_now, p->d, p->mu, p->params, p->X2);
     LAUNCH_CHECK();
@@ -685,20 +1086,56 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
     g.prm = p->params;
     g.cand = p->cand;
     g.ncand = p->ncand;
+    const GemmSmemPlan sp = gemm_smem_plan(p->k_pad, p->Kp, ctx->smem_optin);
+    g.resident = sp.resident;
+    g.n_stages = sp.n_stages;
+    g.stage_bytes = sp.stage_bytes;
+    g.bres_bytes = sp.bres_bytes;
     const unsigned grid = (unsigned)std::min<int64_t>(g.n_tiles, ctx->sm_count);
-    screen_gemm_kernel<<<grid, GEMM_THREADS, gemm_smem_bytes(), st>>>(p->tmA, p->tmB, g);
+    screen_gemm_kernel<<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, g);
     LAUNCH_CHECK();
-    const unsigned vgrid = (unsigned)cdiv(n, 128);
-    if (p->d <= 4)
-        screen_verify_kernel<4><<<vgrid, 128, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind, lloyd, p->params);
-    else if (p->d <= 8)
-        screen_verify_kernel<8><<<vgrid, 128, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind, lloyd, p->params);
-    else if (p->d <= 12)
-        screen_verify_kernel<12><<<vgrid, 128, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind, lloyd, p->params);
-    else if (p->d <= 16)
-        screen_verify_kernel<16><<<vgrid, 128, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind, lloyd, p->params);
-    else
-        screen_verify_kernel<0><<<vgrid, 128, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind, lloyd, p->params);
+    // verify (persistent grids)
+    if (p->d <= 16) {
+        const int ds = (p->d + 3) & ~3;
+        const int rs = (ds % 8 == 4) ? ds : ds + 4;
+        const size_t tab_bytes = (size_t)p->k * rs * 4;
+        const int use_smem = tab_bytes <= 100 * 1024 ? 1 : 0;
+        const size_t vsmem = use_smem ? tab_bytes : 0;
+        const int per_sm = use_smem ? (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(tab_bytes, 1))) : 4;
+        const unsigned vgrid =
+            (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 32), (int64_t)ctx->sm_count * per_sm));
+#define B2K_VERIFY(DR)                                                                                               \
+    do {                                                                                                             \
+        static bool vattr = false;                                                                                   \
+        if (!vattr) {                                                                                                \
+            CUDA_TRY(cudaFuncSetAttribute(screen_verify_small_kernel<DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          100 * 1024));                                                              \
+            vattr = true;                                                                                            \
+        }                                                                                                            \
+        screen_verify_small_kernel<DR><<<vgrid, 256, vsmem, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels,  \
+                                                                  mind, lloyd, p->params, use_smem, rs);             \
+    } while (0)
+        if (p->d <= 4) B2K_VERIFY(4);
+        else if (p->d <= 8) B2K_VERIFY(8);
+        else if (p->d <= 12) B2K_VERIFY(12);
+        else B2K_VERIFY(16);
+#undef B2K_VERIFY
+    } else {
+        const int dpad = (p->d + 3) & ~3;
+        const int rsb = ((dpad / 4) % 2 == 1) ? dpad : dpad + 4;
+        const size_t per_warp = ((size_t)dpad + (size_t)GROUP * rsb) * 4;
+        int wpc = (int)std::min<size_t>(8, (96 * 1024) / per_warp);
+        if (wpc < 1) return set_error(B2K_ERR_INVALID_ARG, "dimension %d too large for the verify kernel", p->d);
+        const size_t vsmem = per_warp * wpc;
+        static bool vattr = false;
+        if (!vattr) {
+            CUDA_TRY(cudaFuncSetAttribute(screen_verify_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            vattr = true;
+        }
+        const unsigned vgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, wpc), (int64_t)ctx->sm_count * 2));
+        screen_verify_big_kernel<<<vgrid, 256, vsmem, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind, lloyd,
+                                                            p->params, rsb, wpc);
+    }
     LAUNCH_CHECK();
     return B2K_OK;
 }

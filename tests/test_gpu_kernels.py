@@ -157,7 +157,7 @@ def test_kmpp_k_larger_than_n(b2k):
 def test_regspace_bit_exact(b2k, oracle, metric, d):
     rng = np.random.RandomState(d)
     X = (rng.randn(6000, d) * 2).astype(np.float32)
-    dmin = {2: 0.7, 20: 9.0, 30: 2.0}[d]
+    dmin = {2: 0.7, 20: 9.0, 30: 3.0}[d]
     ref, ridx, rfull = oracle.regspace(X, dmin, 1000, metric, n_threads=4)
     h = b2k.RegspaceHandle(d, dmin, 1000, metric)
     for a in range(0, len(X), 1700):  # several chunks
