@@ -125,6 +125,8 @@ struct ArgMin {
     __device__ __forceinline__ void merge(float so, int32_t jo) {
         if (jo < 0) return;
         if (j < 0) { s = so; j = jo; return; }
+        if (so < s * 0.99999905f) { s = so; j = jo; return; }  // far enough apart: the sqrt cannot merge them
+        if (s < so * 0.99999905f) return;
         const float ra = __fsqrt_rn(s), rb = __fsqrt_rn(so);
         if (rb < ra || (rb == ra && jo < j)) { s = so; j = jo; }
     }

@@ -22,8 +22,9 @@ template <int D>
 __global__ void __launch_bounds__(256) assign_small_kernel(const float* __restrict__ X, int64_t n,
                                                            const float* __restrict__ C, int k, int kt,
                                                            int32_t* __restrict__ labels, float* __restrict__ mind,
-                                                           int lloyd) {
+                                                           int lloyd, const int* __restrict__ run_if_zero) {
     extern __shared__ __align__(16) float cs[];
+    if (run_if_zero && *run_if_zero != 0) return;
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const bool valid = i < n;
     float x[D];
@@ -89,8 +90,9 @@ template <int MODE>
 __global__ void __launch_bounds__(128) tile_kernel(const float* __restrict__ X, int64_t n, int d,
                                                    const float* __restrict__ C, int k, TileCfg cfg,
                                                    int32_t* __restrict__ labels, float* __restrict__ out,
-                                                   int lloyd) {
+                                                   int lloyd, const int* __restrict__ run_if_zero) {
     extern __shared__ __align__(16) float sm[];
+    if (run_if_zero && *run_if_zero != 0) return;
     float* xs = sm;
     float* cs = sm + (size_t)cfg.FB * cfg.xstride;
     float* red_s = cs + (size_t)cfg.KT * cfg.ds;
@@ -192,10 +194,71 @@ __global__ void __launch_bounds__(256) labeled_dist_kernel(const float* __restri
     out[i] = __fsqrt_rn(euclid_sq_exact(X + i * d, C + (int64_t)a * d, d));
 }
 
+// wide rows (d > 16): a warp takes 8 frames at a time.  Their rows and the rows of their centers are copied
+// coalesced into shared memory (row stride rsb, rsb/4 odd -> conflict free); lane (f = lane/4, l = lane%4) then
+// owns accumulator lane l of frame f -- elements l, l+4, ... in order, the d%4 tail into lane 0 -- i.e. exactly
+// the reference's four interleaved partial sums, closed as ((a0+a1)+a2)+a3 by lane (f,0).
+__global__ void __launch_bounds__(256) labeled_dist_wide_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                                const float* __restrict__ C,
+                                                                const int32_t* __restrict__ labels,
+                                                                float* __restrict__ out, int rsb, int warps_per_cta) {
+    extern __shared__ __align__(16) float lsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp >= warps_per_cta) return;
+    float* xb = lsm + (size_t)warp * 16 * rsb;
+    float* cb = xb + (size_t)8 * rsb;
+    const int f = lane >> 2, l = lane & 3;
+    const int d4 = d & ~3;
+    const bool vec4 = (d & 3) == 0;
+    const int64_t stride = (int64_t)gridDim.x * warps_per_cta * 8;
+    for (int64_t base = ((int64_t)blockIdx.x * warps_per_cta + warp) * 8; base < n; base += stride) {
+        const int rows = (int)min((int64_t)8, n - base);
+        const int32_t my_label = (lane < rows) ? labels[base + lane] : 0;
+        __syncwarp();
+        for (int r = 0; r < rows; ++r) {
+            const int32_t a = __shfl_sync(0xffffffffu, my_label, r);
+            const float* xs = X + (base + r) * d;
+            const float* cs = C + (int64_t)a * d;
+            if (vec4) {
+                for (int t = lane; t < (d >> 2); t += 32) {
+                    reinterpret_cast<float4*>(xb + (size_t)r * rsb)[t] = __ldg(reinterpret_cast<const float4*>(xs) + t);
+                    reinterpret_cast<float4*>(cb + (size_t)r * rsb)[t] = __ldg(reinterpret_cast<const float4*>(cs) + t);
+                }
+            } else {
+                for (int t = lane; t < d; t += 32) {
+                    xb[(size_t)r * rsb + t] = __ldg(xs + t);
+                    cb[(size_t)r * rsb + t] = __ldg(cs + t);
+                }
+            }
+        }
+        __syncwarp();
+        float acc = 0.f;
+        if (f < rows) {
+            const float* xr = xb + (size_t)f * rsb;
+            const float* cr = cb + (size_t)f * rsb;
+#pragma unroll 4
+            for (int e = l; e < d4; e += 4) {
+                const float t = __fsub_rn(xr[e], cr[e]);
+                acc = __fadd_rn(acc, __fmul_rn(t, t));
+            }
+            if (l == 0) {
+                for (int e = d4; e < d; ++e) {
+                    const float t = __fsub_rn(xr[e], cr[e]);
+                    acc = __fadd_rn(acc, __fmul_rn(t, t));
+                }
+            }
+        }
+        const float a1 = __shfl_down_sync(0xffffffffu, acc, 1);
+        const float a2 = __shfl_down_sync(0xffffffffu, acc, 2);
+        const float a3 = __shfl_down_sync(0xffffffffu, acc, 3);
+        if (l == 0 && f < rows) out[base + f] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, a1), a2), a3));
+    }
+}
+
 // -------------------------------------------------------------------------------------------
 template <int D>
 static int launch_small(b2k_ctx* ctx, const float* X, int64_t n, const float* C, int k, int32_t* labels, float* mind,
-                        int lloyd) {
+                        int lloyd, const int* run_if_zero) {
     const size_t budget = 96 * 1024;
     int kt = (int)std::min<int64_t>(k, budget / (D * 4));
     const size_t smem = (size_t)kt * D * 4;
@@ -206,27 +269,41 @@ static int launch_small(b2k_ctx* ctx, const float* X, int64_t n, const float* C,
         attr_set = true;
     }
     const int64_t blocks = cdiv(n, 256);
-    assign_small_kernel<D><<<(unsigned)blocks, 256, smem, ctx->stream>>>(X, n, C, k, kt, labels, mind, lloyd);
+    assign_small_kernel<D><<<(unsigned)blocks, 256, smem, ctx->stream>>>(X, n, C, k, kt, labels, mind, lloyd, run_if_zero);
     LAUNCH_CHECK();
     return B2K_OK;
 }
 
-int launch_assign_exact(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels,
-                        float* mind, int lloyd) {
+static int launch_tile_gated(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels,
+                             float* out, int lloyd, int mode, const int* run_if_zero);
+
+// run_if_zero (device pointer, may be null): the kernel returns at once unless *run_if_zero == 0
+int launch_assign_exact_if(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels,
+                           float* mind, int lloyd, const int* run_if_zero) {
     if (n <= 0) return B2K_OK;
     if (k <= 0) return set_error(B2K_ERR_INVALID_ARG, "assign: no centers");
     switch (d) {
-#define CASE(D) case D: return launch_small<D>(ctx, X, n, C, k, labels, mind, lloyd);
+#define CASE(D) case D: return launch_small<D>(ctx, X, n, C, k, labels, mind, lloyd, run_if_zero);
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
         CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
 #undef CASE
         default: break;
     }
-    return launch_tile(ctx, X, n, d, C, k, labels, mind, lloyd, MODE_ARGMIN);
+    return launch_tile_gated(ctx, X, n, d, C, k, labels, mind, lloyd, MODE_ARGMIN, run_if_zero);
+}
+
+int launch_assign_exact(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels,
+                        float* mind, int lloyd) {
+    return launch_assign_exact_if(ctx, X, n, d, C, k, labels, mind, lloyd, nullptr);
 }
 
 int launch_tile(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels, float* out,
                 int lloyd, int mode) {
+    return launch_tile_gated(ctx, X, n, d, C, k, labels, out, lloyd, mode, nullptr);
+}
+
+static int launch_tile_gated(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels,
+                             float* out, int lloyd, int mode, const int* run_if_zero) {
     if (n <= 0 || k <= 0) return B2K_OK;
     const size_t budget = std::min<size_t>(ctx->smem_optin, 200 * 1024);
     TileCfg cfg = tile_cfg(d, k, budget);
@@ -243,10 +320,10 @@ int launch_tile(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, 
     const int64_t blocks = cdiv(n, cfg.FB);
     if (mode == MODE_ARGMIN)
         tile_kernel<MODE_ARGMIN><<<(unsigned)blocks, 128, cfg.smem, ctx->stream>>>(X, n, d, C, k, cfg, labels, out,
-                                                                                    lloyd);
+                                                                                    lloyd, run_if_zero);
     else
         tile_kernel<MODE_ALL><<<(unsigned)blocks, 128, cfg.smem, ctx->stream>>>(X, n, d, C, k, cfg, labels, out,
-                                                                                 lloyd);
+                                                                                 lloyd, run_if_zero);
     LAUNCH_CHECK();
     return B2K_OK;
 }
@@ -258,6 +335,27 @@ int launch_dist_rows(b2k_ctx* ctx, const float* X, int64_t n, int d, const float
 int launch_labeled_dist(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, const int32_t* labels,
                         float* out) {
     if (n <= 0) return B2K_OK;
+    if (d > 16) {
+        const int dpad = (d + 3) & ~3;
+        const int rsb = ((dpad / 4) % 2 == 1) ? dpad : dpad + 4;
+        const size_t per_warp = (size_t)16 * rsb * 4;
+        const int wpc = (int)std::min<size_t>(8, (96 * 1024) / per_warp);
+        if (wpc >= 1) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                CUDA_TRY(cudaFuncSetAttribute(labeled_dist_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              100 * 1024));
+                attr_set = true;
+            }
+            const size_t smem = per_warp * wpc;
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
+            const unsigned grid =
+                (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 8 * wpc), (int64_t)ctx->sm_count * per_sm));
+            labeled_dist_wide_kernel<<<grid, 256, smem, ctx->stream>>>(X, n, d, C, labels, out, rsb, wpc);
+            LAUNCH_CHECK();
+            return B2K_OK;
+        }
+    }
     labeled_dist_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(X, n, d, C, labels, out);
     LAUNCH_CHECK();
     return B2K_OK;

@@ -9,6 +9,9 @@ enum { MODE_ARGMIN = 0, MODE_ALL = 1 };
 // ---- exact.cu (Euclidean, exact fp32 reference order) -------------------------------------
 int launch_assign_exact(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels,
                         float* mind, int lloyd);
+// same, but the kernel returns at once unless *run_if_zero == 0 (device flag; null = always run)
+int launch_assign_exact_if(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels,
+                           float* mind, int lloyd, const int* run_if_zero);
 int launch_tile(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels, float* out,
                 int lloyd, int mode);
 // out[j][i] = sqrt(dist2(x_i, rows_j)), j < m

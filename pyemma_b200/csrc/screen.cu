@@ -61,6 +61,7 @@ struct ScreenParams {  // device resident; written by the prep kernels, read by 
     float cmax2_now;   // max_j |c~_j|^2 of the current B' operand
     int valid;         // 0: operands unusable -> every frame takes the exact fallback
     unsigned long long cand_chunks, fallback_frames;  // statistics of the last verify
+    unsigned int fb_count, fb_pad;                    // frames handed to the exact fallback kernel
 };
 
 struct ScreenPlan {
@@ -74,6 +75,7 @@ struct ScreenPlan {
     ScreenParams* params = nullptr;
     uint32_t* cand = nullptr;  // [n_pad][CAND_CAP]  chunk id | group mask << 28
     uint8_t* ncand = nullptr;  // [n_pad]  (255: overflow -> exact fallback)
+    uint32_t* fb_list = nullptr;  // [n_pad] frames the verify kernels hand to the fallback kernel
     CUtensorMap tmA, tmB;
     int64_t prepared_n = -1;
 };
@@ -107,6 +109,7 @@ static int make_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint64_t cols, 
 }
 
 // ---- prep kernels ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t cdiv_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __global__ void screen_mu_kernel(const float* __restrict__ C, int k, int d, float* __restrict__ mu) {
     const int dim = blockIdx.x * blockDim.x + threadIdx.x;
     if (dim >= d) return;
@@ -115,15 +118,29 @@ __global__ void screen_mu_kernel(const float* __restrict__ C, int k, int d, floa
     mu[dim] = (float)(s / k);
 }
 
-// max_i |row_i - mu|^2 (fp32, any order; only used to pick the scale) -> *out (float bits, atomicMax)
+// sum_e ((row[e] - mu[e]) * scale)^2 with LPR lanes per row (coalesced for wide rows); any summation order:
+// these sums only pick the scale and feed the margin, which carries its own slack for their rounding.
+template <int LPR>
+__device__ __forceinline__ float row_sqnorm(const float* __restrict__ row, const float* __restrict__ mu, int d,
+                                            float scale, int sub) {
+    float s = 0.f;
+    for (int e = sub; e < d; e += LPR) { const float t = (__ldg(row + e) - __ldg(mu + e)) * scale; s += t * t; }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+// max_i |row_i - mu|^2 -> *out (float bits, atomicMax)
+template <int LPR>
 __global__ void __launch_bounds__(256) screen_maxnorm_kernel(const float* __restrict__ X, int64_t n, int d,
                                                              const float* __restrict__ mu, float* out) {
     float m = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        const float* p = X + i * d;
-        float s = 0.f;
-        for (int e = 0; e < d; ++e) { const float t = p[e] - mu[e]; s += t * t; }
-        m = fmaxf(m, s);  // NaN rows are ignored here and flagged in the operand kernel
+    const int sub = threadIdx.x % LPR;
+    const int64_t rows_per_pass = (int64_t)gridDim.x * (256 / LPR);
+    const int64_t n_round = cdiv_dev(n, rows_per_pass) * rows_per_pass;  // keep whole warps in the shuffles
+    for (int64_t i = (int64_t)blockIdx.x * (256 / LPR) + threadIdx.x / LPR; i < n_round; i += rows_per_pass) {
+        const float s = row_sqnorm<LPR>(X + (i < n ? i : 0) * d, mu, d, 1.f, sub);
+        if (i < n) m = fmaxf(m, s);  // NaN rows are ignored here and flagged in the operand kernel
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -216,20 +233,17 @@ __global__ void __launch_bounds__(256) screen_frames_kernel(const float* __restr
     }
 }
 
+template <int LPR>
 __global__ void __launch_bounds__(256) screen_x2_kernel(const float* __restrict__ X, int64_t n, int64_t n_pad, int d,
                                                         const float* __restrict__ mu,
                                                         const ScreenParams* __restrict__ prm,
                                                         float* __restrict__ X2) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPR;  // n_pad is a multiple of 128: whole warps
     if (i >= n_pad) return;
-    float s = 0.f;
-    if (i < n) {
-        const float sigma = prm->sigma;
-        const float* p = X + i * d;
-        for (int e = 0; e < d; ++e) { const float t = (p[e] - mu[e]) * sigma; s += t * t; }
-        if (!(s < 3.0e38f)) s = __int_as_float(0x7f800000);  // NaN/inf frame -> flagged by the epilogue
-    }
-    X2[i] = s;
+    float s = row_sqnorm<LPR>(X + (i < n ? i : 0) * d, mu, d, prm->sigma, threadIdx.x % LPR);
+    if (i >= n) s = 0.f;
+    else if (!(s < 3.0e38f)) s = __int_as_float(0x7f800000);  // NaN/inf frame -> flagged by the epilogue
+    if (threadIdx.x % LPR == 0) X2[i] = s;
 }
 
 // B' rows (one thread per center): [c_hi | (c_lo | c_hi) | -b1 -b2 -b3 | 0..]; rows >= k: bias -inf
@@ -473,6 +487,7 @@ __device__ __forceinline__ void scan_chunk(const float (&v)[32], uint32_t chunk_
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if (!g.prm->valid) return;  // operands unusable: the exact tile kernel takes the whole call (screen_finish_assign)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* bres = smem;                       // resident B' (bres_bytes, multiple of 1024)
     uint8_t* tiles = smem + g.bres_bytes;       // n_stages * stage_bytes
@@ -693,6 +708,53 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // Every distance is ONE thread's sequential 4-lane sum in the reference order (common.cuh), so the work is
 // spread over (frame, center) pairs, never over the dimensions of one pair.
 
+// a frame the screen could not bound (candidate list overflow, non-finite data): queue it for the
+// CTA-per-frame exact scan below instead of stalling one lane group of a verify warp on k distances
+__device__ __forceinline__ void fallback_push(ScreenParams* prm, uint32_t* fb_list, int64_t frame) {
+    const unsigned int slot = atomicAdd(&prm->fb_count, 1u);
+    fb_list[slot] = (uint32_t)frame;
+}
+
+// exact scan of every center for the queued frames: one CTA per frame, thread t takes centers t, t+256, ...
+// (ascending per thread), then an order-free (sqrt(s), j) merge
+__global__ void __launch_bounds__(256) screen_fallback_kernel(const float* __restrict__ X, int d,
+                                                              const float* __restrict__ Cn, int k,
+                                                              const uint32_t* __restrict__ fb_list,
+                                                              const ScreenParams* __restrict__ prm,
+                                                              int32_t* __restrict__ labels, float* __restrict__ mind,
+                                                              int lloyd) {
+    extern __shared__ __align__(16) float fsm[];
+    float* xs = fsm;                                   // [d]
+    float* red_s = fsm + ((d + 3) & ~3);               // [256]
+    int32_t* red_j = reinterpret_cast<int32_t*>(red_s + 256);
+    if (!prm->valid) return;  // the whole call went to the exact tile kernel instead
+    const unsigned int count = prm->fb_count;
+    for (unsigned int b = blockIdx.x; b < count; b += gridDim.x) {
+        const int64_t i = fb_list[b];
+        __syncthreads();
+        for (int e = threadIdx.x; e < d; e += 256) xs[e] = X[i * d + e];
+        __syncthreads();
+        ArgMin am;
+        am.init();
+        for (int j = threadIdx.x; j < k; j += 256) am.offer(euclid_sq_exact(xs, Cn + (int64_t)j * d, d), j);
+        red_s[threadIdx.x] = am.s;
+        red_j[threadIdx.x] = am.j;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) {
+                am.merge(red_s[threadIdx.x + o], red_j[threadIdx.x + o]);
+                red_s[threadIdx.x] = am.s;
+                red_j[threadIdx.x] = am.j;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
+            if (mind) mind[i] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
+        }
+    }
+}
+
 __device__ __forceinline__ void verify_stats(unsigned long long groups, unsigned long long fb, ScreenParams* prm) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -705,7 +767,92 @@ __device__ __forceinline__ void verify_stats(unsigned long long groups, unsigned
     }
 }
 
-// d <= 16: 8 lanes per frame (4 frames per warp), lane `sub` evaluates center `sub` of every candidate group
+// d <= 16 and a center table that fits shared memory: thread per frame, frame in registers, the 8 centers of a
+// candidate group read with 16-byte loads from the table.  Table layout: row stride ds (= d rounded up to 4) plus
+// 4 floats of skew per 8-row group, so group g starts at bank (ds*8+4)*g mod 32 -- for ds = 4, 12 (and 8, 16 with
+// the extra skew below) consecutive groups rotate through all eight 16-byte bank groups and the lanes of a warp,
+// which look at unrelated groups, spread over the banks instead of piling onto one.
+template <int DREG>
+__global__ void __launch_bounds__(256) screen_verify_table_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                                  const float* __restrict__ Cn, int k,
+                                                                  const uint32_t* __restrict__ cand,
+                                                                  const uint8_t* __restrict__ ncand,
+                                                                  int32_t* __restrict__ labels,
+                                                                  float* __restrict__ mind, int lloyd,
+                                                                  ScreenParams* prm, uint32_t* __restrict__ fb_list,
+                                                                  int gstride /* floats per 8-row group */) {
+    extern __shared__ __align__(16) float ctab[];
+    if (!prm->valid) return;
+    constexpr int DS = DREG;  // row stride inside a group
+    const int n_groups = (k + GROUP - 1) / GROUP;
+    for (int t = threadIdx.x; t < n_groups * GROUP * DS; t += 256) {
+        const int r = t / DS, c = t - r * DS;
+        ctab[(r >> 3) * gstride + (r & 7) * DS + c] = (r < k && c < d) ? __ldg(Cn + (int64_t)r * d + c) : 0.f;
+    }
+    __syncthreads();
+    const int d4 = d & ~3;
+    unsigned long long my_groups = 0, my_fb = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        float xr[DREG];
+#pragma unroll
+        for (int e = 0; e < DREG; ++e) xr[e] = e < d ? __ldg(X + i * d + e) : 0.f;
+        const int nc = ncand[i];
+        if (nc == 255) {
+            fallback_push(prm, fb_list, i);
+            my_fb += 1;
+            continue;
+        }
+        const uint4* cp = reinterpret_cast<const uint4*>(cand + i * CAND_CAP);
+        const uint4 p0 = cp[0];
+        uint4 p1 = make_uint4(0, 0, 0, 0);
+        if (nc > 4) p1 = cp[1];
+        const uint32_t ent[CAND_CAP] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        ArgMin am;
+        am.init();
+#pragma unroll
+        for (int t = 0; t < CAND_CAP; ++t) {
+            if (t < nc) {
+                const int g0 = (int)(ent[t] & ID_MASK) * (CHUNK / GROUP);
+                uint32_t mask = ent[t] >> 28;
+                while (mask) {
+                    const int q = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int g = g0 + q;
+                    const float4* c4 = reinterpret_cast<const float4*>(ctab + (size_t)g * gstride);
+                    const int jn = min(GROUP, k - g * GROUP);
+#pragma unroll
+                    for (int c = 0; c < GROUP; ++c) {
+                        if (c < jn) {
+                            Lanes4 L;
+                            L.init();
+#pragma unroll
+                            for (int e = 0; e < DREG; e += 4) {
+                                if (e < d4) {
+                                    const float4 cv = c4[(c * DS + e) >> 2];
+                                    L.add4(xr[e], xr[e + 1], xr[e + 2], xr[e + 3], cv.x, cv.y, cv.z, cv.w);
+                                }
+                            }
+                            if (d4 < d) {
+                                const float4 cv = c4[(c * DS + d4) >> 2];
+                                const float ct[3] = {cv.x, cv.y, cv.z};
+#pragma unroll
+                                for (int e = 0; e < DREG; ++e)
+                                    if (e >= d4 && e < d) L.tail(xr[e], ct[e & 3]);
+                            }
+                            am.offer(L.result(), g * GROUP + c);
+                        }
+                    }
+                    my_groups += 1;
+                }
+            }
+        }
+        labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
+        if (mind) mind[i] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
+    }
+    verify_stats(my_groups, my_fb, prm);
+}
+
+// d <= 16, table too large for shared memory: 8 lanes per frame (4 frames per warp), lane `sub` evaluates center `sub` of every candidate group
 // with the frame in registers; the center table sits in shared memory when it fits (row stride rs = 4 mod 8
 // floats: the 8 rows of a group then cover all 32 banks, so a 16-byte load per lane is conflict free).
 template <int DREG>
@@ -715,8 +862,10 @@ __global__ void __launch_bounds__(256) screen_verify_small_kernel(const float* _
                                                                   const uint8_t* __restrict__ ncand,
                                                                   int32_t* __restrict__ labels,
                                                                   float* __restrict__ mind, int lloyd,
-                                                                  ScreenParams* prm, int use_smem, int rs) {
+                                                                  ScreenParams* prm, uint32_t* __restrict__ fb_list,
+                                                                  int use_smem, int rs) {
     extern __shared__ __align__(16) float ctab[];
+    if (!prm->valid) return;
     if (use_smem) {
         for (int t = threadIdx.x; t < k * rs; t += 256) {
             const int r = t / rs, c = t - r * rs;
@@ -726,7 +875,6 @@ __global__ void __launch_bounds__(256) screen_verify_small_kernel(const float* _
     }
     const int lane = threadIdx.x & 31, sub = lane & 7, slot = lane >> 3;
     const int d4 = d & ~3;
-    const int n_groups_all = (k + GROUP - 1) / GROUP;
     unsigned long long my_groups = 0, my_fb = 0;
     const int64_t warp_global = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * 256) >> 5;
@@ -783,9 +931,8 @@ __global__ void __launch_bounds__(256) screen_verify_small_kernel(const float* _
                 am.offer(L.result(), j);  // a lane meets its centers in ascending order
             }
         };
-        if (nc == 255) {  // the screen could not bound this frame: exact scan of every center
-            for (int g = 0; g < n_groups_all; ++g) eval_group(g);
-            if (sub == 0) my_fb += 1;
+        if (nc == 255) {  // the screen could not bound this frame
+            if (sub == 0) { fallback_push(prm, fb_list, i); my_fb += 1; }
         } else {
 #pragma unroll
             for (int t = 0; t < CAND_CAP; ++t) {
@@ -808,7 +955,7 @@ __global__ void __launch_bounds__(256) screen_verify_small_kernel(const float* _
             const int32_t jo = __shfl_xor_sync(0xffffffffu, am.j, o);
             am.merge(so, jo);
         }
-        if (live && sub == 0) {
+        if (live && sub == 0 && nc != 255) {
             labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
             if (mind) mind[i] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
         }
@@ -816,104 +963,293 @@ __global__ void __launch_bounds__(256) screen_verify_small_kernel(const float* _
     verify_stats(my_groups, my_fb, prm);
 }
 
-// d > 16: one warp per frame.  The 8 rows of a candidate group (contiguous in memory) are copied coalesced into
-// a per-warp shared-memory buffer (row stride rsb, rsb/4 odd: conflict free below); lane (c = lane/4, l = lane%4)
-// then owns accumulator lane l of center c -- elements l, l+4, l+8, ... in order, the d%4 tail into lane 0 --
-// exactly the reference's four interleaved partial sums, finished as ((a0+a1)+a2)+a3 by lane (c,0).
-__global__ void __launch_bounds__(256) screen_verify_big_kernel(const float* __restrict__ X, int64_t n, int d,
-                                                                const float* __restrict__ Cn, int k,
-                                                                const uint32_t* __restrict__ cand,
-                                                                const uint8_t* __restrict__ ncand,
-                                                                int32_t* __restrict__ labels,
-                                                                float* __restrict__ mind, int lloyd,
-                                                                ScreenParams* prm, int rsb, int warps_per_cta) {
+// d > 16, d % 4 == 0: 8 lanes per frame (4 frames per warp, lane `sub` <-> center `sub` of the candidate group).
+// The dimension is walked in slabs of 32 columns; per slab the warp copies, with 16-byte cp.async (LDGSTS, no
+// register staging), the 4x32 slab of its frames and the 8x32 slab of each frame's candidate group (8 consecutive
+// center rows) into a double-buffered shared-memory stage, then every lane advances ITS OWN four interleaved
+// partial sums (Lanes4) over the slab: the reference's summation order is untouched.  Row stride 36 floats
+// (odd multiple of 4): the 16-byte reads of the 8 lanes of a frame hit 8 different bank groups.
+// (A TMA-box variant of this kernel was measured first: 1 KB boxes cost ~40-100 cycles of TMA issue each and
+// left it 3-8x slower than cp.async at the same traffic -- profiles/r01_notes.md.)
+static constexpr int VC_ROW = 36;                              // floats per staged center row
+static constexpr int VC_FRAME = GROUP * VC_ROW;                // floats per frame's group slab
+static constexpr int VC_STAGE = 4 * VC_FRAME + 4 * 32;         // + the 4 frame slabs
+static constexpr int VC_WARP_FLOATS = 2 * VC_STAGE;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256) screen_verify_stream_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                                   const float* __restrict__ Cn, int k,
+                                                                   const uint32_t* __restrict__ cand,
+                                                                   const uint8_t* __restrict__ ncand,
+                                                                   int32_t* __restrict__ labels,
+                                                                   float* __restrict__ mind, int lloyd,
+                                                                   ScreenParams* prm, uint32_t* __restrict__ fb_list) {
     extern __shared__ __align__(16) float vsm[];
+    if (!prm->valid) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp >= warps_per_cta) return;
-    const int dpad = (d + 3) & ~3;
-    float* xb = vsm + (size_t)warp * (dpad + (size_t)GROUP * rsb);  // frame row
-    float* cb = xb + dpad;                                          // 8 center rows
-    const int c = lane >> 2, l = lane & 3;
-    const int d4 = d & ~3;
-    const int n_groups_all = (k + GROUP - 1) / GROUP;
-    const bool vec4 = (d & 3) == 0;
+    const int sub = lane & 7, slot = lane >> 3;
+    float* wb = vsm + (size_t)warp * VC_WARP_FLOATS;
+    const int nslab = (d + 31) >> 5;
     unsigned long long my_groups = 0, my_fb = 0;
-    for (int64_t i = (int64_t)blockIdx.x * warps_per_cta + warp; i < n; i += (int64_t)gridDim.x * warps_per_cta) {
-        __syncwarp();
-        if (vec4) {
-            const float4* src = reinterpret_cast<const float4*>(X + i * d);
-            for (int t = lane; t < (d >> 2); t += 32) reinterpret_cast<float4*>(xb)[t] = __ldg(src + t);
-        } else {
-            for (int t = lane; t < d; t += 32) xb[t] = __ldg(X + i * d + t);
+    const int64_t n_warps = ((int64_t)gridDim.x * 256) >> 5;
+    const int64_t warp_global = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const unsigned seg_mask = 0xffu << (slot * 8);
+
+    // candidate metadata of the NEXT quad is requested one quad ahead
+    int nc_n = 0;
+    uint32_t ent_n = 0;
+    auto fetch_meta = [&](int64_t b) {
+        const int64_t fi = b + slot;
+        nc_n = fi < n ? (int)ncand[fi] : 0;
+        ent_n = (fi < n && sub < CAND_CAP) ? cand[fi * CAND_CAP + sub] : 0u;
+    };
+    int64_t base = warp_global * 4;
+    if (base < n) fetch_meta(base);
+    for (; base < n; base += n_warps * 4) {
+        const int64_t i = base + slot;
+        const bool live = i < n;
+        const int nc = nc_n;
+        uint32_t ent = (nc != 255 && sub < nc) ? ent_n : 0u;
+        if (base + n_warps * 4 < n) fetch_meta(base + n_warps * 4);
+        const int pc = __popc(ent >> 28);
+        int off = pc;  // inclusive scan over the 8 lanes of the frame
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, off, o, 8);
+            if (sub >= o) off += v;
         }
-        const int nc = ncand[i];
-        uint32_t my_ent = 0;
-        if (nc != 255 && lane < nc) my_ent = cand[i * CAND_CAP + lane];
-        ArgMin am;
-        am.init();
-        auto eval_group = [&](int g) {
-            const int jb = g * GROUP;
-            const int rows = min(GROUP, k - jb);
-            __syncwarp();
-            if (vec4) {
-                const float4* src = reinterpret_cast<const float4*>(Cn + (int64_t)jb * d);
-                const int per_row = d >> 2;
-                for (int t = lane; t < rows * per_row; t += 32) {
-                    const int r = t / per_row, q = t - r * per_row;
-                    *reinterpret_cast<float4*>(cb + (size_t)r * rsb + 4 * q) = __ldg(src + t);
-                }
-            } else {
-                const float* src = Cn + (int64_t)jb * d;
-                for (int t = lane; t < rows * d; t += 32) {
-                    const int r = t / d, q = t - r * d;
-                    cb[(size_t)r * rsb + q] = __ldg(src + t);
-                }
+        int total = __shfl_sync(0xffffffffu, off, 7, 8);
+        off -= pc;
+        if (nc == 255) total = 0;  // queued for the fallback kernel below
+        int rounds = total;
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
+
+        // group of this lane's frame in round r (-1: none); warp-collective
+        auto group_of_round = [&](int r) -> int {
+            const bool mine = nc != 255 && r >= off && r < off + pc;
+            const unsigned who = __ballot_sync(0xffffffffu, mine) & seg_mask;
+            int gm = -1;
+            if (mine) {
+                uint32_t mask = ent >> 28;
+                for (int t = r - off; t > 0; --t) mask &= mask - 1;
+                gm = (int)(ent & ID_MASK) * (CHUNK / GROUP) + (__ffs(mask) - 1);
             }
-            __syncwarp();
-            const float* crow = cb + (size_t)c * rsb;
-            float a = 0.f;
-            if (c < rows) {
-#pragma unroll 4
-                for (int e = l; e < d4; e += 4) {
-                    const float t = __fsub_rn(xb[e], crow[e]);
-                    a = __fadd_rn(a, __fmul_rn(t, t));
-                }
-                if (l == 0) {
-                    for (int e = d4; e < d; ++e) {
-                        const float t = __fsub_rn(xb[e], crow[e]);
-                        a = __fadd_rn(a, __fmul_rn(t, t));
+            const int src = who ? (__ffs(who) - 1) : lane;
+            int g = __shfl_sync(0xffffffffu, gm, src);
+            if (!who) g = -1;
+            return g;
+        };
+        // start the copies of slab `sl` for round-group g into stage `stg`; warp-collective
+        auto issue = [&](int g, int sl, int stg) {
+            float* st = wb + stg * VC_STAGE;
+            const int col0 = sl * 32;
+            __syncwarp();  // every lane is done reading stage `stg`
+            {   // frame slabs: lane (slot, sub) copies 16 bytes of frame `slot`
+                const int col = col0 + sub * 4;
+                if (live && col < d) cp_async16(st + 4 * VC_FRAME + slot * 32 + sub * 4, X + i * d + col);
+            }
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const int gf = __shfl_sync(0xffffffffu, g, f * 8);
+                if (gf >= 0) {
+                    const int rows = min(GROUP, k - gf * GROUP);
+                    const float* src = Cn + (int64_t)gf * GROUP * d + col0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int t = lane + 32 * h, row = t >> 3, c4 = t & 7;
+                        if (row < rows && col0 + c4 * 4 < d)
+                            cp_async16(st + f * VC_FRAME + row * VC_ROW + c4 * 4, src + (int64_t)row * d + c4 * 4);
                     }
                 }
             }
-            const float a1 = __shfl_down_sync(0xffffffffu, a, 1);
-            const float a2 = __shfl_down_sync(0xffffffffu, a, 2);
-            const float a3 = __shfl_down_sync(0xffffffffu, a, 3);
-            if (l == 0 && c < rows) am.offer(__fadd_rn(__fadd_rn(__fadd_rn(a, a1), a2), a3), jb + c);
+            cp_async_commit();
         };
-        if (nc == 255) {
-            for (int g = 0; g < n_groups_all; ++g) eval_group(g);
-            if (lane == 0) my_fb += 1;
-        } else {
-            for (int t = 0; t < nc; ++t) {
-                const uint32_t ent = __shfl_sync(0xffffffffu, my_ent, t);
-                const int g0 = (int)(ent & ID_MASK) * (CHUNK / GROUP);
-                uint32_t mask = ent >> 28;
-                while (mask) {
-                    const int q = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    eval_group(g0 + q);
-                    if (lane == 0) my_groups += 1;
+
+        ArgMin am;
+        am.init();
+        const int steps = rounds * nslab;
+        int g_cur = -1, g_nxt = -1;
+        if (steps > 0) {
+            g_cur = group_of_round(0);
+            issue(g_cur, 0, 0);
+        }
+        Lanes4 L;
+        L.init();
+        int r = 0, sl = 0;
+        for (int step = 0; step < steps; ++step) {
+            const int stg = step & 1;
+            int nr = r, nsl = sl + 1;
+            if (nsl == nslab) { nsl = 0; nr = r + 1; }
+            if (step + 1 < steps) {
+                g_nxt = (nsl == 0) ? group_of_round(nr) : g_cur;
+                issue(g_nxt, nsl, stg ^ 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();  // every lane's copies of this stage have landed
+            const int j = g_cur >= 0 ? g_cur * GROUP + sub : -1;
+            if (j >= 0 && j < k) {
+                const float* st = wb + stg * VC_STAGE;
+                const float* cr = st + slot * VC_FRAME + sub * VC_ROW;
+                const float* xt = st + 4 * VC_FRAME + slot * 32;
+                const int w = min(32, d - sl * 32);  // multiple of 4 (d % 4 == 0)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c * 4 < w) {
+                        const float4 xv = *reinterpret_cast<const float4*>(xt + c * 4);
+                        const float4 cv = *reinterpret_cast<const float4*>(cr + c * 4);
+                        L.add4(xv.x, xv.y, xv.z, xv.w, cv.x, cv.y, cv.z, cv.w);
+                    }
                 }
             }
+            if (sl == nslab - 1) {  // distance complete
+                if (j >= 0 && j < k) am.offer(L.result(), j);
+                if (g_cur >= 0 && sub == 0 && nc != 255) my_groups += 1;
+                L.init();
+            }
+            r = nr;
+            sl = nsl;
+            g_cur = (sl == 0) ? g_nxt : g_cur;
         }
-        // lanes (c,0) hold per-center-slot winners: combine slots (xor 4, 8, 16)
+        if (live && nc == 255 && sub == 0) { fallback_push(prm, fb_list, i); my_fb += 1; }
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
+        for (int o = 1; o < 8; o <<= 1) {
             const float so = __shfl_xor_sync(0xffffffffu, am.s, o);
             const int32_t jo = __shfl_xor_sync(0xffffffffu, am.j, o);
             am.merge(so, jo);
         }
-        if (lane == 0) {
+        if (live && sub == 0 && nc != 255) {
+            labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
+            if (mind) mind[i] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
+        }
+    }
+    verify_stats(my_groups, my_fb, prm);
+}
+
+// d > 16, any d: 8 lanes per frame again (4 frames per warp, lane `sub` <-> center `sub` of the group), but the rows are
+// too wide for registers / a resident table, so the dimension is walked in slabs of SLAB columns: per round the
+// warp copies, coalesced, the slab of its 4 frames and of the 4 candidate groups (8 contiguous center rows each)
+// into shared memory and every lane advances ITS OWN four interleaved partial sums (Lanes4) over the slab -- the
+// sums never leave the thread, so the reference's summation order is untouched.  Row stride SLAB+4 floats
+// (odd multiple of 4): the 8 rows of a group cover all banks, 16-byte loads are conflict free.
+static constexpr int SLAB = 32;
+static constexpr int SLAB_RS = SLAB + 4;
+static constexpr int VW_FLOATS = 4 * (GROUP * SLAB_RS + SLAB);  // shared floats per warp
+
+__global__ void __launch_bounds__(256) screen_verify_wide_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                                 const float* __restrict__ Cn, int k,
+                                                                 const uint32_t* __restrict__ cand,
+                                                                 const uint8_t* __restrict__ ncand,
+                                                                 int32_t* __restrict__ labels,
+                                                                 float* __restrict__ mind, int lloyd,
+                                                                 ScreenParams* prm, uint32_t* __restrict__ fb_list) {
+    extern __shared__ __align__(16) float vsm[];
+    if (!prm->valid) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane & 7, slot = lane >> 3;
+    float* wbuf = vsm + (size_t)warp * VW_FLOATS;
+    float* cb = wbuf + (size_t)slot * (GROUP * SLAB_RS);   // this frame's group rows
+    float* xb = wbuf + 4 * (GROUP * SLAB_RS) + slot * SLAB;  // this frame's slab
+    const int d4 = d & ~3;
+    unsigned long long my_groups = 0, my_fb = 0;
+    const int64_t n_warps = ((int64_t)gridDim.x * 256) >> 5;
+    const int64_t warp_global = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const unsigned seg_mask = 0xffu << (slot * 8);
+    for (int64_t base = warp_global * 4; base < n; base += n_warps * 4) {
+        const int64_t i = base + slot;
+        const bool live = i < n;
+        const int nc = live ? (int)ncand[i] : 0;
+        // lane (slot, sub) holds candidate entry `sub` of its frame; prefix-count the groups of the frame
+        uint32_t ent = 0;
+        if (live && nc != 255 && sub < nc) ent = cand[i * CAND_CAP + sub];
+        const int pc = __popc(ent >> 28);
+        int off = pc;  // inclusive scan over the 8 lanes of the frame
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, off, o, 8);
+            if (sub >= o) off += v;
+        }
+        int total = __shfl_sync(0xffffffffu, off, 7, 8);
+        off -= pc;
+        if (nc == 255) total = 0;  // queued for the fallback kernel below
+        int rounds = total;
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
+        ArgMin am;
+        am.init();
+        for (int r = 0; r < rounds; ++r) {
+            // group of this frame in round r (-1: none)
+            int g;
+            {
+                const bool mine = nc != 255 && r >= off && r < off + pc;
+                const unsigned who = __ballot_sync(0xffffffffu, mine) & seg_mask;
+                int gm = -1;
+                if (mine) {
+                    uint32_t mask = ent >> 28;
+                    for (int t = r - off; t > 0; --t) mask &= mask - 1;
+                    gm = (int)(ent & ID_MASK) * (CHUNK / GROUP) + (__ffs(mask) - 1);
+                }
+                const int src = who ? (__ffs(who) - 1) : lane;
+                g = __shfl_sync(0xffffffffu, gm, src);
+                if (!who) g = -1;
+            }
+            const int j = g >= 0 ? g * GROUP + sub : -1;
+            Lanes4 L;
+            L.init();
+            for (int e0 = 0; e0 < d; e0 += SLAB) {
+                const int w = min(SLAB, d - e0);  // slab width
+                __syncwarp();
+                // ---- stage: 4 frame slabs + 4 x 8 center-row slabs (each row piece contiguous in global memory)
+                for (int t = lane; t < 4 * w; t += 32) {
+                    const int f = t / w, c = t - f * w;
+                    const int64_t fi = base + f;
+                    wbuf[4 * (GROUP * SLAB_RS) + f * SLAB + c] = fi < n ? __ldg(X + fi * d + e0 + c) : 0.f;
+                }
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const int gf = __shfl_sync(0xffffffffu, g, f * 8);
+                    if (gf < 0) continue;
+                    const int rows = min(GROUP, k - gf * GROUP);
+                    const float* src = Cn + (int64_t)gf * GROUP * d + e0;
+                    float* dst = wbuf + (size_t)f * (GROUP * SLAB_RS);
+                    for (int t = lane; t < rows * w; t += 32) {
+                        const int rr = t / w, c = t - rr * w;
+                        dst[rr * SLAB_RS + c] = __ldg(src + (int64_t)rr * d + c);
+                    }
+                }
+                __syncwarp();
+                // ---- advance the partial sums over this slab
+                if (j >= 0 && j < k) {
+                    const float* cr = cb + sub * SLAB_RS;
+                    const int w4 = min(w, d4 - e0) & ~3;  // full 4-blocks of the reference's main loop inside this slab
+                    for (int e = 0; e < w4; e += 4) {
+                        const float4 xv = *reinterpret_cast<const float4*>(xb + e);
+                        const float4 cv = *reinterpret_cast<const float4*>(cr + e);
+                        L.add4(xv.x, xv.y, xv.z, xv.w, cv.x, cv.y, cv.z, cv.w);
+                    }
+                    for (int e = max(w4, 0); e < w; ++e)
+                        if (e0 + e >= d4) L.tail(xb[e], cr[e]);
+                }
+            }
+            if (j >= 0 && j < k) am.offer(L.result(), j);
+            if (g >= 0 && sub == 0 && nc != 255) my_groups += 1;
+        }
+        if (live && nc == 255 && sub == 0) { fallback_push(prm, fb_list, i); my_fb += 1; }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const float so = __shfl_xor_sync(0xffffffffu, am.s, o);
+            const int32_t jo = __shfl_xor_sync(0xffffffffu, am.j, o);
+            am.merge(so, jo);
+        }
+        if (live && sub == 0 && nc != 255) {
             labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
             if (mind) mind[i] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
         }
@@ -961,7 +1297,7 @@ void screen_plan_destroy(ScreenPlan* p) {
     if (!p) return;
     cudaStreamSynchronize(p->ctx->stream);
     cudaFree(p->A); cudaFree(p->B); cudaFree(p->X2); cudaFree(p->mu); cudaFree(p->params); cudaFree(p->cand);
-    cudaFree(p->ncand);
+    cudaFree(p->ncand); cudaFree(p->fb_list);
     delete p;
 }
 
@@ -984,6 +1320,7 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     if (e == cudaSuccess) e = cudaMalloc(&p->params, sizeof(ScreenParams));
     if (e == cudaSuccess) e = cudaMalloc(&p->cand, (size_t)p->n_pad * CAND_CAP * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->ncand, (size_t)p->n_pad);
+    if (e == cudaSuccess) e = cudaMalloc(&p->fb_list, (size_t)p->n_pad * 4);
     if (e != cudaSuccess) {
         cudaGetLastError();
         screen_plan_destroy(p);
@@ -1037,17 +1374,34 @@ int screen_prepare_frames_with_centers(ScreenPlan* p, const float* dX, int64_t n
     CUDA_TRY(cudaMemsetAsync(p->params, 0, sizeof(ScreenParams), st));
     screen_mu_kernel<<<(unsigned)cdiv(p->d, 128), 128, 0, st>>>(dC, p->k, p->d, p->mu);
     LAUNCH_CHECK();
-    screen_maxnorm_kernel<<<capped_grid(ctx, n, 256), 256, 0, st>>>(dX, n, p->d, p->mu, &p->params->xmax2_raw);
-    LAUNCH_CHECK();
-    screen_maxnorm_kernel<<<capped_grid(ctx, p->k, 256), 256, 0, st>>>(dC, p->k, p->d, p->mu, &p->params->cmax2_raw);
-    LAUNCH_CHECK();
+    if (p->d <= 16) {
+        screen_maxnorm_kernel<1><<<capped_grid(ctx, n, 256), 256, 0, st>>>(dX, n, p->d, p->mu, &p->params->xmax2_raw);
+        LAUNCH_CHECK();
+        screen_maxnorm_kernel<1><<<capped_grid(ctx, p->k, 256), 256, 0, st>>>(dC, p->k, p->d, p->mu, &p->params->cmax2_raw);
+        LAUNCH_CHECK();
+    } else if (p->d <= 128) {
+        screen_maxnorm_kernel<8><<<capped_grid(ctx, n, 32), 256, 0, st>>>(dX, n, p->d, p->mu, &p->params->xmax2_raw);
+        LAUNCH_CHECK();
+        screen_maxnorm_kernel<8><<<capped_grid(ctx, p->k, 32), 256, 0, st>>>(dC, p->k, p->d, p->mu, &p->params->cmax2_raw);
+        LAUNCH_CHECK();
+    } else {
+        screen_maxnorm_kernel<32><<<capped_grid(ctx, n, 8), 256, 0, st>>>(dX, n, p->d, p->mu, &p->params->xmax2_raw);
+        LAUNCH_CHECK();
+        screen_maxnorm_kernel<32><<<capped_grid(ctx, p->k, 8), 256, 0, st>>>(dC, p->k, p->d, p->mu, &p->params->cmax2_raw);
+        LAUNCH_CHECK();
+    }
     screen_sigma_kernel<<<1, 1, 0, st>>>(p->params);
     LAUNCH_CHECK();
     const int64_t n_pad_now = cdiv(n, TILE_M) * TILE_M;
     screen_frames_kernel<<<capped_grid(ctx, n_pad_now, 256 / (p->Kp / 8)), 256, 0, st>>>(
         dX, n, n_pad_now, p->d, p->terms, p->Kp, p->mu, p->params, reinterpret_cast<uint4*>(p->A));
     LAUNCH_CHECK();
-    screen_x2_kernel<<<(unsigned)cdiv(n_pad_now, 256), 256, 0, st>>>(dX, n, n_pad_now, p->d, p->mu, p->params, p->X2);
+    if (p->d <= 16)
+        screen_x2_kernel<1><<<(unsigned)cdiv(n_pad_now, 256), 256, 0, st>>>(dX, n, n_pad_now, p->d, p->mu, p->params, p->X2);
+    else if (p->d <= 128)
+        screen_x2_kernel<8><<<(unsigned)cdiv(n_pad_now, 32), 256, 0, st>>>(dX, n, n_pad_now, p->d, p->mu, p->params, p->X2);
+    else
+        screen_x2_kernel<32><<<(unsigned)cdiv(n_pad_now, 8), 256, 0, st>>>(dX, n, n_pad_now, p->d, p->mu, p->params, p->X2);
     LAUNCH_CHECK();
     p->prepared_n = n;
     return B2K_OK;
@@ -1061,6 +1415,18 @@ int screen_prepare_frames(ScreenPlan* p, const float* dX, int64_t n) {
     return B2K_OK;
 }
 
+// tail of every screen_assign: queued frames -> CTA-per-frame exact scan; unusable operands (valid == 0: the
+// screen and verify kernels returned at once) -> the exact tile kernel over all frames, gated on the device flag
+static int screen_finish_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, int32_t* labels,
+                                float* mind, int lloyd) {
+    b2k_ctx* ctx = p->ctx;
+    const size_t fsmem = ((size_t)((p->d + 3) & ~3) + 512) * 4;
+    screen_fallback_kernel<<<ctx->sm_count * 4, 256, fsmem, ctx->stream>>>(dX, p->d, dC, p->k, p->fb_list, p->params, labels,
+                                                                          mind, lloyd);
+    LAUNCH_CHECK();
+    return launch_assign_exact_if(ctx, dX, n, p->d, dC, p->k, labels, mind, lloyd, &p->params->valid);
+}
+
 int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, int32_t* labels, float* mind,
                   int lloyd) {
     b2k_ctx* ctx = p->ctx;
@@ -1068,7 +1434,7 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
     if (p->prepared_n != n) B2K_TRY(screen_prepare_frames_with_centers(p, dX, n, dC));
     // center operand for the current centers
     CUDA_TRY(cudaMemsetAsync(&p->params->cmax2_now, 0, 4, st));
-    CUDA_TRY(cudaMemsetAsync(&p->params->cand_chunks, 0, 16, st));
+    CUDA_TRY(cudaMemsetAsync(&p->params->cand_chunks, 0, 24, st));
     screen_centers_kernel<<<(unsigned)cdiv(p->k_pad, 128), 128, 0, st>>>(dC, p->k, p->k_pad, p->d, p->terms, p->Kp,
                                                                          p->mu, p->params, p->B);
     LAUNCH_CHECK();
@@ -1097,9 +1463,36 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
     // verify (persistent grids)
     if (p->d <= 16) {
         const int ds = (p->d + 3) & ~3;
+        {   // table kernel when the skewed table fits shared memory twice per SM
+            const int gstride = GROUP * ds + (((GROUP * ds / 4) & 1) ? 0 : 4);  // odd number of 16-byte units
+            const size_t tbytes = (size_t)cdiv(p->k, GROUP) * gstride * 4;
+            if (tbytes <= 100 * 1024) {
+                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / tbytes));
+                const unsigned tgrid =
+                    (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * per_sm));
+#define B2K_VTABLE(DR)                                                                                               \
+    do {                                                                                                             \
+        static bool vattr = false;                                                                                   \
+        if (!vattr) {                                                                                                \
+            CUDA_TRY(cudaFuncSetAttribute(screen_verify_table_kernel<DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          100 * 1024));                                                              \
+            vattr = true;                                                                                            \
+        }                                                                                                            \
+        screen_verify_table_kernel<DR><<<tgrid, 256, tbytes, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, \
+                                                                   mind, lloyd, p->params, p->fb_list, gstride);     \
+    } while (0)
+                if (ds == 4) B2K_VTABLE(4);
+                else if (ds == 8) B2K_VTABLE(8);
+                else if (ds == 12) B2K_VTABLE(12);
+                else B2K_VTABLE(16);
+#undef B2K_VTABLE
+                LAUNCH_CHECK();
+                return screen_finish_assign(p, dX, n, dC, labels, mind, lloyd);
+            }
+        }
         const int rs = (ds % 8 == 4) ? ds : ds + 4;
         const size_t tab_bytes = (size_t)p->k * rs * 4;
-        const int use_smem = tab_bytes <= 100 * 1024 ? 1 : 0;
+        const int use_smem = 0;
         const size_t vsmem = use_smem ? tab_bytes : 0;
         const int per_sm = use_smem ? (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(tab_bytes, 1))) : 4;
         const unsigned vgrid =
@@ -1113,7 +1506,7 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
             vattr = true;                                                                                            \
         }                                                                                                            \
         screen_verify_small_kernel<DR><<<vgrid, 256, vsmem, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels,  \
-                                                                  mind, lloyd, p->params, use_smem, rs);             \
+                                                                  mind, lloyd, p->params, p->fb_list, use_smem, rs); \
     } while (0)
         if (p->d <= 4) B2K_VERIFY(4);
         else if (p->d <= 8) B2K_VERIFY(8);
@@ -1121,23 +1514,35 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         else B2K_VERIFY(16);
 #undef B2K_VERIFY
     } else {
-        const int dpad = (p->d + 3) & ~3;
-        const int rsb = ((dpad / 4) % 2 == 1) ? dpad : dpad + 4;
-        const size_t per_warp = ((size_t)dpad + (size_t)GROUP * rsb) * 4;
-        int wpc = (int)std::min<size_t>(8, (96 * 1024) / per_warp);
-        if (wpc < 1) return set_error(B2K_ERR_INVALID_ARG, "dimension %d too large for the verify kernel", p->d);
-        const size_t vsmem = per_warp * wpc;
+        if (p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0) {
+            const size_t tsmem = (size_t)8 * VC_WARP_FLOATS * 4;
+            static bool tattr = false;
+            if (!tattr) {
+                CUDA_TRY(cudaFuncSetAttribute(screen_verify_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                tattr = true;
+            }
+            const int per_sm = (int)std::max<size_t>(1, (220 * 1024) / (tsmem + 1024));
+            const unsigned tgrid =
+                (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 32), (int64_t)ctx->sm_count * per_sm));
+            screen_verify_stream_kernel<<<tgrid, 256, tsmem, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind,
+                                                                   lloyd, p->params, p->fb_list);
+            LAUNCH_CHECK();
+            return screen_finish_assign(p, dX, n, dC, labels, mind, lloyd);
+        }
+        const size_t vsmem = (size_t)8 * VW_FLOATS * 4;
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / vsmem));
         static bool vattr = false;
         if (!vattr) {
-            CUDA_TRY(cudaFuncSetAttribute(screen_verify_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(screen_verify_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             vattr = true;
         }
-        const unsigned vgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, wpc), (int64_t)ctx->sm_count * 2));
-        screen_verify_big_kernel<<<vgrid, 256, vsmem, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind, lloyd,
-                                                            p->params, rsb, wpc);
+        const unsigned vgrid =
+            (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 32), (int64_t)ctx->sm_count * ctas_per_sm));
+        screen_verify_wide_kernel<<<vgrid, 256, vsmem, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind, lloyd,
+                                                             p->params, p->fb_list);
     }
     LAUNCH_CHECK();
-    return B2K_OK;
+    return screen_finish_assign(p, dX, n, dC, labels, mind, lloyd);
 }
 
 int screen_read_stats(ScreenPlan* p, double* cand_chunks, double* fallback_frames) {
