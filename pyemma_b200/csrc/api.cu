@@ -132,6 +132,31 @@ static int assign_any(b2k_ctx* ctx, const float* dX, const float* Ga, int64_t n,
 
 using namespace b2k;
 
+int b2k_ctx::slot(int which, size_t bytes, void** out) {
+    if (bytes > slot_cap[which]) {
+        if (slot_ptr[which]) {
+            cudaStreamSynchronize(stream);
+            cudaFree(slot_ptr[which]);
+        }
+        slot_ptr[which] = nullptr;
+        slot_cap[which] = 0;
+        const size_t want = bytes + bytes / 8;  // a little headroom for the next, slightly larger call
+        if (cudaMalloc(&slot_ptr[which], want) != cudaSuccess) {
+            cudaGetLastError();
+            if (cudaMalloc(&slot_ptr[which], bytes) != cudaSuccess) {
+                cudaGetLastError();
+                slot_ptr[which] = nullptr;
+                return b2k::set_error(B2K_ERR_NOMEM, "cudaMalloc(%zu bytes) failed", bytes);
+            }
+            slot_cap[which] = bytes;
+        } else {
+            slot_cap[which] = want;
+        }
+    }
+    *out = slot_ptr[which];
+    return B2K_OK;
+}
+
 int b2k_ctx::ensure_scratch(size_t bytes) {
     if (bytes <= scratch_cap) return B2K_OK;
     if (scratch) cudaFree(scratch);
@@ -188,6 +213,9 @@ B2K_API int b2k_ctx_destroy(b2k_ctx* c) {
         if (c->ev_done[s]) cudaEventDestroy(c->ev_done[s]);
     }
     screen_plan_release_cached(c);
+    for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+    for (int i = 0; i < b2k_ctx::N_SLOTS; ++i)
+        if (c->slot_ptr[i]) cudaFree(c->slot_ptr[i]);
     if (c->scratch) cudaFree(c->scratch);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -213,6 +241,11 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return set_error(B2K_ERR_INVALID_ARG, "null argument");
     if (!strcmp(name, "assign_engine")) c->engine = (int)value;
     else if (!strcmp(name, "screen_terms")) c->screen_terms = (int)value;
+    else if (!strcmp(name, "profile")) {  // (re)start event timing of the screen kernel launches
+        for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+        c->prof_events.clear();
+        c->profile = value != 0;
+    }
     else if (!strcmp(name, "stage_bytes")) c->stage_bytes = (size_t)std::max<int64_t>(value, 1 << 16);
     else if (!strcmp(name, "own_stream")) {
         if (!c->own_stream) {
@@ -229,6 +262,17 @@ B2K_API int b2k_ctx_get_stat(b2k_ctx* c, const char* name, double* value) {
     if (c->stat_pending && c->assign_plan && !strncmp(name, "screen_", 7)) {  // stats of the last device assign, read lazily
         B2K_TRY(screen_read_stats(static_cast<ScreenPlan*>(c->assign_plan), &c->stat_cand_chunks, &c->stat_fallback_frames));
         c->stat_pending = false;
+    }
+    if (!strcmp(name, "screen_gemm_ms_total") || !strcmp(name, "screen_gemm_launches")) {
+        double total = 0;
+        for (size_t i = 0; i + 1 < c->prof_events.size(); i += 2) {
+            CUDA_TRY(cudaEventSynchronize(c->prof_events[i + 1]));
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]));
+            total += ms;
+        }
+        *value = !strcmp(name, "screen_gemm_ms_total") ? total : (double)(c->prof_events.size() / 2);
+        return B2K_OK;
     }
     if (!strcmp(name, "screen_cand_chunks")) *value = c->stat_cand_chunks;
     else if (!strcmp(name, "screen_fallback_frames")) *value = c->stat_fallback_frames;
@@ -297,31 +341,26 @@ B2K_API int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, 
 }
 
 // Host frames are streamed chunk by chunk: H2D of chunk c+1 (copy stream) overlaps the kernels of
-// chunk c (compute stream) and the D2H of chunk c-1's labels.
-B2K_API int b2k_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* centers, int32_t k,
-                       int metric, int32_t* labels) {
-    if (!ctx || n < 0 || d < 1 || k < 1 || (n > 0 && (!X || !labels)) || !centers)
-        return set_error(B2K_ERR_INVALID_ARG, "assign: bad arguments (n=%lld d=%d k=%d)", (long long)n, d, k);
-    B2K_TRY(check_metric_dim(metric, d));
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    if (n == 0) return B2K_OK;
+// chunk c (compute stream) and the D2H of chunk c-1's labels.  With dX_keep / dL_keep the chunks (and their
+// labels) additionally stay resident in one device array, which is how b2k_kmeans_cluster gets its frames
+// into HBM while the assignment of the first chunks is already running.
+static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* dC, int32_t k, int metric,
+                         int32_t* labels, int lloyd, float* dX_keep, int32_t* dL_keep) {
     cudaStream_t st = ctx->stream;
-    DevMem dC;
-    B2K_TRY(dC.alloc((size_t)k * d * 4));
-    CUDA_TRY(cudaMemcpyAsync(dC.p, centers, (size_t)k * d * 4, cudaMemcpyHostToDevice, st));
     PreparedCenters pc;
-    B2K_TRY(pc.prepare(ctx, dC.as<float>(), k, d, metric));
-
+    B2K_TRY(pc.prepare(ctx, dC, k, d, metric));
     const int64_t row_bytes = (int64_t)d * 4;
     int64_t cf = std::max<int64_t>(1, (int64_t)ctx->stage_bytes / row_bytes);
     cf = std::min(cf, n);
     const bool in_pinned = host_ptr_is_pinned(X), out_pinned = host_ptr_is_pinned(labels);
     B2K_TRY(ensure_pinned(ctx, in_pinned ? 0 : (size_t)cf * row_bytes, out_pinned ? 0 : (size_t)cf * 4));
-    DevMem dX[2], dL[2], dG[2];
+    float* dX[2] = {nullptr, nullptr};
+    int32_t* dL[2] = {nullptr, nullptr};
+    float* dG[2] = {nullptr, nullptr};
     for (int s = 0; s < 2; ++s) {
-        B2K_TRY(dX[s].alloc((size_t)cf * row_bytes));
-        B2K_TRY(dL[s].alloc((size_t)cf * 4));
-        if (metric == B2K_METRIC_MINRMSD) B2K_TRY(dG[s].alloc((size_t)cf * 4));
+        if (!dX_keep) B2K_TRY(ctx->slot(b2k_ctx::SLOT_CHUNK_X0 + s, (size_t)cf * row_bytes, (void**)&dX[s]));
+        if (!dL_keep) B2K_TRY(ctx->slot(b2k_ctx::SLOT_CHUNK_L0 + s, (size_t)cf * 4, (void**)&dL[s]));
+        if (metric == B2K_METRIC_MINRMSD) B2K_TRY(ctx->slot(b2k_ctx::SLOT_CHUNK_G0 + s, (size_t)cf * 4, (void**)&dG[s]));
     }
     const bool use_screen = metric == B2K_METRIC_EUCLIDEAN && ctx->engine != B2K_ENGINE_DIRECT &&
                             screen_supported(ctx, d, k, cf);
@@ -342,23 +381,22 @@ B2K_API int b2k_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const
         pend_off[s] = -1;
         const void* src = X + off * d;
         if (!in_pinned) { std::memcpy(ctx->pinned[s], src, (size_t)len * row_bytes); src = ctx->pinned[s]; }
-        cudaMemcpyAsync(dX[s].p, src, (size_t)len * row_bytes, cudaMemcpyHostToDevice, ctx->copy_stream[s]);
+        float* dx = dX_keep ? dX_keep + off * d : dX[s];
+        int32_t* dl = dL_keep ? dL_keep + off : dL[s];
+        cudaMemcpyAsync(dx, src, (size_t)len * row_bytes, cudaMemcpyHostToDevice, ctx->copy_stream[s]);
         cudaEventRecord(ctx->ev_h2d[s], ctx->copy_stream[s]);
         cudaStreamWaitEvent(st, ctx->ev_h2d[s], 0);
         if (use_screen) {
-            rc = screen_prepare_frames(plan, dX[s].as<float>(), len);
-            if (rc == B2K_OK) rc = screen_assign(plan, dX[s].as<float>(), len, dC.as<float>(), dL[s].as<int32_t>(), nullptr, 0);
+            rc = screen_prepare_frames(plan, dx, len);
+            if (rc == B2K_OK) rc = screen_assign(plan, dx, len, dC, dl, nullptr, lloyd);
         } else {
-            if (metric == B2K_METRIC_MINRMSD)
-                rc = launch_rmsd_center(ctx, dX[s].as<float>(), len, d, nullptr, dG[s].as<float>());
-            if (rc == B2K_OK)
-                rc = assign_any(ctx, dX[s].as<float>(), dG[s].as<float>(), len, d, pc, k, metric, dL[s].as<int32_t>(),
-                                nullptr, 0);
+            if (metric == B2K_METRIC_MINRMSD) rc = launch_rmsd_center(ctx, dx, len, d, nullptr, dG[s]);
+            if (rc == B2K_OK) rc = assign_any(ctx, dx, dG[s], len, d, pc, k, metric, dl, nullptr, lloyd);
         }
         cudaEventRecord(ev_k[s], st);
         cudaStreamWaitEvent(ctx->copy_stream[s], ev_k[s], 0);
         void* dst = out_pinned ? (void*)(labels + off) : ctx->pinned_out[s];
-        cudaMemcpyAsync(dst, dL[s].p, (size_t)len * 4, cudaMemcpyDeviceToHost, ctx->copy_stream[s]);
+        cudaMemcpyAsync(dst, dl, (size_t)len * 4, cudaMemcpyDeviceToHost, ctx->copy_stream[s]);
         cudaEventRecord(ctx->ev_done[s], ctx->copy_stream[s]);
         pend_off[s] = off;
         pend_len[s] = len;
@@ -378,6 +416,19 @@ B2K_API int b2k_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(B2K_ERR_CUDA, "assign: %s", cudaGetErrorString(e));
     return B2K_OK;
+}
+
+B2K_API int b2k_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* centers, int32_t k,
+                       int metric, int32_t* labels) {
+    if (!ctx || n < 0 || d < 1 || k < 1 || (n > 0 && (!X || !labels)) || !centers)
+        return set_error(B2K_ERR_INVALID_ARG, "assign: bad arguments (n=%lld d=%d k=%d)", (long long)n, d, k);
+    B2K_TRY(check_metric_dim(metric, d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n == 0) return B2K_OK;
+    float* dC;
+    B2K_TRY(ctx->slot(b2k_ctx::SLOT_CENTERS, (size_t)k * d * 4, (void**)&dC));
+    CUDA_TRY(cudaMemcpyAsync(dC, centers, (size_t)k * d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return stream_assign(ctx, X, n, d, dC, k, metric, labels, 0, nullptr, nullptr);
 }
 
 // ---- Lloyd session ----------------------------------------------------------------------------
@@ -576,29 +627,39 @@ struct HostFrames {  // frames of a host array made resident in HBM
     }
 };
 
+// One Lloyd step from host frames.  The frames stream into HBM chunk by chunk and every chunk is assigned
+// while the next one is still on the bus (stream_assign); the member sums only need the labels and one exact
+// data-range bound, so they run once over the resident array at the end.
 B2K_API int b2k_kmeans_cluster(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* centers, int32_t k,
                                int metric, float* new_centers, int32_t* labels) {
     if (!ctx || !X || !centers || !new_centers || !labels || n < 1 || d < 1 || k < 1)
         return set_error(B2K_ERR_INVALID_ARG, "kmeans_cluster: bad arguments");
     B2K_TRY(check_metric_dim(metric, d));
     CUDA_TRY(cudaSetDevice(ctx->device));
-    HostFrames F;
-    B2K_TRY(F.load(ctx, X, n, d));
-    DevMem dC, dN, dL, acc;
-    B2K_TRY(dC.alloc((size_t)k * d * 4));
-    B2K_TRY(dN.alloc((size_t)k * d * 4));
-    B2K_TRY(dL.alloc((size_t)n * 4));
-    CUDA_TRY(cudaMemcpyAsync(dC.p, centers, (size_t)k * d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    float *dXf, *dC, *dN;
+    int32_t* dL;
+    int64_t* acc;
+    B2K_TRY(ctx->slot(b2k_ctx::SLOT_FRAMES, (size_t)n * d * 4, (void**)&dXf));
+    B2K_TRY(ctx->slot(b2k_ctx::SLOT_CENTERS, (size_t)k * d * 4, (void**)&dC));
+    B2K_TRY(ctx->slot(b2k_ctx::SLOT_CENTERS2, (size_t)k * d * 4, (void**)&dN));
+    B2K_TRY(ctx->slot(b2k_ctx::SLOT_LABELS, (size_t)n * 4, (void**)&dL));
+    B2K_TRY(ctx->slot(b2k_ctx::SLOT_ACC, ((size_t)k * d + k + 1) * 8, (void**)&acc));
+    CUDA_TRY(cudaMemcpyAsync(dC, centers, (size_t)k * d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    B2K_TRY(stream_assign(ctx, X, n, d, dC, k, metric, labels, 1, dXf, dL));
     float absmax = 0.f;
-    B2K_TRY(b2k_dev_absmax(ctx, F.mem.as<float>(), n * d, &absmax));
+    B2K_TRY(b2k_dev_absmax(ctx, dXf, n * d, &absmax));
     b2k_lloyd* s = nullptr;
-    B2K_TRY(b2k_dev_lloyd_create(ctx, F.mem.as<float>(), n, d, k, metric, n, absmax, &s));
-    int rc = acc.alloc((size_t)b2k_dev_lloyd_acc_len(s) * 8);
-    if (rc == B2K_OK) rc = b2k_dev_lloyd_assign_accumulate(s, dC.as<float>(), dL.as<int32_t>(), acc.as<int64_t>());
-    if (rc == B2K_OK) rc = b2k_dev_lloyd_finalize(s, acc.as<int64_t>(), dC.as<float>(), dN.as<float>());
+    const int saved_engine = ctx->engine;
+    ctx->engine = B2K_ENGINE_DIRECT;  // the session is only used for its fixed-point scales here
+    int rc = b2k_dev_lloyd_create(ctx, dXf, n, d, k, metric, n, absmax, &s);
+    ctx->engine = saved_engine;
+    if (rc != B2K_OK) return rc;
+    rc = cudaMemsetAsync(acc, 0, (size_t)b2k_dev_lloyd_acc_len(s) * 8, ctx->stream) == cudaSuccess
+             ? B2K_OK : set_error(B2K_ERR_CUDA, "kmeans_cluster: memset failed");
+    if (rc == B2K_OK) rc = launch_accumulate(ctx, dXf, n, d, k, dL, s->scale_sum, acc);
+    if (rc == B2K_OK) rc = b2k_dev_lloyd_finalize(s, acc, dC, dN);
     if (rc == B2K_OK) {
-        cudaMemcpyAsync(new_centers, dN.p, (size_t)k * d * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(labels, dL.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(new_centers, dN, (size_t)k * d * 4, cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = set_error(B2K_ERR_CUDA, "kmeans_cluster: %s", cudaGetErrorString(e));
     }

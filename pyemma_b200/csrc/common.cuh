@@ -56,6 +56,9 @@ struct b2k_ctx {
     void* pinned_out[2] = {nullptr, nullptr};
     size_t stage_bytes = size_t(64) << 20;
     size_t pinned_cap = 0, pinned_out_cap = 0;
+    // optional CUDA-event timing of the screen kernel launches (option "profile", stats "screen_gemm_ms_*")
+    int profile = 0;
+    std::vector<cudaEvent_t> prof_events;  // start/stop pairs on `stream`
     // options
     int engine = B2K_ENGINE_AUTO;
     int screen_terms = 0;
@@ -65,6 +68,13 @@ struct b2k_ctx {
     // screen plan of the last b2k_assign / b2k_dev_assign call, kept so that chunked assignment does not
     // reallocate the operand buffers for every chunk (owned here, freed by b2k_ctx_destroy)
     void* assign_plan = nullptr;
+    // grow-only device buffers reused by the host-pointer entry points (frames, labels, ...): a 400 MB
+    // cudaMalloc/cudaFree pair per call costs milliseconds and serialises the device
+    enum { SLOT_FRAMES = 0, SLOT_LABELS, SLOT_CENTERS, SLOT_CENTERS2, SLOT_ACC, SLOT_CHUNK_X0, SLOT_CHUNK_X1,
+           SLOT_CHUNK_L0, SLOT_CHUNK_L1, SLOT_CHUNK_G0, SLOT_CHUNK_G1, N_SLOTS };
+    void* slot_ptr[N_SLOTS] = {};
+    size_t slot_cap[N_SLOTS] = {};
+    int slot(int which, size_t bytes, void** out);
     // generic device scratch (grown on demand)
     void* scratch = nullptr;
     size_t scratch_cap = 0;

@@ -110,12 +110,19 @@ static int make_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint64_t cols, 
 
 // ---- prep kernels ---------------------------------------------------------------------------------------
 __device__ __forceinline__ int64_t cdiv_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
-__global__ void screen_mu_kernel(const float* __restrict__ C, int k, int d, float* __restrict__ mu) {
-    const int dim = blockIdx.x * blockDim.x + threadIdx.x;
-    if (dim >= d) return;
+// mu[dim] = mean of the centers (fp64, fixed tree order): one block per dimension
+__global__ void __launch_bounds__(256) screen_mu_kernel(const float* __restrict__ C, int k, int d, float* __restrict__ mu) {
+    __shared__ double part[256];
+    const int dim = blockIdx.x;
     double s = 0;
-    for (int j = 0; j < k; ++j) s += (double)C[(int64_t)j * d + dim];
-    mu[dim] = (float)(s / k);
+    for (int j = threadIdx.x; j < k; j += 256) s += (double)C[(int64_t)j * d + dim];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mu[dim] = (float)(part[0] / k);
 }
 
 // sum_e ((row[e] - mu[e]) * scale)^2 with LPR lanes per row (coalesced for wide rows); any summation order:
@@ -1372,7 +1379,7 @@ int screen_prepare_frames_with_centers(ScreenPlan* p, const float* dX, int64_t n
     cudaStream_t st = ctx->stream;
     if (n > p->n_cap) return set_error(B2K_ERR_INVALID_ARG, "screen plan too small");
     CUDA_TRY(cudaMemsetAsync(p->params, 0, sizeof(ScreenParams), st));
-    screen_mu_kernel<<<(unsigned)cdiv(p->d, 128), 128, 0, st>>>(dC, p->k, p->d, p->mu);
+    screen_mu_kernel<<<(unsigned)p->d, 256, 0, st>>>(dC, p->k, p->d, p->mu);
     LAUNCH_CHECK();
     if (p->d <= 16) {
         screen_maxnorm_kernel<1><<<capped_grid(ctx, n, 256), 256, 0, st>>>(dX, n, p->d, p->mu, &p->params->xmax2_raw);
@@ -1458,8 +1465,19 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
     g.stage_bytes = sp.stage_bytes;
     g.bres_bytes = sp.bres_bytes;
     const unsigned grid = (unsigned)std::min<int64_t>(g.n_tiles, ctx->sm_count);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->profile) {
+        CUDA_TRY(cudaEventCreate(&ev0));
+        CUDA_TRY(cudaEventCreate(&ev1));
+        CUDA_TRY(cudaEventRecord(ev0, st));
+    }
     screen_gemm_kernel<<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, g);
     LAUNCH_CHECK();
+    if (ctx->profile) {
+        CUDA_TRY(cudaEventRecord(ev1, st));
+        ctx->prof_events.push_back(ev0);
+        ctx->prof_events.push_back(ev1);
+    }
     // verify (persistent grids)
     if (p->d <= 16) {
         const int ds = (p->d + 3) & ~3;
