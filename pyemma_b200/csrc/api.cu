@@ -451,6 +451,15 @@ static int ceil_log2_d(double v) {
     return (m == 0.5) ? e - 1 : e;
 }
 
+// fixed-point exponents of the exchange buffer: |x| <= 2^eM, n_total <= 2^eN  =>  |sum| * 2^q < 2^62
+static void lloyd_scales(float absmax_global, int64_t n_total, int d, int* q_sum, int* q_cost) {
+    const int eM = ceil_log2_d((double)absmax_global);
+    const int eN = ceil_log2_d((double)std::max<int64_t>(n_total, 1)) + 1;
+    *q_sum = 62 - eN - eM;
+    // cost terms l^2 <= d * (2M)^2 (1+eps)
+    *q_cost = 61 - eN - (2 * (eM + 1) + ceil_log2_d((double)d));
+}
+
 B2K_API int b2k_dev_lloyd_create(b2k_ctx* ctx, const float* dX, int64_t n_local, int32_t d, int32_t k, int metric,
                                  int64_t n_total, float absmax_global, b2k_lloyd** out) {
     if (!ctx || !out || n_local < 0 || d < 1 || k < 1 || n_total < n_local || (n_local > 0 && !dX))
@@ -461,12 +470,7 @@ B2K_API int b2k_dev_lloyd_create(b2k_ctx* ctx, const float* dX, int64_t n_local,
     CUDA_TRY(cudaSetDevice(ctx->device));
     b2k_lloyd* s = new b2k_lloyd();
     s->ctx = ctx; s->dX = dX; s->n = n_local; s->n_total = n_total; s->d = d; s->k = k; s->metric = metric;
-    // fixed point: |x| <= 2^eM, n_total <= 2^eN  =>  |sum| * 2^q < 2^62
-    const int eM = ceil_log2_d((double)absmax_global);
-    const int eN = ceil_log2_d((double)std::max<int64_t>(n_total, 1)) + 1;
-    s->q_sum = 62 - eN - eM;
-    // cost terms l^2 <= d * (2M)^2 (1+eps)
-    s->q_cost = 61 - eN - (2 * (eM + 1) + ceil_log2_d((double)d));
+    lloyd_scales(absmax_global, n_total, d, &s->q_sum, &s->q_cost);
     s->scale_sum = std::ldexp(1.0, s->q_sum);
     s->scale_cost = std::ldexp(1.0, s->q_cost);
     int rc = s->l.alloc((size_t)std::max<int64_t>(n_local, 1) * 4);
@@ -648,23 +652,16 @@ B2K_API int b2k_kmeans_cluster(b2k_ctx* ctx, const float* X, int64_t n, int32_t 
     B2K_TRY(stream_assign(ctx, X, n, d, dC, k, metric, labels, 1, dXf, dL));
     float absmax = 0.f;
     B2K_TRY(b2k_dev_absmax(ctx, dXf, n * d, &absmax));
-    b2k_lloyd* s = nullptr;
-    const int saved_engine = ctx->engine;
-    ctx->engine = B2K_ENGINE_DIRECT;  // the session is only used for its fixed-point scales here
-    int rc = b2k_dev_lloyd_create(ctx, dXf, n, d, k, metric, n, absmax, &s);
-    ctx->engine = saved_engine;
-    if (rc != B2K_OK) return rc;
-    rc = cudaMemsetAsync(acc, 0, (size_t)b2k_dev_lloyd_acc_len(s) * 8, ctx->stream) == cudaSuccess
-             ? B2K_OK : set_error(B2K_ERR_CUDA, "kmeans_cluster: memset failed");
-    if (rc == B2K_OK) rc = launch_accumulate(ctx, dXf, n, d, k, dL, s->scale_sum, acc);
-    if (rc == B2K_OK) rc = b2k_dev_lloyd_finalize(s, acc, dC, dN);
-    if (rc == B2K_OK) {
-        cudaMemcpyAsync(new_centers, dN, (size_t)k * d * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = set_error(B2K_ERR_CUDA, "kmeans_cluster: %s", cudaGetErrorString(e));
-    }
-    b2k_dev_lloyd_destroy(s);
-    return rc;
+    if (!std::isfinite(absmax)) return set_error(B2K_ERR_NONFINITE, "kmeans_cluster: data contains NaN or inf");
+    int q_sum = 0, q_cost = 0;
+    lloyd_scales(absmax, n, d, &q_sum, &q_cost);
+    const int64_t acc_len = (int64_t)k * d + k + 1;
+    CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)acc_len * 8, ctx->stream));
+    B2K_TRY(launch_accumulate(ctx, dXf, n, d, k, dL, std::ldexp(1.0, q_sum), acc));
+    B2K_TRY(launch_finalize(ctx, acc, k, d, std::ldexp(1.0, -q_sum), dC, dN));
+    CUDA_TRY(cudaMemcpyAsync(new_centers, dN, (size_t)k * d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B2K_OK;
 }
 
 B2K_API int b2k_kmeans_cost(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* centers, int32_t k,

@@ -976,8 +976,8 @@ __global__ void __launch_bounds__(256) screen_verify_small_kernel(const float* _
 // center rows) into a double-buffered shared-memory stage, then every lane advances ITS OWN four interleaved
 // partial sums (Lanes4) over the slab: the reference's summation order is untouched.  Row stride 36 floats
 // (odd multiple of 4): the 16-byte reads of the 8 lanes of a frame hit 8 different bank groups.
-// (A TMA-box variant of this kernel was measured first: 1 KB boxes cost ~40-100 cycles of TMA issue each and
-// left it 3-8x slower than cp.async at the same traffic -- profiles/r01_notes.md.)
+// (A TMA-box variant -- 8 rows x 128 B, SWIZZLE_128B -- ran at the same speed: the limiter is the L2->SM
+// traffic of 8 center rows per candidate group, not the copy mechanism; profiles/r01_notes.md.)
 static constexpr int VC_ROW = 36;                              // floats per staged center row
 static constexpr int VC_FRAME = GROUP * VC_ROW;                // floats per frame's group slab
 static constexpr int VC_STAGE = 4 * VC_FRAME + 4 * 32;         // + the 4 frame slabs

@@ -1,0 +1,221 @@
+"""GPU: the five BASELINE.json configs.
+
+Each config is checked (a) against the CPU oracle on the same seeded inputs at a size the oracle finishes
+in seconds (full k and d, reduced N except cfg1 which runs at full size), bit-exact labels / picks / centers
+as DESIGN.md section 2 states, and (b) at the config's full per-GPU size through size-independent
+properties: the tcgen05 screen engine and the exact CUDA-core engine -- two independent code paths that are
+each oracle-checked at the small size -- must agree on every label, sums must be run-to-run identical, and
+the Lloyd cost must fall.  Shapes: SURVEY.md section 8 notation.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import pyemma_b200 as coor
+
+pytestmark = pytest.mark.gpu
+FULL = os.environ.get("B2K_TEST_FULL", "1") != "0"  # set to 0 to skip the multi-GB property tests
+
+
+def blobs(rng, n, d, nb, spread, sigma, positive=False):
+    cen = rng.uniform(-spread, spread, size=(nb, d))
+    if positive:
+        cen = np.abs(cen) + 0.3
+    lab = rng.randint(0, nb, size=n)
+    return (cen[lab] + sigma * rng.randn(n, d)).astype(np.float32)
+
+
+def three_well(n, seed):
+    rng = np.random.RandomState(seed)
+    cen = np.array([[-1.5, 0.0], [0.0, 1.2], [1.5, 0.0]])
+    s = np.zeros(n, dtype=int)
+    jump = rng.rand(n) < 0.01
+    tgt = rng.randint(0, 3, n)
+    for i in range(1, n):
+        s[i] = tgt[i] if jump[i] else s[i - 1]
+    return (cen[s] + 0.35 * rng.randn(n, 2)).astype(np.float32)
+
+
+def _centers_close(a, b, rtol=1e-5):
+    assert np.abs(a - b).max() <= rtol * np.abs(b).max(), np.abs(a - b).max() / np.abs(b).max()
+
+
+# ---- cfg1: cluster_kmeans k=100 on 2-D three-well, 1e5 frames, kmeans++ fixed_seed (FULL SIZE vs oracle) --------
+def test_cfg1_full_size_end_to_end(oracle):
+    X = three_well(100_000, 1)
+    km = coor.cluster_kmeans(X, k=100, max_iter=10, fixed_seed=42, kmpp_scan="serial", tolerance=1e-5)
+    c0 = oracle.kmpp_init(X, 100, 42, scan="serial")
+    np.testing.assert_array_equal(km.initial_centers_, c0)                       # k-means++ picks bit-exact
+    rc, rcode, rit, rin = oracle.cluster_loop(X, c0, 10, 1e-5, acc="f64", n_threads=8)
+    assert (int(not km.converged), len(km.inertias_)) == (rcode, rit)            # identical iteration count
+    _centers_close(km.clustercenters, rc)                                        # <= 1e-5 relative
+    np.testing.assert_allclose(km.inertias_, rin, rtol=5e-6)
+    np.testing.assert_array_equal(km.dtrajs[0], oracle.assign(X, km.clustercenters, n_threads=8))  # dtrajs bit-exact
+    # blocked scan mode (the parallel one) is bit-exact against the oracle's blocked mode too
+    kb = coor.cluster_kmeans(X, k=100, max_iter=1, fixed_seed=42, kmpp_scan="blocked")
+    np.testing.assert_array_equal(kb.initial_centers_, oracle.kmpp_init(X, 100, 42, scan="blocked"))
+
+
+# ---- cfg2: 1e7 x 10, k=1000, 10 Lloyd iterations ------------------------------------------------------------------
+def test_cfg2_reduced_vs_oracle(oracle, b2k):
+    rng = np.random.RandomState(2)
+    scale = np.sqrt(np.maximum(1.0 - 0.2 * np.arange(10), 0.05))
+    X = (blobs(rng, 200_000, 10, 20, 1.5, 0.6) * scale).astype(np.float32)
+    C0 = X[rng.choice(len(X), 1000, replace=False)].copy()
+    cen, code, iters, inert = b2k.kmeans_cluster_loop(X, C0, 10, 0.0)             # tolerance 0: exactly 10 iterations
+    rc, rcode, rit, rin, hist, rlab = oracle.cluster_loop(X, C0, 10, 0.0, acc="f64", n_threads=8, history=True)
+    assert (code, iters) == (rcode, rit) == (1, 10)
+    _centers_close(cen, rc)
+    np.testing.assert_allclose(inert, rin, rtol=5e-6)
+    # per-iteration parity: one GPU step from the oracle's centers of every iteration
+    for it in (0, 4, 8):
+        newc, lab = b2k.kmeans_cluster(X, hist[it])
+        onew, olab = oracle.kmeans_cluster(X, hist[it], n_threads=8, acc="f64")
+        np.testing.assert_array_equal(lab, olab)
+        _centers_close(newc, onew)
+    np.testing.assert_array_equal(coor.assign_to_centers(X, rc)[0], oracle.assign(X, rc, n_threads=8))
+
+
+# ---- cfg3: 1e8 x 64, k=2000 (1.25e7 per GPU) ---------------------------------------------------------------------
+def test_cfg3_reduced_vs_oracle(oracle, b2k):
+    rng = np.random.RandomState(3)
+    X = blobs(rng, 60_000, 64, 50, 1.0, 0.3, positive=True)
+    C0 = X[rng.choice(len(X), 2000, replace=False)].copy()
+    cen, code, iters, inert = b2k.kmeans_cluster_loop(X, C0, 3, 0.0)
+    rc, rcode, rit, rin = oracle.cluster_loop(X, C0, 3, 0.0, acc="f64", n_threads=8)
+    assert (code, iters) == (rcode, rit)
+    _centers_close(cen, rc)
+    np.testing.assert_array_equal(b2k.assign(X, rc), oracle.assign(X, rc, n_threads=8))
+
+
+# ---- cfg4: 2e7 x 256, k=5000, kmeans++ + assign -------------------------------------------------------------------
+def test_cfg4_reduced_vs_oracle(oracle, b2k):
+    rng = np.random.RandomState(4)
+    X = blobs(rng, 12_000, 256, 200, 10.0, 1.0)
+    # k-means++ at full d, reduced k (5000 rounds x 10 trials are hours on the CPU): both scan modes bit-exact
+    for scan in ("serial", "blocked"):
+        got, gi = b2k.kmeans_init_centers_kmpp(X, 300, 42, scan=scan, return_indices=True)
+        ref, ri = oracle.kmpp_init(X, 300, 42, scan=scan, n_threads=8, return_indices=True)
+        np.testing.assert_array_equal(gi, ri)
+        np.testing.assert_array_equal(got, ref)
+    C5k = X[rng.choice(len(X), 5000, replace=False)].copy()
+    C5k[:2500] += (0.05 * rng.randn(2500, 256)).astype(np.float32)                # near-duplicates: tiny gaps
+    np.testing.assert_array_equal(b2k.assign(X, C5k), oracle.assign(X, C5k, n_threads=8))
+
+
+# ---- cfg5: cluster_regspace + metric='minRMSD' assign, 300 atoms, dmin sweep ------------------------------------
+def _conformations(rng, n, n_atoms, n_templates):
+    T = rng.uniform(-2, 2, size=(n_templates, n_atoms, 3))
+    out = np.empty((n, n_atoms, 3), np.float32)
+    for i in range(n):
+        q = rng.randn(4)
+        q /= np.linalg.norm(q)
+        a, b, c, d = q
+        R = np.array([[a * a + b * b - c * c - d * d, 2 * (b * c - a * d), 2 * (b * d + a * c)],
+                      [2 * (b * c + a * d), a * a - b * b + c * c - d * d, 2 * (c * d - a * b)],
+                      [2 * (b * d - a * c), 2 * (c * d + a * b), a * a - b * b - c * c + d * d]])
+        out[i] = (T[rng.randint(n_templates)] + 0.05 * rng.randn(n_atoms, 3)) @ R.T + rng.uniform(-5, 5, 3)
+    return out.reshape(n, n_atoms * 3)
+
+
+def test_cfg5_reduced_vs_oracle(oracle):
+    rng = np.random.RandomState(5)
+    X = _conformations(rng, 3000, 300, 30)
+    for dmin in (0.05, 0.1, 0.2, 0.4, 0.8):
+        with _nowarn():
+            rs = coor.cluster_regspace(X, dmin=dmin, max_centers=60, metric="minRMSD")
+        ref_c, ref_idx, full = oracle.regspace(X, dmin, 60, "minRMSD", n_threads=8)
+        np.testing.assert_array_equal(rs.clustercenters, ref_c)                   # same frames, same order
+        np.testing.assert_array_equal(rs.dtrajs[0], oracle.assign(X, ref_c, "minRMSD", n_threads=8))
+    # the 30 templates are recovered at a dmin between the noise (0.05*sqrt(3)) and the template spacing
+    rs = coor.cluster_regspace(X, dmin=0.4, max_centers=1000, metric="minRMSD")
+    assert len(rs.clustercenters) == 30
+
+
+class _nowarn:
+    def __enter__(self):
+        import warnings
+        self._cm = warnings.catch_warnings()
+        self._cm.__enter__()
+        warnings.simplefilter("ignore")
+
+    def __exit__(self, *a):
+        return self._cm.__exit__(*a)
+
+
+# ---- full-size properties (device-generated data, no oracle) -----------------------------------------------------
+def _device_blobs(n, d, nb, spread, sigma, seed):
+    import torch
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    means = torch.randn((nb, d), generator=g, device=dev) * spread
+    X = torch.randn((n, d), generator=g, device=dev, dtype=torch.float32)
+    step = 1 << 22
+    for a in range(0, n, step):
+        lab = torch.randint(0, nb, (min(step, n - a),), generator=g, device=dev)
+        X[a:a + step].mul_(sigma).add_(means[lab])
+    return X, g
+
+
+def _engines_agree(b2k, n, d, k, nb, spread, sigma, seed, lloyd_steps=2):
+    import torch
+    ctx = b2k.context()
+    lib = ctx.lib
+    X, g = _device_blobs(n, d, nb, spread, sigma, seed)
+    dev = X.device
+    cur = X[torch.randperm(n, generator=g, device=dev)[:k]].clone()
+    labs = {}
+    costs = {}
+    try:
+        for name, eng in (("screen", b2k.ENGINE_SCREEN), ("direct", b2k.ENGINE_DIRECT)):
+            ctx.set_option("assign_engine", eng)
+            c = cur.clone()
+            lab = torch.empty(n, dtype=torch.int32, device=dev)
+            code, iters = C.c_int(0), C.c_int(0)
+            inert = np.zeros(lloyd_steps, np.float32)
+            torch.cuda.synchronize()
+            b2k.check(lib.b2k_dev_kmeans_cluster_loop(ctx.handle, C.c_void_p(X.data_ptr()), n, d,
+                                                      C.c_void_p(c.data_ptr()), k, 0, lloyd_steps, C.c_float(0.0),
+                                                      b2k.CALLBACK(0), None, C.byref(code), C.byref(iters),
+                                                      C.c_void_p(inert.ctypes.data), lloyd_steps,
+                                                      C.c_void_p(lab.data_ptr())))
+            torch.cuda.synchronize()
+            labs[name] = (lab, c)
+            costs[name] = inert.copy()
+    finally:
+        ctx.set_option("assign_engine", b2k.ENGINE_AUTO)
+    assert bool((labs["screen"][0] == labs["direct"][0]).all())                   # every label identical
+    assert bool((labs["screen"][1] == labs["direct"][1]).all())                   # exact sums -> identical centers
+    np.testing.assert_array_equal(costs["screen"], costs["direct"])
+    assert costs["screen"][-1] <= costs["screen"][0]                              # Lloyd cost does not rise
+    lab = labs["screen"][0]
+    assert int(lab.min()) >= 0 and int(lab.max()) < k
+
+
+@pytest.mark.skipif(not FULL, reason="B2K_TEST_FULL=0")
+def test_cfg2_full_size_engines_agree(b2k):
+    _engines_agree(b2k, 10_000_000, 10, 1000, 20, 1.5, 0.6, seed=2)
+
+
+@pytest.mark.skipif(not FULL, reason="B2K_TEST_FULL=0")
+def test_cfg3_per_gpu_size_engines_agree(b2k):
+    _engines_agree(b2k, 12_500_000, 64, 2000, 50, 1.0, 0.3, seed=3, lloyd_steps=1)
+
+
+@pytest.mark.skipif(not FULL, reason="B2K_TEST_FULL=0")
+def test_cfg4_tenth_size_engines_agree(b2k):
+    # 2e6 x 256 (a tenth of cfg4's frames, full k and d): the exact engine needs ~1 s per pass at this size
+    _engines_agree(b2k, 2_000_000, 256, 5000, 200, 5.0, 1.0, seed=4, lloyd_steps=1)
+
+
+@pytest.mark.skipif(not FULL, reason="B2K_TEST_FULL=0")
+def test_cfg4_full_size_engines_agree(b2k):
+    # 2e7 x 256 fp32 = 20.5 GB of frames + 33 GB of fp16 screen operand; the exact engine needs ~8 s
+    import torch
+    free, _total = torch.cuda.mem_get_info()
+    if free < 90e9:
+        pytest.skip("needs ~90 GB of free HBM")
+    _engines_agree(b2k, 20_000_000, 256, 5000, 200, 5.0, 1.0, seed=44, lloyd_steps=1)
