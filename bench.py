@@ -279,33 +279,45 @@ def main():
                     "frac": achieved_tf / peak_tf, "traffic": None, "kernel": "b2k::assign_small_kernel (exact fp32)",
                     "kernel_ms": ms, "peak_source": peak_src}
 
-    # ---- e2e: C-ABI host-pointer call with pinned host buffers (H2D + step + D2H timed) ----
-    e2e = None
-    if rank == 0 or ws > 1:
-        hx = torch.empty((n, D), dtype=torch.float32, pin_memory=True)
-        hx.copy_(X)
-        hc = cur.cpu().numpy().copy()
-        hl = torch.empty(n, dtype=torch.int32, pin_memory=True)
-        hn = np.empty_like(hc)
-        e2e_steps = max(3, min(args.steps, 8))
+    # ---- e2e: the same Lloyd iteration, but the frames start in PINNED HOST memory every step:
+    #      b2k_stage_assign (H2D chunk by chunk, each chunk assigned while the next is on the bus, labels D2H)
+    #      -> accumulate -> all-reduce -> finalize -> cost -> all-reduce -> cost to the host.
+    hx = torch.empty((n, D), dtype=torch.float32, pin_memory=True)
+    hx.copy_(X)
+    hl = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    e2e_steps = max(3, min(args.steps, 8))
 
-        def e2e_step():
-            _lib.check(lib.b2k_kmeans_cluster(ctx.handle, C.c_void_p(hx.data_ptr()), n, D, C.c_void_p(hc.ctypes.data),
-                                              K, _lib.EUCLIDEAN, C.c_void_p(hn.ctypes.data),
-                                              C.c_void_p(hl.data_ptr())))
-        e2e_step()
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    def e2e_step():
+        nonlocal cur, nxt
+        _lib.check(lib.b2k_stage_assign(ctx.handle, C.c_void_p(hx.data_ptr()), n, D, C.c_void_p(cur.data_ptr()), K,
+                                        _lib.EUCLIDEAN, 1, C.c_void_p(X.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                        C.c_void_p(hl.data_ptr())))
+        _lib.check(lib.b2k_dev_lloyd_accumulate(sess, C.c_void_p(labels.data_ptr()), C.c_void_p(acc.data_ptr())))
         if ws > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n * ws * e2e_steps / float(dt.item()), "unit": "frames/s",
-               "h2d_bytes_per_step": n * D * 4 + K * D * 4, "d2h_bytes_per_step": n * 4 + K * D * 4,
-               "api": "b2k_kmeans_cluster (host pointers, pinned)", "steps": e2e_steps}
+            dist.all_reduce(acc[:acc_len - 1])
+        _lib.check(lib.b2k_dev_lloyd_finalize(sess, C.c_void_p(acc.data_ptr()), C.c_void_p(cur.data_ptr()),
+                                              C.c_void_p(nxt.data_ptr())))
+        _lib.check(lib.b2k_dev_lloyd_cost(sess, C.c_void_p(nxt.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                          C.c_void_p(acc.data_ptr())))
+        if ws > 1:
+            dist.all_reduce(acc[acc_len - 1:])
+        costs.append(lib.b2k_dev_lloyd_decode_cost(sess, int(acc[acc_len - 1].item())))
+        cur, nxt = nxt, cur
+
+    e2e_step()
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if ws > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e = {"value": n * ws * e2e_steps / float(dt.item()), "unit": "frames/s",
+           "h2d_bytes_per_step": n * D * 4, "d2h_bytes_per_step": n * 4 + 8,
+           "api": "b2k_stage_assign (pinned host frames -> HBM + labels back) + b2k_dev_lloyd_accumulate/finalize/cost",
+           "steps": e2e_steps, "ms_per_step": float(dt.item()) / e2e_steps * 1e3}
 
     cpu = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:

@@ -94,6 +94,13 @@ int b2k_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* 
 int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, const float* dcenters, int32_t k,
                    int metric, int32_t* dlabels, float* dmindist_or_null);
 
+/* the gather pass of KmeansClustering._estimate (kmeans.py:220-230, 326-338) fused with the first assignment:
+ * host frames are staged chunk by chunk through pinned memory into the caller's DEVICE array dX_out (n*d floats)
+ * and every chunk is assigned against dcenters while the next one is on the bus; labels go to dlabels_out (device,
+ * n) and, if labels_host_or_null is given, to the host as well.  lloyd != 0: kmeans.cluster label semantics. */
+int b2k_stage_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* dcenters, int32_t k, int metric,
+                     int lloyd, float* dX_out, int32_t* dlabels_out, int32_t* labels_host_or_null);
+
 /* ---- k-means  (deeptime kmeans.cluster / cost_function / cluster_loop; kmeans.py:254-258) */
 /* one Lloyd step: labels from `centers`, new centers = member mean (empty cluster keeps the old) */
 int b2k_kmeans_cluster(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* centers, int32_t k,
@@ -123,6 +130,8 @@ int b2k_dev_lloyd_destroy(b2k_lloyd* s);
 int64_t b2k_dev_lloyd_acc_len(const b2k_lloyd* s);
 /* labels (n_local) <- argmin vs dcenters (Lloyd tie/NaN semantics); acc <- local sums+counts (cost slot zeroed) */
 int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dcenters, int32_t* dlabels, int64_t* dacc);
+/* acc <- local sums+counts for GIVEN labels (e.g. those b2k_stage_assign produced); cost slot zeroed */
+int b2k_dev_lloyd_accumulate(b2k_lloyd* s, const int32_t* dlabels, int64_t* dacc);
 /* new centers from (all-reduced) acc; count==0 keeps old */
 int b2k_dev_lloyd_finalize(b2k_lloyd* s, const int64_t* dacc, const float* dcenters_old, float* dcenters_new);
 /* acc[k*d+k] <- local fixed-point sum of compute(x_i, new_centers[label_i])^2 */

@@ -24,6 +24,7 @@ CALLBACK = C.CFUNCTYPE(None, C.c_void_p)
 SYMBOLS = [
     "b2k_last_error", "b2k_version", "b2k_launch_count", "b2k_ctx_create", "b2k_ctx_destroy", "b2k_ctx_set_stream",
     "b2k_ctx_sync", "b2k_ctx_set_option", "b2k_ctx_get_stat", "b2k_compute_metric", "b2k_assign", "b2k_dev_assign",
+    "b2k_stage_assign", "b2k_dev_lloyd_accumulate",
     "b2k_kmeans_cluster", "b2k_kmeans_cost", "b2k_kmeans_cluster_loop", "b2k_kmeans_init_centers_kmpp",
     "b2k_dev_lloyd_create", "b2k_dev_lloyd_destroy", "b2k_dev_lloyd_acc_len", "b2k_dev_lloyd_assign_accumulate",
     "b2k_dev_lloyd_finalize", "b2k_dev_lloyd_cost", "b2k_dev_lloyd_decode_cost", "b2k_dev_absmax",
@@ -81,6 +82,8 @@ def load():
         L.b2k_dev_lloyd_acc_len.restype = i64
         L.b2k_dev_lloyd_assign_accumulate.argtypes = [vp, vp, vp, vp]
         L.b2k_dev_lloyd_finalize.argtypes = [vp, vp, vp, vp]
+        L.b2k_dev_lloyd_accumulate.argtypes = [vp, vp, vp]
+        L.b2k_stage_assign.argtypes = [vp, vp, i64, i32, vp, i32, C.c_int, C.c_int, vp, vp, vp]
         L.b2k_dev_lloyd_cost.argtypes = [vp, vp, vp, vp]
         L.b2k_dev_lloyd_decode_cost.argtypes = [vp, i64]
         L.b2k_dev_lloyd_decode_cost.restype = C.c_double

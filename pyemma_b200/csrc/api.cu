@@ -352,7 +352,8 @@ static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, con
     const int64_t row_bytes = (int64_t)d * 4;
     int64_t cf = std::max<int64_t>(1, (int64_t)ctx->stage_bytes / row_bytes);
     cf = std::min(cf, n);
-    const bool in_pinned = host_ptr_is_pinned(X), out_pinned = host_ptr_is_pinned(labels);
+    const bool want_host = labels != nullptr;
+    const bool in_pinned = host_ptr_is_pinned(X), out_pinned = !want_host || host_ptr_is_pinned(labels);
     B2K_TRY(ensure_pinned(ctx, in_pinned ? 0 : (size_t)cf * row_bytes, out_pinned ? 0 : (size_t)cf * 4));
     float* dX[2] = {nullptr, nullptr};
     int32_t* dL[2] = {nullptr, nullptr};
@@ -395,8 +396,10 @@ static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, con
         }
         cudaEventRecord(ev_k[s], st);
         cudaStreamWaitEvent(ctx->copy_stream[s], ev_k[s], 0);
-        void* dst = out_pinned ? (void*)(labels + off) : ctx->pinned_out[s];
-        cudaMemcpyAsync(dst, dl, (size_t)len * 4, cudaMemcpyDeviceToHost, ctx->copy_stream[s]);
+        if (want_host) {
+            void* dst = out_pinned ? (void*)(labels + off) : ctx->pinned_out[s];
+            cudaMemcpyAsync(dst, dl, (size_t)len * 4, cudaMemcpyDeviceToHost, ctx->copy_stream[s]);
+        }
         cudaEventRecord(ctx->ev_done[s], ctx->copy_stream[s]);
         pend_off[s] = off;
         pend_len[s] = len;
@@ -429,6 +432,16 @@ B2K_API int b2k_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const
     B2K_TRY(ctx->slot(b2k_ctx::SLOT_CENTERS, (size_t)k * d * 4, (void**)&dC));
     CUDA_TRY(cudaMemcpyAsync(dC, centers, (size_t)k * d * 4, cudaMemcpyHostToDevice, ctx->stream));
     return stream_assign(ctx, X, n, d, dC, k, metric, labels, 0, nullptr, nullptr);
+}
+
+B2K_API int b2k_stage_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* dcenters, int32_t k,
+                             int metric, int lloyd, float* dX_out, int32_t* dlabels_out, int32_t* labels_host) {
+    if (!ctx || n < 0 || d < 1 || k < 1 || !dcenters || (n > 0 && (!X || !dX_out || !dlabels_out)))
+        return set_error(B2K_ERR_INVALID_ARG, "stage_assign: bad arguments (n=%lld d=%d k=%d)", (long long)n, d, k);
+    B2K_TRY(check_metric_dim(metric, d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n == 0) return B2K_OK;
+    return stream_assign(ctx, X, n, d, dcenters, k, metric, labels_host, lloyd, dX_out, dlabels_out);
 }
 
 // ---- Lloyd session ----------------------------------------------------------------------------
@@ -510,6 +523,15 @@ B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32
         B2K_TRY(s->pc.prepare(ctx, dC, s->k, s->d, s->metric));
         B2K_TRY(assign_any(ctx, s->dX, s->Ga.as<float>(), s->n, s->d, s->pc, s->k, s->metric, dlabels, nullptr, 1));
     }
+    return launch_accumulate(ctx, s->dX, s->n, s->d, s->k, dlabels, s->scale_sum, dacc);
+}
+
+B2K_API int b2k_dev_lloyd_accumulate(b2k_lloyd* s, const int32_t* dlabels, int64_t* dacc) {
+    if (!s || !dacc || (s->n > 0 && !dlabels)) return set_error(B2K_ERR_INVALID_ARG, "lloyd accumulate: null argument");
+    b2k_ctx* ctx = s->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemsetAsync(dacc, 0, (size_t)b2k_dev_lloyd_acc_len(s) * 8, ctx->stream));
+    if (s->n == 0) return B2K_OK;
     return launch_accumulate(ctx, s->dX, s->n, s->d, s->k, dlabels, s->scale_sum, dacc);
 }
 
