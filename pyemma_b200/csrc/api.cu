@@ -167,6 +167,16 @@ int b2k_ctx::ensure_scratch(size_t bytes) {
     return B2K_OK;
 }
 
+int b2k_ctx::ensure_scratch2(size_t bytes) {
+    if (bytes <= scratch2_cap) return B2K_OK;
+    if (scratch2) cudaFree(scratch2);
+    scratch2 = nullptr;
+    scratch2_cap = 0;
+    CUDA_TRY(cudaMalloc(&scratch2, bytes));
+    scratch2_cap = bytes;
+    return B2K_OK;
+}
+
 // =================================================================================================
 B2K_API const char* b2k_last_error(void) { return g_last_error.c_str(); }
 B2K_API int b2k_version(void) { return 100; }
@@ -217,6 +227,7 @@ B2K_API int b2k_ctx_destroy(b2k_ctx* c) {
     for (int i = 0; i < b2k_ctx::N_SLOTS; ++i)
         if (c->slot_ptr[i]) cudaFree(c->slot_ptr[i]);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->scratch2) cudaFree(c->scratch2);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return B2K_OK;
@@ -241,6 +252,8 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return set_error(B2K_ERR_INVALID_ARG, "null argument");
     if (!strcmp(name, "assign_engine")) c->engine = (int)value;
     else if (!strcmp(name, "screen_terms")) c->screen_terms = (int)value;
+    else if (!strcmp(name, "accumulate_mode")) c->accumulate_mode = (int)value;
+    else if (!strcmp(name, "cost_kernel")) c->cost_kernel = (int)value;
     else if (!strcmp(name, "profile")) {  // (re)start event timing of the screen kernel launches
         for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
         c->prof_events.clear();

@@ -62,6 +62,8 @@ struct b2k_ctx {
     // options
     int engine = B2K_ENGINE_AUTO;
     int screen_terms = 0;
+    int cost_kernel = 0;      // 0: quad kernel for wide rows, 1: the shared-memory staged variant
+    int accumulate_mode = 0;  // 0: segmented member sums (counting sort by label), 1: one RED per element
     // stats of the last screen call
     double stat_cand_chunks = 0, stat_fallback_frames = 0, stat_screen_frames = 0;
     bool stat_pending = false;
@@ -79,6 +81,9 @@ struct b2k_ctx {
     void* scratch = nullptr;
     size_t scratch_cap = 0;
     int ensure_scratch(size_t bytes);
+    void* scratch2 = nullptr;  // second scratch (per-CTA label histograms of the segmented member sums)
+    size_t scratch2_cap = 0;
+    int ensure_scratch2(size_t bytes);
 };
 
 // ---- device helpers: the exact fp32 arithmetic of the reference path -------------------------

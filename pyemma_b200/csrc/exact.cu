@@ -255,6 +255,204 @@ __global__ void __launch_bounds__(256) labeled_dist_wide_kernel(const float* __r
     }
 }
 
+// wide rows (d > 16): FOUR lanes per frame.  Lane l of the quad owns accumulator lane l of the reference's sum --
+// elements l, l+4, ... in order, the d%4 tail into lane 0 -- and reads exactly those elements straight from
+// global memory (a warp instruction touches 8 rows x 16 contiguous bytes; the other half of every 32-byte sector
+// is consumed by the next iteration out of L1).  No staging, no barriers: enough loads are in flight (8 per lane)
+// to cover the HBM latency.  Closed as ((a0+a1)+a2)+a3 by lane 0 of the quad.
+__global__ void __launch_bounds__(256) labeled_dist_quad_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                                const float* __restrict__ C,
+                                                                const int32_t* __restrict__ labels,
+                                                                float* __restrict__ out) {
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 2;
+    const int l = threadIdx.x & 3;
+    const bool live = i < n;
+    const int64_t ii = live ? i : 0;
+    const float* xr = X + ii * d;
+    const float* cr = C + (int64_t)labels[ii] * d;
+    const int d4 = d & ~3;
+    float acc = 0.f;
+    int e = l;
+    for (; e + 28 < d4; e += 32) {
+        float xv[8], cv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { xv[u] = __ldg(xr + e + 4 * u); cv[u] = __ldg(cr + e + 4 * u); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float t = __fsub_rn(xv[u], cv[u]);
+            acc = __fadd_rn(acc, __fmul_rn(t, t));
+        }
+    }
+    for (; e < d4; e += 4) {
+        const float t = __fsub_rn(__ldg(xr + e), __ldg(cr + e));
+        acc = __fadd_rn(acc, __fmul_rn(t, t));
+    }
+    if (l == 0) {
+        for (int q = d4; q < d; ++q) {
+            const float t = __fsub_rn(__ldg(xr + q), __ldg(cr + q));
+            acc = __fadd_rn(acc, __fmul_rn(t, t));
+        }
+    }
+    const float a1 = __shfl_down_sync(0xffffffffu, acc, 1);
+    const float a2 = __shfl_down_sync(0xffffffffu, acc, 2);
+    const float a3 = __shfl_down_sync(0xffffffffu, acc, 3);
+    if (l == 0 && live) out[i] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, a1), a2), a3));
+}
+
+// 4x4 transpose inside a quad of lanes: lane l holds v[c] = element 4l+c of a 16-element chunk (one coalesced 16-byte
+// load per lane); afterwards lane l holds v[q] = element 4q+l, i.e. the next four addends of accumulator lane l in
+// order.  Two butterfly stages, 4 SHFL + 8 SEL.
+__device__ __forceinline__ void quad_transpose(float (&v)[4], int l) {
+    const bool b0 = l & 1, b1 = l & 2;
+    float ta = __shfl_xor_sync(0xffffffffu, b0 ? v[0] : v[1], 1);
+    float tb = __shfl_xor_sync(0xffffffffu, b0 ? v[2] : v[3], 1);
+    if (b0) { v[0] = ta; v[2] = tb; } else { v[1] = ta; v[3] = tb; }
+    ta = __shfl_xor_sync(0xffffffffu, b1 ? v[0] : v[2], 2);
+    tb = __shfl_xor_sync(0xffffffffu, b1 ? v[1] : v[3], 2);
+    if (b1) { v[0] = ta; v[1] = tb; } else { v[2] = ta; v[3] = tb; }
+}
+
+// d % 4 == 0 and 16-byte aligned rows: the quad reads 64 contiguous bytes per step (full sectors, no reliance on
+// L1), squares the differences where they were loaded -- (x-c)^2 is elementwise, only the ORDER of the additions is
+// pinned -- and transposes the squares so that every accumulator lane receives its addends in reference order.
+__global__ void __launch_bounds__(256) labeled_dist_quad_vec_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                                    const float* __restrict__ C,
+                                                                    const int32_t* __restrict__ labels,
+                                                                    float* __restrict__ out) {
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 2;
+    const int l = threadIdx.x & 3;
+    const bool live = i < n;
+    const int64_t ii = live ? i : 0;
+    const float4* xr = reinterpret_cast<const float4*>(X + ii * d);
+    const float4* cr = reinterpret_cast<const float4*>(C + (int64_t)labels[ii] * d);
+    const int nv = d >> 2;  // float4 per row
+    float acc = 0.f;
+    for (int t0 = 0; t0 < nv; t0 += 16) {  // 4 chunks of 16 elements per trip: 8 loads in flight per lane
+        float4 xv[4], cv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + 4 * u + l;
+            xv[u] = t < nv ? __ldg(xr + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+            cv[u] = t < nv ? __ldg(cr + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (t0 + 4 * u < nv) {  // uniform over the quad
+                float sq[4];
+                float t = __fsub_rn(xv[u].x, cv[u].x); sq[0] = __fmul_rn(t, t);
+                t = __fsub_rn(xv[u].y, cv[u].y); sq[1] = __fmul_rn(t, t);
+                t = __fsub_rn(xv[u].z, cv[u].z); sq[2] = __fmul_rn(t, t);
+                t = __fsub_rn(xv[u].w, cv[u].w); sq[3] = __fmul_rn(t, t);
+                quad_transpose(sq, l);
+                acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, sq[0]), sq[1]), sq[2]), sq[3]);
+            }
+        }
+    }
+    const float a1 = __shfl_down_sync(0xffffffffu, acc, 1);
+    const float a2 = __shfl_down_sync(0xffffffffu, acc, 2);
+    const float a3 = __shfl_down_sync(0xffffffffu, acc, 3);
+    if (l == 0 && live) out[i] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, a1), a2), a3));
+}
+
+// out[j][i] = sqrt(dist2(x_i, rows_j)) for a FEW rows (k-means++ candidates: m = 2 + floor(ln k)).  Quad layout as
+// above, TWO frames per quad.  The m rows sit in shared memory re-ordered per accumulator lane
+// (cs[j][l][s] = row_j[4s+l], lane stride padded by 16 bytes so the four lanes of a quad hit four different bank
+// groups): one 16-byte shared load feeds four steps of a lane's sum for both frames, i.e. 24 fp32 instructions per
+// shared-memory wavefront group -- CUDA-core bound (3 non-fusable instructions per frame, row and dimension), not
+// LDS bound.  VEC (d % 4 == 0, aligned): frames are read with coalesced 16-byte loads and transposed in registers;
+// otherwise lane l reads its own elements and lane 0 adds the d%4 tail.
+template <int MR, bool VEC>
+__global__ void __launch_bounds__(256) dist_rows_quad_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                             const float* __restrict__ rows, int m,
+                                                             float* __restrict__ out, int T) {
+    extern __shared__ __align__(16) float rsm[];
+    const int Tp = T + 4;
+    float* cs = rsm;                          // [m][4][Tp]
+    float* tl = rsm + (size_t)m * 4 * Tp;     // [m][4] tail elements
+    const int d4 = d & ~3;
+    for (int idx = threadIdx.x; idx < m * 4 * T; idx += 256) {
+        const int j = idx / (4 * T), r = idx - j * 4 * T, l = r / T, s = r - l * T;
+        const int e = 4 * s + l;
+        cs[((size_t)j * 4 + l) * Tp + s] = e < d4 ? __ldg(rows + (int64_t)j * d + e) : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < m * 4; idx += 256) {
+        const int j = idx >> 2, e = d4 + (idx & 3);
+        tl[idx] = e < d ? __ldg(rows + (int64_t)j * d + e) : 0.f;
+    }
+    __syncthreads();
+    const int64_t i0 = (((int64_t)blockIdx.x * 256 + threadIdx.x) >> 2) * 2;  // frames i0, i0+1
+    const int l = threadIdx.x & 3;
+    const bool live0 = i0 < n, live1 = i0 + 1 < n;
+    const float* xr0 = X + (live0 ? i0 : 0) * d;
+    const float* xr1 = X + (live1 ? i0 + 1 : 0) * d;
+    const int nv = d >> 2;
+    auto fetch = [&](const float* xr, bool live, int s0, float (&x)[4]) {
+        if (VEC) {
+            const float4 v = (live && s0 + l < nv) ? __ldg(reinterpret_cast<const float4*>(xr) + s0 + l)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int e = 4 * (s0 + q) + l; x[q] = (live && e < d4) ? __ldg(xr + e) : 0.f; }
+        }
+    };
+    for (int j0 = 0; j0 < m; j0 += MR) {
+        float acc0[MR], acc1[MR];
+#pragma unroll
+        for (int jj = 0; jj < MR; ++jj) { acc0[jj] = 0.f; acc1[jj] = 0.f; }
+        float n0[4], n1[4];
+        fetch(xr0, live0, 0, n0);
+        fetch(xr1, live1, 0, n1);
+        for (int s0 = 0; s0 < T; s0 += 4) {
+            float x0[4], x1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { x0[q] = n0[q]; x1[q] = n1[q]; }
+            if (s0 + 4 < T) { fetch(xr0, live0, s0 + 4, n0); fetch(xr1, live1, s0 + 4, n1); }
+            if (VEC) { quad_transpose(x0, l); quad_transpose(x1, l); }
+#pragma unroll
+            for (int jj = 0; jj < MR; ++jj) {
+                if (j0 + jj < m) {
+                    const float4 c = *reinterpret_cast<const float4*>(cs + ((size_t)(j0 + jj) * 4 + l) * Tp + s0);
+                    float t = __fsub_rn(x0[0], c.x), u = __fsub_rn(x1[0], c.x);
+                    float a = __fadd_rn(acc0[jj], __fmul_rn(t, t)), b = __fadd_rn(acc1[jj], __fmul_rn(u, u));
+                    t = __fsub_rn(x0[1], c.y); u = __fsub_rn(x1[1], c.y);
+                    a = __fadd_rn(a, __fmul_rn(t, t)); b = __fadd_rn(b, __fmul_rn(u, u));
+                    t = __fsub_rn(x0[2], c.z); u = __fsub_rn(x1[2], c.z);
+                    a = __fadd_rn(a, __fmul_rn(t, t)); b = __fadd_rn(b, __fmul_rn(u, u));
+                    t = __fsub_rn(x0[3], c.w); u = __fsub_rn(x1[3], c.w);
+                    acc0[jj] = __fadd_rn(a, __fmul_rn(t, t));
+                    acc1[jj] = __fadd_rn(b, __fmul_rn(u, u));
+                }
+            }
+        }
+        if (!VEC && l == 0) {
+            for (int q = 0; q < d - d4; ++q) {
+                const float xv0 = live0 ? __ldg(xr0 + d4 + q) : 0.f, xv1 = live1 ? __ldg(xr1 + d4 + q) : 0.f;
+#pragma unroll
+                for (int jj = 0; jj < MR; ++jj) {
+                    if (j0 + jj < m) {
+                        const float c = tl[(j0 + jj) * 4 + q];
+                        const float t = __fsub_rn(xv0, c), u = __fsub_rn(xv1, c);
+                        acc0[jj] = __fadd_rn(acc0[jj], __fmul_rn(t, t));
+                        acc1[jj] = __fadd_rn(acc1[jj], __fmul_rn(u, u));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < MR; ++jj) {
+            const float a1 = __shfl_down_sync(0xffffffffu, acc0[jj], 1), b1 = __shfl_down_sync(0xffffffffu, acc1[jj], 1);
+            const float a2 = __shfl_down_sync(0xffffffffu, acc0[jj], 2), b2 = __shfl_down_sync(0xffffffffu, acc1[jj], 2);
+            const float a3 = __shfl_down_sync(0xffffffffu, acc0[jj], 3), b3 = __shfl_down_sync(0xffffffffu, acc1[jj], 3);
+            if (l == 0 && j0 + jj < m) {
+                float* o = out + (int64_t)(j0 + jj) * n + i0;
+                if (live0) o[0] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc0[jj], a1), a2), a3));
+                if (live1) o[1] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc1[jj], b1), b2), b3));
+            }
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------------------
 template <int D>
 static int launch_small(b2k_ctx* ctx, const float* X, int64_t n, const float* C, int k, int32_t* labels, float* mind,
@@ -329,12 +527,43 @@ static int launch_tile_gated(b2k_ctx* ctx, const float* X, int64_t n, int d, con
 }
 
 int launch_dist_rows(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out) {
+    if (n <= 0 || m <= 0) return B2K_OK;
+    const int T = std::max(4, (int)cdiv(d / 4, 4) * 4);  // steps per accumulator lane, padded to whole 16-byte loads
+    const size_t smem = ((size_t)m * 4 * (T + 4) + (size_t)m * 4) * 4;
+    if (m <= 32 && smem <= 160 * 1024 && n >= 64) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr_set = true;
+        }
+        const unsigned grid = (unsigned)cdiv(cdiv(n, 2) * 4, 256);
+        const bool vec = (d % 4 == 0) && (((uintptr_t)X) & 15) == 0;
+        if (vec && m <= 8) dist_rows_quad_kernel<8, true><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T);
+        else if (vec) dist_rows_quad_kernel<16, true><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T);
+        else if (m <= 8) dist_rows_quad_kernel<8, false><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T);
+        else dist_rows_quad_kernel<16, false><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T);
+        LAUNCH_CHECK();
+        return B2K_OK;
+    }
     return launch_tile(ctx, X, n, d, rows, m, nullptr, out, 0, MODE_ALL);
 }
 
 int launch_labeled_dist(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, const int32_t* labels,
                         float* out) {
     if (n <= 0) return B2K_OK;
+    if (d > 16 && ctx->cost_kernel != 1 && d % 4 == 0 && ((((uintptr_t)X) | ((uintptr_t)C)) & 15) == 0) {
+        labeled_dist_quad_vec_kernel<<<(unsigned)cdiv(n * 4, 256), 256, 0, ctx->stream>>>(X, n, d, C, labels, out);
+        LAUNCH_CHECK();
+        return B2K_OK;
+    }
+    if (d > 16 && ctx->cost_kernel != 1) {
+        labeled_dist_quad_kernel<<<(unsigned)cdiv(n * 4, 256), 256, 0, ctx->stream>>>(X, n, d, C, labels, out);
+        LAUNCH_CHECK();
+        return B2K_OK;
+    }
     if (d > 16) {
         const int dpad = (d + 3) & ~3;
         const int rsb = ((dpad / 4) % 2 == 1) ? dpad : dpad + 4;

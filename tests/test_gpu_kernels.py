@@ -135,7 +135,9 @@ def test_cluster_loop_converges_trivial(b2k, oracle):
 
 @pytest.mark.parametrize("scan", ["serial", "blocked"])
 @pytest.mark.parametrize("n,d,k,metric", [(3000, 2, 20, "euclidean"), (1500, 10, 40, "euclidean"),
-                                          (1100, 70, 12, "euclidean"), (300, 45, 6, "minRMSD")])
+                                          (1100, 70, 12, "euclidean"), (300, 45, 6, "minRMSD"),
+                                          (5000, 5, 3000, "euclidean"), (2500, 33, 1200, "euclidean"),
+                                          (2000, 3, 150, "euclidean"), (4000, 64, 3000, "euclidean")])
 def test_kmpp_bit_exact(b2k, oracle, scan, n, d, k, metric):
     rng = np.random.RandomState(n)
     X = blobs(rng, n, d, 5)
@@ -179,3 +181,74 @@ def test_regspace_max_centers(b2k, oracle):
         h.partial_fit(X)
     np.testing.assert_array_equal(h.centers(), ref)
     h.close()
+
+
+# ---- member sums: segmented (counting sort by label + warp run sums) == one RED per element == numpy integers -----
+SEG_SHAPES = [(70000, 1, 5), (40000, 2, 100), (30000, 3, 1), (20000, 10, 1000), (9000, 17, 64), (5000, 64, 2000),
+              (3000, 100, 13000), (1500, 256, 50), (800, 300, 40), (300, 1030, 7)]
+
+
+@pytest.mark.parametrize("n,d,k", SEG_SHAPES)
+def test_member_sums_segmented_exact(b2k, n, d, k):
+    import ctypes as C
+    import torch
+    rng = np.random.RandomState(n + d)
+    X = (rng.randn(n, d) * 3).astype(np.float32)
+    lab = rng.randint(0, k, n).astype(np.int32)
+    lab[::97] = -1                                   # frames without a label are skipped
+    run = rng.randint(0, n - 40)
+    lab[run:run + 40] = lab[run]                     # a run of equal neighbours (warp-aggregated scatter)
+    ctx = b2k.context()
+    dev = torch.device("cuda", ctx.device)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    Xd, ld = torch.from_numpy(X).to(dev), torch.from_numpy(lab).to(dev)
+    am = float(np.abs(X).max())
+    sess = C.c_void_p()
+    b2k.check(ctx.lib.b2k_dev_lloyd_create(ctx.handle, C.c_void_p(Xd.data_ptr()), n, d, k, 0, n, C.c_float(am),
+                                           C.byref(sess)))
+    got = {}
+    try:
+        acc_len = int(ctx.lib.b2k_dev_lloyd_acc_len(sess))
+        for mode in (0, 1):
+            ctx.set_option("accumulate_mode", mode)
+            acc = torch.full((acc_len,), 7, dtype=torch.int64, device=dev)
+            b2k.check(ctx.lib.b2k_dev_lloyd_accumulate(sess, C.c_void_p(ld.data_ptr()), C.c_void_p(acc.data_ptr())))
+            torch.cuda.synchronize()
+            got[mode] = acc.cpu().numpy()
+    finally:
+        ctx.set_option("accumulate_mode", 0)
+        ctx.lib.b2k_dev_lloyd_destroy(sess)
+    np.testing.assert_array_equal(got[0], got[1])
+    # independent integer reference: q such that |sum| * 2^q < 2^62 (api.cu lloyd_scales)
+    def clog2(v):
+        m, e = np.frexp(v)
+        return int(e - 1 if m == 0.5 else e)
+    q = 62 - (clog2(float(n)) + 1) - clog2(am)
+    fx = np.rint(X.astype(np.float64) * 2.0 ** q).astype(np.int64)
+    ok = lab >= 0
+    sums = np.zeros((k, d), np.int64)
+    np.add.at(sums, lab[ok], fx[ok])
+    np.testing.assert_array_equal(got[0][:k * d].reshape(k, d), sums)
+    np.testing.assert_array_equal(got[0][k * d:k * d + k], np.bincount(lab[ok], minlength=k))
+    assert got[0][-1] == 0
+
+
+@pytest.mark.parametrize("n,d,k", [(5000, 17, 30), (4001, 64, 200), (3000, 70, 9), (1000, 256, 50), (700, 301, 12)])
+def test_cost_wide_rows_kernels_agree(b2k, oracle, n, d, k):
+    """the 4-lanes-per-frame cost kernel and the shared-memory staged one evaluate every l_i in the reference
+    order: identical fixed-point sums, and both match the oracle's cost."""
+    rng = np.random.RandomState(d)
+    X = blobs(rng, n, d, 6)
+    Cn = X[rng.choice(n, k, replace=False)].copy() + np.float32(0.01)
+    lab = oracle.assign(X, Cn, n_threads=4)
+    ctx = b2k.context()
+    vals = []
+    try:
+        for mode in (0, 1):
+            ctx.set_option("cost_kernel", mode)
+            vals.append(b2k.kmeans_cost(X, Cn, lab))
+    finally:
+        ctx.set_option("cost_kernel", 0)
+    assert vals[0].tobytes() == vals[1].tobytes()
+    ref = oracle.cost(X, Cn, lab, acc="f64")
+    assert abs(float(vals[0]) - float(ref)) <= 2e-7 * float(ref)
