@@ -254,6 +254,7 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "screen_terms")) c->screen_terms = (int)value;
     else if (!strcmp(name, "accumulate_mode")) c->accumulate_mode = (int)value;
     else if (!strcmp(name, "cost_kernel")) c->cost_kernel = (int)value;
+    else if (!strcmp(name, "rmsd_kernel")) c->rmsd_kernel = (int)value;
     else if (!strcmp(name, "profile")) {  // (re)start event timing of the screen kernel launches
         for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
         c->prof_events.clear();

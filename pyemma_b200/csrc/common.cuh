@@ -62,6 +62,7 @@ struct b2k_ctx {
     // options
     int engine = B2K_ENGINE_AUTO;
     int screen_terms = 0;
+    int rmsd_kernel = 0;      // 0: slab-streaming QCP kernel, 1: whole-row tile kernel
     int cost_kernel = 0;      // 0: quad kernel for wide rows, 1: the shared-memory staged variant
     int accumulate_mode = 0;  // 0: segmented member sums (counting sort by label), 1: one RED per element
     // stats of the last screen call

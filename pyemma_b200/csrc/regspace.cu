@@ -180,10 +180,8 @@ B2K_API int b2k_regspace_get_centers(b2k_regspace* r, float* centers_out) {
     return B2K_OK;
 }
 
-B2K_API int b2k_dev_regspace_partial_fit(b2k_regspace* r, const float* dX, int64_t n) {
-    if (!r) return set_error(B2K_ERR_INVALID_ARG, "null handle");
-    if (r->full) return set_error(B2K_ERR_MAX_CENTERS, "Maximum number of cluster centers reached (%lld).", (long long)r->max_centers);
-    if (n <= 0) return B2K_OK;
+// one sub-chunk of frames (the algorithm is streaming: feeding a chunk in pieces gives the same centers)
+static int reg_fit_piece(b2k_regspace* r, const float* dX, int64_t n) {
     b2k_ctx* ctx = r->ctx;
     cudaStream_t st = ctx->stream;
     const int d = r->d;
@@ -238,6 +236,22 @@ B2K_API int b2k_dev_regspace_partial_fit(b2k_regspace* r, const float* dX, int64
     if (hs.status == 4) {
         r->full = true;
         return set_error(B2K_ERR_MAX_CENTERS, "Maximum number of cluster centers reached (%lld).", (long long)r->max_centers);
+    }
+    return B2K_OK;
+}
+
+B2K_API int b2k_dev_regspace_partial_fit(b2k_regspace* r, const float* dX, int64_t n) {
+    if (!r) return set_error(B2K_ERR_INVALID_ARG, "null handle");
+    if (r->full) return set_error(B2K_ERR_MAX_CENTERS, "Maximum number of cluster centers reached (%lld).", (long long)r->max_centers);
+    if (n <= 0) return B2K_OK;
+    CUDA_TRY(cudaSetDevice(r->ctx->device));
+    // Every ordered step evaluates the distance of ALL frames of the piece to the new center, so the piece is kept
+    // to ~64 MB of frames: a step then costs a few launches, and a max_centers stop does not pay for the frames
+    // behind it.  Frames that die against the known centers (pass 1) are the bulk of the work either way.
+    const int64_t piece = std::max<int64_t>(16384, std::min<int64_t>(int64_t(1) << 22, (int64_t(64) << 20) / ((int64_t)r->d * 4)));
+    for (int64_t off = 0; off < n; off += piece) {
+        const int rc = reg_fit_piece(r, dX + off * r->d, std::min(piece, n - off));
+        if (rc != B2K_OK) return rc;
     }
     return B2K_OK;
 }

@@ -259,6 +259,147 @@ __global__ void __launch_bounds__(128) rmsd_tile_kernel(const float* __restrict_
     }
 }
 
+// ---- slab kernel: 32 frames x 8*CPT centers per CTA, atoms streamed in slabs of 16 -----------------------------
+// The tile kernel above stages whole rows (3.6 KB for 300 atoms), which leaves one 128-thread CTA per SM and a
+// barrier between every load and compute phase.  Here a CTA of 256 threads (lane = frame, warp = center slot, CPT
+// centers per thread) walks the atoms in slabs of 16 (192 bytes per row): the slab of step t+1 is copied with
+// cp.async while step t is being summed, the 36 lane sums of every pair stay in registers across slabs, and 20 KB
+// of shared memory per CTA lets two CTAs share an SM.  Per 4 atoms a warp issues 3 conflict-free 16-byte loads
+// of its frames, 3*CPT broadcast loads of its centers and 72*CPT fp32 instructions: CUDA-core bound.
+// The per-pair arithmetic (Cov36 lane order, qcp_msd) is the one of the tile kernel, so results are identical.
+static constexpr int RS_ATOMS = 16;               // atoms per slab
+static constexpr int RS_ROW = RS_ATOMS * 3;       // floats per slab row
+static constexpr int RS_XROW = RS_ROW + 4;        // padded frame row: 13 x 16 B -> conflict-free 16-byte loads
+
+__device__ __forceinline__ void rs_cp16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+
+template <int MODE, int CPT, bool ALIGNED>
+__global__ void __launch_bounds__(256, 2) rmsd_slab_kernel(const float* __restrict__ X, const float* __restrict__ Ga,
+                                                           int64_t n, int d, const float* __restrict__ Cc,
+                                                           const float* __restrict__ Gb, int k,
+                                                           int32_t* __restrict__ labels, float* __restrict__ out,
+                                                           int lloyd) {
+    constexpr int KT = 8 * CPT;
+    constexpr int STAGE = 32 * RS_XROW + KT * RS_ROW;
+    __shared__ __align__(16) float sm[2 * STAGE];
+    __shared__ float red_s[256];
+    __shared__ int32_t red_j[256];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t base = (int64_t)blockIdx.x * 32;
+    const int n_atoms = d / 3;
+    const int n_slabs = (n_atoms + RS_ATOMS - 1) / RS_ATOMS;
+    const int n_ctiles = (k + KT - 1) / KT;
+    const int64_t fi = base + lane;
+    const bool fvalid = fi < n;
+    const float ga = fvalid ? Ga[fi] : 0.f;
+
+    // copy the slab of step (center tile jt, slab sl) into stage buffer `buf`
+    auto stage = [&](int jt, int sl, int buf) {
+        float* xs = sm + buf * STAGE;
+        float* cs = xs + 32 * RS_XROW;
+        const int col0 = sl * RS_ROW;
+        for (int t = tid; t < 32 * (RS_ROW / 4); t += 256) {
+            const int r = t / (RS_ROW / 4), c4 = t - r * (RS_ROW / 4);
+            const int col = col0 + c4 * 4;
+            float* dst = xs + r * RS_XROW + c4 * 4;
+            const int64_t row = base + r;
+            if (ALIGNED && row < n && col + 4 <= d) rs_cp16(dst, X + row * d + col);
+            else {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = (row < n && col + e < d) ? __ldg(X + row * d + col + e) : 0.f;
+                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+        for (int t = tid; t < KT * (RS_ROW / 4); t += 256) {
+            const int r = t / (RS_ROW / 4), c4 = t - r * (RS_ROW / 4);
+            const int col = col0 + c4 * 4;
+            float* dst = cs + r * RS_ROW + c4 * 4;
+            const int j = jt * KT + r;
+            if (ALIGNED && j < k && col + 4 <= d) rs_cp16(dst, Cc + (int64_t)j * d + col);
+            else {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = (j < k && col + e < d) ? __ldg(Cc + (int64_t)j * d + col + e) : 0.f;
+                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    ArgMin am;
+    am.init();
+    const int steps = n_ctiles * n_slabs;
+    stage(0, 0, 0);
+    Cov36 cov[CPT];
+    int jt = 0, sl = 0;
+    for (int step = 0; step < steps; ++step) {
+        const int buf = step & 1;
+        int njt = jt, nsl = sl + 1;
+        if (nsl == n_slabs) { nsl = 0; njt = jt + 1; }
+        if (step + 1 < steps) {
+            stage(njt, nsl, buf ^ 1);  // the other buffer was released by the barrier that ended step-1
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();  // this step's slab is visible to every thread
+        if (sl == 0) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) cov[c].init();
+        }
+        const float* xr = sm + buf * STAGE + lane * RS_XROW;
+        const float* cr = sm + buf * STAGE + 32 * RS_XROW + (w * CPT) * RS_ROW;
+#pragma unroll
+        for (int q = 0; q < RS_ATOMS / 4; ++q) {
+            const float4 x0 = *reinterpret_cast<const float4*>(xr + 12 * q);
+            const float4 x1 = *reinterpret_cast<const float4*>(xr + 12 * q + 4);
+            const float4 x2 = *reinterpret_cast<const float4*>(xr + 12 * q + 8);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const float4 c0 = *reinterpret_cast<const float4*>(cr + c * RS_ROW + 12 * q);
+                const float4 c1 = *reinterpret_cast<const float4*>(cr + c * RS_ROW + 12 * q + 4);
+                const float4 c2 = *reinterpret_cast<const float4*>(cr + c * RS_ROW + 12 * q + 8);
+                cov[c].template atom<0>(x0.x, x0.y, x0.z, c0.x, c0.y, c0.z);
+                cov[c].template atom<1>(x0.w, x1.x, x1.y, c0.w, c1.x, c1.y);
+                cov[c].template atom<2>(x1.z, x1.w, x2.x, c1.z, c1.w, c2.x);
+                cov[c].template atom<3>(x2.y, x2.z, x2.w, c2.y, c2.z, c2.w);
+            }
+        }
+        if (sl == n_slabs - 1) {  // the pairs of this center tile are complete
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int j = jt * KT + w * CPT + c;
+                if (j < k && fvalid) {
+                    float M[9];
+                    cov[c].finish(M);
+                    const float s = qcp_msd(M, ga, Gb[j], n_atoms);
+                    if (MODE == MODE_ARGMIN) am.offer(s, j);
+                    else out[(int64_t)j * n + fi] = __fsqrt_rn(s);
+                }
+            }
+        }
+        __syncthreads();  // everyone is done reading `buf` before the next iteration refills it
+        jt = njt;
+        sl = nsl;
+    }
+    if (MODE == MODE_ARGMIN) {
+        red_s[tid] = am.s;
+        red_j[tid] = am.j;
+        __syncthreads();
+        if (w == 0) {
+            for (int g = 1; g < 8; ++g) am.merge(red_s[g * 32 + lane], red_j[g * 32 + lane]);
+            if (fvalid) {
+                labels[fi] = (lloyd && am.j < 0) ? 0 : am.j;
+                if (out) out[fi] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) rmsd_labeled_kernel(const float* __restrict__ X,
                                                            const float* __restrict__ Ga, int64_t n, int d,
                                                            const float* __restrict__ Cc,
@@ -281,6 +422,22 @@ int launch_rmsd_center(b2k_ctx* ctx, const float* src, int64_t m, int d, float* 
 static int launch_rtile(b2k_ctx* ctx, const float* X, const float* Ga, int64_t n, int d, const float* Cc,
                         const float* Gb, int k, int32_t* labels, float* out, int lloyd, int mode) {
     if (n <= 0 || k <= 0) return B2K_OK;
+    if (ctx->rmsd_kernel != 1 && n >= 32) {
+        const unsigned grid = (unsigned)cdiv(n, 32);
+        const bool al = (d % 4 == 0) && ((((uintptr_t)X) | ((uintptr_t)Cc)) & 15) == 0;
+#define B2K_RS(MODE_, CPT_, AL_) \
+    rmsd_slab_kernel<MODE_, CPT_, AL_><<<grid, 256, 0, ctx->stream>>>(X, Ga, n, d, Cc, Gb, k, labels, out, lloyd)
+        if (mode == MODE_ARGMIN) {
+            if (k > 8) { if (al) B2K_RS(MODE_ARGMIN, 2, true); else B2K_RS(MODE_ARGMIN, 2, false); }
+            else { if (al) B2K_RS(MODE_ARGMIN, 1, true); else B2K_RS(MODE_ARGMIN, 1, false); }
+        } else {
+            if (k > 8) { if (al) B2K_RS(MODE_ALL, 2, true); else B2K_RS(MODE_ALL, 2, false); }
+            else { if (al) B2K_RS(MODE_ALL, 1, true); else B2K_RS(MODE_ALL, 1, false); }
+        }
+#undef B2K_RS
+        LAUNCH_CHECK();
+        return B2K_OK;
+    }
     const size_t budget = std::min<size_t>(ctx->smem_optin, 200 * 1024);
     RTileCfg cfg = rtile_cfg(d, k, budget);
     if (cfg.smem > ctx->smem_optin)

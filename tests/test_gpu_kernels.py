@@ -252,3 +252,25 @@ def test_cost_wide_rows_kernels_agree(b2k, oracle, n, d, k):
     assert vals[0].tobytes() == vals[1].tobytes()
     ref = oracle.cost(X, Cn, lab, acc="f64")
     assert abs(float(vals[0]) - float(ref)) <= 2e-7 * float(ref)
+
+
+def test_regspace_multi_piece_chunk(b2k, oracle):
+    """a chunk larger than the ~64 MB piece the device pass works on (d=1100 -> 16384-frame pieces): same centers,
+    same order as the oracle's single pass; and the max_centers stop still keeps exactly max_centers centers."""
+    rng = np.random.RandomState(77)
+    d, n = 1100, 35000
+    cen = rng.uniform(-1, 1, size=(40, d))
+    X = (cen[rng.randint(0, 40, n)] + 0.01 * rng.randn(n, d)).astype(np.float32)
+    dmin = 5.0                                         # blob spacing ~ sqrt(2/3*1100) = 27, blob radius ~ 0.47
+    h = b2k.RegspaceHandle(d, dmin, 1000)
+    h.partial_fit(X)
+    ref_c, ref_idx, full = oracle.regspace(X, dmin, 1000, "euclidean", n_threads=8)
+    assert not full and len(ref_c) == 40
+    np.testing.assert_array_equal(h.centers(), ref_c)
+    h.close()
+    h = b2k.RegspaceHandle(d, 0.1, 25)                 # every frame is a new center -> stops in the first piece
+    with pytest.raises(b2k.MaxCentersReachedException):
+        h.partial_fit(X)
+    assert h.n_centers == 25
+    np.testing.assert_array_equal(h.centers(), X[:25])
+    h.close()
