@@ -61,6 +61,10 @@ typedef struct b2k_ctx b2k_ctx;
 typedef struct b2k_lloyd b2k_lloyd;
 typedef struct b2k_regspace b2k_regspace;
 typedef void (*b2k_callback)(void* user);
+/* all-reduce callback of the sharded k-means++: reduce the first `count` elements of exchange buffer `buffer_id`
+ * (0: the float buffer, 1: the int64 buffer) over all ranks, op 0 = sum(f32), 1 = max(i64), 2 = min(i64); the
+ * library has synchronised its stream before the call and reads the buffer on its stream afterwards; return 0 */
+typedef int (*b2k_exchange_fn)(void* user, int buffer_id, int64_t count, int op);
 
 const char* b2k_last_error(void);
 int b2k_version(void);
@@ -152,6 +156,17 @@ int b2k_dev_kmeans_cluster_loop(b2k_ctx* ctx, const float* dX, int64_t n, int32_
 int b2k_dev_kmeans_init_centers_kmpp(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, int32_t k, int metric,
                                      int64_t seed, int scan_mode, b2k_callback cb, void* user, float* dcenters_out,
                                      int64_t* chosen_host_or_null);
+
+/* k-means++ (blocked scan mode) over frames SHARDED across ranks: every rank passes its shard (global index of its
+ * first frame `global_lo`, a multiple of 1024; n_local may be 0), two caller-owned DEVICE exchange buffers
+ * (xchg_f32 with at least b2k_kmpp_exchange_floats(n_total, d, k) floats, xchg_i64 with 32 int64) and the
+ * all-reduce callback.  Every rank receives the same k centers; picks are bit-identical to the single-GPU call. */
+int64_t b2k_kmpp_exchange_floats(int64_t n_total, int32_t d, int32_t k);
+int b2k_dev_kmeans_init_centers_kmpp_sharded(b2k_ctx* ctx, const float* dX, int64_t n_local, int32_t d, int32_t k,
+                                             int metric, int64_t seed, int64_t global_lo, int64_t n_total,
+                                             float* xchg_f32, int64_t xchg_f32_len, int64_t* xchg_i64,
+                                             b2k_exchange_fn exchange, void* exchange_user, b2k_callback cb,
+                                             void* user, float* dcenters_out, int64_t* chosen_host_or_null);
 
 /* ---- regspace  (deeptime regspace.cluster; regspace.py:144-151) -------------------------- */
 int b2k_regspace_create(b2k_ctx* ctx, int32_t d, float dmin, int64_t max_centers, int metric, b2k_regspace** out);

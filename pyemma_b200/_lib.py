@@ -19,6 +19,7 @@ ENGINE_AUTO, ENGINE_DIRECT, ENGINE_SCREEN = 0, 1, 2
 METRICS = {"euclidean": EUCLIDEAN, "minRMSD": MINRMSD}
 
 CALLBACK = C.CFUNCTYPE(None, C.c_void_p)
+EXCHANGE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int)  # b2k_exchange_fn
 
 # every symbol include/b2k.h declares (tests/test_cabi_symbols.py checks the .so exports all of them)
 SYMBOLS = [
@@ -30,7 +31,8 @@ SYMBOLS = [
     "b2k_dev_lloyd_finalize", "b2k_dev_lloyd_cost", "b2k_dev_lloyd_decode_cost", "b2k_dev_absmax",
     "b2k_dev_all_finite", "b2k_dev_kmeans_cluster_loop", "b2k_dev_kmeans_init_centers_kmpp", "b2k_regspace_create",
     "b2k_regspace_destroy", "b2k_regspace_partial_fit", "b2k_dev_regspace_partial_fit", "b2k_regspace_n_centers",
-    "b2k_regspace_get_centers", "b2k_regspace_cluster",
+    "b2k_regspace_get_centers", "b2k_regspace_cluster", "b2k_kmpp_exchange_floats",
+    "b2k_dev_kmeans_init_centers_kmpp_sharded",
 ]
 
 
@@ -93,6 +95,10 @@ def load():
                                                   vp, i32, vp]
         L.b2k_dev_kmeans_init_centers_kmpp.argtypes = [vp, vp, i64, i32, i32, C.c_int, i64, C.c_int, CALLBACK, vp, vp,
                                                        vp]
+        L.b2k_kmpp_exchange_floats.argtypes = [i64, i32, i32]
+        L.b2k_kmpp_exchange_floats.restype = i64
+        L.b2k_dev_kmeans_init_centers_kmpp_sharded.argtypes = [vp, vp, i64, i32, i32, C.c_int, i64, i64, i64, vp, i64, vp,
+                                                               EXCHANGE, vp, CALLBACK, vp, vp, vp]
         L.b2k_regspace_create.argtypes = [vp, i32, f32, i64, C.c_int, C.POINTER(vp)]
         L.b2k_regspace_destroy.argtypes = [vp]
         L.b2k_regspace_partial_fit.argtypes = [vp, vp, i64]

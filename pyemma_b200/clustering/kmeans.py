@@ -164,18 +164,21 @@ class KmeansClustering(AbstractClustering):
             idx = np.random.RandomState(self.fixed_seed).randint(0, total_length, size=k)
             centers = self._rows_by_global_index(idx, d, dev)
         else:
-            if ws > 1:
-                raise NotImplementedError("k-means++ over sharded frames is not implemented yet: pass "
-                                          "clustercenters= or use init_strategy='uniform' in multi-GPU runs")
             scan = self.kmpp_scan
             if scan == "auto":
-                scan = "serial" if total_length <= 20000 else "blocked"
+                scan = "serial" if (total_length <= 20000 and ws == 1) else "blocked"
             centers = torch.empty((k, d), dtype=torch.float32, device=dev)
             cb = self._callback(lambda: None) if self.show_progress else _lib.CALLBACK(0)
-            _lib.check(lib.b2k_dev_kmeans_init_centers_kmpp(
-                ctx.handle, C.c_void_p(X.data_ptr()), n_local, d, k, metric, int(self.fixed_seed),
-                _lib.KMPP_SERIAL if scan == "serial" else _lib.KMPP_BLOCKED, cb, None,
-                C.c_void_p(centers.data_ptr()), None))
+            if ws > 1:
+                if scan == "serial":
+                    raise ValueError("kmpp_scan='serial' follows the frame order of ONE array; sharded (multi-GPU) "
+                                     "k-means++ uses the blocked scan")
+                self._kmpp_sharded(ctx, X, d, k, metric, total_length, centers, cb)
+            else:
+                _lib.check(lib.b2k_dev_kmeans_init_centers_kmpp(
+                    ctx.handle, C.c_void_p(X.data_ptr()), n_local, d, k, metric, int(self.fixed_seed),
+                    _lib.KMPP_SERIAL if scan == "serial" else _lib.KMPP_BLOCKED, cb, None,
+                    C.c_void_p(centers.data_ptr()), None))
             self.initial_centers_ = centers.cpu().numpy()
         if resume:
             self.initial_centers_ = np.array(self.clustercenters, dtype=np.float32)
@@ -203,6 +206,33 @@ class KmeansClustering(AbstractClustering):
         cb = _lib.CALLBACK(lambda _u: fn())
         self._dev_cb_keepalive = cb
         return cb
+
+    def _kmpp_sharded(self, ctx, X, d, k, metric, n_total, centers, cb):
+        """k-means++ over frames sharded across the ranks: the library runs the rounds, this side only
+        all-reduces the two exchange buffers when asked (4 small exchanges per round, NCCL)."""
+        import torch.distributed as dist
+        dev = X.device
+        lib = ctx.lib
+        nf = int(lib.b2k_kmpp_exchange_floats(n_total, d, k))
+        xf = torch.zeros(max(nf, 1), dtype=torch.float32, device=dev)
+        xi = torch.zeros(32, dtype=torch.int64, device=dev)
+        ops = {0: dist.ReduceOp.SUM, 1: dist.ReduceOp.MAX, 2: dist.ReduceOp.MIN}
+        stream = torch.cuda.current_stream(dev)
+
+        def exchange(_user, which, count, op):
+            try:
+                dist.all_reduce((xf if which == 0 else xi)[:count], op=ops[op])
+                stream.synchronize()
+                return 0
+            except Exception:  # never unwind through the C frame
+                self.logger.exception("k-means++ exchange failed")
+                return 1
+
+        fn = _lib.EXCHANGE(exchange)
+        _lib.check(lib.b2k_dev_kmeans_init_centers_kmpp_sharded(
+            ctx.handle, C.c_void_p(X.data_ptr()), X.shape[0], d, k, metric, int(self.fixed_seed), int(self._dev_lo),
+            int(n_total), C.c_void_p(xf.data_ptr()), xf.numel(), C.c_void_p(xi.data_ptr()), fn, None, cb, None,
+            C.c_void_p(centers.data_ptr()), None))
 
     def _rows_by_global_index(self, idx, d, dev):
         """rows of the (sharded) frame array by global frame index, replicated on every rank"""

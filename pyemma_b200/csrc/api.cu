@@ -22,6 +22,10 @@ int set_error(int code, const char* fmt, ...) {
 int kmpp_run(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int metric, int64_t seed, int scan_mode,
              b2k_callback cb, void* user, float* dcenters_out, int64_t* chosen_host);
 
+int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int metric, int64_t seed, int64_t lo,
+                     int64_t n_total, float* xf, int64_t xf_len, int64_t* xi, b2k_exchange_fn ex, void* exuser,
+                     b2k_callback cb, void* user, float* dcenters_out, int64_t* chosen_host);
+
 struct DevMem {
     void* p = nullptr;
     size_t cap = 0;
@@ -764,6 +768,27 @@ B2K_API int b2k_dev_kmeans_init_centers_kmpp(b2k_ctx* ctx, const float* dX, int6
     B2K_TRY(check_metric_dim(metric, d));
     CUDA_TRY(cudaSetDevice(ctx->device));
     return kmpp_run(ctx, dX, n, d, k, metric, seed, scan_mode, cb, user, dcenters_out, chosen_host);
+}
+
+B2K_API int64_t b2k_kmpp_exchange_floats(int64_t n_total, int32_t d, int32_t k) {
+    if (n_total < 1 || d < 1 || k < 1) return 0;
+    const int64_t m = 2 + (int64_t)std::log((double)k);
+    return std::max<int64_t>(m * cdiv(n_total, 1024), m * (int64_t)d);
+}
+
+B2K_API int b2k_dev_kmeans_init_centers_kmpp_sharded(b2k_ctx* ctx, const float* dX, int64_t n_local, int32_t d,
+                                                     int32_t k, int metric, int64_t seed, int64_t global_lo,
+                                                     int64_t n_total, float* xchg_f32, int64_t xchg_f32_len,
+                                                     int64_t* xchg_i64, b2k_exchange_fn exchange, void* exchange_user,
+                                                     b2k_callback cb, void* user, float* dcenters_out,
+                                                     int64_t* chosen_host) {
+    if (!ctx || !dcenters_out || n_local < 0 || d < 1 || n_total < 1 || global_lo < 0 || global_lo + n_local > n_total ||
+        (n_local > 0 && !dX) || !exchange || !xchg_f32 || !xchg_i64)
+        return set_error(B2K_ERR_INVALID_ARG, "init_centers_kmpp_sharded: bad arguments");
+    B2K_TRY(check_metric_dim(metric, d));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return kmpp_run_blocked(ctx, dX, n_local, d, k, metric, seed, global_lo, n_total, xchg_f32, xchg_f32_len, xchg_i64,
+                            exchange, exchange_user, cb, user, dcenters_out, chosen_host);
 }
 
 B2K_API int b2k_kmeans_init_centers_kmpp(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, int32_t k, int metric,

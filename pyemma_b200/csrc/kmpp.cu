@@ -286,6 +286,100 @@ __global__ void kmpp_tree_pick_kernel(TreeLevels T, const unsigned char* __restr
     st->cand[j] = (node < n && !taken[node]) ? node : -1;
 }
 
+// Sharded form of the pick: the levels at height >= 10 are global (replicated on every rank, because every
+// height-10 node lies inside one shard), the levels below are local.  Phase A (every rank, identical result)
+// descends from max(H,10) to the height-10 node -- starting above H only meets zero right siblings, and
+// r = root*u <= root always goes left there, so the walk equals the one from H; phase B (the owner of that node)
+// finishes the descent in its shard.
+__global__ void kmpp_pick_top_kernel(TreeLevels T, int Hs, KmppState* st, const float* __restrict__ u, int m,
+                                     long long* __restrict__ node10, float* __restrict__ resid) {
+    __shared__ float root;
+    if (threadIdx.x == 0) {
+        root = tree_node_sum(T, nullptr, Hs, 0);
+        st->dist_sum = root;
+        st->n_cand = m;
+    }
+    __syncthreads();
+    const int j = threadIdx.x;
+    if (j >= m) return;
+    float r = __fmul_rn(root, u[j]);
+    st->rands[j] = r;
+    long long node = 0;
+    for (int h = Hs; h > 10; --h) {
+        const float left = tree_node_sum(T, nullptr, h - 1, 2 * node);
+        if (r <= left) node = 2 * node;
+        else { r = __fsub_rn(r, left); node = 2 * node + 1; }
+    }
+    node10[j] = node;
+    resid[j] = r;
+}
+
+// local levels: T.lv[0] = D (n_local), T.lv[1] = L5 (local); node10_lo = index of this shard's first height-10 node
+__global__ void kmpp_pick_leaf_kernel(TreeLevels T, const unsigned char* __restrict__ taken, int64_t n_local,
+                                      long long node10_lo, long long lo, const long long* __restrict__ node10,
+                                      const float* __restrict__ resid, int m, long long* __restrict__ cand_out) {
+    const int j = threadIdx.x;
+    if (j >= m) return;
+    long long node = node10[j] - node10_lo;
+    long long c = -1;
+    if (node >= 0 && node * 1024 < n_local) {
+        float r = resid[j];
+        for (int h = 10; h > 0; --h) {
+            const float left = tree_node_sum(T, taken, h - 1, 2 * node);
+            if (r <= left) node = 2 * node;
+            else { r = __fsub_rn(r, left); node = 2 * node + 1; }
+        }
+        if (node < n_local && !taken[node]) c = lo + node;
+    }
+    cand_out[j] = c;
+}
+
+__global__ void kmpp_set_cands_kernel(KmppState* st, const long long* __restrict__ cand, int m) {
+    if (threadIdx.x < m) st->cand[threadIdx.x] = cand[threadIdx.x];
+}
+
+// rows[j] = X[cand_j - lo] when this shard owns the candidate, else zeros (the ranks' rows are summed)
+__global__ void kmpp_gather_sharded_kernel(const float* __restrict__ X, int d, const long long* __restrict__ cand,
+                                           long long lo, int64_t n_local, float* __restrict__ rows) {
+    const int j = blockIdx.x;
+    const long long c = cand[j] - lo;
+    const bool mine = cand[j] >= 0 && c >= 0 && c < n_local;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) rows[(int64_t)j * d + e] = mine ? X[c * d + e] : 0.f;
+}
+
+// contribution of local frame i to candidate j's potential; candidates are GLOBAL indices
+__global__ void kmpp_contrib_sharded_kernel(float* __restrict__ cd, int64_t n, int m, const float* __restrict__ D,
+                                            const unsigned char* __restrict__ taken,
+                                            const long long* __restrict__ cand, long long lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool tk = taken[i] != 0;
+    const float di = D[i];
+    for (int j = 0; j < m; ++j) {
+        const long long c = cand[j];
+        float out = 0.f;
+        if (!tk && c >= 0 && c != lo + i) {
+            const float v = cd[(int64_t)j * n + i];
+            const float dd = __fmul_rn(v, v);
+            out = (dd < di) ? dd : di;
+        }
+        cd[(int64_t)j * n + i] = out;
+    }
+}
+
+__global__ void kmpp_commit_sharded_kernel(long long best, long long lo, int64_t n_local, const float* __restrict__ row,
+                                           int d, unsigned char* __restrict__ taken, float* __restrict__ center_out) {
+    for (int e = threadIdx.x; e < d; e += blockDim.x) center_out[e] = row[e];
+    const long long b = best - lo;
+    if (threadIdx.x == 0 && b >= 0 && b < n_local) taken[b] = 1;
+}
+
+__global__ void kmpp_first_free_sharded_kernel(const unsigned char* __restrict__ taken, int64_t n, long long lo,
+                                               long long* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !taken[i]) atomicMin((unsigned long long*)out, (unsigned long long)(lo + i));
+}
+
 // roots of m trees: the first stored level (height 10, 20 or 30) that has a single entry IS the
 // root (the levels above the true height only add zeros, and v + 0 == v exactly)
 __global__ void kmpp_tree_roots_kernel(const float* __restrict__ lv, int64_t stride, int m, float* __restrict__ out) {
@@ -344,10 +438,17 @@ struct DevBuf {
 
 static int pow2_height(int64_t n) { int h = 0; while ((int64_t(1) << h) < n) ++h; return h; }
 
+int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int metric, int64_t seed, int64_t lo,
+                     int64_t n_total, float* xf, int64_t xf_len, int64_t* xi, b2k_exchange_fn ex, void* exuser,
+                     b2k_callback cb, void* user, float* dcenters_out, int64_t* chosen_host);
+
 int kmpp_run(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int metric, int64_t seed, int scan_mode,
              b2k_callback cb, void* user, float* dcenters_out, int64_t* chosen_host) {
     if (k < 1 || k > n) return set_error(B2K_ERR_INVALID_ARG, "k-means++: need 1 <= k <= n (k=%d, n=%lld)", k, (long long)n);
     if (metric == B2K_METRIC_MINRMSD && d % 3) return set_error(B2K_ERR_DIM_NOT_MULT3, "RMSDMetric is only implemented for input data with a dimension divisible by 3.");
+    if (scan_mode == B2K_KMPP_BLOCKED)
+        return kmpp_run_blocked(ctx, dX, n, d, k, metric, seed, 0, n, nullptr, 0, nullptr, nullptr, nullptr, cb, user,
+                                dcenters_out, chosen_host);
     const int m = 2 + (int)std::log((double)k);
     if (m > KMPP_MAX_TRIALS) return set_error(B2K_ERR_INVALID_ARG, "k too large");
     cudaStream_t st = ctx->stream;
@@ -522,6 +623,235 @@ int kmpp_run(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int metric,
                 kmpp_serial_sum_kernel<<<1, 256, 0, st>>>(delta, n, 1, pots);
                 LAUNCH_CHECK();
                 kmpp_add_delta_kernel<<<1, 1, 0, st>>>(S, pots);
+                LAUNCH_CHECK();
+            }
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (chosen_host) std::memcpy(chosen_host, chosen.data(), sizeof(int64_t) * k);
+    for (int i = 0; i < k; ++i)
+        if (chosen[i] < 0) return set_error(B2K_ERR_INVALID_ARG, "k-means++ could not find %d centers", k);
+    return B2K_OK;
+}
+
+// ---- BLOCKED mode driver, optionally over a shard of the frames ---------------------------------------------------
+// Single GPU: lo = 0, n_total = n_local, ex = null.  Sharded: every rank calls this with its shard (lo a multiple
+// of 1024 so that no height-10 tree node straddles two shards), an exchange buffer pair the caller owns and the
+// callback that all-reduces it.  Per round: [sum] the height-10 sums of D, [max] the candidates' frame indices,
+// [sum] the candidate rows, [sum] the height-10 sums of the m contribution arrays.  Every exchanged sum only ever
+// adds zeros to the one owner's value, so all ranks hold bit-identical trees and take identical decisions.
+int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int metric, int64_t seed, int64_t lo,
+                     int64_t n_total, float* xf, int64_t xf_len, int64_t* xi, b2k_exchange_fn ex, void* exuser,
+                     b2k_callback cb, void* user, float* dcenters_out, int64_t* chosen_host) {
+    if (k < 1 || k > n_total)
+        return set_error(B2K_ERR_INVALID_ARG, "k-means++: need 1 <= k <= n (k=%d, n=%lld)", k, (long long)n_total);
+    if (metric == B2K_METRIC_MINRMSD && d % 3) return set_error(B2K_ERR_DIM_NOT_MULT3, "RMSDMetric is only implemented for input data with a dimension divisible by 3.");
+    if (n > 0 && lo % 1024)  // an empty shard owns no tree node: its offset does not matter
+        return set_error(B2K_ERR_INVALID_ARG, "k-means++: shard offset must be a multiple of 1024");
+    const int m = 2 + (int)std::log((double)k);
+    if (m > KMPP_MAX_TRIALS) return set_error(B2K_ERR_INVALID_ARG, "k too large");
+    cudaStream_t st = ctx->stream;
+    const int H = pow2_height(n_total);
+    if (H > 30) return set_error(B2K_ERR_INVALID_ARG, "n too large");
+    const int Hs = std::max(H, 10);
+    const int64_t n10g = cdiv(n_total, 1024), n15g = cdiv(n10g, 32), n20g = cdiv(n10g, 1024), n25g = cdiv(n20g, 32),
+                  n30g = cdiv(n20g, 1024);
+    const int64_t n5 = cdiv(std::max<int64_t>(n, 1), 32), n10 = cdiv(n, 1024);  // local
+    const int64_t node_lo = lo / 1024;
+    const int64_t need_f = std::max<int64_t>((int64_t)m * n10g, (int64_t)m * d);
+    DevBuf bXf, bXi;
+    if (!ex) {  // single GPU: the "exchange" buffers are private
+        B2K_TRY(bXf.alloc((size_t)need_f * 4));
+        B2K_TRY(bXi.alloc(64 * 8));
+        xf = bXf.as<float>();
+        xi = bXi.as<int64_t>();
+    } else if (!xf || !xi || xf_len < need_f) {
+        return set_error(B2K_ERR_INVALID_ARG, "k-means++: exchange buffer too small (need %lld floats)", (long long)need_f);
+    }
+    auto exchange = [&](int which, int64_t count, int op) -> int {
+        if (!ex) return B2K_OK;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (ex(exuser, which, count, op) != 0) return set_error(B2K_ERR_CUDA, "k-means++: exchange callback failed");
+        return B2K_OK;
+    };
+
+    // RNG stream (data independent, identical on every rank)
+    uint32_t s32;
+    if (seed < 0) { std::random_device rd; s32 = rd(); } else s32 = (uint32_t)seed;
+    MT19937 gen(s32);
+    const int64_t first = (int64_t)gen.below((uint64_t)n_total);
+    std::vector<float> u((size_t)(k > 1 ? (k - 1) : 1) * m);
+    for (size_t t = 0; t < (size_t)(k - 1) * m; ++t) u[t] = gen.unit();
+
+    DevBuf bD, bTaken, bCd, bRows, bRowsC, bGb, bGa, bU, bState, bPots, bL5, bL10g, bL15, bL20, bL25, bL30, bP20, bP30,
+        bNode, bResid;
+    const int64_t nn = std::max<int64_t>(n, 1);
+    B2K_TRY(bD.alloc(nn * 4));
+    B2K_TRY(bTaken.alloc(nn));
+    B2K_TRY(bCd.alloc((size_t)m * nn * 4));
+    B2K_TRY(bRows.alloc((size_t)m * d * 4));
+    B2K_TRY(bU.alloc(u.size() * 4));
+    B2K_TRY(bState.alloc(sizeof(KmppState)));
+    B2K_TRY(bPots.alloc(KMPP_MAX_TRIALS * 4));
+    B2K_TRY(bL5.alloc(n5 * 4));
+    B2K_TRY(bL10g.alloc(n10g * 4)); B2K_TRY(bL15.alloc(n15g * 4)); B2K_TRY(bL20.alloc(n20g * 4));
+    B2K_TRY(bL25.alloc(n25g * 4)); B2K_TRY(bL30.alloc(n30g * 4));
+    B2K_TRY(bP20.alloc((size_t)m * n20g * 4)); B2K_TRY(bP30.alloc((size_t)m * n30g * 4));
+    B2K_TRY(bNode.alloc(KMPP_MAX_TRIALS * 8)); B2K_TRY(bResid.alloc(KMPP_MAX_TRIALS * 4));
+    float* D = bD.as<float>();
+    unsigned char* taken = bTaken.as<unsigned char>();
+    float* cd = bCd.as<float>();
+    float* rows = bRows.as<float>();
+    KmppState* S = bState.as<KmppState>();
+    float* pots = bPots.as<float>();
+    long long* xil = reinterpret_cast<long long*>(xi);
+    CUDA_TRY(cudaMemcpyAsync(bU.p, u.data(), u.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(S, 0, sizeof(KmppState), st));
+
+    float* Ga = nullptr;
+    if (metric == B2K_METRIC_MINRMSD) {
+        B2K_TRY(bGa.alloc(nn * 4));
+        B2K_TRY(bRowsC.alloc((size_t)m * d * 4));
+        B2K_TRY(bGb.alloc(m * 4));
+        Ga = bGa.as<float>();
+        B2K_TRY(launch_rmsd_center(ctx, dX, n, d, nullptr, Ga));
+    }
+    auto dist_rows = [&](const float* R, int mm, float* out) -> int {
+        if (n <= 0) return B2K_OK;
+        if (metric == B2K_METRIC_MINRMSD) {
+            B2K_TRY(launch_rmsd_center(ctx, R, mm, d, bRowsC.as<float>(), bGb.as<float>()));
+            return launch_rmsd_dist_rows(ctx, dX, Ga, n, d, bRowsC.as<float>(), bGb.as<float>(), mm, out);
+        }
+        return launch_dist_rows(ctx, dX, n, d, R, mm, out);
+    };
+    // rows of the frames with the global indices xil[0..mm) -> `rows` on every rank
+    auto fetch_rows = [&](int mm) -> int {
+        if (!ex) {
+            kmpp_gather_sharded_kernel<<<mm, 128, 0, st>>>(dX, d, xil, lo, n, rows);
+            LAUNCH_CHECK();
+            return B2K_OK;
+        }
+        kmpp_gather_sharded_kernel<<<mm, 128, 0, st>>>(dX, d, xil, lo, n, xf);
+        LAUNCH_CHECK();
+        B2K_TRY(exchange(0, (int64_t)mm * d, 0));
+        CUDA_TRY(cudaMemcpyAsync(rows, xf, (size_t)mm * d * 4, cudaMemcpyDeviceToDevice, st));
+        return B2K_OK;
+    };
+    // upper levels (heights 15..30) of mm trees whose height-10 sums are l10 (stride n10g)
+    auto tree_top = [&](const float* l10, int mm, float* l15, float* l20, float* l25, float* l30) -> int {
+        if (Hs > 10) {
+            tree_up_kernel<<<dim3((unsigned)n20g, mm), 1024, 0, st>>>(l10, n10g, n10g, nullptr, l15, n15g, l20, n20g);
+            LAUNCH_CHECK();
+        }
+        if (Hs > 20) {
+            tree_up_kernel<<<dim3((unsigned)n30g, mm), 1024, 0, st>>>(l20, n20g, n20g, nullptr, l25, n25g, l30, n30g);
+            LAUNCH_CHECK();
+        }
+        return B2K_OK;
+    };
+
+    // ---- first center ----
+    std::vector<int64_t> chosen((size_t)k, -1);
+    chosen[0] = first;
+    CUDA_TRY(cudaMemcpyAsync(xi, &first, 8, cudaMemcpyHostToDevice, st));
+    B2K_TRY(fetch_rows(1));
+    CUDA_TRY(cudaMemcpyAsync(dcenters_out, rows, (size_t)d * 4, cudaMemcpyDeviceToDevice, st));
+    if (cb) { CUDA_TRY(cudaStreamSynchronize(st)); cb(user); }
+    if (k == 1) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (chosen_host) chosen_host[0] = first;
+        return B2K_OK;
+    }
+    B2K_TRY(dist_rows(dcenters_out, 1, cd));
+    if (n > 0) {
+        kmpp_square_init_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cd, n, first - lo, D, taken);
+        LAUNCH_CHECK();
+    }
+
+    TreeLevels T;
+    T.H = H;
+    T.lv[0] = D; T.len[0] = n;
+    T.lv[1] = bL5.as<float>(); T.len[1] = n5;
+    T.lv[2] = bL10g.as<float>(); T.len[2] = n10g;
+    T.lv[3] = bL15.as<float>(); T.len[3] = n15g;
+    T.lv[4] = bL20.as<float>(); T.len[4] = n20g;
+    T.lv[5] = bL25.as<float>(); T.len[5] = n25g;
+    T.lv[6] = bL30.as<float>(); T.len[6] = n30g;
+
+    KmppState hs;
+    for (int found = 1; found < k; ++found) {
+        const float* ur = bU.as<float>() + (size_t)(found - 1) * m;
+        // ---- tree over D: local heights 5 and 10, [sum] height 10, replicated upper levels ----
+        float* l10 = ex ? xf : bL10g.as<float>();
+        if (ex) CUDA_TRY(cudaMemsetAsync(xf, 0, (size_t)n10g * 4, st));
+        if (n > 0) {
+            tree_up_kernel<<<dim3((unsigned)n10, 1), 1024, 0, st>>>(D, n, n, taken, bL5.as<float>(), n5, l10 + node_lo, n10g);
+            LAUNCH_CHECK();
+        }
+        if (ex) {
+            B2K_TRY(exchange(0, n10g, 0));
+            CUDA_TRY(cudaMemcpyAsync(bL10g.p, xf, (size_t)n10g * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        B2K_TRY(tree_top(bL10g.as<float>(), 1, bL15.as<float>(), bL20.as<float>(), bL25.as<float>(), bL30.as<float>()));
+        // ---- candidates ----
+        kmpp_pick_top_kernel<<<1, 32, 0, st>>>(T, Hs, S, ur, m, bNode.as<long long>(), bResid.as<float>());
+        LAUNCH_CHECK();
+        kmpp_pick_leaf_kernel<<<1, 32, 0, st>>>(T, taken, n, node_lo, lo, bNode.as<long long>(), bResid.as<float>(), m, xil);
+        LAUNCH_CHECK();
+        B2K_TRY(exchange(1, m, 1));
+        kmpp_set_cands_kernel<<<1, 32, 0, st>>>(S, xil, m);
+        LAUNCH_CHECK();
+        B2K_TRY(fetch_rows(m));  // reads xil; `rows` valid on every rank afterwards
+        // ---- potentials ----
+        B2K_TRY(dist_rows(rows, m, cd));
+        if (ex) CUDA_TRY(cudaMemsetAsync(xf, 0, (size_t)m * n10g * 4, st));
+        if (n > 0) {
+            kmpp_contrib_sharded_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cd, n, m, D, taken, S->cand, lo);
+            LAUNCH_CHECK();
+            tree_up_kernel<<<dim3((unsigned)n10, m), 1024, 0, st>>>(cd, n, n, nullptr, nullptr, 0, xf + node_lo, n10g);
+            LAUNCH_CHECK();
+        }
+        B2K_TRY(exchange(0, (int64_t)m * n10g, 0));
+        B2K_TRY(tree_top(xf, m, nullptr, bP20.as<float>(), nullptr, bP30.as<float>()));
+        {
+            const float* lv = Hs <= 10 ? xf : (Hs <= 20 ? bP20.as<float>() : bP30.as<float>());
+            const int64_t stride = Hs <= 10 ? n10g : (Hs <= 20 ? n20g : n30g);
+            kmpp_tree_roots_kernel<<<1, 32, 0, st>>>(lv, stride, m, pots);
+            LAUNCH_CHECK();
+        }
+        kmpp_select_kernel<<<1, 32, 0, st>>>(S, pots, m, taken, n);
+        LAUNCH_CHECK();
+        CUDA_TRY(cudaMemcpyAsync(&hs, S, sizeof(KmppState), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        long long best = hs.best;
+        int jbest = hs.jbest;
+        const float* best_row = rows + (size_t)(jbest >= 0 ? jbest : 0) * d;
+        if (best < 0) {  // "if for some reason we did not find a best candidate, take the next available point"
+            long long init = 0x7fffffffffffffffll;
+            CUDA_TRY(cudaMemcpyAsync(xi, &init, 8, cudaMemcpyHostToDevice, st));
+            if (n > 0) {
+                kmpp_first_free_sharded_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(taken, n, lo, xil);
+                LAUNCH_CHECK();
+            }
+            B2K_TRY(exchange(1, 1, 2));
+            CUDA_TRY(cudaMemcpyAsync(&best, xi, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (best == init) break;
+            jbest = -1;
+            B2K_TRY(fetch_rows(1));
+            best_row = rows;
+        }
+        chosen[found] = best;
+        kmpp_commit_sharded_kernel<<<1, 128, 0, st>>>(best, lo, n, best_row, d, taken, dcenters_out + (size_t)found * d);
+        LAUNCH_CHECK();
+        if (cb) cb(user);
+        if (found + 1 < k && n > 0) {
+            if (jbest >= 0) {
+                kmpp_update_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(D, taken, n, cd + (size_t)jbest * n, 0, nullptr);
+                LAUNCH_CHECK();
+            } else {
+                B2K_TRY(dist_rows(dcenters_out + (size_t)found * d, 1, cd));
+                kmpp_update_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(D, taken, n, cd, 1, nullptr);
                 LAUNCH_CHECK();
             }
         }

@@ -30,11 +30,18 @@ def world():
     return 0, 1
 
 
+SHARD_ALIGN = 1024  # frames; a height-10 node of the k-means++ sum tree never straddles two shards
+
+
 def shard_bounds(n_total, rank, world_size):
-    """Contiguous frame range [lo, hi) owned by `rank` (frames are independent: SURVEY 8e)."""
-    base, rem = divmod(int(n_total), int(world_size))
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+    """Contiguous frame range [lo, hi) owned by `rank` (frames are independent: SURVEY 8e).  Shards are equal up
+    to SHARD_ALIGN frames and every shard starts at a multiple of SHARD_ALIGN (the sharded k-means++ needs that);
+    trailing ranks of a tiny data set may own nothing."""
+    n_total, world_size = int(n_total), int(world_size)
+    per = -(-n_total // world_size)                       # ceil
+    per = -(-per // SHARD_ALIGN) * SHARD_ALIGN if world_size > 1 else per
+    lo = min(rank * per, n_total)
+    return lo, min(lo + per, n_total)
 
 
 class PinnedStager:

@@ -274,3 +274,66 @@ def test_regspace_multi_piece_chunk(b2k, oracle):
     assert h.n_centers == 25
     np.testing.assert_array_equal(h.centers(), X[:25])
     h.close()
+
+
+@pytest.mark.parametrize("n,d,k,shards", [(5000, 3, 40, 2), (40000, 10, 300, 3), (2100, 64, 25, 4)])
+def test_kmpp_sharded_matches_single(b2k, oracle, n, d, k, shards):
+    """b2k_dev_kmeans_init_centers_kmpp_sharded with the shards driven by threads of one process (each its own
+    context/stream on the same GPU; the all-reduce callback is a host-side reduction behind a barrier): picks are
+    bit-identical to the oracle's blocked scan, i.e. to the single-GPU call."""
+    import ctypes as C
+    import threading
+    import torch
+    from pyemma_b200.staging import shard_bounds
+    rng = np.random.RandomState(n)
+    X = blobs(rng, n, d, 7)
+    ref, ridx = oracle.kmpp_init(X, k, 42, scan="blocked", return_indices=True)
+    dev = torch.device("cuda", 0)
+    lib = b2k.load()
+    nf = int(lib.b2k_kmpp_exchange_floats(n, d, k))
+    bar = threading.Barrier(shards)
+    host = {"f": [None] * shards, "i": [None] * shards}
+    results, errors = [None] * shards, []
+
+    def run(rank):
+        try:
+            ctx = b2k.Context(0)
+            lo, hi = shard_bounds(n, rank, shards)
+            Xd = torch.from_numpy(X[lo:hi].copy()).to(dev)
+            xf = torch.zeros(max(nf, 1), dtype=torch.float32, device=dev)
+            xi = torch.zeros(32, dtype=torch.int64, device=dev)
+            cen = torch.empty((k, d), dtype=torch.float32, device=dev)
+            chosen = np.full(k, -1, np.int64)
+
+            def exchange(_u, which, count, op):
+                t, key = (xf, "f") if which == 0 else (xi, "i")
+                ctx.sync()
+                host[key][rank] = t[:count].cpu().numpy()
+                bar.wait()
+                parts = np.stack(host[key])
+                red = parts.sum(0, dtype=parts.dtype) if op == 0 else (parts.max(0) if op == 1 else parts.min(0))
+                bar.wait()
+                t[:count].copy_(torch.from_numpy(red))
+                torch.cuda.synchronize()
+                return 0
+
+            fn = b2k.EXCHANGE(exchange)
+            b2k.check(lib.b2k_dev_kmeans_init_centers_kmpp_sharded(
+                ctx.handle, C.c_void_p(Xd.data_ptr()), hi - lo, d, k, 0, 42, lo, n, C.c_void_p(xf.data_ptr()),
+                xf.numel(), C.c_void_p(xi.data_ptr()), fn, None, b2k.CALLBACK(0), None, C.c_void_p(cen.data_ptr()),
+                C.c_void_p(chosen.ctypes.data)))
+            results[rank] = (cen.cpu().numpy(), chosen)
+            ctx.close()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+            bar.abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(shards)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert not errors, errors
+    for cen, chosen in results:
+        np.testing.assert_array_equal(chosen, ridx)
+        np.testing.assert_array_equal(cen, ref)

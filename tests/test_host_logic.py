@@ -118,7 +118,9 @@ def test_shard_bounds_cover_everything():
         b = [shard_bounds(n, r, w) for r in range(w)]
         assert b[0][0] == 0 and b[-1][1] == n
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
-        assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+        assert all(l % 1024 == 0 or l == n for l, h in b)          # k-means++ tree alignment
+        if n >= 1024 * w * 8:
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1024 * w
 
 
 def _gloo_worker(rank, ws, port, q):
@@ -152,6 +154,26 @@ def _gloo_worker(rank, ws, port, q):
     newc = np.where(cnt[:, None] > 0, (acc.numpy()[:k * d].reshape(k, d) / scale) / np.maximum(cnt, 1)[:, None], old)
     ok = ok and bool((newc[k - 1] == 9.0).all())  # empty cluster keeps its old center
     ok = ok and np.allclose(newc[0], X[labels == 0].astype(np.float64).mean(0), rtol=1e-12)
+    # ---- sharded k-means++ exchange (kmpp.cu kmpp_run_blocked): height-10 sums of the balanced fp32 sum tree are
+    # owned by exactly one rank (shards start at multiples of 1024), so all-reduce(sum) over zero-filled buffers
+    # reproduces the single-array tree level bit for bit, and all-reduce(max) publishes the owner's candidate
+    def tree10(v):  # balanced pairwise fp32 sums of aligned 1024-blocks (zero padded)
+        v = np.concatenate([v, np.zeros((-len(v)) % 1024, np.float32)]).reshape(-1, 1024)
+        while v.shape[1] > 1:
+            v = (v[:, 0::2] + v[:, 1::2]).astype(np.float32)
+        return v[:, 0]
+    D2 = (rng.rand(n).astype(np.float32)) ** 2
+    n10 = -(-n // 1024)
+    buf = torch.zeros(n10, dtype=torch.float32)
+    if hi > lo:
+        assert lo % 1024 == 0
+        part = tree10(D2[lo:hi])
+        buf[lo // 1024: lo // 1024 + len(part)] = torch.from_numpy(part)
+    dist.all_reduce(buf)
+    ok = ok and bool((buf.numpy() == tree10(D2)).all())
+    cand = torch.tensor([4000 if lo <= 4000 < hi else -1, 17 if lo <= 17 < hi else -1], dtype=torch.int64)
+    dist.all_reduce(cand, op=dist.ReduceOp.MAX)
+    ok = ok and cand.tolist() == [4000, 17]
     dist.destroy_process_group()
     q.put((rank, ok))
 

@@ -33,7 +33,14 @@ for (n, d, k, iters) in ((200_003, 10, 1000, 4), (60_001, 64, 2000, 2), (100_000
     idx = np.random.RandomState(7).randint(0, n, size=k)
     same_init = np.array_equal(ku.initial_centers_ if ku.initial_centers_ is not None and len(ku.initial_centers_) == k
                               else X[idx], X[idx]) or True
+    # k-means++ over the sharded frames (blocked scan): same picks as the single-GPU call
+    kp = coor.KmeansClustering(min(k, 200), max_iter=1, init_strategy="kmeans++", fixed_seed=42)
+    kp.estimate(X)
     if rank == 0:
+        ref_pp = _lib.kmeans_init_centers_kmpp(X, min(k, 200), 42, scan="blocked")
+        e0 = np.array_equal(ref_pp, kp.initial_centers_)
+        print("n=%d d=%d k=%d ws=%d: sharded k-means++ picks identical=%s" % (n, d, min(k, 200), ws, e0), flush=True)
+        ok = ok and e0
         ref_c, code, it, ref_in = _lib.kmeans_cluster_loop(X, C0, iters, 0.0)
         e1 = np.array_equal(ref_c, got_c)
         e2 = np.array_equal(np.asarray(ref_in, np.float32), np.asarray(got_in, np.float32))
