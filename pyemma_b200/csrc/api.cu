@@ -256,6 +256,8 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return set_error(B2K_ERR_INVALID_ARG, "null argument");
     if (!strcmp(name, "assign_engine")) c->engine = (int)value;
     else if (!strcmp(name, "screen_terms")) c->screen_terms = (int)value;
+    else if (!strcmp(name, "screen_group")) c->screen_group = (int)value;
+    else if (!strcmp(name, "verify_mode")) c->verify_mode = (int)value;
     else if (!strcmp(name, "accumulate_mode")) c->accumulate_mode = (int)value;
     else if (!strcmp(name, "cost_kernel")) c->cost_kernel = (int)value;
     else if (!strcmp(name, "rmsd_kernel")) c->rmsd_kernel = (int)value;
@@ -277,8 +279,9 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
 
 B2K_API int b2k_ctx_get_stat(b2k_ctx* c, const char* name, double* value) {
     if (!c || !name || !value) return set_error(B2K_ERR_INVALID_ARG, "null argument");
-    if (c->stat_pending && c->assign_plan && !strncmp(name, "screen_", 7)) {  // stats of the last device assign, read lazily
-        B2K_TRY(screen_read_stats(static_cast<ScreenPlan*>(c->assign_plan), &c->stat_cand_chunks, &c->stat_fallback_frames));
+    if (c->stat_pending && !strncmp(name, "screen_", 7)) {  // stats of the last screened assign, read lazily
+        void* plan = c->stat_plan ? c->stat_plan : c->assign_plan;
+        if (plan) B2K_TRY(screen_read_stats(static_cast<ScreenPlan*>(plan), &c->stat_cand_chunks, &c->stat_fallback_frames));
         c->stat_pending = false;
     }
     if (!strcmp(name, "screen_gemm_ms_total") || !strcmp(name, "screen_gemm_launches")) {
@@ -350,6 +353,7 @@ B2K_API int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, 
         int rc = screen_prepare_frames(plan, dX, n);
         if (rc == B2K_OK) rc = screen_assign(plan, dX, n, dC, dlabels, dmind, 0);
         ctx->stat_screen_frames = (double)n;
+        ctx->stat_plan = nullptr;
         ctx->stat_pending = rc == B2K_OK;
         return rc;
     }
@@ -431,6 +435,7 @@ static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, con
     cudaStreamSynchronize(st);
     if (use_screen) {  // candidate statistics of the LAST chunk are readable through b2k_ctx_get_stat
         ctx->stat_screen_frames = (double)(n - (int64_t)(c - 1) * cf);
+        ctx->stat_plan = nullptr;
         ctx->stat_pending = rc == B2K_OK;
     }
     if (rc != B2K_OK) return rc;
@@ -522,6 +527,12 @@ B2K_API int b2k_dev_lloyd_create(b2k_ctx* ctx, const float* dX, int64_t n_local,
 B2K_API int b2k_dev_lloyd_destroy(b2k_lloyd* s) {
     if (!s) return B2K_OK;
     cudaStreamSynchronize(s->ctx->stream);
+    if (s->plan && s->ctx->stat_plan == s->plan) {  // keep the numbers of the last step readable
+        if (s->ctx->stat_pending)
+            screen_read_stats(s->plan, &s->ctx->stat_cand_chunks, &s->ctx->stat_fallback_frames);
+        s->ctx->stat_pending = false;
+        s->ctx->stat_plan = nullptr;
+    }
     if (s->plan) screen_plan_destroy(s->plan);
     delete s;
     return B2K_OK;
@@ -537,6 +548,9 @@ B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32
     if (s->n == 0) return B2K_OK;
     if (s->plan) {
         B2K_TRY(screen_assign(s->plan, s->dX, s->n, dC, dlabels, nullptr, 1));
+        ctx->stat_screen_frames = (double)s->n;
+        ctx->stat_plan = s->plan;
+        ctx->stat_pending = true;
     } else {
         B2K_TRY(s->pc.prepare(ctx, dC, s->k, s->d, s->metric));
         B2K_TRY(assign_any(ctx, s->dX, s->Ga.as<float>(), s->n, s->d, s->pc, s->k, s->metric, dlabels, nullptr, 1));

@@ -62,6 +62,8 @@ struct b2k_ctx {
     // options
     int engine = B2K_ENGINE_AUTO;
     int screen_terms = 0;
+    int verify_mode = 0;      // wide rows: 0 direct (no staging) verify kernel, 1 shared-memory staged variants
+    int screen_group = 0;     // centers per candidate group of the screen (0: automatic; 8, 4, 2)
     int rmsd_kernel = 0;      // 0: slab-streaming QCP kernel, 1: whole-row tile kernel
     int cost_kernel = 0;      // 0: quad kernel for wide rows, 1: the shared-memory staged variant
     int accumulate_mode = 0;  // 0: segmented member sums (counting sort by label), 1: one RED per element
@@ -71,6 +73,7 @@ struct b2k_ctx {
     // screen plan of the last b2k_assign / b2k_dev_assign call, kept so that chunked assignment does not
     // reallocate the operand buffers for every chunk (owned here, freed by b2k_ctx_destroy)
     void* assign_plan = nullptr;
+    void* stat_plan = nullptr;  // plan the pending statistics belong to (a Lloyd session's, else assign_plan)
     // grow-only device buffers reused by the host-pointer entry points (frames, labels, ...): a 400 MB
     // cudaMalloc/cudaFree pair per call costs milliseconds and serialises the device
     enum { SLOT_FRAMES = 0, SLOT_LABELS, SLOT_CENTERS, SLOT_CENTERS2, SLOT_ACC, SLOT_CHUNK_X0, SLOT_CHUNK_X1,

@@ -45,10 +45,18 @@ static constexpr int TILE_N = 256;    // centers per accumulator stage (UMMA N)
 static constexpr int BLOCK_K = 64;    // fp16 elements per k-block (one 128-byte swizzle row)
 static constexpr int STAGES = 4;
 static constexpr int CHUNK = 32;      // columns per candidate chunk (one tcgen05.ld.32x32b.x32)
-static constexpr int GROUP = 8;       // columns per candidate group: a chunk entry carries a 4-bit group mask
+static constexpr int GROUP = 8;       // center rows per block of the verify kernels' tables / staged slabs
+// A candidate entry is (chunk id | group mask << id bits): the chunk's 32 columns are split into groups of CG = 8, 4
+// or 2 centers (4-, 8- or 16-bit mask).  Finer groups cost the epilogue a few more compares per chunk and save the
+// verify kernels most of their center traffic (they re-evaluate whole groups).
 static constexpr int LIST_CAP = 16;   // running candidate chunks remembered per frame and column half
 static constexpr int CAND_CAP = 8;    // candidate chunks handed to the verify kernel per frame
-static constexpr uint32_t ID_MASK = 0x0fffffffu;  // candidate entry: chunk id | group mask << 28
+__host__ __device__ constexpr int cand_id_bits(int cg) { return 32 - CHUNK / cg; }
+__host__ __device__ constexpr uint32_t cand_id_mask(int cg) { return (1u << cand_id_bits(cg)) - 1u; }
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {  // position of the n-th (0-based) set bit
+    for (; n > 0; --n) m &= m - 1;
+    return __ffs(m) - 1;
+}
 static constexpr int A_BYTES = TILE_M * BLOCK_K * 2;
 static constexpr int B_BYTES = TILE_N * BLOCK_K * 2;
 static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -68,6 +76,7 @@ struct ScreenPlan {
     b2k_ctx* ctx = nullptr;
     int64_t n_cap = 0, n_pad = 0;
     int d = 0, k = 0, k_pad = 0, terms = 3, Kc = 0, Kp = 0, nk16 = 0;
+    int cg = 4;                // centers per candidate group (8, 4 or 2)
     __half* A = nullptr;       // [n_pad][Kp]
     __half* B = nullptr;       // [k_pad][Kp]
     float* X2 = nullptr;       // [n_pad] |x~|^2
@@ -458,20 +467,31 @@ struct RowScan {
     }
 };
 
+template <int CG>
 __device__ __forceinline__ void scan_chunk(const float (&v)[32], uint32_t chunk_id, RowScan& rs, const Margin& mg,
                                            uint32_t* lid, float* lv /* this thread's column of the list arrays */) {
-    float gm[4];
+    constexpr int NG = CHUNK / CG;
+    float gm[NG];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float* w = v + q * GROUP;
-        gm[q] = fmaxf(fmaxf(fmaxf(fmaxf(w[0], w[1]), w[2]), fmaxf(fmaxf(w[3], w[4]), w[5])), fmaxf(w[6], w[7]));
+    for (int q = 0; q < NG; ++q) {
+        const float* w = v + q * CG;
+        if (CG == 8) gm[q] = fmaxf(fmaxf(fmaxf(fmaxf(w[0], w[1]), w[2]), fmaxf(fmaxf(w[3], w[4]), w[5])), fmaxf(w[6], w[7]));
+        else if (CG == 4) gm[q] = fmaxf(fmaxf(fmaxf(w[0], w[1]), w[2]), w[3]);
+        else gm[q] = fmaxf(w[0], w[1]);
     }
-    const float cm = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), gm[3]);
+    float t3[(NG + 2) / 3 + 1];
+    int nt = 0;
+#pragma unroll
+    for (int q = 0; q + 2 < NG; q += 3) t3[nt++] = fmaxf(fmaxf(gm[q], gm[q + 1]), gm[q + 2]);
+    float cm = (NG % 3 == 1) ? gm[NG - 1] : fmaxf(gm[NG - 2], gm[NG - 1]);
+#pragma unroll
+    for (int q = 0; q < nt; ++q) cm = fmaxf(cm, t3[q]);
     if (cm > rs.m) { rs.m = cm; rs.thr = mg.threshold(cm); }
     if (cm >= rs.thr) {
         // groups below the CURRENT threshold can never pass the final (higher) one
-        const uint32_t mask = (gm[0] >= rs.thr ? 1u : 0u) | (gm[1] >= rs.thr ? 2u : 0u) | (gm[2] >= rs.thr ? 4u : 0u) |
-                              (gm[3] >= rs.thr ? 8u : 0u);
+        uint32_t mask = 0;
+#pragma unroll
+        for (int q = 0; q < NG; ++q) mask |= (gm[q] >= rs.thr ? 1u : 0u) << q;
         if (rs.cnt == LIST_CAP) {  // compact: drop entries the risen threshold has already excluded
             int w = 0;
             for (int t = 0; t < LIST_CAP; ++t) {
@@ -481,7 +501,7 @@ __device__ __forceinline__ void scan_chunk(const float (&v)[32], uint32_t chunk_
             rs.cnt = w;
         }
         if (rs.cnt < LIST_CAP) {
-            lid[rs.cnt * TILE_M] = chunk_id | (mask << 28);
+            lid[rs.cnt * TILE_M] = chunk_id | (mask << cand_id_bits(CG));
             lv[rs.cnt * TILE_M] = cm;
             ++rs.cnt;
         } else {
@@ -491,6 +511,7 @@ __device__ __forceinline__ void scan_chunk(const float (&v)[32], uint32_t chunk_
 }
 
 // ---- the screen kernel ---------------------------------------------------------------------------------------------
+template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -659,8 +680,8 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             tmem_ld32(lane_addr + nacc * TILE_N, va);  // HALF_CHUNKS is even: chunk 0 always lands in va
                         }
                     }
-                    if (c & 1) scan_chunk(vb, cbase + c, rs, mg, lid, lv);
-                    else scan_chunk(va, cbase + c, rs, mg, lid, lv);
+                    if (c & 1) scan_chunk<CG>(vb, cbase + c, rs, mg, lid, lv);
+                    else scan_chunk<CG>(va, cbase + c, rs, mg, lid, lv);
                 }
             }
             // ---- merge the two column halves of this frame ----
@@ -692,7 +713,7 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     for (int w = 0; w < kept; ++w) {
                         const uint32_t ia = a < n0 ? T->out_id[0][a][row] : 0xffffffffu;
                         const uint32_t ib = b < n1 ? T->out_id[1][b][row] : 0xffffffffu;
-                        if (a < n0 && (b >= n1 || (ia & ID_MASK) < (ib & ID_MASK))) { ids[w] = ia; ++a; }
+                        if (a < n0 && (b >= n1 || (ia & cand_id_mask(CG)) < (ib & cand_id_mask(CG)))) { ids[w] = ia; ++a; }
                         else { ids[w] = ib; ++b; }
                     }
                 }
@@ -787,8 +808,10 @@ __global__ void __launch_bounds__(256) screen_verify_table_kernel(const float* _
                                                                   int32_t* __restrict__ labels,
                                                                   float* __restrict__ mind, int lloyd,
                                                                   ScreenParams* prm, uint32_t* __restrict__ fb_list,
-                                                                  int gstride /* floats per 8-row group */) {
+                                                                  int gstride /* floats per 8-row group */, int cg) {
     extern __shared__ __align__(16) float ctab[];
+    const int idb = cand_id_bits(cg);
+    const uint32_t idm = cand_id_mask(cg);
     if (!prm->valid) return;
     constexpr int DS = DREG;  // row stride inside a group
     const int n_groups = (k + GROUP - 1) / GROUP;
@@ -819,16 +842,16 @@ __global__ void __launch_bounds__(256) screen_verify_table_kernel(const float* _
 #pragma unroll
         for (int t = 0; t < CAND_CAP; ++t) {
             if (t < nc) {
-                const int g0 = (int)(ent[t] & ID_MASK) * (CHUNK / GROUP);
-                uint32_t mask = ent[t] >> 28;
+                const int j0 = (int)(ent[t] & idm) * CHUNK;
+                uint32_t mask = ent[t] >> idb;
                 while (mask) {
                     const int q = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const int g = g0 + q;
-                    const float4* c4 = reinterpret_cast<const float4*>(ctab + (size_t)g * gstride);
-                    const int jn = min(GROUP, k - g * GROUP);
-#pragma unroll
-                    for (int c = 0; c < GROUP; ++c) {
+                    const int jb = j0 + q * cg;  // first center of the group; a group never crosses an 8-row block
+                    const float4* c4 = reinterpret_cast<const float4*>(ctab + (size_t)(jb >> 3) * gstride + (jb & 7) * DS);
+                    const int jn = min(cg, k - jb);
+#pragma unroll 2
+                    for (int c = 0; c < cg; ++c) {
                         if (c < jn) {
                             Lanes4 L;
                             L.init();
@@ -846,7 +869,7 @@ __global__ void __launch_bounds__(256) screen_verify_table_kernel(const float* _
                                 for (int e = 0; e < DREG; ++e)
                                     if (e >= d4 && e < d) L.tail(xr[e], ct[e & 3]);
                             }
-                            am.offer(L.result(), g * GROUP + c);
+                            am.offer(L.result(), jb + c);
                         }
                     }
                     my_groups += 1;
@@ -870,8 +893,10 @@ __global__ void __launch_bounds__(256) screen_verify_small_kernel(const float* _
                                                                   int32_t* __restrict__ labels,
                                                                   float* __restrict__ mind, int lloyd,
                                                                   ScreenParams* prm, uint32_t* __restrict__ fb_list,
-                                                                  int use_smem, int rs) {
+                                                                  int use_smem, int rs, int cg) {
     extern __shared__ __align__(16) float ctab[];
+    const int idb = cand_id_bits(cg);
+    const uint32_t idm = cand_id_mask(cg);
     if (!prm->valid) return;
     if (use_smem) {
         for (int t = threadIdx.x; t < k * rs; t += 256) {
@@ -903,9 +928,9 @@ __global__ void __launch_bounds__(256) screen_verify_small_kernel(const float* _
         }
         ArgMin am;
         am.init();
-        auto eval_group = [&](int g) {
-            const int j = g * GROUP + sub;
-            if (j < k) {
+        auto eval_group = [&](int jb) {  // lanes sub < cg take the centers of the group that starts at jb
+            const int j = jb + sub;
+            if (sub < cg && j < k) {
                 Lanes4 L;
                 L.init();
                 if (use_smem) {
@@ -944,12 +969,12 @@ __global__ void __launch_bounds__(256) screen_verify_small_kernel(const float* _
 #pragma unroll
             for (int t = 0; t < CAND_CAP; ++t) {
                 if (t < nc) {
-                    const int g0 = (int)(ent[t] & ID_MASK) * (CHUNK / GROUP);
-                    uint32_t mask = ent[t] >> 28;
+                    const int j0 = (int)(ent[t] & idm) * CHUNK;
+                    uint32_t mask = ent[t] >> idb;
                     while (mask) {
                         const int q = __ffs(mask) - 1;
                         mask &= mask - 1;
-                        eval_group(g0 + q);
+                        eval_group(j0 + q * cg);
                         if (sub == 0) my_groups += 1;
                     }
                 }
@@ -996,11 +1021,16 @@ __global__ void __launch_bounds__(256) screen_verify_stream_kernel(const float* 
                                                                    const uint8_t* __restrict__ ncand,
                                                                    int32_t* __restrict__ labels,
                                                                    float* __restrict__ mind, int lloyd,
-                                                                   ScreenParams* prm, uint32_t* __restrict__ fb_list) {
+                                                                   ScreenParams* prm, uint32_t* __restrict__ fb_list,
+                                                                   int cg) {
     extern __shared__ __align__(16) float vsm[];
     if (!prm->valid) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 7, slot = lane >> 3;
+    // a round evaluates 8 centers per frame = S candidate groups of cg centers: lane sub <-> (group slot, center)
+    const int idb = cand_id_bits(cg), ng = CHUNK / cg, S = GROUP / cg;
+    const uint32_t idm = cand_id_mask(cg);
+    const int gslot = sub / cg, within = sub - gslot * cg;
     float* wb = vsm + (size_t)warp * VC_WARP_FLOATS;
     const int nslab = (d + 31) >> 5;
     unsigned long long my_groups = 0, my_fb = 0;
@@ -1024,7 +1054,7 @@ __global__ void __launch_bounds__(256) screen_verify_stream_kernel(const float* 
         const int nc = nc_n;
         uint32_t ent = (nc != 255 && sub < nc) ? ent_n : 0u;
         if (base + n_warps * 4 < n) fetch_meta(base + n_warps * 4);
-        const int pc = __popc(ent >> 28);
+        const int pc = __popc(ent >> idb);
         int off = pc;  // inclusive scan over the 8 lanes of the frame
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {
@@ -1034,24 +1064,23 @@ __global__ void __launch_bounds__(256) screen_verify_stream_kernel(const float* 
         int total = __shfl_sync(0xffffffffu, off, 7, 8);
         off -= pc;
         if (nc == 255) total = 0;  // queued for the fallback kernel below
-        int rounds = total;
+        int rounds = (total + S - 1) / S;
 #pragma unroll
         for (int o = 8; o < 32; o <<= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
 
-        // group of this lane's frame in round r (-1: none); warp-collective
+        // candidate group (index into the k/cg groups) this lane works on in round r: the (r*S + gslot)-th group of
+        // its frame's flattened candidate list (-1: none); warp-collective
         auto group_of_round = [&](int r) -> int {
-            const bool mine = nc != 255 && r >= off && r < off + pc;
-            const unsigned who = __ballot_sync(0xffffffffu, mine) & seg_mask;
-            int gm = -1;
-            if (mine) {
-                uint32_t mask = ent >> 28;
-                for (int t = r - off; t > 0; --t) mask &= mask - 1;
-                gm = (int)(ent & ID_MASK) * (CHUNK / GROUP) + (__ffs(mask) - 1);
+            const int gi = r * S + gslot;
+            int g = -1;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const uint32_t et = __shfl_sync(0xffffffffu, ent, t, 8);
+                const int ot = __shfl_sync(0xffffffffu, off, t, 8);
+                const int pt = __shfl_sync(0xffffffffu, pc, t, 8);
+                if (gi >= ot && gi < ot + pt) g = (int)(et & idm) * ng + nth_set_bit(et >> idb, gi - ot);
             }
-            const int src = who ? (__ffs(who) - 1) : lane;
-            int g = __shfl_sync(0xffffffffu, gm, src);
-            if (!who) g = -1;
-            return g;
+            return gi < total ? g : -1;
         };
         // start the copies of slab `sl` for round-group g into stage `stg`; warp-collective
         auto issue = [&](int g, int sl, int stg) {
@@ -1064,16 +1093,14 @@ __global__ void __launch_bounds__(256) screen_verify_stream_kernel(const float* 
             }
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
-                const int gf = __shfl_sync(0xffffffffu, g, f * 8);
-                if (gf >= 0) {
-                    const int rows = min(GROUP, k - gf * GROUP);
-                    const float* src = Cn + (int64_t)gf * GROUP * d + col0;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int t = lane + 32 * h, row = t >> 3, c4 = t & 7;
-                        if (row < rows && col0 + c4 * 4 < d)
-                            cp_async16(st + f * VC_FRAME + row * VC_ROW + c4 * 4, src + (int64_t)row * d + c4 * 4);
-                    }
+                for (int h = 0; h < 2; ++h) {
+                    // staged row `row` of frame f belongs to the lane (f, sub = row): its group and center
+                    const int t = lane + 32 * h, row = t >> 3, c4 = t & 7;
+                    const int gr = __shfl_sync(0xffffffffu, g, f * 8 + row);
+                    const int64_t j = (int64_t)gr * cg + (row % cg);
+                    if (gr >= 0 && j < k && col0 + c4 * 4 < d)
+                        cp_async16(st + f * VC_FRAME + row * VC_ROW + c4 * 4, Cn + j * d + col0 + c4 * 4);
                 }
             }
             cp_async_commit();
@@ -1102,7 +1129,7 @@ __global__ void __launch_bounds__(256) screen_verify_stream_kernel(const float* 
                 cp_async_wait<0>();
             }
             __syncwarp();  // every lane's copies of this stage have landed
-            const int j = g_cur >= 0 ? g_cur * GROUP + sub : -1;
+            const int j = g_cur >= 0 ? g_cur * cg + within : -1;
             if (j >= 0 && j < k) {
                 const float* st = wb + stg * VC_STAGE;
                 const float* cr = st + slot * VC_FRAME + sub * VC_ROW;
@@ -1119,7 +1146,7 @@ __global__ void __launch_bounds__(256) screen_verify_stream_kernel(const float* 
             }
             if (sl == nslab - 1) {  // distance complete
                 if (j >= 0 && j < k) am.offer(L.result(), j);
-                if (g_cur >= 0 && sub == 0 && nc != 255) my_groups += 1;
+                if (g_cur >= 0 && within == 0 && nc != 255) my_groups += 1;
                 L.init();
             }
             r = nr;
@@ -1157,11 +1184,15 @@ __global__ void __launch_bounds__(256) screen_verify_wide_kernel(const float* __
                                                                  const uint8_t* __restrict__ ncand,
                                                                  int32_t* __restrict__ labels,
                                                                  float* __restrict__ mind, int lloyd,
-                                                                 ScreenParams* prm, uint32_t* __restrict__ fb_list) {
+                                                                 ScreenParams* prm, uint32_t* __restrict__ fb_list,
+                                                                 int cg) {
     extern __shared__ __align__(16) float vsm[];
     if (!prm->valid) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 7, slot = lane >> 3;
+    const int idb = cand_id_bits(cg), ng = CHUNK / cg, S = GROUP / cg;
+    const uint32_t idm = cand_id_mask(cg);
+    const int gslot = sub / cg, within = sub - gslot * cg;
     float* wbuf = vsm + (size_t)warp * VW_FLOATS;
     float* cb = wbuf + (size_t)slot * (GROUP * SLAB_RS);   // this frame's group rows
     float* xb = wbuf + 4 * (GROUP * SLAB_RS) + slot * SLAB;  // this frame's slab
@@ -1177,7 +1208,7 @@ __global__ void __launch_bounds__(256) screen_verify_wide_kernel(const float* __
         // lane (slot, sub) holds candidate entry `sub` of its frame; prefix-count the groups of the frame
         uint32_t ent = 0;
         if (live && nc != 255 && sub < nc) ent = cand[i * CAND_CAP + sub];
-        const int pc = __popc(ent >> 28);
+        const int pc = __popc(ent >> idb);
         int off = pc;  // inclusive scan over the 8 lanes of the frame
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {
@@ -1187,28 +1218,26 @@ __global__ void __launch_bounds__(256) screen_verify_wide_kernel(const float* __
         int total = __shfl_sync(0xffffffffu, off, 7, 8);
         off -= pc;
         if (nc == 255) total = 0;  // queued for the fallback kernel below
-        int rounds = total;
+        int rounds = (total + S - 1) / S;
 #pragma unroll
         for (int o = 8; o < 32; o <<= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
         ArgMin am;
         am.init();
         for (int r = 0; r < rounds; ++r) {
-            // group of this frame in round r (-1: none)
-            int g;
+            // candidate group of this lane in round r: the (r*S + gslot)-th of its frame's flattened list (-1: none)
+            int g = -1;
             {
-                const bool mine = nc != 255 && r >= off && r < off + pc;
-                const unsigned who = __ballot_sync(0xffffffffu, mine) & seg_mask;
-                int gm = -1;
-                if (mine) {
-                    uint32_t mask = ent >> 28;
-                    for (int t = r - off; t > 0; --t) mask &= mask - 1;
-                    gm = (int)(ent & ID_MASK) * (CHUNK / GROUP) + (__ffs(mask) - 1);
+                const int gi = r * S + gslot;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const uint32_t et = __shfl_sync(0xffffffffu, ent, t, 8);
+                    const int ot = __shfl_sync(0xffffffffu, off, t, 8);
+                    const int pt = __shfl_sync(0xffffffffu, pc, t, 8);
+                    if (gi >= ot && gi < ot + pt) g = (int)(et & idm) * ng + nth_set_bit(et >> idb, gi - ot);
                 }
-                const int src = who ? (__ffs(who) - 1) : lane;
-                g = __shfl_sync(0xffffffffu, gm, src);
-                if (!who) g = -1;
+                if (gi >= total) g = -1;
             }
-            const int j = g >= 0 ? g * GROUP + sub : -1;
+            const int j = g >= 0 ? g * cg + within : -1;
             Lanes4 L;
             L.init();
             for (int e0 = 0; e0 < d; e0 += SLAB) {
@@ -1222,14 +1251,12 @@ __global__ void __launch_bounds__(256) screen_verify_wide_kernel(const float* __
                 }
 #pragma unroll
                 for (int f = 0; f < 4; ++f) {
-                    const int gf = __shfl_sync(0xffffffffu, g, f * 8);
-                    if (gf < 0) continue;
-                    const int rows = min(GROUP, k - gf * GROUP);
-                    const float* src = Cn + (int64_t)gf * GROUP * d + e0;
                     float* dst = wbuf + (size_t)f * (GROUP * SLAB_RS);
-                    for (int t = lane; t < rows * w; t += 32) {
-                        const int rr = t / w, c = t - rr * w;
-                        dst[rr * SLAB_RS + c] = __ldg(src + (int64_t)rr * d + c);
+                    for (int t = lane; t < ((GROUP * w + 31) & ~31); t += 32) {  // whole-warp trips: the shuffle below
+                        const int rr = min(t / w, GROUP - 1), c = t - (t / w) * w;
+                        const int gr = __shfl_sync(0xffffffffu, g, f * 8 + rr);  // group of the lane that owns row rr
+                        const int64_t jr = (int64_t)gr * cg + (rr % cg);
+                        if (t < GROUP * w && gr >= 0 && jr < k) dst[rr * SLAB_RS + c] = __ldg(Cn + jr * d + e0 + c);
                     }
                 }
                 __syncwarp();
@@ -1247,7 +1274,114 @@ __global__ void __launch_bounds__(256) screen_verify_wide_kernel(const float* __
                 }
             }
             if (j >= 0 && j < k) am.offer(L.result(), j);
-            if (g >= 0 && sub == 0 && nc != 255) my_groups += 1;
+            if (g >= 0 && within == 0 && nc != 255) my_groups += 1;
+        }
+        if (live && nc == 255 && sub == 0) { fallback_push(prm, fb_list, i); my_fb += 1; }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const float so = __shfl_xor_sync(0xffffffffu, am.s, o);
+            const int32_t jo = __shfl_xor_sync(0xffffffffu, am.j, o);
+            am.merge(so, jo);
+        }
+        if (live && sub == 0 && nc != 255) {
+            labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
+            if (mind) mind[i] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
+        }
+    }
+    verify_stats(my_groups, my_fb, prm);
+}
+
+// d > 16, no staging: 8 lanes per frame (4 frames per warp); lane (group slot, center) streams ITS center row and the
+// frame row straight from global memory / L2 with 16-byte loads (the frame row is the same address for the lanes
+// of a frame -> one broadcast transaction) and advances its own Lanes4 sums.  A frame typically has one or two
+// candidate groups, so this kernel is bound by load latency, not by bandwidth or arithmetic: no shared memory and
+// ~64 registers keep 32+ warps per SM in flight, which is what the staged variants above lacked (2 CTAs of 8 warps
+// per SM: measured 4.2 ms for 1.25e7 x 64 against ~1 ms of L2 traffic).
+template <bool VEC>
+__global__ void __launch_bounds__(256) screen_verify_direct_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                                   const float* __restrict__ Cn, int k,
+                                                                   const uint32_t* __restrict__ cand,
+                                                                   const uint8_t* __restrict__ ncand,
+                                                                   int32_t* __restrict__ labels,
+                                                                   float* __restrict__ mind, int lloyd,
+                                                                   ScreenParams* prm, uint32_t* __restrict__ fb_list,
+                                                                   int cg) {
+    if (!prm->valid) return;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & 7, slot = lane >> 3;
+    const int idb = cand_id_bits(cg), ng = CHUNK / cg, S = GROUP / cg;
+    const uint32_t idm = cand_id_mask(cg);
+    const int gslot = sub / cg, within = sub - gslot * cg;
+    const int d4 = d & ~3;
+    unsigned long long my_groups = 0, my_fb = 0;
+    const int64_t n_warps = ((int64_t)gridDim.x * 256) >> 5;
+    const int64_t warp_global = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    for (int64_t base = warp_global * 4; base < n; base += n_warps * 4) {
+        const int64_t i = base + slot;
+        const bool live = i < n;
+        const int nc = live ? (int)ncand[i] : 0;
+        uint32_t ent = 0;
+        if (live && nc != 255 && sub < nc) ent = cand[i * CAND_CAP + sub];
+        const int pc = __popc(ent >> idb);
+        int off = pc;  // inclusive scan over the 8 lanes of the frame
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, off, o, 8);
+            if (sub >= o) off += v;
+        }
+        int total = __shfl_sync(0xffffffffu, off, 7, 8);
+        off -= pc;
+        if (nc == 255) total = 0;  // queued for the fallback kernel below
+        int rounds = (total + S - 1) / S;
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
+        ArgMin am;
+        am.init();
+        const float* xr = X + (live ? i : 0) * d;
+        for (int r = 0; r < rounds; ++r) {
+            int g = -1;
+            {
+                const int gi = r * S + gslot;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const uint32_t et = __shfl_sync(0xffffffffu, ent, t, 8);
+                    const int ot = __shfl_sync(0xffffffffu, off, t, 8);
+                    const int pt = __shfl_sync(0xffffffffu, pc, t, 8);
+                    if (gi >= ot && gi < ot + pt) g = (int)(et & idm) * ng + nth_set_bit(et >> idb, gi - ot);
+                }
+                if (gi >= total) g = -1;
+            }
+            const int j = g >= 0 ? g * cg + within : -1;
+            if (j >= 0 && j < k) {
+                const float* cr = Cn + (int64_t)j * d;
+                Lanes4 L;
+                L.init();
+                if (VEC) {
+                    const float4* x4 = reinterpret_cast<const float4*>(xr);
+                    const float4* c4 = reinterpret_cast<const float4*>(cr);
+                    const int nv = d >> 2;
+                    int t = 0;
+                    for (; t + 4 <= nv; t += 4) {
+                        float4 xv[4], cv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { xv[u] = __ldg(x4 + t + u); cv[u] = __ldg(c4 + t + u); }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            L.add4(xv[u].x, xv[u].y, xv[u].z, xv[u].w, cv[u].x, cv[u].y, cv[u].z, cv[u].w);
+                    }
+                    for (; t < nv; ++t) {
+                        const float4 xv = __ldg(x4 + t), cv = __ldg(c4 + t);
+                        L.add4(xv.x, xv.y, xv.z, xv.w, cv.x, cv.y, cv.z, cv.w);
+                    }
+                } else {
+                    for (int e = 0; e < d4; e += 4)
+                        L.add4(__ldg(xr + e), __ldg(xr + e + 1), __ldg(xr + e + 2), __ldg(xr + e + 3), __ldg(cr + e),
+                               __ldg(cr + e + 1), __ldg(cr + e + 2), __ldg(cr + e + 3));
+                    for (int e = d4; e < d; ++e) L.tail(__ldg(xr + e), __ldg(cr + e));
+                }
+                am.offer(L.result(), j);
+            }
+            if (g >= 0 && within == 0 && nc != 255) my_groups += 1;
         }
         if (live && nc == 255 && sub == 0) { fallback_push(prm, fb_list, i); my_fb += 1; }
 #pragma unroll
@@ -1317,6 +1451,12 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     p->k = k;
     p->k_pad = (int)(cdiv(k, TILE_N) * TILE_N);
     p->terms = ctx->screen_terms == 1 ? 1 : 3;  // hi-only operands leave too many candidates
+    // candidate group size: narrow rows (d <= 16) leave the TMEM-read-bound epilogue no slack (measured at 1e7 x 10,
+    // k=1000: screen kernel 2.32 / 2.44 / 2.90 ms for groups of 8 / 4 / 2, step time 3.40 / 3.36 / 3.75 ms) -> 8; wide
+    // rows are MMA bound and their verify pays 4*d bytes of L2 traffic per candidate center -> 2 (16-bit chunk ids)
+    p->cg = (ctx->screen_group == 8 || ctx->screen_group == 4 || ctx->screen_group == 2) ? ctx->screen_group
+                                                                                          : (d > 16 ? 2 : 8);
+    if (p->cg == 2 && p->k_pad / CHUNK > (1 << 16)) p->cg = 4;
     p->Kc = p->terms * d + 3;
     p->Kp = (int)(cdiv(p->Kc, BLOCK_K) * BLOCK_K);
     p->nk16 = (int)cdiv(p->Kc, 16);
@@ -1338,8 +1478,12 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     if (rc != B2K_OK) { screen_plan_destroy(p); return rc; }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t ae = cudaFuncSetAttribute(screen_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t ae = cudaFuncSetAttribute(screen_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)ctx->smem_optin);
+        if (ae == cudaSuccess)
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+        if (ae == cudaSuccess)
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
         if (ae != cudaSuccess) { screen_plan_destroy(p); return set_error(B2K_ERR_CUDA, "screen smem attr: %s", cudaGetErrorString(ae)); }
         attr_set = true;
     }
@@ -1350,7 +1494,8 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
 int screen_plan_acquire(b2k_ctx* ctx, int64_t n, int d, int k, ScreenPlan** out) {
     ScreenPlan* c = static_cast<ScreenPlan*>(ctx->assign_plan);
     const int terms = ctx->screen_terms == 1 ? 1 : 3;
-    if (c && c->d == d && c->k == k && c->terms == terms && n <= c->n_cap) {
+    const int want_cg = (ctx->screen_group == 8 || ctx->screen_group == 4 || ctx->screen_group == 2) ? ctx->screen_group : 0;
+    if (c && c->d == d && c->k == k && c->terms == terms && n <= c->n_cap && (want_cg == 0 || want_cg == c->cg)) {
         c->prepared_n = -1;
         *out = c;
         return B2K_OK;
@@ -1471,7 +1616,9 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, st));
     }
-    screen_gemm_kernel<<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, g);
+    if (p->cg == 8) screen_gemm_kernel<8><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, g);
+    else if (p->cg == 4) screen_gemm_kernel<4><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, g);
+    else screen_gemm_kernel<2><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, g);
     LAUNCH_CHECK();
     if (ctx->profile) {
         CUDA_TRY(cudaEventRecord(ev1, st));
@@ -1497,7 +1644,8 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
             vattr = true;                                                                                            \
         }                                                                                                            \
         screen_verify_table_kernel<DR><<<tgrid, 256, tbytes, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, \
-                                                                   mind, lloyd, p->params, p->fb_list, gstride);     \
+                                                                   mind, lloyd, p->params, p->fb_list, gstride,     \
+                                                                   p->cg);                                           \
     } while (0)
                 if (ds == 4) B2K_VTABLE(4);
                 else if (ds == 8) B2K_VTABLE(8);
@@ -1524,13 +1672,23 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
             vattr = true;                                                                                            \
         }                                                                                                            \
         screen_verify_small_kernel<DR><<<vgrid, 256, vsmem, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels,  \
-                                                                  mind, lloyd, p->params, p->fb_list, use_smem, rs); \
+                                                                  mind, lloyd, p->params, p->fb_list, use_smem, rs, \
+                                                                  p->cg);                                            \
     } while (0)
         if (p->d <= 4) B2K_VERIFY(4);
         else if (p->d <= 8) B2K_VERIFY(8);
         else if (p->d <= 12) B2K_VERIFY(12);
         else B2K_VERIFY(16);
 #undef B2K_VERIFY
+    } else if (ctx->verify_mode != 1) {
+        const bool vec = p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0;
+        const unsigned dgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 32), (int64_t)ctx->sm_count * 8));
+        if (vec)
+            screen_verify_direct_kernel<true><<<dgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind,
+                                                                     lloyd, p->params, p->fb_list, p->cg);
+        else
+            screen_verify_direct_kernel<false><<<dgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind,
+                                                                      lloyd, p->params, p->fb_list, p->cg);
     } else {
         if (p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0) {
             const size_t tsmem = (size_t)8 * VC_WARP_FLOATS * 4;
@@ -1543,7 +1701,7 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
             const unsigned tgrid =
                 (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 32), (int64_t)ctx->sm_count * per_sm));
             screen_verify_stream_kernel<<<tgrid, 256, tsmem, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind,
-                                                                   lloyd, p->params, p->fb_list);
+                                                                   lloyd, p->params, p->fb_list, p->cg);
             LAUNCH_CHECK();
             return screen_finish_assign(p, dX, n, dC, labels, mind, lloyd);
         }
@@ -1557,7 +1715,7 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         const unsigned vgrid =
             (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 32), (int64_t)ctx->sm_count * ctas_per_sm));
         screen_verify_wide_kernel<<<vgrid, 256, vsmem, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind, lloyd,
-                                                             p->params, p->fb_list);
+                                                             p->params, p->fb_list, p->cg);
     }
     LAUNCH_CHECK();
     return screen_finish_assign(p, dX, n, dC, labels, mind, lloyd);

@@ -18,6 +18,8 @@ def screen_ctx(b2k):
     yield ctx
     ctx.set_option("assign_engine", b2k.ENGINE_AUTO)
     ctx.set_option("screen_terms", 0)
+    ctx.set_option("screen_group", 0)
+    ctx.set_option("verify_mode", 0)
 
 
 SHAPES = [(5000, 2, 100, 0), (20000, 10, 1000, 1), (20000, 10, 1000, 3), (4096, 3, 257, 0), (3000, 16, 300, 0),
@@ -33,8 +35,12 @@ def test_screen_assign_bit_exact(b2k, oracle, screen_ctx, n, d, k, terms):
     C[: k // 2] += (0.05 * rng.randn(k // 2, d)).astype(np.float32)  # near-duplicates: small gaps
     screen_ctx.set_option("screen_terms", terms)
     ref = oracle.assign(X, C, n_threads=8)
-    got = b2k.assign(X, C)
-    np.testing.assert_array_equal(got, ref)
+    for group in (0, 8, 4, 2):  # centers per candidate group handed to the exact verify (0: automatic)
+        for vmode in ((0, 1) if d > 16 else (0,)):  # wide rows: direct / shared-memory staged verify kernels
+            screen_ctx.set_option("screen_group", group)
+            screen_ctx.set_option("verify_mode", vmode)
+            got = b2k.assign(X, C)
+            np.testing.assert_array_equal(got, ref, err_msg="screen_group=%d verify_mode=%d" % (group, vmode))
 
 
 def test_screen_offset_data_and_ties(b2k, oracle, screen_ctx):
