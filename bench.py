@@ -77,7 +77,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.1)
 
     def stop(self):
         self._halt.set()
@@ -135,7 +135,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU")

@@ -66,7 +66,8 @@ struct b2k_ctx {
     int screen_group = 0;     // centers per candidate group of the screen (0: automatic; 8, 4, 2)
     int rmsd_kernel = 0;      // 0: slab-streaming QCP kernel, 1: whole-row tile kernel
     int cost_kernel = 0;      // 0: quad kernel for wide rows, 1: the shared-memory staged variant
-    int accumulate_mode = 0;  // 0: segmented member sums (counting sort by label), 1: one RED per element
+    int accumulate_mode = 0;  // 0: automatic (shared-memory table when it fits, else segmented), 1: one RED per
+                              // element, 2: segmented (counting sort by label), 3: shared-memory table
     // stats of the last screen call
     double stat_cand_chunks = 0, stat_fallback_frames = 0, stat_screen_frames = 0;
     bool stat_pending = false;
