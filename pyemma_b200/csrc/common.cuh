@@ -67,7 +67,7 @@ struct b2k_ctx {
     int rmsd_kernel = 0;      // 0: slab-streaming QCP kernel, 1: whole-row tile kernel
     int cost_kernel = 0;      // 0: quad kernel for wide rows, 1: the shared-memory staged variant
     int accumulate_mode = 0;  // 0: automatic (shared-memory table when it fits, else segmented), 1: one RED per
-                              // element, 2: segmented (counting sort by label), 3: shared-memory table
+                              // element, 2: segmented (counting sort by label), 3: shared-memory table, 4: tile-sorted
     // stats of the last screen call
     double stat_cand_chunks = 0, stat_fallback_frames = 0, stat_screen_frames = 0;
     bool stat_pending = false;

@@ -209,7 +209,7 @@ def test_member_sums_segmented_exact(b2k, n, d, k):
     got = {}
     try:
         acc_len = int(ctx.lib.b2k_dev_lloyd_acc_len(sess))
-        for mode in (0, 1, 2, 3):
+        for mode in (0, 1, 2, 3, 4):
             ctx.set_option("accumulate_mode", mode)
             acc = torch.full((acc_len,), 7, dtype=torch.int64, device=dev)
             b2k.check(ctx.lib.b2k_dev_lloyd_accumulate(sess, C.c_void_p(ld.data_ptr()), C.c_void_p(acc.data_ptr())))
@@ -218,7 +218,7 @@ def test_member_sums_segmented_exact(b2k, n, d, k):
     finally:
         ctx.set_option("accumulate_mode", 0)
         ctx.lib.b2k_dev_lloyd_destroy(sess)
-    for mode in (1, 2, 3):
+    for mode in (1, 2, 3, 4):
         np.testing.assert_array_equal(got[0], got[mode], err_msg="accumulate_mode=%d" % mode)
     # independent integer reference: q such that |sum| * 2^q < 2^62 (api.cu lloyd_scales)
     def clog2(v):
