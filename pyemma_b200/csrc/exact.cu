@@ -183,6 +183,96 @@ __global__ void __launch_bounds__(128) tile_kernel(const float* __restrict__ X, 
 }
 
 // -------------------------------------------------------------------------------------------
+// The tile kernel over an INDEX LIST of frames whose length lives on the device: the exact scan of the frames the
+// tcgen05 screen could not bound (screen.cu fb_list / fb_count).  Persistent grid, so a zero count costs one
+// empty launch; rows are gathered while staging, labels scattered through the same list.
+__global__ void __launch_bounds__(128) tile_indexed_kernel(const float* __restrict__ X, int d,
+                                                           const float* __restrict__ C, int k, TileCfg cfg,
+                                                           const uint32_t* __restrict__ row_index,
+                                                           const unsigned int* __restrict__ count_dev,
+                                                           const int* __restrict__ run_if_nonzero,
+                                                           int32_t* __restrict__ labels, float* __restrict__ mind,
+                                                           int lloyd) {
+    extern __shared__ __align__(16) float sm[];
+    if (run_if_nonzero && *run_if_nonzero == 0) return;
+    const unsigned int count = *count_dev;
+    float* xs = sm;
+    float* cs = sm + (size_t)cfg.FB * cfg.xstride;
+    float* red_s = cs + (size_t)cfg.KT * cfg.ds;
+    int32_t* red_j = (int32_t*)(red_s + 128);
+    const int tid = threadIdx.x;
+    const int f = tid % cfg.FB, g = tid / cfg.FB;
+    const int d4 = d & ~3;
+    for (unsigned int base = blockIdx.x * (unsigned)cfg.FB; base < count; base += gridDim.x * (unsigned)cfg.FB) {
+        const int nf = (int)min((unsigned)cfg.FB, count - base);
+        __syncthreads();  // previous tile fully consumed
+        for (int r = 0; r < nf; ++r) {
+            const float* src = X + (int64_t)row_index[base + r] * d;
+            for (int c = tid; c < d; c += 128) xs[(size_t)r * cfg.xstride + c] = __ldg(src + c);
+        }
+        ArgMin am;
+        am.init();
+        const float* xrow = xs + (size_t)f * cfg.xstride;
+        const bool valid = f < nf;
+        for (int j0 = 0; j0 < k; j0 += cfg.KT) {
+            const int kk = min(cfg.KT, k - j0);
+            __syncthreads();
+            {
+                const float* src = C + (int64_t)j0 * d;
+                const int total = kk * d;
+                for (int t = tid; t < total; t += 128) {
+                    const int r = t / d, c = t - r * d;
+                    cs[(size_t)r * cfg.ds + c] = __ldg(src + t);
+                }
+            }
+            __syncthreads();
+            if (!valid) continue;
+            for (int jj = g; jj < kk; jj += 4 * cfg.G) {
+                const float* cr[4];
+                int jx[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    jx[c] = jj + c * cfg.G;
+                    cr[c] = cs + (size_t)min(jx[c], kk - 1) * cfg.ds;
+                }
+                Lanes4 L[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) L[c].init();
+                for (int e = 0; e < d4; e += 4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xrow + e);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 cv = *reinterpret_cast<const float4*>(cr[c] + e);
+                        L[c].add4(xv.x, xv.y, xv.z, xv.w, cv.x, cv.y, cv.z, cv.w);
+                    }
+                }
+                for (int e = d4; e < d; ++e) {
+                    const float xv = xrow[e];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) L[c].tail(xv, cr[c][e]);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (jx[c] < kk) am.offer(L[c].result(), j0 + jx[c]);
+            }
+        }
+        if (cfg.G > 1) {
+            __syncthreads();
+            red_s[tid] = am.s;
+            red_j[tid] = am.j;
+            __syncthreads();
+            if (g == 0)
+                for (int gg = 1; gg < cfg.G; ++gg) am.merge(red_s[gg * cfg.FB + f], red_j[gg * cfg.FB + f]);
+        }
+        if (g == 0 && valid) {
+            const int64_t i = row_index[base + f];
+            labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
+            if (mind) mind[i] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // l_i = sqrt(dist2(x_i, C[label_i]))  -- thread per frame, rows streamed from global/L1.
 __global__ void __launch_bounds__(256) labeled_dist_kernel(const float* __restrict__ X, int64_t n, int d,
                                                            const float* __restrict__ C,
@@ -522,6 +612,26 @@ static int launch_tile_gated(b2k_ctx* ctx, const float* X, int64_t n, int d, con
     else
         tile_kernel<MODE_ALL><<<(unsigned)blocks, 128, cfg.smem, ctx->stream>>>(X, n, d, C, k, cfg, labels, out,
                                                                                  lloyd, run_if_zero);
+    LAUNCH_CHECK();
+    return B2K_OK;
+}
+
+int launch_tile_indexed(b2k_ctx* ctx, const float* X, int d, const float* C, int k, const uint32_t* row_index,
+                        const unsigned int* count_dev, const int* run_if_nonzero, int32_t* labels, float* mind,
+                        int lloyd) {
+    if (k <= 0) return B2K_OK;
+    const size_t budget = std::min<size_t>(ctx->smem_optin, 100 * 1024);  // two CTAs per SM
+    TileCfg cfg = tile_cfg(d, k, budget);
+    if (cfg.smem > ctx->smem_optin)
+        return set_error(B2K_ERR_INVALID_ARG, "dimension %d too large for the exact tile kernel", d);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(tile_indexed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)ctx->smem_optin));
+        attr_set = true;
+    }
+    tile_indexed_kernel<<<ctx->sm_count * 2, 128, cfg.smem, ctx->stream>>>(X, d, C, k, cfg, row_index, count_dev,
+                                                                          run_if_nonzero, labels, mind, lloyd);
     LAUNCH_CHECK();
     return B2K_OK;
 }

@@ -14,6 +14,10 @@ int launch_assign_exact_if(b2k_ctx* ctx, const float* X, int64_t n, int d, const
                            float* mind, int lloyd, const int* run_if_zero);
 int launch_tile(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, int32_t* labels, float* out,
                 int lloyd, int mode);
+// exact argmin for the frames row_index[0 .. *count_dev) (device-side count; skipped when *run_if_nonzero == 0)
+int launch_tile_indexed(b2k_ctx* ctx, const float* X, int d, const float* C, int k, const uint32_t* row_index,
+                        const unsigned int* count_dev, const int* run_if_nonzero, int32_t* labels, float* mind,
+                        int lloyd);
 // out[j][i] = sqrt(dist2(x_i, rows_j)), j < m
 int launch_dist_rows(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out);
 int launch_labeled_dist(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, const int32_t* labels,

@@ -1572,10 +1572,15 @@ int screen_prepare_frames(ScreenPlan* p, const float* dX, int64_t n) {
 static int screen_finish_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, int32_t* labels,
                                 float* mind, int lloyd) {
     b2k_ctx* ctx = p->ctx;
-    const size_t fsmem = ((size_t)((p->d + 3) & ~3) + 512) * 4;
-    screen_fallback_kernel<<<ctx->sm_count * 4, 256, fsmem, ctx->stream>>>(dX, p->d, dC, p->k, p->fb_list, p->params, labels,
-                                                                          mind, lloyd);
-    LAUNCH_CHECK();
+    if (ctx->fallback_mode == 1) {  // CTA per frame (first version; 36.7 ms for 8.4e3 frames at cfg4)
+        const size_t fsmem = ((size_t)((p->d + 3) & ~3) + 512) * 4;
+        screen_fallback_kernel<<<ctx->sm_count * 4, 256, fsmem, ctx->stream>>>(dX, p->d, dC, p->k, p->fb_list, p->params,
+                                                                              labels, mind, lloyd);
+        LAUNCH_CHECK();
+    } else {  // register-tiled exact tile kernel over the queued frames
+        B2K_TRY(launch_tile_indexed(ctx, dX, p->d, dC, p->k, p->fb_list, &p->params->fb_count, &p->params->valid, labels,
+                                    mind, lloyd));
+    }
     return launch_assign_exact_if(ctx, dX, n, p->d, dC, p->k, labels, mind, lloyd, &p->params->valid);
 }
 

@@ -98,3 +98,35 @@ def test_screen_candidate_statistics(b2k, screen_ctx):
     fb = screen_ctx.get_stat("screen_fallback_frames") / frames
     print("candidate chunks per frame %.3f, fallback fraction %.5f" % (chunks, fb))
     assert chunks < 3.0 and fb < 0.01
+
+
+@pytest.mark.parametrize("d,k", [(8, 1500), (64, 2000)])
+def test_screen_list_overflow_goes_to_exact_scan(b2k, oracle, screen_ctx, d, k):
+    """centers on a sphere around the frames: hundreds of centers sit within the screen's margin of the best one, the
+    candidate lists overflow and the frames take the exact fallback scan (both implementations), which must still
+    give the oracle's labels; the statistic shows the path was really taken."""
+    import ctypes as C
+    import torch
+    rng = np.random.RandomState(d)
+    dirs = rng.randn(k, d)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    Cn = (3.0 * dirs).astype(np.float32)
+    X = np.zeros((6000, d), np.float32)                      # frames AT the sphere's centre: every center ties
+    X[::2] = (Cn[rng.randint(0, k, 3000)] + 0.05 * rng.randn(3000, d)).astype(np.float32)  # ordinary frames
+    ref = oracle.assign(X, Cn, n_threads=8)
+    for mode in (0, 1):
+        screen_ctx.set_option("fallback_mode", mode)
+        try:
+            np.testing.assert_array_equal(b2k.assign(X, Cn), ref, err_msg="fallback_mode=%d" % mode)
+        finally:
+            screen_ctx.set_option("fallback_mode", 0)
+    dev = torch.device("cuda", screen_ctx.device)
+    dX, dC = torch.from_numpy(X).to(dev), torch.from_numpy(Cn).to(dev)
+    lab = torch.empty(len(X), dtype=torch.int32, device=dev)
+    b2k.check(screen_ctx.lib.b2k_dev_assign(screen_ctx.handle, C.c_void_p(dX.data_ptr()), len(X), d,
+                                            C.c_void_p(dC.data_ptr()), k, 0, C.c_void_p(lab.data_ptr()), None))
+    screen_ctx.sync()
+    fb = screen_ctx.get_stat("screen_fallback_frames")
+    print("fallback frames: %d of %d" % (fb, len(X)))
+    assert fb >= 1000
+    np.testing.assert_array_equal(lab.cpu().numpy(), ref)

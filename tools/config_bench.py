@@ -150,7 +150,7 @@ def cfg4(ctx, args):
     X, _ = device_blobs(n, 256, 200, 5.0, 1.0, 4)
     res = lloyd_and_assign(ctx, X, 5000, 2, "cfg4 %gx256 k=5000" % n)
     # k-means++ (HBM-bound: k rounds over X)
-    for nk, kk in ((min(n, 2_000_000), 5000),) + (((n, 5000),) if args.kmpp_full else ()):
+    for nk, kk in (() if args.no_kmpp else ((min(n, 2_000_000), 5000),)) + (((n, 5000),) if args.kmpp_full else ()):
         cen = torch.empty((kk, 256), dtype=torch.float32, device=DEV)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--cfg4-frames", type=int, default=20_000_000)
     ap.add_argument("--cfg5-frames", type=int, default=1_000_000)
     ap.add_argument("--kmpp-full", action="store_true")
+    ap.add_argument("--no-kmpp", action="store_true")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     ctx = _lib.context(0)
