@@ -62,6 +62,7 @@ struct b2k_ctx {
     // options
     int engine = B2K_ENGINE_AUTO;
     int screen_terms = 0;
+    int operand_kernel = 0;   // frame operand builder: 0 per-input-element tile kernel, 1 per-output-piece kernel
     int fallback_mode = 0;    // frames the screen cannot bound: 0 indexed exact tile kernel, 1 CTA-per-frame scan
     int verify_mode = 0;      // wide rows: 0 direct (no staging) verify kernel, 1 shared-memory staged variants
     int screen_group = 0;     // centers per candidate group of the screen (0: automatic; 8, 4, 2)

@@ -130,3 +130,23 @@ def test_screen_list_overflow_goes_to_exact_scan(b2k, oracle, screen_ctx, d, k):
     print("fallback frames: %d of %d" % (fb, len(X)))
     assert fb >= 1000
     np.testing.assert_array_equal(lab.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("n,d,k", [(20000, 10, 1000), (5000, 64, 2000), (2500, 256, 1000), (3000, 3, 200), (1000, 300, 64)])
+def test_screen_operand_builders_agree(b2k, oracle, screen_ctx, n, d, k):
+    """both frame-operand builders (per input element / per output piece) feed the screen identical operands:
+    same labels as the oracle, same candidate statistics."""
+    rng = np.random.RandomState(n + d)
+    X = blobs(rng, n, d, 9)
+    X[5] *= 300.0                                            # an outlier sets the scale: small values get flushed
+    Cn = X[rng.choice(n, k, replace=False)].copy()
+    ref = oracle.assign(X, Cn, n_threads=8)
+    stats = []
+    for mode in (0, 1):
+        screen_ctx.set_option("operand_kernel", mode)
+        try:
+            np.testing.assert_array_equal(b2k.assign(X, Cn), ref, err_msg="operand_kernel=%d" % mode)
+            stats.append((screen_ctx.get_stat("screen_cand_chunks"), screen_ctx.get_stat("screen_fallback_frames")))
+        finally:
+            screen_ctx.set_option("operand_kernel", 0)
+    assert stats[0] == stats[1]
