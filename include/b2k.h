@@ -183,6 +183,16 @@ int b2k_regspace_get_centers(b2k_regspace* r, float* centers_out /* n_centers*d 
 int b2k_regspace_cluster(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, float* centers_io,
                          int64_t* n_centers_io, float dmin, int64_t max_centers, int metric);
 
+/* ---- dtraj consumers: pyemma/util/discrete_trajectories.py:146-181 (count_states) and the lagged
+ * transition count matrix the MSM estimators take from the dtrajs (msm/estimators/_msm_estimator_base.py:3,229) --- */
+/* dcounts[s] += #{t : labels[t] == s}; negative labels are skipped, a label >= nstates is B2K_ERR_INVALID_ARG */
+int b2k_dev_count_states(b2k_ctx* ctx, const int32_t* dlabels, int64_t n, int32_t nstates, int64_t* dcounts);
+/* dC[i*nstates+j] += #{t : labels[t] == i, labels[t+lag] == j} over ONE trajectory of n frames; sliding != 0: every t,
+ * else t = 0, lag, 2 lag, ...; pairs with a negative label are skipped.  The caller zeroes dC and calls once per
+ * trajectory (pairs never span trajectories). */
+int b2k_dev_count_matrix(b2k_ctx* ctx, const int32_t* dlabels, int64_t n, int32_t nstates, int64_t lag, int sliding,
+                         int64_t* dC);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,6 +219,29 @@ def cfg5(ctx, args):
     return res
 
 
+def cfg6(ctx, args):
+    """dtraj consumers: count matrix at lag 10 and state histogram of 1e7 metastable labels, k=1000"""
+    from pyemma_b200 import dtraj
+    n, k = 10_000_000, 1000
+    g = torch.Generator(device=DEV)
+    g.manual_seed(6)
+    lab = torch.randint(0, k, (n // 20 + 1,), generator=g, device=DEV, dtype=torch.int32).repeat_interleave(20)[:n].contiguous()
+    rnd = torch.randint(0, k, (n,), generator=g, device=DEV, dtype=torch.int32)
+    lib = ctx.lib
+    res = {"cfg": "dtraj consumers 1e7 labels k=1000"}
+    for name, l in (("metastable(dwell 20)", lab), ("uniform random", rnd)):
+        Cm = torch.zeros((k, k), dtype=torch.int64, device=DEV)
+        hist = torch.zeros(k, dtype=torch.int64, device=DEV)
+        ms_c = timed(lambda: _lib.check(lib.b2k_dev_count_matrix(ctx.handle, C.c_void_p(l.data_ptr()), n, k, 10, 1,
+                                                                 C.c_void_p(Cm.data_ptr()))), 5, warm=1)
+        ms_h = timed(lambda: _lib.check(lib.b2k_dev_count_states(ctx.handle, C.c_void_p(l.data_ptr()), n, k,
+                                                                 C.c_void_p(hist.data_ptr()))), 5, warm=1)
+        res[name] = {"count_matrix_ms": ms_c, "count_matrix_pairs_per_s": n / ms_c * 1e3,
+                     "count_matrix_hbm_frac": 8.0 * n / (ms_c * 1e-3) / 1e9 / HBM,
+                     "count_states_ms": ms_h, "count_states_hbm_frac": 4.0 * n / (ms_h * 1e-3) / 1e9 / HBM}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", default="1,2,3,4,5")
@@ -231,7 +254,7 @@ def main():
     torch.cuda.set_device(0)
     ctx = _lib.context(0)
     ctx.set_stream(torch.cuda.current_stream(DEV).cuda_stream)
-    fns = {"1": cfg1, "2": cfg2, "3": cfg3, "4": cfg4, "5": cfg5}
+    fns = {"1": cfg1, "2": cfg2, "3": cfg3, "4": cfg4, "5": cfg5, "6": cfg6}
     results = []
     for c in args.cfg.split(","):
         t0 = time.perf_counter()
