@@ -7,5 +7,6 @@ ctypes); there is no CPU fallback.
 """
 __version__ = "0.1.0"
 
-from .api import assign_to_centers, cluster_kmeans, cluster_regspace  # noqa: E402,F401
-from .clustering import AssignCenters, KmeansClustering, RegularSpaceClustering  # noqa: E402,F401
+from .api import assign_to_centers, cluster_kmeans, cluster_mini_batch_kmeans, cluster_regspace  # noqa: E402,F401
+from .clustering import (AssignCenters, KmeansClustering, MiniBatchKmeansClustering,  # noqa: E402,F401
+                         RegularSpaceClustering)

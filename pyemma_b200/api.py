@@ -5,9 +5,9 @@ cluster_regspace :1953-2055, assign_to_centers :2060-2156, _check_old_chunksize_
 """
 import warnings
 
-from .clustering import AssignCenters, KmeansClustering, RegularSpaceClustering
+from .clustering import AssignCenters, KmeansClustering, MiniBatchKmeansClustering, RegularSpaceClustering
 
-__all__ = ["cluster_kmeans", "cluster_regspace", "assign_to_centers"]
+__all__ = ["cluster_kmeans", "cluster_mini_batch_kmeans", "cluster_regspace", "assign_to_centers"]
 
 _NOTSET = object()
 
@@ -35,6 +35,20 @@ def cluster_kmeans(data=None, k=None, max_iter=10, tolerance=1e-5, stride=1, met
     res = KmeansClustering(n_clusters=k, max_iter=max_iter, metric=metric, tolerance=tolerance,
                            init_strategy=init_strategy, fixed_seed=fixed_seed, n_jobs=n_jobs, skip=skip,
                            keep_data=keep_data, clustercenters=clustercenters, stride=stride, kmpp_scan=kmpp_scan)
+    if data is not None:
+        res.estimate(data, chunksize=cs)
+    else:
+        res.chunksize = cs
+    return res
+
+
+def cluster_mini_batch_kmeans(data=None, k=100, max_iter=10, batch_size=0.2, metric="euclidean",
+                              init_strategy="kmeans++", n_jobs=None, chunksize=None, skip=0, clustercenters=None,
+                              **kwargs):
+    """k-means with the mini-batch strategy (api.py:1671-1723)."""
+    cs = _check_old_chunksize_arg(chunksize, None, **kwargs)
+    res = MiniBatchKmeansClustering(n_clusters=k, max_iter=max_iter, metric=metric, init_strategy=init_strategy,
+                                    batch_size=batch_size, n_jobs=n_jobs, skip=skip, clustercenters=clustercenters)
     if data is not None:
         res.estimate(data, chunksize=cs)
     else:

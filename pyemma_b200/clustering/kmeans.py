@@ -22,7 +22,7 @@ import torch
 from .. import _lib, staging
 from .interface import AbstractClustering
 
-__all__ = ["KmeansClustering"]
+__all__ = ["KmeansClustering", "MiniBatchKmeansClustering"]
 
 
 class KmeansClustering(AbstractClustering):
@@ -36,9 +36,10 @@ class KmeansClustering(AbstractClustering):
         self._converged = False
         self.initial_centers_ = None
         self.inertias_ = np.zeros(0, np.float32)
+        self.kmpp_scan = kmpp_scan  # not a reference parameter: set directly so that subclasses need not list it
         self.set_params(n_clusters=n_clusters, max_iter=max_iter, tolerance=tolerance, init_strategy=init_strategy,
                         oom_strategy=oom_strategy, fixed_seed=fixed_seed, stride=stride, skip=skip,
-                        clustercenters=clustercenters, keep_data=keep_data, kmpp_scan=kmpp_scan)
+                        clustercenters=clustercenters, keep_data=keep_data)
 
     # ---- parameters ---------------------------------------------------------------------------
     @property
@@ -300,3 +301,137 @@ class KmeansClustering(AbstractClustering):
             return cur, converged, inertias
         finally:
             lib.b2k_dev_lloyd_destroy(sess)
+
+
+class MiniBatchKmeansClustering(KmeansClustering):
+    """Mini-batch k-means (pyemma/coordinates/clustering/kmeans.py:341-447).
+
+    Every pass draws, per trajectory, floor(len/total * ceil(total*batch_size)) frame indices without replacement
+    with `np.random.choice` (sorted), gathers those frames and hands them to deeptime's
+    `MiniBatchKMeans.partial_fit` (:428): ONE Lloyd step on the batch (`kmeans.cluster`) followed by
+    `kmeans.cost_function`, i.e. the batch is re-assigned to the NEW centers and the squared distances are summed;
+    the pass loop stops when the relative change of that cost is <= tolerance (:432-440).  Here the batch is
+    uploaded once per pass and both halves run in libb2k (Lloyd session + assign + cost).  The first pass without
+    given centers seeds them with k-means++ on the batch, like `_pick_initial_centers`.
+    """
+
+    def __init__(self, n_clusters, max_iter=5, metric="euclidean", tolerance=1e-5, init_strategy="kmeans++",
+                 batch_size=0.2, oom_strategy="memmap", fixed_seed=False, stride=None, n_jobs=None, skip=0,
+                 clustercenters=None, keep_data=False):
+        if stride is not None:
+            raise ValueError("stride is a dummy value in MiniBatch Kmeans")
+        if batch_size > 1:
+            raise ValueError("batch_size should be less or equal to 1, but was %s" % batch_size)
+        if keep_data:
+            raise ValueError("keep_data is a dummy value in MiniBatch Kmeans")
+        super().__init__(n_clusters, max_iter, metric, tolerance, init_strategy, False, oom_strategy, stride=stride,
+                         n_jobs=n_jobs, skip=skip, clustercenters=clustercenters, keep_data=False)
+        if fixed_seed is not False:
+            self.fixed_seed = fixed_seed  # the reference always seeds randomly (:361 passes False); kept settable
+        self.batch_size = batch_size
+
+    def _draw_mini_batch_sample(self):
+        """kmeans.py:369-384 -- (n_samples, 2) array of (trajectory, sorted frame index)"""
+        ra = np.empty((self._n_samples, 2), dtype=int)
+        offset = 0
+        for idx, traj_len in enumerate(self._traj_lengths):
+            m = self._n_samples_traj[idx]
+            ra[offset:offset + m, 0] = idx
+            ra[offset:offset + m, 1] = np.sort(np.random.choice(traj_len, m, replace=False))
+            offset += m
+        return ra
+
+    def _init_batches(self, iterable):
+        """kmeans.py:386-399"""
+        self._traj_lengths = [int(l) for l in iterable.trajectory_lengths(skip=self.skip)]
+        self._total_length = sum(self._traj_lengths)
+        samples = int(math.ceil(self._total_length * self.batch_size))
+        self._n_samples = 0
+        self._n_samples_traj = {}
+        for idx, traj_len in enumerate(self._traj_lengths):
+            m = int(math.floor(traj_len / float(self._total_length) * samples))
+            self._n_samples_traj[idx] = m
+            self._n_samples += m
+
+    def _estimate(self, iterable, **kw):
+        if not hasattr(iterable, "ra_gather"):
+            raise NotImplementedError("mini-batch k-means needs a random-access data source (DataInMemory)")
+        self.stride = None
+        self._init_batches(iterable)
+        if not self.n_clusters:
+            self.n_clusters = min(int(math.sqrt(self._total_length)), 5000)
+        k = int(self.n_clusters)
+        if self._n_samples < k:
+            raise ValueError("mini batch of %d frames is smaller than n_clusters=%d" % (self._n_samples, k))
+        ctx = _lib.context()
+        lib = ctx.lib
+        dev = staging.device(ctx)
+        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        metric = _lib.metric_id(self.metric)
+        d = iterable.dimension()
+        centers = None
+        if self._check_resume_iteration():
+            if len(self.clustercenters) != k:
+                raise RuntimeError("Passed clustercenters do not match n_clusters: {} vs. {}".format(
+                    len(self.clustercenters), k))
+            centers = torch.from_numpy(np.array(self.clustercenters, dtype=np.float32)).to(dev)
+            self.initial_centers_ = np.array(self.clustercenters, dtype=np.float32)
+        self._converged = False
+        inertias = []
+        self._draw_mini_batch_sample()  # the reference draws one sample to open its iterator (:413) and discards it
+        i_pass, prev_cost = 0, 0.0
+        pinned = torch.empty((self._n_samples, d), dtype=torch.float32, pin_memory=True)
+        X = torch.empty((self._n_samples, d), dtype=torch.float32, device=dev)
+        labels = torch.empty(self._n_samples, dtype=torch.int32, device=dev)
+        while not (self._converged or i_pass + 1 > self.max_iter):
+            ra = self._draw_mini_batch_sample()
+            np.copyto(pinned.numpy(), iterable.ra_gather(ra, skip=self.skip), casting="unsafe")
+            X.copy_(pinned, non_blocking=True)
+            n = self._n_samples
+            if centers is None:  # _pick_initial_centers on the first batch
+                centers = torch.empty((k, d), dtype=torch.float32, device=dev)
+                if self.init_strategy == "uniform":
+                    idx = np.random.RandomState(self.fixed_seed).randint(0, n, size=k)
+                    centers.copy_(X[torch.as_tensor(idx, device=dev)])
+                else:
+                    _lib.check(lib.b2k_dev_kmeans_init_centers_kmpp(
+                        ctx.handle, C.c_void_p(X.data_ptr()), n, d, k, metric, int(self.fixed_seed), _lib.KMPP_BLOCKED,
+                        _lib.CALLBACK(0), None, C.c_void_p(centers.data_ptr()), None))
+                self.initial_centers_ = centers.cpu().numpy()
+            absmax = C.c_float(0)
+            _lib.check(lib.b2k_dev_absmax(ctx.handle, C.c_void_p(X.data_ptr()), n * d, C.byref(absmax)))
+            amax = max(absmax.value, float(centers.abs().max()))
+            if not math.isfinite(amax):
+                raise _lib.InvalidDataInStreamException("Found invalid values (NaN/inf) in the input frames")
+            sess = C.c_void_p()
+            _lib.check(lib.b2k_dev_lloyd_create(ctx.handle, C.c_void_p(X.data_ptr()), n, d, k, metric, n,
+                                                C.c_float(amax), C.byref(sess)))
+            try:
+                acc = torch.zeros(int(lib.b2k_dev_lloyd_acc_len(sess)), dtype=torch.int64, device=dev)
+                newc = torch.empty_like(centers)
+                _lib.check(lib.b2k_dev_lloyd_assign_accumulate(sess, C.c_void_p(centers.data_ptr()),
+                                                               C.c_void_p(labels.data_ptr()), C.c_void_p(acc.data_ptr())))
+                _lib.check(lib.b2k_dev_lloyd_finalize(sess, C.c_void_p(acc.data_ptr()), C.c_void_p(centers.data_ptr()),
+                                                      C.c_void_p(newc.data_ptr())))
+                # cost_function: assignments against the NEW centers, then the squared distances
+                _lib.check(lib.b2k_dev_assign(ctx.handle, C.c_void_p(X.data_ptr()), n, d, C.c_void_p(newc.data_ptr()), k,
+                                              metric, C.c_void_p(labels.data_ptr()), None))
+                _lib.check(lib.b2k_dev_lloyd_cost(sess, C.c_void_p(newc.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                                  C.c_void_p(acc.data_ptr())))
+                cost = float(np.float32(lib.b2k_dev_lloyd_decode_cost(sess, int(acc[-1].item()))))
+            finally:
+                lib.b2k_dev_lloyd_destroy(sess)
+            centers = newc
+            self.clustercenters = centers.cpu().numpy()
+            inertias.append(cost)
+            rel_change = abs(cost - prev_cost) / cost if cost != 0.0 else 0.0
+            prev_cost = cost
+            if rel_change <= self.tolerance:
+                self._converged = True
+                self.logger.info("Cluster centers converged after %i steps.", i_pass + 1)
+            i_pass += 1
+        self.inertias_ = np.asarray(inertias, dtype=np.float32)
+        if not self._converged:
+            self.logger.info("Algorithm did not reach convergence criterion"
+                             " of %g in %i iterations. Consider increasing max_iter.", self.tolerance, self.max_iter)
+        return self

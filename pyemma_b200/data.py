@@ -111,6 +111,23 @@ class DataInMemory:
     def get_output(self, stride=1, skip=0, chunk=None):
         return [x[skip::stride] for x in self.data]
 
+    def ra_gather(self, ra_stride, skip=0):
+        """frames of a random-access stride: an (n, 2) int array of (trajectory, frame) pairs, sorted, `skip` added to
+        the frame column (data/_base/datasource.py:691-712) -> (n, dim) array in that order"""
+        ra = np.asarray(ra_stride)
+        if ra.ndim != 2 or ra.shape[1] != 2:
+            raise ValueError("random access stride must be an (n, 2) array of (trajectory, frame) indices")
+        out = np.empty((len(ra), self._ndim), dtype=self.data[0].dtype)
+        for itraj in np.unique(ra[:, 0]):
+            sel = ra[:, 0] == itraj
+            frames = ra[sel, 1] + skip
+            if len(frames) and (frames.min() < 0 or frames.max() >= self._lengths[int(itraj)]):
+                raise IndexError("random access stride points outside trajectory %d" % int(itraj))
+            out[sel] = self.data[int(itraj)][frames]
+        if self.check_output and np.issubdtype(out.dtype, np.floating) and not np.all(np.isfinite(out)):
+            raise InvalidDataInStreamException("Found invalid values in the random-access frames")
+        return out
+
 
 class DataIterator:
     """Chunk iterator over a DataInMemory (uniform stride only)."""

@@ -227,3 +227,45 @@ def test_save_dtrajs(tmp_path):
     np.testing.assert_array_equal(np.load(tmp_path / "pre_1.npy"), cl.dtrajs[1])
     with pytest.raises(EnvironmentError):
         cl.save_dtrajs(prefix="pre", output_dir=str(tmp_path))
+
+
+def test_mini_batch_kmeans_matches_oracle_emulation(oracle):
+    """MiniBatchKmeansClustering (kmeans.py:341-447): with the numpy RNG seeded the batches are reproducible, so the
+    whole pass loop -- one Lloyd step per batch, cost with the batch re-assigned to the new centers, relative-change
+    stop -- is emulated with the oracle on the same batches."""
+    import pyemma_b200 as coor
+    rng = np.random.RandomState(9)
+    cen = rng.uniform(-4, 4, size=(12, 3))
+    trajs = [(cen[rng.randint(0, 12, L)] + 0.3 * rng.randn(L, 3)).astype(np.float32) for L in (9000, 4000, 500)]
+    C0 = np.concatenate(trajs)[rng.choice(13500, 40, replace=False)].copy()
+    np.random.seed(123)
+    mb = coor.cluster_mini_batch_kmeans(trajs, k=40, max_iter=5, batch_size=0.3, clustercenters=C0)
+    # emulation
+    emu = coor.MiniBatchKmeansClustering(40, max_iter=5, batch_size=0.3)
+    src = DataInMemory(trajs)
+    emu.skip = 0
+    emu._init_batches(src)
+    np.random.seed(123)
+    emu._draw_mini_batch_sample()
+    c, prev, inert, conv = C0, 0.0, [], False
+    for _ in range(5):
+        batch = np.ascontiguousarray(src.ra_gather(emu._draw_mini_batch_sample()), dtype=np.float32)
+        c, _lab = oracle.kmeans_cluster(batch, c, n_threads=4, acc="f64")
+        lab2 = oracle.assign(batch, c, n_threads=4)
+        cost = float(oracle.cost(batch, c, lab2, acc="f64"))
+        inert.append(cost)
+        rel = abs(cost - prev) / cost if cost != 0 else 0.0
+        prev = cost
+        if rel <= 1e-5:
+            conv = True
+            break
+    assert mb.converged == conv and len(mb.inertias_) == len(inert)
+    np.testing.assert_allclose(mb.inertias_, inert, rtol=5e-6)
+    assert np.abs(mb.clustercenters - c).max() <= 1e-5 * np.abs(c).max()
+    assert len(mb.dtrajs) == 3 and [len(x) for x in mb.dtrajs] == [9000, 4000, 500]
+    np.testing.assert_array_equal(np.concatenate(mb.dtrajs), oracle.assign(np.concatenate(trajs), mb.clustercenters))
+    # without given centers: k-means++ on the first batch, then the same loop; result is a usable clustering
+    np.random.seed(5)
+    mb2 = coor.cluster_mini_batch_kmeans(trajs, k=12, max_iter=8, batch_size=0.5)
+    assert mb2.clustercenters.shape == (12, 3) and mb2.initial_centers_.shape == (12, 3)
+    assert len(np.unique(np.concatenate(mb2.dtrajs))) == 12

@@ -190,3 +190,31 @@ def test_two_rank_exchange_gloo():
     for pr in procs:
         pr.join(timeout=30)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_mini_batch_parameters_and_sampling():
+    """kmeans.py:346-399: dummy-parameter errors, per-trajectory sample counts, sorted draws without replacement"""
+    with pytest.raises(ValueError):
+        p.MiniBatchKmeansClustering(5, stride=2)
+    with pytest.raises(ValueError):
+        p.MiniBatchKmeansClustering(5, batch_size=1.5)
+    with pytest.raises(ValueError):
+        p.MiniBatchKmeansClustering(5, keep_data=True)
+    mb = p.MiniBatchKmeansClustering(5, batch_size=0.25)
+    src = DataInMemory([np.zeros((100, 2)), np.zeros((60, 2)), np.zeros((7, 2))])
+    mb.skip = 0
+    mb._init_batches(src)
+    total, samples = 167, int(np.ceil(167 * 0.25))
+    assert [mb._n_samples_traj[i] for i in range(3)] == [int(np.floor(l / total * samples)) for l in (100, 60, 7)]
+    np.random.seed(3)
+    ra = mb._draw_mini_batch_sample()
+    assert ra.shape == (mb._n_samples, 2)
+    for i, L in enumerate((100, 60, 7)):
+        fr = ra[ra[:, 0] == i, 1]
+        assert len(fr) == mb._n_samples_traj[i] and len(set(fr)) == len(fr) and (np.diff(fr) > 0).all() and fr.max() < L
+    X = [np.arange(200.).reshape(100, 2), np.arange(120.).reshape(60, 2) + 1000, np.arange(14.).reshape(7, 2) + 5000]
+    got = DataInMemory(X).ra_gather(ra)
+    want = np.array([X[i][f] for i, f in ra])
+    np.testing.assert_array_equal(got, want)
+    with pytest.raises(IndexError):
+        DataInMemory(X).ra_gather(np.array([[2, 7]]))
