@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--engine", default="auto", choices=["auto", "direct", "screen"])
+    ap.add_argument("--stage-mb", type=int, default=0, help="pinned staging chunk of the e2e leg in MB (0: library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -304,6 +305,8 @@ def main():
         costs.append(lib.b2k_dev_lloyd_decode_cost(sess, int(acc[acc_len - 1].item())))
         cur, nxt = nxt, cur
 
+    if args.stage_mb > 0:
+        ctx.set_option("stage_bytes", args.stage_mb << 20)
     e2e_step()
     e2e_step()
     barrier()

@@ -18,7 +18,7 @@ import warnings
 
 import numpy as np
 
-from .. import _lib
+from .. import _lib, staging
 from ..data import DataInMemory, as_source
 
 
@@ -307,7 +307,10 @@ class AbstractClustering:
         if src is None:
             raise RuntimeError("no data producer set")
         out = []
-        if isinstance(src, DataInMemory):
+        rank, ws = staging.world()
+        if isinstance(src, DataInMemory) and ws > 1:
+            out = self._get_output_sharded(src, stride, skip, rank, ws)
+        elif isinstance(src, DataInMemory):
             for x in src.data:
                 out.append(self._transform_array(x[skip::stride]))
         else:
@@ -319,6 +322,33 @@ class AbstractClustering:
                     out[itraj][it.pos:it.pos + len(X)] = self._transform_array(X)
         if self._in_memory and stride == 1 and skip == 0:
             self._Y = out
+        return out
+
+    def _get_output_sharded(self, src, stride, skip, rank, ws):
+        """assign / dtrajs under torchrun: frames are independent, so every rank assigns one contiguous
+        range of the (strided, concatenated) frames and the int32 labels are combined with one all-reduce(sum) over
+        zero-filled buffers; every rank returns the complete dtrajs."""
+        import torch
+        import torch.distributed as dist
+        views = [x[skip::stride] for x in src.data]
+        lengths = [len(v) for v in views]
+        total = int(sum(lengths))
+        lo, hi = staging.shard_bounds(total, rank, ws)
+        dev = staging.device()
+        flat = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)
+        off = 0
+        for v, L in zip(views, lengths):
+            a, b = max(lo, off), min(hi, off + L)
+            if a < b:
+                lab = self._transform_array(v[a - off:b - off])[:, 0]
+                flat[a:b] = torch.from_numpy(np.ascontiguousarray(lab)).to(dev)
+            off += L
+        dist.all_reduce(flat)
+        host = flat[:total].cpu().numpy()
+        out, off = [], 0
+        for L in lengths:
+            out.append(host[off:off + L].reshape(-1, 1).copy())
+            off += L
         return out
 
     def iterator(self, stride=1, skip=0, chunk=None, return_trajindex=True):

@@ -27,6 +27,11 @@ for (n, d, k, iters) in ((200_003, 10, 1000, 4), (60_001, 64, 2000, 2), (100_000
     km = coor.KmeansClustering(k, max_iter=iters, tolerance=0.0, clustercenters=C0, keep_data=False)
     km.estimate(X)
     got_c, got_in = km.clustercenters, km.inertias_
+    # dtrajs: every rank assigns its frame range, one all-reduce combines the labels (two trajectories here)
+    cut = n // 3
+    ka = coor.AssignCenters(got_c)
+    ka.estimate([X[:cut], X[cut:]])
+    dts = ka.dtrajs
     # 'uniform' initialisation over the sharded array (rows fetched by global index)
     ku = coor.KmeansClustering(k, max_iter=1, init_strategy="uniform", fixed_seed=7)
     ku.estimate(X)
@@ -46,6 +51,10 @@ for (n, d, k, iters) in ((200_003, 10, 1000, 4), (60_001, 64, 2000, 2), (100_000
         e2 = np.array_equal(np.asarray(ref_in, np.float32), np.asarray(got_in, np.float32))
         ref_u, _, _, _ = _lib.kmeans_cluster_loop(X, X[idx], 1, 1e-5)
         e3 = np.array_equal(ref_u, ku.clustercenters)
+        ref_l = _lib.assign(X, got_c)
+        e4 = len(dts) == 2 and np.array_equal(np.concatenate(dts), ref_l) and len(dts[0]) == cut
+        print("n=%d d=%d k=%d ws=%d: sharded dtrajs identical=%s" % (n, d, k, ws, e4), flush=True)
+        ok = ok and e4
         print("n=%d d=%d k=%d ws=%d: centers bit-identical=%s inertias identical=%s uniform-init identical=%s"
               % (n, d, k, ws, e1, e2, e3), flush=True)
         ok = ok and e1 and e2 and e3
