@@ -451,10 +451,12 @@ __global__ void __launch_bounds__(256) labeled_dist_quad_vec_kernel(const float*
 // shared-memory wavefront group -- CUDA-core bound (3 non-fusable instructions per frame, row and dimension), not
 // LDS bound.  VEC (d % 4 == 0, aligned): frames are read with coalesced 16-byte loads and transposed in registers;
 // otherwise lane l reads its own elements and lane 0 adds the d%4 tail.
-template <int MR, bool VEC>
+template <int MR, bool VEC, bool FULL>
 __global__ void __launch_bounds__(256) dist_rows_quad_kernel(const float* __restrict__ X, int64_t n, int d,
                                                              const float* __restrict__ rows, int m,
                                                              float* __restrict__ out, int T) {
+    // FULL: m == MR, one pass over the rows without per-row bounds checks (the instantiations 2..14 cover every
+    // k-means++ trial count up to k = 1.6e5); otherwise the rows are walked in groups of MR.
     extern __shared__ __align__(16) float rsm[];
     const int Tp = T + 4;
     float* cs = rsm;                          // [m][4][Tp]
@@ -490,19 +492,14 @@ __global__ void __launch_bounds__(256) dist_rows_quad_kernel(const float* __rest
         float acc0[MR], acc1[MR];
 #pragma unroll
         for (int jj = 0; jj < MR; ++jj) { acc0[jj] = 0.f; acc1[jj] = 0.f; }
-        float n0[4], n1[4];
-        fetch(xr0, live0, 0, n0);
-        fetch(xr1, live1, 0, n1);
-        for (int s0 = 0; s0 < T; s0 += 4) {
-            float x0[4], x1[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { x0[q] = n0[q]; x1[q] = n1[q]; }
-            if (s0 + 4 < T) { fetch(xr0, live0, s0 + 4, n0); fetch(xr1, live1, s0 + 4, n1); }
+        const float* crow = cs + ((size_t)j0 * 4 + l) * Tp;  // row jj of this lane: crow + jj*4*Tp
+        const int rstride = 4 * Tp;
+        auto advance = [&](float (&x0)[4], float (&x1)[4], int s0) {  // four steps of every row sum, both frames
             if (VEC) { quad_transpose(x0, l); quad_transpose(x1, l); }
 #pragma unroll
             for (int jj = 0; jj < MR; ++jj) {
-                if (j0 + jj < m) {
-                    const float4 c = *reinterpret_cast<const float4*>(cs + ((size_t)(j0 + jj) * 4 + l) * Tp + s0);
+                if (FULL || j0 + jj < m) {
+                    const float4 c = *reinterpret_cast<const float4*>(crow + jj * rstride + s0);
                     float t = __fsub_rn(x0[0], c.x), u = __fsub_rn(x1[0], c.x);
                     float a = __fadd_rn(acc0[jj], __fmul_rn(t, t)), b = __fadd_rn(acc1[jj], __fmul_rn(u, u));
                     t = __fsub_rn(x0[1], c.y); u = __fsub_rn(x1[1], c.y);
@@ -514,13 +511,25 @@ __global__ void __launch_bounds__(256) dist_rows_quad_kernel(const float* __rest
                     acc1[jj] = __fadd_rn(b, __fmul_rn(u, u));
                 }
             }
+        };
+        // ping-pong prefetch: buffer A holds chunk s0, buffer B chunk s0+4 (no register rotation)
+        float a0[4], a1[4], b0[4], b1[4];
+        fetch(xr0, live0, 0, a0);
+        fetch(xr1, live1, 0, a1);
+        for (int s0 = 0; s0 < T; s0 += 8) {
+            if (s0 + 4 < T) { fetch(xr0, live0, s0 + 4, b0); fetch(xr1, live1, s0 + 4, b1); }
+            advance(a0, a1, s0);
+            if (s0 + 4 < T) {
+                if (s0 + 8 < T) { fetch(xr0, live0, s0 + 8, a0); fetch(xr1, live1, s0 + 8, a1); }
+                advance(b0, b1, s0 + 4);
+            }
         }
         if (!VEC && l == 0) {
             for (int q = 0; q < d - d4; ++q) {
                 const float xv0 = live0 ? __ldg(xr0 + d4 + q) : 0.f, xv1 = live1 ? __ldg(xr1 + d4 + q) : 0.f;
 #pragma unroll
                 for (int jj = 0; jj < MR; ++jj) {
-                    if (j0 + jj < m) {
+                    if (FULL || j0 + jj < m) {
                         const float c = tl[(j0 + jj) * 4 + q];
                         const float t = __fsub_rn(xv0, c), u = __fsub_rn(xv1, c);
                         acc0[jj] = __fadd_rn(acc0[jj], __fmul_rn(t, t));
@@ -531,13 +540,13 @@ __global__ void __launch_bounds__(256) dist_rows_quad_kernel(const float* __rest
         }
 #pragma unroll
         for (int jj = 0; jj < MR; ++jj) {
-            const float a1 = __shfl_down_sync(0xffffffffu, acc0[jj], 1), b1 = __shfl_down_sync(0xffffffffu, acc1[jj], 1);
-            const float a2 = __shfl_down_sync(0xffffffffu, acc0[jj], 2), b2 = __shfl_down_sync(0xffffffffu, acc1[jj], 2);
-            const float a3 = __shfl_down_sync(0xffffffffu, acc0[jj], 3), b3 = __shfl_down_sync(0xffffffffu, acc1[jj], 3);
-            if (l == 0 && j0 + jj < m) {
+            const float a1s = __shfl_down_sync(0xffffffffu, acc0[jj], 1), b1s = __shfl_down_sync(0xffffffffu, acc1[jj], 1);
+            const float a2s = __shfl_down_sync(0xffffffffu, acc0[jj], 2), b2s = __shfl_down_sync(0xffffffffu, acc1[jj], 2);
+            const float a3s = __shfl_down_sync(0xffffffffu, acc0[jj], 3), b3s = __shfl_down_sync(0xffffffffu, acc1[jj], 3);
+            if (l == 0 && (FULL || j0 + jj < m)) {
                 float* o = out + (int64_t)(j0 + jj) * n + i0;
-                if (live0) o[0] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc0[jj], a1), a2), a3));
-                if (live1) o[1] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc1[jj], b1), b2), b3));
+                if (live0) o[0] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc0[jj], a1s), a2s), a3s));
+                if (live1) o[1] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc1[jj], b1s), b2s), b3s));
             }
         }
     }
@@ -636,27 +645,35 @@ int launch_tile_indexed(b2k_ctx* ctx, const float* X, int d, const float* C, int
     return B2K_OK;
 }
 
+template <int MR, bool FULL>
+static int launch_dist_rows_quad(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out,
+                                 int T, size_t smem, bool vec) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<MR, true, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<MR, false, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)cdiv(cdiv(n, 2) * 4, 256);
+    if (vec) dist_rows_quad_kernel<MR, true, FULL><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T);
+    else dist_rows_quad_kernel<MR, false, FULL><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T);
+    LAUNCH_CHECK();
+    return B2K_OK;
+}
+
 int launch_dist_rows(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out) {
     if (n <= 0 || m <= 0) return B2K_OK;
     const int T = std::max(4, (int)cdiv(d / 4, 4) * 4);  // steps per accumulator lane, padded to whole 16-byte loads
     const size_t smem = ((size_t)m * 4 * (T + 4) + (size_t)m * 4) * 4;
     if (m <= 32 && smem <= 160 * 1024 && n >= 64) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            attr_set = true;
-        }
-        const unsigned grid = (unsigned)cdiv(cdiv(n, 2) * 4, 256);
         const bool vec = (d % 4 == 0) && (((uintptr_t)X) & 15) == 0;
-        if (vec && m <= 8) dist_rows_quad_kernel<8, true><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T);
-        else if (vec) dist_rows_quad_kernel<16, true><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T);
-        else if (m <= 8) dist_rows_quad_kernel<8, false><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T);
-        else dist_rows_quad_kernel<16, false><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T);
-        LAUNCH_CHECK();
-        return B2K_OK;
+        switch (m) {
+#define B2K_DR(M) case M: return launch_dist_rows_quad<M, true>(ctx, X, n, d, rows, m, out, T, smem, vec);
+            B2K_DR(1) B2K_DR(2) B2K_DR(3) B2K_DR(4) B2K_DR(5) B2K_DR(6) B2K_DR(7) B2K_DR(8) B2K_DR(9) B2K_DR(10)
+            B2K_DR(11) B2K_DR(12) B2K_DR(13) B2K_DR(14)
+#undef B2K_DR
+            default: return launch_dist_rows_quad<8, false>(ctx, X, n, d, rows, m, out, T, smem, vec);
+        }
     }
     return launch_tile(ctx, X, n, d, rows, m, nullptr, out, 0, MODE_ALL);
 }
