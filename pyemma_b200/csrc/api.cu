@@ -260,6 +260,7 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "verify_mode")) c->verify_mode = (int)value;
     else if (!strcmp(name, "fallback_mode")) c->fallback_mode = (int)value;
     else if (!strcmp(name, "operand_kernel")) c->operand_kernel = (int)value;
+    else if (!strcmp(name, "kmpp_prune")) c->kmpp_prune = (int)value;
     else if (!strcmp(name, "accumulate_mode")) c->accumulate_mode = (int)value;
     else if (!strcmp(name, "cost_kernel")) c->cost_kernel = (int)value;
     else if (!strcmp(name, "rmsd_kernel")) c->rmsd_kernel = (int)value;

@@ -392,13 +392,13 @@ __global__ void __launch_bounds__(256) labeled_dist_quad_kernel(const float* __r
 // 4x4 transpose inside a quad of lanes: lane l holds v[c] = element 4l+c of a 16-element chunk (one coalesced 16-byte
 // load per lane); afterwards lane l holds v[q] = element 4q+l, i.e. the next four addends of accumulator lane l in
 // order.  Two butterfly stages, 4 SHFL + 8 SEL.
-__device__ __forceinline__ void quad_transpose(float (&v)[4], int l) {
+__device__ __forceinline__ void quad_transpose(float (&v)[4], int l, unsigned mask = 0xffffffffu) {
     const bool b0 = l & 1, b1 = l & 2;
-    float ta = __shfl_xor_sync(0xffffffffu, b0 ? v[0] : v[1], 1);
-    float tb = __shfl_xor_sync(0xffffffffu, b0 ? v[2] : v[3], 1);
+    float ta = __shfl_xor_sync(mask, b0 ? v[0] : v[1], 1);
+    float tb = __shfl_xor_sync(mask, b0 ? v[2] : v[3], 1);
     if (b0) { v[0] = ta; v[2] = tb; } else { v[1] = ta; v[3] = tb; }
-    ta = __shfl_xor_sync(0xffffffffu, b1 ? v[0] : v[2], 2);
-    tb = __shfl_xor_sync(0xffffffffu, b1 ? v[1] : v[3], 2);
+    ta = __shfl_xor_sync(mask, b1 ? v[0] : v[2], 2);
+    tb = __shfl_xor_sync(mask, b1 ? v[1] : v[3], 2);
     if (b1) { v[0] = ta; v[1] = tb; } else { v[2] = ta; v[3] = tb; }
 }
 
@@ -451,13 +451,64 @@ __global__ void __launch_bounds__(256) labeled_dist_quad_vec_kernel(const float*
 // shared-memory wavefront group -- CUDA-core bound (3 non-fusable instructions per frame, row and dimension), not
 // LDS bound.  VEC (d % 4 == 0, aligned): frames are read with coalesced 16-byte loads and transposed in registers;
 // otherwise lane l reads its own elements and lane 0 adds the d%4 tail.
-template <int MR, bool VEC, bool FULL>
+// PRUNE (k-means++ only, FULL kernels): a (frame, candidate) pair whose distance provably cannot undercut the frame's
+// current D2 is not evaluated -- out = +inf, which the contribution min(D2, dist^2) turns into D2, exactly what the
+// evaluation would have given.  Proof obligation: with a = the chosen center that realises D2_i, r = |x_i - c_a|,
+// R = |c_a - cand|: |x_i - cand| >= R - r, and the fp32 reference-order value dd satisfies dd >= |x_i-cand|^2 (1-g),
+// sqrt(D2_i) >= r (1-g), g <= (d/4+10) 2^-24; so R >= (2 + slack) sqrt(D2_i) implies dd >= D2_i.  R is computed in
+// fp64 and rounded down (kmpp.cu), slack = 1e-4 + 4e-7 d >> g.
+// Two phases so that the survivors are dense: kmpp_prune_scan_kernel (thread per frame) decides every pair, writes
+// +inf for all pairs of the frame and appends frames with at least one live pair to a list; the quad kernel then
+// walks that list (two listed frames per quad) instead of all frames, so no warp idles on pruned neighbours.
+struct DistRowsPrune {
+    const float* D;                // [n] current D2
+    const int32_t* assigned;       // [n] index (into the chosen centers) of the center realising D2
+    const unsigned char* taken;    // [n]
+    const float* Rc;               // [m][rc_stride] lower bounds of |chosen center a - candidate j|
+    int rc_stride;
+    float factor;                  // 2 + slack
+    uint32_t* list;                // [n] frames with live pairs
+    uint32_t* masks;               // [n] their candidate masks (by list position)
+    unsigned int* count;           // device counter (zeroed by the launcher)
+};
+
+__global__ void __launch_bounds__(256) kmpp_prune_scan_kernel(int64_t n, int m, float* __restrict__ out, DistRowsPrune pr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_round = (n + 31) & ~(int64_t)31;
+    const float inf = __int_as_float(0x7f800000);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_round; i += (int64_t)gridDim.x * 256) {
+        uint32_t need = 0u;
+        if (i < n) {
+            if (!pr.taken[i]) {
+                const float thr = sqrtf(pr.D[i]) * pr.factor;
+                const float* rc = pr.Rc + pr.assigned[i];
+                for (int j = 0; j < m; ++j)
+                    if (!(__ldg(rc + (size_t)j * pr.rc_stride) >= thr)) need |= 1u << j;
+            }
+            for (int j = 0; j < m; ++j) out[(int64_t)j * n + i] = inf;  // live pairs are overwritten by the quad kernel
+        }
+        const unsigned live = __ballot_sync(0xffffffffu, need != 0u);
+        if (live) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(pr.count, (unsigned)__popc(live));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (need) {
+                const unsigned pos = base + __popc(live & ((1u << lane) - 1u));
+                pr.list[pos] = (uint32_t)i;
+                pr.masks[pos] = need;
+            }
+        }
+    }
+}
+
+template <int MR, bool VEC, bool FULL, bool PRUNE>
 __global__ void __launch_bounds__(256) dist_rows_quad_kernel(const float* __restrict__ X, int64_t n, int d,
                                                              const float* __restrict__ rows, int m,
-                                                             float* __restrict__ out, int T) {
+                                                             float* __restrict__ out, int T, DistRowsPrune pr) {
     // FULL: m == MR, one pass over the rows without per-row bounds checks (the instantiations 2..14 cover every
     // k-means++ trial count up to k = 1.6e5); otherwise the rows are walked in groups of MR.
     extern __shared__ __align__(16) float rsm[];
+    if (PRUNE && (int64_t)blockIdx.x * 128 >= (int64_t)*pr.count) return;  // beyond the survivor list
     const int Tp = T + 4;
     float* cs = rsm;                          // [m][4][Tp]
     float* tl = rsm + (size_t)m * 4 * Tp;     // [m][4] tail elements
@@ -472,12 +523,27 @@ __global__ void __launch_bounds__(256) dist_rows_quad_kernel(const float* __rest
         tl[idx] = e < d ? __ldg(rows + (int64_t)j * d + e) : 0.f;
     }
     __syncthreads();
-    const int64_t i0 = (((int64_t)blockIdx.x * 256 + threadIdx.x) >> 2) * 2;  // frames i0, i0+1
+    // frames of this quad: i0, i0+1 -- or, PRUNE, two consecutive entries of the survivor list
+    const int64_t q0 = (((int64_t)blockIdx.x * 256 + threadIdx.x) >> 2) * 2;
     const int l = threadIdx.x & 3;
-    const bool live0 = i0 < n, live1 = i0 + 1 < n;
+    int64_t i0 = q0, i1 = q0 + 1;
+    bool live0 = i0 < n, live1 = i1 < n;
+    unsigned need0 = 0xffffffffu, need1 = 0xffffffffu;
+    if (PRUNE) {
+        const unsigned int count = *pr.count;
+        live0 = q0 < count;
+        live1 = q0 + 1 < count;
+        i0 = live0 ? pr.list[q0] : 0;
+        i1 = live1 ? pr.list[q0 + 1] : 0;
+        need0 = live0 ? pr.masks[q0] : 0u;
+        need1 = live1 ? pr.masks[q0 + 1] : 0u;
+    }
     const float* xr0 = X + (live0 ? i0 : 0) * d;
-    const float* xr1 = X + (live1 ? i0 + 1 : 0) * d;
+    const float* xr1 = X + (live1 ? i1 : 0) * d;
     const int nv = d >> 2;
+    const unsigned qmask = PRUNE ? (0xFu << (threadIdx.x & 28)) : 0xffffffffu;  // shuffles stay inside the quad
+    const unsigned needq = need0 | need1;
+    const bool load0 = live0 && need0 != 0u, load1 = live1 && need1 != 0u;
     auto fetch = [&](const float* xr, bool live, int s0, float (&x)[4]) {
         if (VEC) {
             const float4 v = (live && s0 + l < nv) ? __ldg(reinterpret_cast<const float4*>(xr) + s0 + l)
@@ -495,10 +561,10 @@ __global__ void __launch_bounds__(256) dist_rows_quad_kernel(const float* __rest
         const float* crow = cs + ((size_t)j0 * 4 + l) * Tp;  // row jj of this lane: crow + jj*4*Tp
         const int rstride = 4 * Tp;
         auto advance = [&](float (&x0)[4], float (&x1)[4], int s0) {  // four steps of every row sum, both frames
-            if (VEC) { quad_transpose(x0, l); quad_transpose(x1, l); }
+            if (VEC) { quad_transpose(x0, l, qmask); quad_transpose(x1, l, qmask); }
 #pragma unroll
             for (int jj = 0; jj < MR; ++jj) {
-                if (FULL || j0 + jj < m) {
+                if ((FULL || j0 + jj < m) && (!PRUNE || ((needq >> jj) & 1u))) {
                     const float4 c = *reinterpret_cast<const float4*>(crow + jj * rstride + s0);
                     float t = __fsub_rn(x0[0], c.x), u = __fsub_rn(x1[0], c.x);
                     float a = __fadd_rn(acc0[jj], __fmul_rn(t, t)), b = __fadd_rn(acc1[jj], __fmul_rn(u, u));
@@ -514,19 +580,21 @@ __global__ void __launch_bounds__(256) dist_rows_quad_kernel(const float* __rest
         };
         // ping-pong prefetch: buffer A holds chunk s0, buffer B chunk s0+4 (no register rotation)
         float a0[4], a1[4], b0[4], b1[4];
-        fetch(xr0, live0, 0, a0);
-        fetch(xr1, live1, 0, a1);
-        for (int s0 = 0; s0 < T; s0 += 8) {
-            if (s0 + 4 < T) { fetch(xr0, live0, s0 + 4, b0); fetch(xr1, live1, s0 + 4, b1); }
-            advance(a0, a1, s0);
-            if (s0 + 4 < T) {
-                if (s0 + 8 < T) { fetch(xr0, live0, s0 + 8, a0); fetch(xr1, live1, s0 + 8, a1); }
-                advance(b0, b1, s0 + 4);
+        if (!PRUNE || needq != 0u) {
+            fetch(xr0, load0, 0, a0);
+            fetch(xr1, load1, 0, a1);
+            for (int s0 = 0; s0 < T; s0 += 8) {
+                if (s0 + 4 < T) { fetch(xr0, load0, s0 + 4, b0); fetch(xr1, load1, s0 + 4, b1); }
+                advance(a0, a1, s0);
+                if (s0 + 4 < T) {
+                    if (s0 + 8 < T) { fetch(xr0, load0, s0 + 8, a0); fetch(xr1, load1, s0 + 8, a1); }
+                    advance(b0, b1, s0 + 4);
+                }
             }
         }
-        if (!VEC && l == 0) {
+        if (!VEC && l == 0 && (!PRUNE || needq != 0u)) {
             for (int q = 0; q < d - d4; ++q) {
-                const float xv0 = live0 ? __ldg(xr0 + d4 + q) : 0.f, xv1 = live1 ? __ldg(xr1 + d4 + q) : 0.f;
+                const float xv0 = load0 ? __ldg(xr0 + d4 + q) : 0.f, xv1 = load1 ? __ldg(xr1 + d4 + q) : 0.f;
 #pragma unroll
                 for (int jj = 0; jj < MR; ++jj) {
                     if (FULL || j0 + jj < m) {
@@ -540,13 +608,15 @@ __global__ void __launch_bounds__(256) dist_rows_quad_kernel(const float* __rest
         }
 #pragma unroll
         for (int jj = 0; jj < MR; ++jj) {
-            const float a1s = __shfl_down_sync(0xffffffffu, acc0[jj], 1), b1s = __shfl_down_sync(0xffffffffu, acc1[jj], 1);
-            const float a2s = __shfl_down_sync(0xffffffffu, acc0[jj], 2), b2s = __shfl_down_sync(0xffffffffu, acc1[jj], 2);
-            const float a3s = __shfl_down_sync(0xffffffffu, acc0[jj], 3), b3s = __shfl_down_sync(0xffffffffu, acc1[jj], 3);
+            const float a1s = __shfl_down_sync(qmask, acc0[jj], 1), b1s = __shfl_down_sync(qmask, acc1[jj], 1);
+            const float a2s = __shfl_down_sync(qmask, acc0[jj], 2), b2s = __shfl_down_sync(qmask, acc1[jj], 2);
+            const float a3s = __shfl_down_sync(qmask, acc0[jj], 3), b3s = __shfl_down_sync(qmask, acc1[jj], 3);
             if (l == 0 && (FULL || j0 + jj < m)) {
-                float* o = out + (int64_t)(j0 + jj) * n + i0;
-                if (live0) o[0] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc0[jj], a1s), a2s), a3s));
-                if (live1) o[1] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc1[jj], b1s), b2s), b3s));
+                float* o = out + (int64_t)(j0 + jj) * n;
+                if (live0 && (!PRUNE || ((need0 >> jj) & 1u)))
+                    o[i0] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc0[jj], a1s), a2s), a3s));
+                if (live1 && (!PRUNE || ((need1 >> jj) & 1u)))
+                    o[i1] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc1[jj], b1s), b2s), b3s));
             }
         }
     }
@@ -647,35 +717,59 @@ int launch_tile_indexed(b2k_ctx* ctx, const float* X, int d, const float* C, int
 
 template <int MR, bool FULL>
 static int launch_dist_rows_quad(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out,
-                                 int T, size_t smem, bool vec) {
+                                 int T, size_t smem, bool vec, const DistRowsPrune* prune) {
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<MR, true, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<MR, false, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<MR, true, FULL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<MR, false, FULL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        if (FULL) {
+            CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<MR, true, FULL, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<MR, false, FULL, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        }
         attr_set = true;
     }
     const unsigned grid = (unsigned)cdiv(cdiv(n, 2) * 4, 256);
-    if (vec) dist_rows_quad_kernel<MR, true, FULL><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T);
-    else dist_rows_quad_kernel<MR, false, FULL><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T);
+    DistRowsPrune none = {};
+    if (FULL && prune) {
+        CUDA_TRY(cudaMemsetAsync(prune->count, 0, 4, ctx->stream));
+        const unsigned sg = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16));
+        kmpp_prune_scan_kernel<<<sg, 256, 0, ctx->stream>>>(n, m, out, *prune);
+        LAUNCH_CHECK();
+        if (vec) dist_rows_quad_kernel<MR, true, FULL, FULL><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T, *prune);
+        else dist_rows_quad_kernel<MR, false, FULL, FULL><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T, *prune);
+    } else {
+        if (vec) dist_rows_quad_kernel<MR, true, FULL, false><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T, none);
+        else dist_rows_quad_kernel<MR, false, FULL, false><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T, none);
+    }
     LAUNCH_CHECK();
     return B2K_OK;
 }
 
-int launch_dist_rows(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out) {
+// prune (optional, k-means++): see DistRowsPrune; ignored when the quad kernel does not apply
+int launch_dist_rows_pruned(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out,
+                            const float* D, const int32_t* assigned, const unsigned char* taken, const float* Rc,
+                            int rc_stride, uint32_t* list, uint32_t* masks, unsigned int* count) {
     if (n <= 0 || m <= 0) return B2K_OK;
     const int T = std::max(4, (int)cdiv(d / 4, 4) * 4);  // steps per accumulator lane, padded to whole 16-byte loads
     const size_t smem = ((size_t)m * 4 * (T + 4) + (size_t)m * 4) * 4;
     if (m <= 32 && smem <= 160 * 1024 && n >= 64) {
         const bool vec = (d % 4 == 0) && (((uintptr_t)X) & 15) == 0;
+        DistRowsPrune pr = {D, assigned, taken, Rc, rc_stride, 2.0f * (1.0f + 1e-4f + 4e-7f * (float)d), list, masks, count};
+        const DistRowsPrune* pp = (D && n < (int64_t(1) << 32)) ? &pr : nullptr;
         switch (m) {
-#define B2K_DR(M) case M: return launch_dist_rows_quad<M, true>(ctx, X, n, d, rows, m, out, T, smem, vec);
+#define B2K_DR(M) case M: return launch_dist_rows_quad<M, true>(ctx, X, n, d, rows, m, out, T, smem, vec, pp);
             B2K_DR(1) B2K_DR(2) B2K_DR(3) B2K_DR(4) B2K_DR(5) B2K_DR(6) B2K_DR(7) B2K_DR(8) B2K_DR(9) B2K_DR(10)
             B2K_DR(11) B2K_DR(12) B2K_DR(13) B2K_DR(14)
 #undef B2K_DR
-            default: return launch_dist_rows_quad<8, false>(ctx, X, n, d, rows, m, out, T, smem, vec);
+            default: return launch_dist_rows_quad<8, false>(ctx, X, n, d, rows, m, out, T, smem, vec, nullptr);
         }
     }
     return launch_tile(ctx, X, n, d, rows, m, nullptr, out, 0, MODE_ALL);
+}
+
+int launch_dist_rows(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out) {
+    return launch_dist_rows_pruned(ctx, X, n, d, rows, m, out, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
+                                   nullptr);
 }
 
 int launch_labeled_dist(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, const int32_t* labels,

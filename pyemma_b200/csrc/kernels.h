@@ -20,6 +20,10 @@ int launch_tile_indexed(b2k_ctx* ctx, const float* X, int d, const float* C, int
                         int lloyd);
 // out[j][i] = sqrt(dist2(x_i, rows_j)), j < m
 int launch_dist_rows(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out);
+// same with the k-means++ triangle-inequality pruning (exact.cu DistRowsPrune); D == null: no pruning
+int launch_dist_rows_pruned(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out,
+                            const float* D, const int32_t* assigned, const unsigned char* taken, const float* Rc,
+                            int rc_stride, uint32_t* list, uint32_t* masks, unsigned int* count);
 int launch_labeled_dist(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, const int32_t* labels,
                         float* out);
 

@@ -122,7 +122,8 @@ __global__ void kmpp_gather_kernel(const float* __restrict__ X, int d, const Kmp
 // D[i] <- min(D[i], d2(x_i,best)) using the stored contributions; delta[i] <- change (serial mode)
 __global__ void kmpp_update_kernel(float* __restrict__ D, const unsigned char* __restrict__ taken, int64_t n,
                                    const float* __restrict__ src /* cd[jbest] or fresh distances (sqrt'd) */,
-                                   int src_is_sqrt, float* __restrict__ delta) {
+                                   int src_is_sqrt, float* __restrict__ delta, int32_t* __restrict__ assigned = nullptr,
+                                   int32_t center_index = 0) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float dl = 0.f;
@@ -130,9 +131,37 @@ __global__ void kmpp_update_kernel(float* __restrict__ D, const unsigned char* _
         float dd = src[i];
         if (src_is_sqrt) dd = __fmul_rn(dd, dd);
         const float old = D[i];
-        if (dd < old) { dl = __fsub_rn(dd, old); D[i] = dd; }
+        if (dd < old) {
+            dl = __fsub_rn(dd, old);
+            D[i] = dd;
+            if (assigned) assigned[i] = center_index;  // the chosen center that realises D2 (pruning, exact.cu)
+        }
     }
     if (delta) delta[i] = dl;
+}
+
+// Rc[j][a] = lower bound of |center_a - candidate_j| (fp64 sum, rounded down): one warp per (a, j)
+__global__ void __launch_bounds__(256) kmpp_center_cand_dist_kernel(const float* __restrict__ centers, int found,
+                                                                    const float* __restrict__ rows, int m, int d,
+                                                                    float* __restrict__ Rc, int rc_stride) {
+    const int w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= found * m) return;
+    const int a = w / m, j = w - a * m;
+    const float* c = centers + (size_t)a * d;
+    const float* r = rows + (size_t)j * d;
+    double s = 0.0;
+    for (int e = lane; e < d; e += 32) {
+        const double t = (double)c[e] - (double)r[e];
+        s += t * t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const double R = sqrt(s) * (1.0 - 1e-6);
+        float f = (float)R;
+        if ((double)f > R) f = nextafterf(f, 0.f);  // never above the true distance
+        Rc[(size_t)j * rc_stride + a] = (s == s) ? f : 0.f;  // NaN data: no pruning
+    }
 }
 
 // ---- SERIAL ordered sums: one warp, values fetched coalesced, summed in frame order ------------
@@ -684,7 +713,9 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
     for (size_t t = 0; t < (size_t)(k - 1) * m; ++t) u[t] = gen.unit();
 
     DevBuf bD, bTaken, bCd, bRows, bRowsC, bGb, bGa, bU, bState, bPots, bL5, bL10g, bL15, bL20, bL25, bL30, bP20, bP30,
-        bNode, bResid;
+        bNode, bResid, bAssigned, bRc, bList, bMasks, bCount;
+    const bool prune = ctx->kmpp_prune != 0 && metric == B2K_METRIC_EUCLIDEAN && m <= 14;
+    const int rc_stride = (k + 3) & ~3;
     const int64_t nn = std::max<int64_t>(n, 1);
     B2K_TRY(bD.alloc(nn * 4));
     B2K_TRY(bTaken.alloc(nn));
@@ -698,6 +729,14 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
     B2K_TRY(bL25.alloc(n25g * 4)); B2K_TRY(bL30.alloc(n30g * 4));
     B2K_TRY(bP20.alloc((size_t)m * n20g * 4)); B2K_TRY(bP30.alloc((size_t)m * n30g * 4));
     B2K_TRY(bNode.alloc(KMPP_MAX_TRIALS * 8)); B2K_TRY(bResid.alloc(KMPP_MAX_TRIALS * 4));
+    if (prune) {
+        B2K_TRY(bAssigned.alloc(nn * 4));
+        B2K_TRY(bRc.alloc((size_t)m * rc_stride * 4));
+        B2K_TRY(bList.alloc(nn * 4));
+        B2K_TRY(bMasks.alloc(nn * 4));
+        B2K_TRY(bCount.alloc(16));
+        CUDA_TRY(cudaMemsetAsync(bAssigned.p, 0, nn * 4, st));  // D2 starts as the distance to center 0
+    }
     float* D = bD.as<float>();
     unsigned char* taken = bTaken.as<unsigned char>();
     float* cd = bCd.as<float>();
@@ -803,7 +842,17 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         LAUNCH_CHECK();
         B2K_TRY(fetch_rows(m));  // reads xil; `rows` valid on every rank afterwards
         // ---- potentials ----
-        B2K_TRY(dist_rows(rows, m, cd));
+        if (prune && n > 0) {
+            // distances of the m candidates to the `found` centers chosen so far, then the pruned distance rows
+            kmpp_center_cand_dist_kernel<<<(unsigned)cdiv((int64_t)found * m * 32, 256), 256, 0, st>>>(
+                dcenters_out, found, rows, m, d, bRc.as<float>(), rc_stride);
+            LAUNCH_CHECK();
+            B2K_TRY(launch_dist_rows_pruned(ctx, dX, n, d, rows, m, cd, D, bAssigned.as<int32_t>(), taken,
+                                            bRc.as<float>(), rc_stride, bList.as<uint32_t>(), bMasks.as<uint32_t>(),
+                                            bCount.as<unsigned int>()));
+        } else {
+            B2K_TRY(dist_rows(rows, m, cd));
+        }
         if (ex) CUDA_TRY(cudaMemsetAsync(xf, 0, (size_t)m * n10g * 4, st));
         if (n > 0) {
             kmpp_contrib_sharded_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cd, n, m, D, taken, S->cand, lo);
@@ -847,11 +896,13 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         if (cb) cb(user);
         if (found + 1 < k && n > 0) {
             if (jbest >= 0) {
-                kmpp_update_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(D, taken, n, cd + (size_t)jbest * n, 0, nullptr);
+                kmpp_update_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(D, taken, n, cd + (size_t)jbest * n, 0, nullptr,
+                                                                           prune ? bAssigned.as<int32_t>() : nullptr, found);
                 LAUNCH_CHECK();
             } else {
                 B2K_TRY(dist_rows(dcenters_out + (size_t)found * d, 1, cd));
-                kmpp_update_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(D, taken, n, cd, 1, nullptr);
+                kmpp_update_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(D, taken, n, cd, 1, nullptr,
+                                                                           prune ? bAssigned.as<int32_t>() : nullptr, found);
                 LAUNCH_CHECK();
             }
         }

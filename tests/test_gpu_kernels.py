@@ -338,3 +338,24 @@ def test_kmpp_sharded_matches_single(b2k, oracle, n, d, k, shards):
     for cen, chosen in results:
         np.testing.assert_array_equal(chosen, ridx)
         np.testing.assert_array_equal(cen, ref)
+
+
+@pytest.mark.parametrize("n,d,k", [(30000, 16, 400), (20000, 64, 300), (8000, 256, 150), (9000, 7, 500)])
+def test_kmpp_pruning_is_exact(b2k, oracle, n, d, k):
+    """triangle-inequality pruning of the candidate distances (well separated blobs: most pairs are skipped) must not
+    change a single pick: pruned == unpruned == oracle"""
+    rng = np.random.RandomState(d)
+    cen = rng.uniform(-40, 40, size=(25, d))
+    X = (cen[rng.randint(0, 25, n)] + rng.randn(n, d)).astype(np.float32)
+    X[::50] = X[1::50]                                      # exact duplicates: D2 == 0 frames
+    ctx = b2k.context()
+    picks = []
+    for prune in (1, 0):
+        ctx.set_option("kmpp_prune", prune)
+        try:
+            picks.append(b2k.kmeans_init_centers_kmpp(X, k, 7, scan="blocked", return_indices=True)[1])
+        finally:
+            ctx.set_option("kmpp_prune", 1)
+    np.testing.assert_array_equal(picks[0], picks[1])
+    ref = oracle.kmpp_init(X, k, 7, scan="blocked", n_threads=8, return_indices=True)[1]
+    np.testing.assert_array_equal(picks[0], ref)
