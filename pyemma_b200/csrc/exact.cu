@@ -457,35 +457,45 @@ __global__ void __launch_bounds__(256) labeled_dist_quad_vec_kernel(const float*
 // R = |c_a - cand|: |x_i - cand| >= R - r, and the fp32 reference-order value dd satisfies dd >= |x_i-cand|^2 (1-g),
 // sqrt(D2_i) >= r (1-g), g <= (d/4+10) 2^-24; so R >= (2 + slack) sqrt(D2_i) implies dd >= D2_i.  R is computed in
 // fp64 and rounded down (kmpp.cu), slack = 1e-4 + 4e-7 d >> g.
-// Two phases so that the survivors are dense: kmpp_prune_scan_kernel (thread per frame) decides every pair, writes
-// +inf for all pairs of the frame and appends frames with at least one live pair to a list; the quad kernel then
-// walks that list (two listed frames per quad) instead of all frames, so no warp idles on pruned neighbours.
+// Two phases so that the survivors are dense: kmpp_prune_scan_kernel (thread per frame) decides every pair, records
+// the frame's candidate mask and appends frames with at least one live pair to a list; the quad kernel then walks
+// that list (two listed frames per quad) instead of all frames, so no warp idles on pruned neighbours, and writes
+// distances for live pairs only -- consumers (kmpp.cu potentials / D2 update) read the mask first.
 struct DistRowsPrune {
     const float* D;                // [n] current D2
     const int32_t* assigned;       // [n] index (into the chosen centers) of the center realising D2
     const unsigned char* taken;    // [n]
-    const float* Rc;               // [m][rc_stride] lower bounds of |chosen center a - candidate j|
-    int rc_stride;
+    const float* Rc;               // [found][16] lower bounds of |chosen center a - candidate j| (j < m <= 14)
+    int rc_stride;                 // = 16
     float factor;                  // 2 + slack
     uint32_t* list;                // [n] frames with live pairs
     uint32_t* masks;               // [n] their candidate masks (by list position)
     unsigned int* count;           // device counter (zeroed by the launcher)
+    uint16_t* framemask;           // [n] candidate mask of every frame (0: all pairs pruned)
 };
 
-__global__ void __launch_bounds__(256) kmpp_prune_scan_kernel(int64_t n, int m, float* __restrict__ out, DistRowsPrune pr) {
+__global__ void __launch_bounds__(256) kmpp_prune_scan_kernel(int64_t n, int m, DistRowsPrune pr) {
     const int lane = threadIdx.x & 31;
     const int64_t n_round = (n + 31) & ~(int64_t)31;
-    const float inf = __int_as_float(0x7f800000);
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_round; i += (int64_t)gridDim.x * 256) {
         uint32_t need = 0u;
         if (i < n) {
             if (!pr.taken[i]) {
                 const float thr = sqrtf(pr.D[i]) * pr.factor;
-                const float* rc = pr.Rc + pr.assigned[i];
-                for (int j = 0; j < m; ++j)
-                    if (!(__ldg(rc + (size_t)j * pr.rc_stride) >= thr)) need |= 1u << j;
+                const float4* rc = reinterpret_cast<const float4*>(pr.Rc + (size_t)pr.assigned[i] * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (4 * q < m) {
+                        const float4 r = __ldg(rc + q);
+                        need |= (!(r.x >= thr) ? 1u : 0u) << (4 * q);
+                        need |= (!(r.y >= thr) ? 1u : 0u) << (4 * q + 1);
+                        need |= (!(r.z >= thr) ? 1u : 0u) << (4 * q + 2);
+                        need |= (!(r.w >= thr) ? 1u : 0u) << (4 * q + 3);
+                    }
+                }
+                need &= (1u << m) - 1u;
             }
-            for (int j = 0; j < m; ++j) out[(int64_t)j * n + i] = inf;  // live pairs are overwritten by the quad kernel
+            pr.framemask[i] = (uint16_t)need;
         }
         const unsigned live = __ballot_sync(0xffffffffu, need != 0u);
         if (live) {
@@ -733,7 +743,7 @@ static int launch_dist_rows_quad(b2k_ctx* ctx, const float* X, int64_t n, int d,
     if (FULL && prune) {
         CUDA_TRY(cudaMemsetAsync(prune->count, 0, 4, ctx->stream));
         const unsigned sg = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 16));
-        kmpp_prune_scan_kernel<<<sg, 256, 0, ctx->stream>>>(n, m, out, *prune);
+        kmpp_prune_scan_kernel<<<sg, 256, 0, ctx->stream>>>(n, m, *prune);
         LAUNCH_CHECK();
         if (vec) dist_rows_quad_kernel<MR, true, FULL, FULL><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T, *prune);
         else dist_rows_quad_kernel<MR, false, FULL, FULL><<<grid, 256, smem, ctx->stream>>>(X, n, d, rows, m, out, T, *prune);
@@ -748,28 +758,35 @@ static int launch_dist_rows_quad(b2k_ctx* ctx, const float* X, int64_t n, int d,
 // prune (optional, k-means++): see DistRowsPrune; ignored when the quad kernel does not apply
 int launch_dist_rows_pruned(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out,
                             const float* D, const int32_t* assigned, const unsigned char* taken, const float* Rc,
-                            int rc_stride, uint32_t* list, uint32_t* masks, unsigned int* count) {
+                            int rc_stride, uint32_t* list, uint32_t* masks, unsigned int* count, uint16_t* framemask) {
     if (n <= 0 || m <= 0) return B2K_OK;
     const int T = std::max(4, (int)cdiv(d / 4, 4) * 4);  // steps per accumulator lane, padded to whole 16-byte loads
     const size_t smem = ((size_t)m * 4 * (T + 4) + (size_t)m * 4) * 4;
-    if (m <= 32 && smem <= 160 * 1024 && n >= 64) {
+    const bool want_prune = D != nullptr && n < (int64_t(1) << 32);
+    if (m <= 32 && smem <= 160 * 1024 && (n >= 64 || (want_prune && m <= 14))) {
         const bool vec = (d % 4 == 0) && (((uintptr_t)X) & 15) == 0;
-        DistRowsPrune pr = {D, assigned, taken, Rc, rc_stride, 2.0f * (1.0f + 1e-4f + 4e-7f * (float)d), list, masks, count};
-        const DistRowsPrune* pp = (D && n < (int64_t(1) << 32)) ? &pr : nullptr;
+        DistRowsPrune pr = {D, assigned, taken, Rc, rc_stride, 2.0f * (1.0f + 1e-4f + 4e-7f * (float)d), list, masks, count,
+                            framemask};
+        const DistRowsPrune* pp = want_prune ? &pr : nullptr;
+        if (!pp && framemask) CUDA_TRY(cudaMemsetAsync(framemask, 0xFF, (size_t)n * 2, ctx->stream));
         switch (m) {
 #define B2K_DR(M) case M: return launch_dist_rows_quad<M, true>(ctx, X, n, d, rows, m, out, T, smem, vec, pp);
             B2K_DR(1) B2K_DR(2) B2K_DR(3) B2K_DR(4) B2K_DR(5) B2K_DR(6) B2K_DR(7) B2K_DR(8) B2K_DR(9) B2K_DR(10)
             B2K_DR(11) B2K_DR(12) B2K_DR(13) B2K_DR(14)
 #undef B2K_DR
-            default: return launch_dist_rows_quad<8, false>(ctx, X, n, d, rows, m, out, T, smem, vec, nullptr);
+            default:
+                // every pair is evaluated: consumers of the frame masks must see them all live
+                if (framemask) CUDA_TRY(cudaMemsetAsync(framemask, 0xFF, (size_t)n * 2, ctx->stream));
+                return launch_dist_rows_quad<8, false>(ctx, X, n, d, rows, m, out, T, smem, vec, nullptr);
         }
     }
+    if (framemask) CUDA_TRY(cudaMemsetAsync(framemask, 0xFF, (size_t)n * 2, ctx->stream));
     return launch_tile(ctx, X, n, d, rows, m, nullptr, out, 0, MODE_ALL);
 }
 
 int launch_dist_rows(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out) {
     return launch_dist_rows_pruned(ctx, X, n, d, rows, m, out, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
-                                   nullptr);
+                                   nullptr, nullptr);
 }
 
 int launch_labeled_dist(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, const int32_t* labels,

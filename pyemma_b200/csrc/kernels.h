@@ -23,7 +23,7 @@ int launch_dist_rows(b2k_ctx* ctx, const float* X, int64_t n, int d, const float
 // same with the k-means++ triangle-inequality pruning (exact.cu DistRowsPrune); D == null: no pruning
 int launch_dist_rows_pruned(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out,
                             const float* D, const int32_t* assigned, const unsigned char* taken, const float* Rc,
-                            int rc_stride, uint32_t* list, uint32_t* masks, unsigned int* count);
+                            int rc_stride, uint32_t* list, uint32_t* masks, unsigned int* count, uint16_t* framemask);
 int launch_labeled_dist(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, const int32_t* labels,
                         float* out);
 

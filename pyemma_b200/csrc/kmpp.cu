@@ -123,11 +123,13 @@ __global__ void kmpp_gather_kernel(const float* __restrict__ X, int d, const Kmp
 __global__ void kmpp_update_kernel(float* __restrict__ D, const unsigned char* __restrict__ taken, int64_t n,
                                    const float* __restrict__ src /* cd[jbest] or fresh distances (sqrt'd) */,
                                    int src_is_sqrt, float* __restrict__ delta, int32_t* __restrict__ assigned = nullptr,
-                                   int32_t center_index = 0) {
+                                   int32_t center_index = 0, const uint16_t* __restrict__ framemask = nullptr,
+                                   int jbit = 0) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float dl = 0.f;
-    if (!taken[i]) {
+    // framemask: src holds a distance only where the pair was not pruned (a pruned pair cannot lower D2)
+    if (!taken[i] && (!framemask || ((framemask[i] >> jbit) & 1u))) {
         float dd = src[i];
         if (src_is_sqrt) dd = __fmul_rn(dd, dd);
         const float old = D[i];
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(256) kmpp_center_cand_dist_kernel(const float*
         const double R = sqrt(s) * (1.0 - 1e-6);
         float f = (float)R;
         if ((double)f > R) f = nextafterf(f, 0.f);  // never above the true distance
-        Rc[(size_t)j * rc_stride + a] = (s == s) ? f : 0.f;  // NaN data: no pruning
+        Rc[(size_t)a * rc_stride + j] = (s == s) ? f : 0.f;  // [center][candidate]; NaN data: no pruning
     }
 }
 
@@ -407,6 +409,63 @@ __global__ void kmpp_first_free_sharded_kernel(const unsigned char* __restrict__
                                                long long* out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && !taken[i]) atomicMin((unsigned long long*)out, (unsigned long long)(lo + i));
+}
+
+// Height-10 sums of the m contribution trees straight from the pruned distance rows: frame i contributes to tree j
+//   0 (taken / the candidate itself / no candidate), D2_i (pair pruned), min(D2_i, dist^2) otherwise
+// -- the values kmpp_contrib_sharded_kernel writes -- and the sums run in tree_up_kernel's order (xor butterfly over
+// the warp = balanced tree of 32, then over the 32 warp sums), so the potentials are bit-identical; the m x n
+// contribution arrays are neither written nor re-read.
+__global__ void __launch_bounds__(1024) kmpp_pot_tree_kernel(const float* __restrict__ cd, int64_t n, int m,
+                                                             const float* __restrict__ D,
+                                                             const unsigned char* __restrict__ taken,
+                                                             const uint16_t* __restrict__ framemask,
+                                                             const long long* __restrict__ cand, long long lo,
+                                                             float* __restrict__ out10, int64_t out10_stride) {
+    __shared__ float ws[4][32];
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool in = i < n;
+    const bool tk = in ? taken[i] != 0 : true;
+    const float di = in ? D[i] : 0.f;
+    const unsigned mask = in ? framemask[i] : 0u;
+    for (int j0 = 0; j0 < m; j0 += 4) {
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = j0 + q;
+            float c = 0.f;
+            if (j < m && !tk) {
+                const long long cj = cand[j];
+                if (cj >= 0 && cj != lo + i) {
+                    c = di;
+                    if ((mask >> j) & 1u) {
+                        const float dv = cd[(int64_t)j * n + i];
+                        const float dd = __fmul_rn(dv, dv);
+                        c = (dd < di) ? dd : di;
+                    }
+                }
+            }
+            v[q] = c;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = __fadd_rn(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
+        }
+        __syncthreads();  // ws of the previous group consumed
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ws[q][w] = v[q];
+        }
+        __syncthreads();
+        if (w < 4 && j0 + w < m) {
+            float s = ws[w][lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+            if (lane == 0) out10[(int64_t)(j0 + w) * out10_stride + blockIdx.x] = s;
+        }
+    }
 }
 
 // roots of m trees: the first stored level (height 10, 20 or 30) that has a single entry IS the
@@ -713,9 +772,9 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
     for (size_t t = 0; t < (size_t)(k - 1) * m; ++t) u[t] = gen.unit();
 
     DevBuf bD, bTaken, bCd, bRows, bRowsC, bGb, bGa, bU, bState, bPots, bL5, bL10g, bL15, bL20, bL25, bL30, bP20, bP30,
-        bNode, bResid, bAssigned, bRc, bList, bMasks, bCount;
+        bNode, bResid, bAssigned, bRc, bList, bMasks, bCount, bFrameMask;
     const bool prune = ctx->kmpp_prune != 0 && metric == B2K_METRIC_EUCLIDEAN && m <= 14;
-    const int rc_stride = (k + 3) & ~3;
+    const int rc_stride = 16;  // Rc is [center][16]
     const int64_t nn = std::max<int64_t>(n, 1);
     B2K_TRY(bD.alloc(nn * 4));
     B2K_TRY(bTaken.alloc(nn));
@@ -731,7 +790,9 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
     B2K_TRY(bNode.alloc(KMPP_MAX_TRIALS * 8)); B2K_TRY(bResid.alloc(KMPP_MAX_TRIALS * 4));
     if (prune) {
         B2K_TRY(bAssigned.alloc(nn * 4));
-        B2K_TRY(bRc.alloc((size_t)m * rc_stride * 4));
+        B2K_TRY(bRc.alloc((size_t)k * rc_stride * 4));
+        CUDA_TRY(cudaMemsetAsync(bRc.p, 0, (size_t)k * rc_stride * 4, st));
+        B2K_TRY(bFrameMask.alloc(nn * 2));
         B2K_TRY(bList.alloc(nn * 4));
         B2K_TRY(bMasks.alloc(nn * 4));
         B2K_TRY(bCount.alloc(16));
@@ -849,12 +910,16 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
             LAUNCH_CHECK();
             B2K_TRY(launch_dist_rows_pruned(ctx, dX, n, d, rows, m, cd, D, bAssigned.as<int32_t>(), taken,
                                             bRc.as<float>(), rc_stride, bList.as<uint32_t>(), bMasks.as<uint32_t>(),
-                                            bCount.as<unsigned int>()));
+                                            bCount.as<unsigned int>(), bFrameMask.as<uint16_t>()));
         } else {
             B2K_TRY(dist_rows(rows, m, cd));
         }
         if (ex) CUDA_TRY(cudaMemsetAsync(xf, 0, (size_t)m * n10g * 4, st));
-        if (n > 0) {
+        if (n > 0 && prune) {
+            kmpp_pot_tree_kernel<<<(unsigned)n10, 1024, 0, st>>>(cd, n, m, D, taken, bFrameMask.as<uint16_t>(), S->cand, lo,
+                                                                 xf + node_lo, n10g);
+            LAUNCH_CHECK();
+        } else if (n > 0) {
             kmpp_contrib_sharded_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cd, n, m, D, taken, S->cand, lo);
             LAUNCH_CHECK();
             tree_up_kernel<<<dim3((unsigned)n10, m), 1024, 0, st>>>(cd, n, n, nullptr, nullptr, 0, xf + node_lo, n10g);
@@ -896,8 +961,11 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         if (cb) cb(user);
         if (found + 1 < k && n > 0) {
             if (jbest >= 0) {
-                kmpp_update_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(D, taken, n, cd + (size_t)jbest * n, 0, nullptr,
-                                                                           prune ? bAssigned.as<int32_t>() : nullptr, found);
+                // pruned mode: cd holds raw distances of the live pairs only (no contribution pass rewrote it)
+                kmpp_update_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(D, taken, n, cd + (size_t)jbest * n, prune ? 1 : 0,
+                                                                           nullptr, prune ? bAssigned.as<int32_t>() : nullptr,
+                                                                           found, prune ? bFrameMask.as<uint16_t>() : nullptr,
+                                                                           jbest);
                 LAUNCH_CHECK();
             } else {
                 B2K_TRY(dist_rows(dcenters_out + (size_t)found * d, 1, cd));
