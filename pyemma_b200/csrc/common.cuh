@@ -40,6 +40,13 @@ int set_error(int code, const char* fmt, ...);
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute is per device: one-time kernel attribute setup is tracked per device ordinal
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool need(int dev) const { return !((mask.load() >> (dev & 63)) & 1ull); }
+    void done(int dev) { mask.fetch_or(1ull << (dev & 63)); }
+};
+
 }  // namespace b2k
 
 // ---- context -------------------------------------------------------------------------------

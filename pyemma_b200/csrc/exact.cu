@@ -639,11 +639,11 @@ static int launch_small(b2k_ctx* ctx, const float* X, int64_t n, const float* C,
     const size_t budget = 96 * 1024;
     int kt = (int)std::min<int64_t>(k, budget / (D * 4));
     const size_t smem = (size_t)kt * D * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.need(ctx->device)) {
         CUDA_TRY(cudaFuncSetAttribute(assign_small_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)budget));
-        attr_set = true;
+        attr_set.done(ctx->device);
     }
     const int64_t blocks = cdiv(n, 256);
     assign_small_kernel<D><<<(unsigned)blocks, 256, smem, ctx->stream>>>(X, n, C, k, kt, labels, mind, lloyd, run_if_zero);
@@ -686,13 +686,13 @@ static int launch_tile_gated(b2k_ctx* ctx, const float* X, int64_t n, int d, con
     TileCfg cfg = tile_cfg(d, k, budget);
     if (cfg.smem > ctx->smem_optin)
         return set_error(B2K_ERR_INVALID_ARG, "dimension %d too large for the exact tile kernel", d);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.need(ctx->device)) {
         CUDA_TRY(cudaFuncSetAttribute(tile_kernel<MODE_ARGMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)ctx->smem_optin));
         CUDA_TRY(cudaFuncSetAttribute(tile_kernel<MODE_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)ctx->smem_optin));
-        attr_set = true;
+        attr_set.done(ctx->device);
     }
     const int64_t blocks = cdiv(n, cfg.FB);
     if (mode == MODE_ARGMIN)
@@ -713,11 +713,11 @@ int launch_tile_indexed(b2k_ctx* ctx, const float* X, int d, const float* C, int
     TileCfg cfg = tile_cfg(d, k, budget);
     if (cfg.smem > ctx->smem_optin)
         return set_error(B2K_ERR_INVALID_ARG, "dimension %d too large for the exact tile kernel", d);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.need(ctx->device)) {
         CUDA_TRY(cudaFuncSetAttribute(tile_indexed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)ctx->smem_optin));
-        attr_set = true;
+        attr_set.done(ctx->device);
     }
     tile_indexed_kernel<<<ctx->sm_count * 2, 128, cfg.smem, ctx->stream>>>(X, d, C, k, cfg, row_index, count_dev,
                                                                           run_if_nonzero, labels, mind, lloyd);
@@ -728,15 +728,15 @@ int launch_tile_indexed(b2k_ctx* ctx, const float* X, int d, const float* C, int
 template <int MR, bool FULL>
 static int launch_dist_rows_quad(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out,
                                  int T, size_t smem, bool vec, const DistRowsPrune* prune) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.need(ctx->device)) {
         CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<MR, true, FULL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<MR, false, FULL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         if (FULL) {
             CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<MR, true, FULL, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(dist_rows_quad_kernel<MR, false, FULL, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         }
-        attr_set = true;
+        attr_set.done(ctx->device);
     }
     const unsigned grid = (unsigned)cdiv(cdiv(n, 2) * 4, 256);
     DistRowsPrune none = {};
@@ -808,11 +808,11 @@ int launch_labeled_dist(b2k_ctx* ctx, const float* X, int64_t n, int d, const fl
         const size_t per_warp = (size_t)16 * rsb * 4;
         const int wpc = (int)std::min<size_t>(8, (96 * 1024) / per_warp);
         if (wpc >= 1) {
-            static bool attr_set = false;
-            if (!attr_set) {
+            static PerDeviceOnce attr_set;
+            if (attr_set.need(ctx->device)) {
                 CUDA_TRY(cudaFuncSetAttribute(labeled_dist_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               100 * 1024));
-                attr_set = true;
+                attr_set.done(ctx->device);
             }
             const size_t smem = per_warp * wpc;
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));

@@ -441,10 +441,10 @@ int launch_accumulate(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, con
     const bool small_job = total <= (int64_t(1) << 22);
     if (((ctx->accumulate_mode == 0 && small_job) || ctx->accumulate_mode == 3) && total >= (int64_t(1) << 16) &&
         table_bytes <= (size_t)200 * 1024 && (int64_t)k * d < (int64_t(1) << 24)) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr_set;
+        if (attr_set.need(ctx->device)) {
             CUDA_TRY(cudaFuncSetAttribute(accumulate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
+            attr_set.done(ctx->device);
         }
         const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(total, 1024 * 8), ctx->sm_count));
         accumulate_smem_kernel<<<grid, 1024, table_bytes, ctx->stream>>>(X, n, d, k, labels, scale, (unsigned long long*)acc);
@@ -459,11 +459,11 @@ int launch_accumulate(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, con
         unsigned long long* a64 = (unsigned long long*)acc;
 #define B2K_ST(LPF)                                                                                          \
     do {                                                                                                     \
-        static bool at = false;                                                                              \
-        if (!at) {                                                                                           \
+        static PerDeviceOnce at;                                                                              \
+        if (at.need(ctx->device)) {                                                                                           \
             CUDA_TRY(cudaFuncSetAttribute(seg_tile_kernel<LPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (2 * ST_KMAX + 1) * 4 + ST_TILE * 2 + 16));                        \
-            at = true;                                                                                       \
+            at.done(ctx->device);                                                                                       \
         }                                                                                                    \
         seg_tile_kernel<LPF><<<grid, 256, smem, ctx->stream>>>(X, n, d, k, labels, scale, a64);              \
     } while (0)
@@ -493,11 +493,11 @@ int launch_accumulate(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, con
             n_cta = (int)cdiv(n, per_cta);
             B2K_TRY(ctx->ensure_scratch2((size_t)n_cta * k * 4));
             uint32_t* hist2 = reinterpret_cast<uint32_t*>(ctx->scratch2);
-            static bool attr_set = false;
-            if (!attr_set) {
+            static PerDeviceOnce attr_set;
+            if (attr_set.need(ctx->device)) {
                 CUDA_TRY(cudaFuncSetAttribute(seg_hist2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_TABLE_MAX * 4));
                 CUDA_TRY(cudaFuncSetAttribute(seg_scatter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_TABLE_MAX * 4));
-                attr_set = true;
+                attr_set.done(ctx->device);
             }
             seg_hist2_kernel<<<n_cta, 256, (size_t)k * 4, st>>>(labels, n, k, per_cta, hist2);
             LAUNCH_CHECK();

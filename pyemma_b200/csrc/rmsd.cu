@@ -442,13 +442,13 @@ static int launch_rtile(b2k_ctx* ctx, const float* X, const float* Ga, int64_t n
     RTileCfg cfg = rtile_cfg(d, k, budget);
     if (cfg.smem > ctx->smem_optin)
         return set_error(B2K_ERR_INVALID_ARG, "dimension %d too large for the minRMSD tile kernel", d);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.need(ctx->device)) {
         CUDA_TRY(cudaFuncSetAttribute(rmsd_tile_kernel<MODE_ARGMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)ctx->smem_optin));
         CUDA_TRY(cudaFuncSetAttribute(rmsd_tile_kernel<MODE_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)ctx->smem_optin));
-        attr_set = true;
+        attr_set.done(ctx->device);
     }
     const int64_t blocks = cdiv(n, cfg.FB);
     if (mode == MODE_ARGMIN)

@@ -1535,8 +1535,8 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     int rc = make_tmap(&p->tmA, p->A, (uint64_t)p->n_pad, (uint64_t)p->Kp, TILE_M);
     if (rc == B2K_OK) rc = make_tmap(&p->tmB, p->B, (uint64_t)p->k_pad, (uint64_t)p->Kp, TILE_N);
     if (rc != B2K_OK) { screen_plan_destroy(p); return rc; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.need(ctx->device)) {
         cudaError_t ae = cudaFuncSetAttribute(screen_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)ctx->smem_optin);
         if (ae == cudaSuccess)
@@ -1544,7 +1544,7 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
         if (ae == cudaSuccess)
             ae = cudaFuncSetAttribute(screen_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
         if (ae != cudaSuccess) { screen_plan_destroy(p); return set_error(B2K_ERR_CUDA, "screen smem attr: %s", cudaGetErrorString(ae)); }
-        attr_set = true;
+        attr_set.done(ctx->device);
     }
     *out = p;
     return B2K_OK;
@@ -1710,11 +1710,11 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
                     (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * per_sm));
 #define B2K_VTABLE(DR)                                                                                               \
     do {                                                                                                             \
-        static bool vattr = false;                                                                                   \
-        if (!vattr) {                                                                                                \
+        static PerDeviceOnce vattr;                                                                                   \
+        if (vattr.need(ctx->device)) {                                                                                                \
             CUDA_TRY(cudaFuncSetAttribute(screen_verify_table_kernel<DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           100 * 1024));                                                              \
-            vattr = true;                                                                                            \
+            vattr.done(ctx->device);                                                                                            \
         }                                                                                                            \
         screen_verify_table_kernel<DR><<<tgrid, 256, tbytes, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, \
                                                                    mind, lloyd, p->params, p->fb_list, gstride,     \
@@ -1738,11 +1738,11 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
             (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 32), (int64_t)ctx->sm_count * per_sm));
 #define B2K_VERIFY(DR)                                                                                               \
     do {                                                                                                             \
-        static bool vattr = false;                                                                                   \
-        if (!vattr) {                                                                                                \
+        static PerDeviceOnce vattr;                                                                                   \
+        if (vattr.need(ctx->device)) {                                                                                                \
             CUDA_TRY(cudaFuncSetAttribute(screen_verify_small_kernel<DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           100 * 1024));                                                              \
-            vattr = true;                                                                                            \
+            vattr.done(ctx->device);                                                                                            \
         }                                                                                                            \
         screen_verify_small_kernel<DR><<<vgrid, 256, vsmem, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels,  \
                                                                   mind, lloyd, p->params, p->fb_list, use_smem, rs, \
@@ -1765,10 +1765,10 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
     } else {
         if (p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0) {
             const size_t tsmem = (size_t)8 * VC_WARP_FLOATS * 4;
-            static bool tattr = false;
-            if (!tattr) {
+            static PerDeviceOnce tattr;
+            if (tattr.need(ctx->device)) {
                 CUDA_TRY(cudaFuncSetAttribute(screen_verify_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                tattr = true;
+                tattr.done(ctx->device);
             }
             const int per_sm = (int)std::max<size_t>(1, (220 * 1024) / (tsmem + 1024));
             const unsigned tgrid =
@@ -1780,10 +1780,10 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         }
         const size_t vsmem = (size_t)8 * VW_FLOATS * 4;
         const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / vsmem));
-        static bool vattr = false;
-        if (!vattr) {
+        static PerDeviceOnce vattr;
+        if (vattr.need(ctx->device)) {
             CUDA_TRY(cudaFuncSetAttribute(screen_verify_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            vattr = true;
+            vattr.done(ctx->device);
         }
         const unsigned vgrid =
             (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 32), (int64_t)ctx->sm_count * ctas_per_sm));
