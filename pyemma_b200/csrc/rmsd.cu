@@ -262,14 +262,14 @@ __global__ void __launch_bounds__(128) rmsd_tile_kernel(const float* __restrict_
 // ---- slab kernel: 32 frames x 8*CPT centers per CTA, atoms streamed in slabs of 16 -----------------------------
 // The tile kernel above stages whole rows (3.6 KB for 300 atoms), which leaves one 128-thread CTA per SM and a
 // barrier between every load and compute phase.  Here a CTA of 256 threads (lane = frame, warp = center slot, CPT
-// centers per thread) walks the atoms in slabs of 16 (192 bytes per row): the slab of step t+1 is copied with
-// cp.async while step t is being summed, the 36 lane sums of every pair stay in registers across slabs, and 20 KB
+// centers per thread) walks the atoms in slabs of 32 (384 bytes per row): the slab of step t+1 is copied with
+// cp.async while step t is being summed, the 36 lane sums of every pair stay in registers across slabs, and 38 KB
 // of shared memory per CTA lets two CTAs share an SM.  Per 4 atoms a warp issues 3 conflict-free 16-byte loads
 // of its frames, 3*CPT broadcast loads of its centers and 72*CPT fp32 instructions: CUDA-core bound.
 // The per-pair arithmetic (Cov36 lane order, qcp_msd) is the one of the tile kernel, so results are identical.
-static constexpr int RS_ATOMS = 16;               // atoms per slab
+static constexpr int RS_ATOMS = 32;               // atoms per slab
 static constexpr int RS_ROW = RS_ATOMS * 3;       // floats per slab row
-static constexpr int RS_XROW = RS_ROW + 4;        // padded frame row: 13 x 16 B -> conflict-free 16-byte loads
+static constexpr int RS_XROW = RS_ROW + 4;        // padded frame row: 25 x 16 B (odd) -> conflict-free 16-byte loads
 
 __device__ __forceinline__ void rs_cp16(float* dst, const float* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)

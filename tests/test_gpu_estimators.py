@@ -269,3 +269,32 @@ def test_mini_batch_kmeans_matches_oracle_emulation(oracle):
     mb2 = coor.cluster_mini_batch_kmeans(trajs, k=12, max_iter=8, batch_size=0.5)
     assert mb2.clustercenters.shape == (12, 3) and mb2.initial_centers_.shape == (12, 3)
     assert len(np.unique(np.concatenate(mb2.dtrajs))) == 12
+
+
+def test_minrmsd_clustering_is_rotation_translation_invariant(b2k):
+    """reference tests/test_kmeans.py:266-316: noisy, randomly rotated and translated copies of 5 template structures
+    -- k-means++ (metric minRMSD) picks one center per template and every copy lands in its template's cluster."""
+    rng = np.random.RandomState(0)
+    n_atoms, n_templates, copies = 30, 5, 60
+    T = rng.uniform(-3, 3, size=(n_templates, n_atoms, 3))
+    frames, truth = [], []
+    for t in range(n_templates):
+        for _ in range(copies):
+            q = rng.randn(4)
+            q /= np.linalg.norm(q)
+            a, b, c, d = q
+            R = np.array([[a * a + b * b - c * c - d * d, 2 * (b * c - a * d), 2 * (b * d + a * c)],
+                          [2 * (b * c + a * d), a * a - b * b + c * c - d * d, 2 * (c * d - a * b)],
+                          [2 * (b * d - a * c), 2 * (c * d + a * b), a * a - b * b - c * c + d * d]])
+            frames.append(((T[t] + 0.01 * rng.randn(n_atoms, 3)) @ R.T + rng.uniform(-10, 10, 3)).reshape(-1))
+            truth.append(t)
+    X = np.array(frames, np.float32)
+    truth = np.array(truth)
+    centers = b2k.kmeans_init_centers_kmpp(X, n_templates, 3, metric="minRMSD", scan="blocked")
+    dt = coor.assign_to_centers(X, centers, metric="minRMSD")[0]
+    assert len(np.unique(dt)) == n_templates
+    for t in range(n_templates):
+        assert len(np.unique(dt[truth == t])) == 1
+    km = coor.cluster_kmeans(X, k=n_templates, max_iter=3, metric="minRMSD", fixed_seed=3)
+    for t in range(n_templates):
+        assert len(np.unique(km.dtrajs[0][truth == t])) == 1
