@@ -6,8 +6,9 @@ k=1000, euclidean.  One "step" = one Lloyd iteration over all resident frames:
     assign (argmin over 1000 centers) + centroid update + cost, exactly what
     deeptime kmeans.cluster_loop does per iteration (pyemma/coordinates/clustering/kmeans.py:254-258).
 `value` = frames assigned per second over the whole job (all GPUs), frames resident in HBM.
-`e2e`   = the same metric through the C-ABI host-pointer call b2k_kmeans_cluster with PINNED HOST
-          buffers: H2D of all frames + the Lloyd step + D2H of labels and centers inside the timing.
+`e2e`   = the same iteration with the frames in PINNED HOST memory every step (C-ABI call
+          b2k_stage_lloyd_assign_accumulate: H2D chunk by chunk, every chunk assigned and summed while the
+          next one is on the bus, labels D2H) + finalize + cost; the cost word is read on the host.
 Multi-GPU: frames shard over ranks (weak scaling: 1e7 frames per GPU), one int64 all-reduce of
 [k*d sums | k counts] + one cost word per iteration over NCCL.
 
@@ -281,8 +282,8 @@ def main():
                     "kernel_ms": ms, "peak_source": peak_src}
 
     # ---- e2e: the same Lloyd iteration, but the frames start in PINNED HOST memory every step:
-    #      b2k_stage_assign (H2D chunk by chunk, each chunk assigned while the next is on the bus, labels D2H)
-    #      -> accumulate -> all-reduce -> finalize -> cost -> all-reduce -> cost to the host.
+    #      b2k_stage_lloyd_assign_accumulate (H2D chunk by chunk, each chunk assigned and its member sums added while the
+    #      next is on the bus, labels D2H) -> all-reduce -> finalize -> cost -> all-reduce -> cost to the host.
     hx = torch.empty((n, D), dtype=torch.float32, pin_memory=True)
     hx.copy_(X)
     hl = torch.empty(n, dtype=torch.int32, pin_memory=True)
@@ -290,10 +291,9 @@ def main():
 
     def e2e_step():
         nonlocal cur, nxt
-        _lib.check(lib.b2k_stage_assign(ctx.handle, C.c_void_p(hx.data_ptr()), n, D, C.c_void_p(cur.data_ptr()), K,
-                                        _lib.EUCLIDEAN, 1, C.c_void_p(X.data_ptr()), C.c_void_p(labels.data_ptr()),
-                                        C.c_void_p(hl.data_ptr())))
-        _lib.check(lib.b2k_dev_lloyd_accumulate(sess, C.c_void_p(labels.data_ptr()), C.c_void_p(acc.data_ptr())))
+        _lib.check(lib.b2k_stage_lloyd_assign_accumulate(sess, C.c_void_p(hx.data_ptr()), C.c_void_p(cur.data_ptr()),
+                                                         C.c_void_p(X.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                                         C.c_void_p(hl.data_ptr()), C.c_void_p(acc.data_ptr())))
         if ws > 1:
             dist.all_reduce(acc[:acc_len - 1])
         _lib.check(lib.b2k_dev_lloyd_finalize(sess, C.c_void_p(acc.data_ptr()), C.c_void_p(cur.data_ptr()),
@@ -319,7 +319,8 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e = {"value": n * ws * e2e_steps / float(dt.item()), "unit": "frames/s",
            "h2d_bytes_per_step": n * D * 4, "d2h_bytes_per_step": n * 4 + 8,
-           "api": "b2k_stage_assign (pinned host frames -> HBM + labels back) + b2k_dev_lloyd_accumulate/finalize/cost",
+           "api": "b2k_stage_lloyd_assign_accumulate (pinned host frames -> HBM chunk by chunk, each chunk assigned and "
+                  "summed while the next is on the bus, labels back) + b2k_dev_lloyd_finalize/cost",
            "steps": e2e_steps, "ms_per_step": float(dt.item()) / e2e_steps * 1e3}
 
     cpu = None

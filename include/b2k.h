@@ -137,6 +137,11 @@ int b2k_dev_lloyd_destroy(b2k_lloyd* s);
 int64_t b2k_dev_lloyd_acc_len(const b2k_lloyd* s);
 /* labels (n_local) <- argmin vs dcenters (Lloyd tie/NaN semantics); acc <- local sums+counts (cost slot zeroed) */
 int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dcenters, int32_t* dlabels, int64_t* dacc);
+/* the two calls above for frames that are still on the HOST: the shard's frames X (n_local x d, host) are staged chunk
+ * by chunk into the session's device array dX_out (the pointer given to b2k_dev_lloyd_create), every chunk is assigned
+ * and its member sums are added to acc while the next chunk is on the bus; labels also go to labels_host if given */
+int b2k_stage_lloyd_assign_accumulate(b2k_lloyd* s, const float* X, const float* dcenters, float* dX_out,
+                                      int32_t* dlabels_out, int32_t* labels_host_or_null, int64_t* dacc);
 /* acc <- local sums+counts for GIVEN labels (e.g. those b2k_stage_assign produced); cost slot zeroed */
 int b2k_dev_lloyd_accumulate(b2k_lloyd* s, const int32_t* dlabels, int64_t* dacc);
 /* new centers from (all-reduced) acc; count==0 keeps old */

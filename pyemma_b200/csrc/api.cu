@@ -370,7 +370,8 @@ B2K_API int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, 
 // labels) additionally stay resident in one device array, which is how b2k_kmeans_cluster gets its frames
 // into HBM while the assignment of the first chunks is already running.
 static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* dC, int32_t k, int metric,
-                         int32_t* labels, int lloyd, float* dX_keep, int32_t* dL_keep) {
+                         int32_t* labels, int lloyd, float* dX_keep, int32_t* dL_keep, double acc_scale = 0.0,
+                         int64_t* dacc = nullptr) {
     cudaStream_t st = ctx->stream;
     PreparedCenters pc;
     B2K_TRY(pc.prepare(ctx, dC, k, d, metric));
@@ -419,6 +420,8 @@ static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, con
             if (metric == B2K_METRIC_MINRMSD) rc = launch_rmsd_center(ctx, dx, len, d, nullptr, dG[s]);
             if (rc == B2K_OK) rc = assign_any(ctx, dx, dG[s], len, d, pc, k, metric, dl, nullptr, lloyd);
         }
+        // member sums of this chunk while the next one is on the bus (exact integer sums: any chunking gives the same bits)
+        if (rc == B2K_OK && dacc) rc = launch_accumulate(ctx, dx, len, d, k, dl, acc_scale, dacc);
         cudaEventRecord(ev_k[s], st);
         cudaStreamWaitEvent(ctx->copy_stream[s], ev_k[s], 0);
         if (want_host) {
@@ -471,6 +474,9 @@ B2K_API int b2k_stage_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d,
 }
 
 // ---- Lloyd session ----------------------------------------------------------------------------
+struct b2k_lloyd;
+static double lloyd_scale_sum(const b2k_lloyd* s);
+
 struct b2k_lloyd {
     b2k_ctx* ctx = nullptr;
     const float* dX = nullptr;
@@ -539,6 +545,21 @@ B2K_API int b2k_dev_lloyd_destroy(b2k_lloyd* s) {
     if (s->plan) screen_plan_destroy(s->plan);
     delete s;
     return B2K_OK;
+}
+
+static double lloyd_scale_sum(const b2k_lloyd* s) { return s->scale_sum; }
+
+B2K_API int b2k_stage_lloyd_assign_accumulate(b2k_lloyd* s, const float* X, const float* dcenters, float* dX_out,
+                                              int32_t* dlabels_out, int32_t* labels_host, int64_t* dacc) {
+    if (!s || !dcenters || !dacc || (s->n > 0 && (!X || !dX_out || !dlabels_out)))
+        return set_error(B2K_ERR_INVALID_ARG, "stage_lloyd_assign_accumulate: null argument");
+    if (dX_out != s->dX) return set_error(B2K_ERR_INVALID_ARG, "stage_lloyd_assign_accumulate: dX_out must be the session's frame array");
+    b2k_ctx* ctx = s->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemsetAsync(dacc, 0, (size_t)((int64_t)s->k * s->d + s->k + 1) * 8, ctx->stream));
+    if (s->n == 0) return B2K_OK;
+    return stream_assign(ctx, X, s->n, s->d, dcenters, s->k, s->metric, labels_host, 1, dX_out, dlabels_out,
+                         lloyd_scale_sum(s), dacc);
 }
 
 B2K_API int64_t b2k_dev_lloyd_acc_len(const b2k_lloyd* s) { return s ? (int64_t)s->k * s->d + s->k + 1 : 0; }

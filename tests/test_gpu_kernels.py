@@ -359,3 +359,47 @@ def test_kmpp_pruning_is_exact(b2k, oracle, n, d, k):
     np.testing.assert_array_equal(picks[0], picks[1])
     ref = oracle.kmpp_init(X, k, 7, scan="blocked", n_threads=8, return_indices=True)[1]
     np.testing.assert_array_equal(picks[0], ref)
+
+
+def test_staged_lloyd_step_equals_resident_step(b2k):
+    """b2k_stage_lloyd_assign_accumulate (host frames, chunk by chunk, member sums per chunk) gives the same labels and
+    the same exchange buffer, bit for bit, as the device-resident b2k_dev_lloyd_assign_accumulate"""
+    import ctypes as C
+    import torch
+    rng = np.random.RandomState(21)
+    n, d, k = 70_001, 10, 300
+    X = blobs(rng, n, d, 9)
+    Cn = X[rng.choice(n, k, replace=False)].copy()
+    ctx = b2k.context()
+    dev = torch.device("cuda", ctx.device)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    hx = torch.from_numpy(X).pin_memory()
+    dXa = torch.from_numpy(X).to(dev)
+    dXb = torch.zeros_like(dXa)
+    dC = torch.from_numpy(Cn).to(dev)
+    out = {}
+    ctx.set_option("stage_bytes", 1 << 19)  # ~13000 frames per chunk
+    try:
+        for name, dX in (("resident", dXa), ("staged", dXb)):
+            sess = C.c_void_p()
+            b2k.check(ctx.lib.b2k_dev_lloyd_create(ctx.handle, C.c_void_p(dX.data_ptr()), n, d, k, 0, n,
+                                                   C.c_float(float(np.abs(X).max())), C.byref(sess)))
+            acc = torch.full((int(ctx.lib.b2k_dev_lloyd_acc_len(sess)),), -5, dtype=torch.int64, device=dev)
+            lab = torch.empty(n, dtype=torch.int32, device=dev)
+            hl = torch.empty(n, dtype=torch.int32).pin_memory()
+            if name == "resident":
+                b2k.check(ctx.lib.b2k_dev_lloyd_assign_accumulate(sess, C.c_void_p(dC.data_ptr()), C.c_void_p(lab.data_ptr()),
+                                                                  C.c_void_p(acc.data_ptr())))
+            else:
+                b2k.check(ctx.lib.b2k_stage_lloyd_assign_accumulate(sess, C.c_void_p(hx.data_ptr()), C.c_void_p(dC.data_ptr()),
+                                                                    C.c_void_p(dX.data_ptr()), C.c_void_p(lab.data_ptr()),
+                                                                    C.c_void_p(hl.data_ptr()), C.c_void_p(acc.data_ptr())))
+            torch.cuda.synchronize()
+            out[name] = (lab.cpu().numpy(), acc.cpu().numpy(), hl.numpy().copy())
+            ctx.lib.b2k_dev_lloyd_destroy(sess)
+    finally:
+        ctx.set_option("stage_bytes", 64 << 20)
+    np.testing.assert_array_equal(out["staged"][0], out["resident"][0])
+    np.testing.assert_array_equal(out["staged"][1], out["resident"][1])
+    np.testing.assert_array_equal(out["staged"][2], out["resident"][0])      # labels on the host too
+    assert torch.equal(dXb, dXa)                                             # frames landed in the session's array
