@@ -198,6 +198,15 @@ int b2k_dev_count_states(b2k_ctx* ctx, const int32_t* dlabels, int64_t n, int32_
 int b2k_dev_count_matrix(b2k_ctx* ctx, const int32_t* dlabels, int64_t n, int32_t nstates, int64_t lag, int sliding,
                          int64_t* dC);
 
+/* ---- the step before the path: linear projection of TICA / PCA fused into the chunk hand-off,
+ * Y = (X - mean) . W[:, :dout]  (pyemma/coordinates/transform/_tica_base.py:130-133, pca.py:263-265); mean (din) and
+ * W (din x ldw, row-major, ldw >= dout) are fp64 DEVICE arrays like the reference's model, Y is fp32 (n x dout) */
+int b2k_dev_project(b2k_ctx* ctx, const float* dX, int64_t n, int32_t din, const double* dmean_or_null,
+                    const double* dW, int32_t ldw, int32_t dout, float* dY);
+/* same with HOST frames X (n x din): staged chunk by chunk, only the projected rows stay in HBM (dY, device) */
+int b2k_stage_project(b2k_ctx* ctx, const float* X, int64_t n, int32_t din, const double* dmean_or_null,
+                      const double* dW, int32_t ldw, int32_t dout, float* dY);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,8 +90,11 @@ def gather_frames(source, stride=1, skip=0, chunksize=None, ctx=None, rank=0, wo
     cs = source.chunksize if chunksize is None else chunksize
     stage_rows = max(1, min(n_local if n_local else 1, (64 << 20) // max(4 * d, 1)))
     stager = PinnedStager(stage_rows, d, dev)
+    # a LinearProjection source: project every RAW chunk on the device while it is staged (transform.py)
+    fused = getattr(source, "project_host_chunk", None)
+    it_source = source.raw if fused is not None else source
     t = 0
-    with source.iterator(stride=stride, skip=skip, chunk=cs, return_trajindex=True) as it:
+    with it_source.iterator(stride=stride, skip=skip, chunk=cs, return_trajindex=True) as it:
         for _itraj, X in it:
             a, b = t, t + len(X)
             t = b
@@ -100,7 +103,10 @@ def gather_frames(source, stride=1, skip=0, chunksize=None, ctx=None, rank=0, wo
             if b <= lo or a >= hi:
                 continue
             xa, xb = max(a, lo) - a, min(b, hi) - a
-            stager.send(X[xa:xb], out[a + xa - lo:a + xb - lo])
+            if fused is not None:
+                fused(X[xa:xb], out[a + xa - lo:a + xb - lo], ctx)
+            else:
+                stager.send(X[xa:xb], out[a + xa - lo:a + xb - lo])
     stager.finish()
     torch.cuda.current_stream(dev).wait_stream(stager.stream)
     return out, n_total, lo
