@@ -797,7 +797,7 @@ int launch_labeled_dist(b2k_ctx* ctx, const float* X, int64_t n, int d, const fl
         LAUNCH_CHECK();
         return B2K_OK;
     }
-    if (d > 16 && ctx->cost_kernel != 1) {
+    if (d > 16 && ctx->cost_kernel != 1) {  // (d = 10: the thread-per-frame kernel is faster, 0.16 vs 0.26 ms per 1e7)
         labeled_dist_quad_kernel<<<(unsigned)cdiv(n * 4, 256), 256, 0, ctx->stream>>>(X, n, d, C, labels, out);
         LAUNCH_CHECK();
         return B2K_OK;
