@@ -1420,6 +1420,14 @@ __global__ void __launch_bounds__(256) screen_verify_direct_kernel(const float* 
                     const float4* c4 = reinterpret_cast<const float4*>(cr);
                     const int nv = d >> 2;
                     int t = 0;
+                    for (; t + 8 <= nv; t += 8) {  // 16 loads of 16 bytes in flight per lane: the kernel is L2-latency bound
+                        float4 xv[8], cv[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { xv[u] = __ldg(x4 + t + u); cv[u] = __ldg(c4 + t + u); }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            L.add4(xv[u].x, xv[u].y, xv[u].z, xv[u].w, cv[u].x, cv[u].y, cv[u].z, cv[u].w);
+                    }
                     for (; t + 4 <= nv; t += 4) {
                         float4 xv[4], cv[4];
 #pragma unroll
