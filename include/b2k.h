@@ -88,7 +88,8 @@ int b2k_ctx_sync(b2k_ctx* ctx);
 int b2k_ctx_set_option(b2k_ctx* ctx, const char* name, int64_t value);
 /* stats: "screen_frames", "screen_cand_chunks" (8-center groups re-evaluated exactly), "screen_fallback_frames"
  * of the last screened assign (host-pointer calls: of its last chunk); "screen_gemm_ms_total" and
- * "screen_gemm_launches" since "profile" was set; "sm_count" */
+ * "screen_gemm_launches" since "profile" was set; "sm_count"; "fp32_lane_instr_per_s" (measures the fp32 CUDA-core
+ * issue rate of non-fusable FMUL/FADD chains on the spot: the denominator quoted for the CUDA-core bound kernels) */
 int b2k_ctx_get_stat(b2k_ctx* ctx, const char* name, double* value);
 
 /* ---- compute_metric  (clustering_module.cpp:41-43) -------------------------------------- */

@@ -302,6 +302,10 @@ B2K_API int b2k_ctx_get_stat(b2k_ctx* c, const char* name, double* value) {
     else if (!strcmp(name, "screen_fallback_frames")) *value = c->stat_fallback_frames;
     else if (!strcmp(name, "screen_frames")) *value = c->stat_screen_frames;
     else if (!strcmp(name, "sm_count")) *value = c->sm_count;
+    else if (!strcmp(name, "fp32_lane_instr_per_s")) {  // measured now: non-fusable FMUL+FADD chains on every SM
+        CUDA_TRY(cudaSetDevice(c->device));
+        return measure_fp32_rate(c, value);
+    }
     else return set_error(B2K_ERR_INVALID_ARG, "unknown stat '%s'", name);
     return B2K_OK;
 }

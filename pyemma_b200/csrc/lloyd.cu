@@ -423,6 +423,42 @@ __global__ void __launch_bounds__(256) all_finite_kernel(const float* __restrict
     if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) *flag = 0;
 }
 
+// fp32 CUDA-core issue rate ("the builder must measure it"): 16 independent chains of the path's
+// own instruction mix -- FMUL and FADD that may not fuse -- per thread, all SMs resident
+__global__ void __launch_bounds__(256) fp32_rate_kernel(float* out, int iters, float c, float e) {
+    float a[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a[q] = (float)(threadIdx.x + q) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) a[q] = __fadd_rn(__fmul_rn(a[q], c), e);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s += a[q];
+    if (s == 12345.678f) out[0] = s;  // never true: keeps the chains alive
+}
+
+int measure_fp32_rate(b2k_ctx* ctx, double* lane_instr_per_s) {
+    B2K_TRY(ctx->ensure_scratch(64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 20000, blocks = ctx->sm_count * 8;
+    fp32_rate_kernel<<<blocks, 256, 0, ctx->stream>>>((float*)ctx->scratch, 200, 0.999f, 1e-3f);  // warm-up
+    CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    fp32_rate_kernel<<<blocks, 256, 0, ctx->stream>>>((float*)ctx->scratch, iters, 0.999f, 1e-3f);
+    CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *lane_instr_per_s = (double)blocks * 256.0 * iters * 32.0 / (ms * 1e-3);
+    return B2K_OK;
+}
+
 static unsigned grid_for(b2k_ctx* ctx, int64_t work_items, int per_block) {
     int64_t b = cdiv(work_items, per_block);
     const int64_t cap = (int64_t)ctx->sm_count * 8;
