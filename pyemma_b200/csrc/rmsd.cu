@@ -296,35 +296,51 @@ __global__ void __launch_bounds__(256, 2) rmsd_slab_kernel(const float* __restri
     const bool fvalid = fi < n;
     const float ga = fvalid ? Ga[fi] : 0.f;
 
-    // copy the slab of step (center tile jt, slab sl) into stage buffer `buf`
-    auto stage = [&](int jt, int sl, int buf) {
-        float* xs = sm + buf * STAGE;
-        float* cs = xs + 32 * RS_XROW;
-        const int col0 = sl * RS_ROW;
-        for (int t = tid; t < 32 * (RS_ROW / 4); t += 256) {
-            const int r = t / (RS_ROW / 4), c4 = t - r * (RS_ROW / 4);
-            const int col = col0 + c4 * 4;
-            float* dst = xs + r * RS_XROW + c4 * 4;
-            const int64_t row = base + r;
-            if (ALIGNED && row < n && col + 4 <= d) rs_cp16(dst, X + row * d + col);
-            else {
-                float v[4];
+    // copy the slab of step (center tile jt, slab sl) into stage buffer `buf`.  Which 16-byte pieces a thread copies
+    // never changes (piece t -> row t / 24, column group t % 24), so rows, offsets and source row pointers are set
+    // up once; a stage only adds the slab's column offset.
+    constexpr int PPR = RS_ROW / 4;                         // 16-byte pieces per slab row
+    constexpr int XP = (32 * PPR + 255) / 256;              // frame pieces per thread
+    constexpr int CP = (KT * PPR + 255) / 256;              // center pieces per thread
+    int x_dst[XP], x_c4[XP];
+    const float* x_src[XP];
+    bool x_ok[XP];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = (row < n && col + e < d) ? __ldg(X + row * d + col + e) : 0.f;
-                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            }
+    for (int u = 0; u < XP; ++u) {
+        const int t = tid + 256 * u, r = t / PPR, c4 = t - r * PPR;
+        x_ok[u] = t < 32 * PPR && base + r < n;
+        x_dst[u] = t < 32 * PPR ? r * RS_XROW + c4 * 4 : -1;
+        x_c4[u] = c4 * 4;
+        x_src[u] = X + (x_ok[u] ? base + r : 0) * d + c4 * 4;
+    }
+    int c_dst[CP], c_c4[CP], c_r[CP];
+#pragma unroll
+    for (int u = 0; u < CP; ++u) {
+        const int t = tid + 256 * u, r = t / PPR, c4 = t - r * PPR;
+        c_dst[u] = t < KT * PPR ? 32 * RS_XROW + r * RS_ROW + c4 * 4 : -1;
+        c_c4[u] = c4 * 4;
+        c_r[u] = r;
+    }
+    auto copy_piece = [&](float* dst, const float* src, bool row_ok, int col) {
+        if (ALIGNED && row_ok && col + 4 <= d) rs_cp16(dst, src);
+        else {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = (row_ok && col + e < d) ? __ldg(src + e) : 0.f;
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
         }
-        for (int t = tid; t < KT * (RS_ROW / 4); t += 256) {
-            const int r = t / (RS_ROW / 4), c4 = t - r * (RS_ROW / 4);
-            const int col = col0 + c4 * 4;
-            float* dst = cs + r * RS_ROW + c4 * 4;
-            const int j = jt * KT + r;
-            if (ALIGNED && j < k && col + 4 <= d) rs_cp16(dst, Cc + (int64_t)j * d + col);
-            else {
-                float v[4];
+    };
+    auto stage = [&](int jt, int sl, int buf) {
+        float* sb = sm + buf * STAGE;
+        const int col0 = sl * RS_ROW;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = (j < k && col + e < d) ? __ldg(Cc + (int64_t)j * d + col + e) : 0.f;
-                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        for (int u = 0; u < XP; ++u)
+            if (x_dst[u] >= 0) copy_piece(sb + x_dst[u], x_src[u] + col0, x_ok[u], col0 + x_c4[u]);
+#pragma unroll
+        for (int u = 0; u < CP; ++u) {
+            if (c_dst[u] >= 0) {
+                const int j = jt * KT + c_r[u];
+                copy_piece(sb + c_dst[u], Cc + (int64_t)(j < k ? j : 0) * d + col0 + c_c4[u], j < k, col0 + c_c4[u]);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
