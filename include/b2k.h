@@ -81,7 +81,8 @@ int b2k_ctx_set_stream(b2k_ctx* ctx, void* cuda_stream);
 int b2k_ctx_sync(b2k_ctx* ctx);
 /* options: "assign_engine" (B2K_ENGINE_*), "screen_terms" (1: hi-only fp16 operands, else hi+lo split),
  * "screen_group" (centers per candidate group the screen hands to the exact verify: 0 automatic, 8, 4 or 2),
- * "stage_bytes" (pinned staging buffer size per slot), "accumulate_mode" (member sums: 0 automatic, 1 one 64-bit
+ * "stage_bytes" (pinned staging buffer size per slot), "host_copy_threads" (threads of the
+ * pageable -> pinned bounce copy, default 8), "accumulate_mode" (member sums: 0 automatic, 1 one 64-bit
  * RED per frame element, 2 segmented = counting sort by label + warp run sums, 3 per-CTA shared-memory table,
  * 4 tile-sorted = per-tile shared-memory sort + run sums, narrow rows), "own_stream", "profile" (1: time every launch of the
  * tcgen05 screen kernel with CUDA events on the context stream; setting it again clears the record) */

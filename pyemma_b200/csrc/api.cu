@@ -3,6 +3,7 @@
 #include "kernels.h"
 #include <cstdarg>
 #include <algorithm>
+#include <thread>
 
 namespace b2k {
 
@@ -44,6 +45,22 @@ struct DevMem {
     }
     template <class T> T* as() const { return (T*)p; }
 };
+
+// pageable host memory -> pinned staging slot.  One memcpy thread moves ~10 GB/s, PCIe Gen5 takes 55: large copies
+// are split over a few threads so that the bounce stays off the critical path (option "host_copy_threads").
+static void host_copy(const b2k_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    const int nt = (int)std::min<size_t>((size_t)std::max(ctx->host_copy_threads, 1), bytes / (size_t(4) << 20));
+    if (nt <= 1) { std::memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t part = ((bytes / nt) + 4095) & ~size_t(4095);
+    for (int t = 1; t < nt; ++t) {
+        const size_t off = (size_t)t * part;
+        if (off >= bytes) break;
+        th.emplace_back([=] { std::memcpy((char*)dst + off, (const char*)src + off, std::min(part, bytes - off)); });
+    }
+    std::memcpy(dst, src, std::min(part, bytes));
+    for (auto& x : th) x.join();
+}
 
 static bool host_ptr_is_pinned(const void* p) {
     cudaPointerAttributes a;
@@ -87,7 +104,7 @@ int upload_host(b2k_ctx* ctx, const void* src, void* dst, size_t bytes) {
         const int s = c & 1;
         const size_t len = std::min(chunk, bytes - off);
         CUDA_TRY(cudaEventSynchronize(ctx->ev_done[s]));
-        std::memcpy(ctx->pinned[s], (const char*)src + off, len);
+        host_copy(ctx, ctx->pinned[s], (const char*)src + off, len);
         CUDA_TRY(cudaMemcpyAsync((char*)dst + off, ctx->pinned[s], len, cudaMemcpyHostToDevice, ctx->copy_stream[s]));
         CUDA_TRY(cudaEventRecord(ctx->ev_done[s], ctx->copy_stream[s]));
         off += len;
@@ -261,6 +278,7 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "fallback_mode")) c->fallback_mode = (int)value;
     else if (!strcmp(name, "operand_kernel")) c->operand_kernel = (int)value;
     else if (!strcmp(name, "kmpp_prune")) c->kmpp_prune = (int)value;
+    else if (!strcmp(name, "host_copy_threads")) c->host_copy_threads = (int)std::max<int64_t>(1, std::min<int64_t>(value, 32));
     else if (!strcmp(name, "accumulate_mode")) c->accumulate_mode = (int)value;
     else if (!strcmp(name, "cost_kernel")) c->cost_kernel = (int)value;
     else if (!strcmp(name, "rmsd_kernel")) c->rmsd_kernel = (int)value;
@@ -411,7 +429,7 @@ static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, con
             std::memcpy(labels + pend_off[s], ctx->pinned_out[s], (size_t)pend_len[s] * 4);
         pend_off[s] = -1;
         const void* src = X + off * d;
-        if (!in_pinned) { std::memcpy(ctx->pinned[s], src, (size_t)len * row_bytes); src = ctx->pinned[s]; }
+        if (!in_pinned) { host_copy(ctx, ctx->pinned[s], src, (size_t)len * row_bytes); src = ctx->pinned[s]; }
         float* dx = dX_keep ? dX_keep + off * d : dX[s];
         int32_t* dl = dL_keep ? dL_keep + off : dL[s];
         cudaMemcpyAsync(dx, src, (size_t)len * row_bytes, cudaMemcpyHostToDevice, ctx->copy_stream[s]);
