@@ -81,7 +81,9 @@ int b2k_ctx_set_stream(b2k_ctx* ctx, void* cuda_stream);
 int b2k_ctx_sync(b2k_ctx* ctx);
 /* options: "assign_engine" (B2K_ENGINE_*), "screen_terms" (1: hi-only fp16 operands, else hi+lo split),
  * "screen_group" (centers per candidate group the screen hands to the exact verify: 0 automatic, 8, 4 or 2),
- * "stage_bytes" (pinned staging buffer size per slot), "host_copy_threads" (threads of the
+ * "stage_bytes" (pinned staging buffer size per slot), "check_finite" (1: the host-pointer
+ * assign / stage entry points check every staged chunk on the device and return B2K_ERR_NONFINITE for NaN/inf frames,
+ * the guard of datasource.py:1067-1075; default 1), "host_copy_threads" (threads of the
  * pageable -> pinned bounce copy, default 8), "accumulate_mode" (member sums: 0 automatic, 1 one 64-bit
  * RED per frame element, 2 segmented = counting sort by label + warp run sums, 3 per-CTA shared-memory table,
  * 4 tile-sorted = per-tile shared-memory sort + run sums, narrow rows), "own_stream", "profile" (1: time every launch of the
@@ -92,6 +94,10 @@ int b2k_ctx_set_option(b2k_ctx* ctx, const char* name, int64_t value);
  * "screen_gemm_launches" since "profile" was set; "sm_count"; "fp32_lane_instr_per_s" (measures the fp32 CUDA-core
  * issue rate of non-fusable FMUL/FADD chains on the spot: the denominator quoted for the CUDA-core bound kernels) */
 int b2k_ctx_get_stat(b2k_ctx* ctx, const char* name, double* value);
+
+/* the chunk hand-off on its own: host bytes -> device array through the pinned staging slots (pageable sources are
+ * bounced with several copy threads); synchronous */
+int b2k_upload(b2k_ctx* ctx, const void* src_host, void* dst_dev, int64_t bytes);
 
 /* ---- compute_metric  (clustering_module.cpp:41-43) -------------------------------------- */
 int b2k_compute_metric(b2k_ctx* ctx, const float* x, const float* y, int64_t d, int metric, float* out);

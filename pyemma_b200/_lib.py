@@ -33,7 +33,7 @@ SYMBOLS = [
     "b2k_regspace_destroy", "b2k_regspace_partial_fit", "b2k_dev_regspace_partial_fit", "b2k_regspace_n_centers",
     "b2k_regspace_get_centers", "b2k_regspace_cluster", "b2k_kmpp_exchange_floats",
     "b2k_dev_kmeans_init_centers_kmpp_sharded", "b2k_dev_count_states", "b2k_dev_count_matrix",
-    "b2k_stage_lloyd_assign_accumulate", "b2k_dev_project", "b2k_stage_project",
+    "b2k_stage_lloyd_assign_accumulate", "b2k_dev_project", "b2k_stage_project", "b2k_upload",
 ]
 
 
@@ -101,6 +101,7 @@ def load():
         L.b2k_dev_kmeans_init_centers_kmpp_sharded.argtypes = [vp, vp, i64, i32, i32, C.c_int, i64, i64, i64, vp, i64, vp,
                                                                EXCHANGE, vp, CALLBACK, vp, vp, vp]
         L.b2k_stage_lloyd_assign_accumulate.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.b2k_upload.argtypes = [vp, vp, vp, i64]
         L.b2k_dev_project.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, vp]
         L.b2k_stage_project.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, vp]
         L.b2k_dev_count_states.argtypes = [vp, vp, i64, i32, vp]

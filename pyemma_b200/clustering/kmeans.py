@@ -156,6 +156,18 @@ class KmeansClustering(AbstractClustering):
         ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
         metric = _lib.metric_id(self.metric)
         lib = ctx.lib
+        # NaN / inf frames are rejected here, on the device, before any seeding (the reference's guard is the
+        # iterator's optional per-chunk host check, datasource.py:1067-1075)
+        finite = C.c_int(1)
+        _lib.check(lib.b2k_dev_all_finite(ctx.handle, C.c_void_p(X.data_ptr()), n_local * d, C.byref(finite)))
+        am = torch.tensor([finite.value], dtype=torch.int32, device=dev)
+        if ws > 1:
+            import torch.distributed as dist
+            dist.all_reduce(am, op=dist.ReduceOp.MIN)
+        if int(am.item()) == 0:
+            self._dev_frames = None
+            self._in_memory_chunks_set = False
+            raise _lib.InvalidDataInStreamException("Found invalid values (NaN/inf) in the input frames")
 
         # ---- initial centers ----
         if resume:

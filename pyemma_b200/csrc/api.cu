@@ -278,6 +278,7 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "fallback_mode")) c->fallback_mode = (int)value;
     else if (!strcmp(name, "operand_kernel")) c->operand_kernel = (int)value;
     else if (!strcmp(name, "kmpp_prune")) c->kmpp_prune = (int)value;
+    else if (!strcmp(name, "check_finite")) c->check_finite = value != 0;
     else if (!strcmp(name, "host_copy_threads")) c->host_copy_threads = (int)std::max<int64_t>(1, std::min<int64_t>(value, 32));
     else if (!strcmp(name, "accumulate_mode")) c->accumulate_mode = (int)value;
     else if (!strcmp(name, "cost_kernel")) c->cost_kernel = (int)value;
@@ -325,6 +326,16 @@ B2K_API int b2k_ctx_get_stat(b2k_ctx* c, const char* name, double* value) {
         return measure_fp32_rate(c, value);
     }
     else return set_error(B2K_ERR_INVALID_ARG, "unknown stat '%s'", name);
+    return B2K_OK;
+}
+
+// host array -> device array through the context's pinned staging (multi-threaded bounce for pageable memory);
+// returns when the data is in place
+B2K_API int b2k_upload(b2k_ctx* ctx, const void* src_host, void* dst_dev, int64_t bytes) {
+    if (!ctx || bytes < 0 || (bytes > 0 && (!src_host || !dst_dev))) return set_error(B2K_ERR_INVALID_ARG, "upload: bad arguments");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    B2K_TRY(upload_host(ctx, src_host, dst_dev, (size_t)bytes));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B2K_OK;
 }
 
@@ -417,6 +428,15 @@ static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, con
     if (use_screen) B2K_TRY(screen_plan_acquire(ctx, cf, d, k, &plan));
     cudaEvent_t ev_k[2];
     for (int s = 0; s < 2; ++s) CUDA_TRY(cudaEventCreateWithFlags(&ev_k[s], cudaEventDisableTiming));
+    // NaN / inf guard of the reference's chunk iterator (datasource.py:1067-1075), on the device while the chunk is
+    // there anyway: one flag for the whole call, read at the end
+    int* d_finite = nullptr;
+    if (ctx->check_finite) {
+        B2K_TRY(ctx->ensure_scratch(64));
+        d_finite = reinterpret_cast<int*>((char*)ctx->scratch + 32);
+        const int one = 1;
+        CUDA_TRY(cudaMemcpyAsync(d_finite, &one, 4, cudaMemcpyHostToDevice, st));
+    }
     int64_t pend_off[2] = {-1, -1}, pend_len[2] = {0, 0};
     int rc = B2K_OK;
     int c = 0;
@@ -435,6 +455,8 @@ static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, con
         cudaMemcpyAsync(dx, src, (size_t)len * row_bytes, cudaMemcpyHostToDevice, ctx->copy_stream[s]);
         cudaEventRecord(ctx->ev_h2d[s], ctx->copy_stream[s]);
         cudaStreamWaitEvent(st, ctx->ev_h2d[s], 0);
+        if (d_finite) rc = launch_all_finite(ctx, dx, len * d, d_finite);
+        if (rc != B2K_OK) break;
         if (use_screen) {
             rc = screen_prepare_frames(plan, dx, len);
             if (rc == B2K_OK) rc = screen_assign(plan, dx, len, dC, dl, nullptr, lloyd);
@@ -469,6 +491,11 @@ static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, con
     if (rc != B2K_OK) return rc;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(B2K_ERR_CUDA, "assign: %s", cudaGetErrorString(e));
+    if (d_finite) {
+        int ok = 1;
+        CUDA_TRY(cudaMemcpy(&ok, d_finite, 4, cudaMemcpyDeviceToHost));
+        if (!ok) return set_error(B2K_ERR_NONFINITE, "Found invalid values (NaN/inf) in the input frames");
+    }
     return B2K_OK;
 }
 

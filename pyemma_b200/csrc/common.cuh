@@ -69,6 +69,7 @@ struct b2k_ctx {
     // options
     int engine = B2K_ENGINE_AUTO;
     int screen_terms = 0;
+    int check_finite = 1;       // host-pointer assign entry points reject NaN/inf frames (B2K_ERR_NONFINITE)
     int host_copy_threads = 8;  // threads of the pageable -> pinned bounce copy (1e7 x 10 frames: 32.7 ms with 1, 18.2 ms with 8)
     int kmpp_prune = 1;       // k-means++ (blocked, euclidean): skip candidate distances the triangle inequality decides
     int operand_kernel = 0;   // frame operand builder: 0 per-input-element tile kernel, 1 per-output-piece kernel

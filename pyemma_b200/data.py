@@ -57,7 +57,10 @@ class DataInMemory:
         self._ndim = fixed[0].shape[1]
         self._lengths = [len(x) for x in fixed]
         self._chunksize = chunksize
-        self.check_output = True  # the reference test-suite always runs with this on (conftest.py:14)
+        # per-chunk host-side NaN/inf check of the iterator (datasource.py:1067-1075).  Off by default like the reference
+        # (pyemma.cfg: coordinates_check_output = False; its test-suite switches it on, conftest.py:14): the estimators
+        # reject non-finite frames on the device anyway (absmax of the gathered frames, finite flag of staged assigns)
+        self.check_output = False
 
     # -- DataSource surface -------------------------------------------------------------------
     def dimension(self):

@@ -9,6 +9,8 @@ with an async copy on a side stream, so the cast of chunk c+1 overlaps the DMA o
 PyTorch is used for what it is good at here -- device / pinned allocations, streams and (in
 distributed runs) the NCCL process group; all arithmetic is in libb2k.
 """
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -103,10 +105,16 @@ def gather_frames(source, stride=1, skip=0, chunksize=None, ctx=None, rank=0, wo
             if b <= lo or a >= hi:
                 continue
             xa, xb = max(a, lo) - a, min(b, hi) - a
+            part, dst = X[xa:xb], out[a + xa - lo:a + xb - lo]
             if fused is not None:
-                fused(X[xa:xb], out[a + xa - lo:a + xb - lo], ctx)
+                fused(part, dst, ctx)
+            elif part.dtype == np.float32 and part.flags.c_contiguous and part.shape[0] > 0:
+                # fp32 chunks need no cast: libb2k's own staging (several bounce-copy threads for pageable memory)
+                c = ctx or _lib.context()
+                _lib.check(c.lib.b2k_upload(c.handle, C.c_void_p(part.ctypes.data), C.c_void_p(dst.data_ptr()),
+                                            part.nbytes))
             else:
-                stager.send(X[xa:xb], out[a + xa - lo:a + xb - lo])
+                stager.send(part, dst)
     stager.finish()
     torch.cuda.current_stream(dev).wait_stream(stager.stream)
     return out, n_total, lo

@@ -93,6 +93,14 @@ def test_kmeans_rejects_nan():
     X[17, 1] = np.nan
     with pytest.raises(Exception, match="invalid"):
         coor.cluster_kmeans(X, k=3)
+    # assignment: the staged chunks are checked on the device (no host-side pass over the frames)
+    good = np.random.RandomState(1).rand(5000, 2)
+    cen = good[:7].copy()
+    bad = good.copy()
+    bad[4321, 0] = np.inf
+    with pytest.raises(Exception, match="invalid"):
+        coor.assign_to_centers(bad, cen)
+    assert len(coor.assign_to_centers(good, cen)[0]) == 5000
 
 
 # ---- oracle parity end to end (cfg1 shape at reduced N, golden fixture) ------------------------------------

@@ -97,6 +97,9 @@ def test_iterator_chunks_and_positions():
     whole = list(src.iterator(chunk=0, return_trajindex=False))
     assert [len(x) for x in whole] == [20, 7]
     src2 = DataInMemory(np.array([1.0, np.nan, 2.0]))
+    assert src2.check_output is False                       # pyemma.cfg default: coordinates_check_output = False
+    assert len(list(src2.iterator(chunk=2))) == 2
+    src2.check_output = True                                # what the reference test-suite switches on (conftest.py:14)
     with pytest.raises(Exception, match="invalid"):
         list(src2.iterator(chunk=2))
 
