@@ -7,6 +7,7 @@ ctypes); there is no CPU fallback.
 """
 __version__ = "0.1.0"
 
-from .api import assign_to_centers, cluster_kmeans, cluster_mini_batch_kmeans, cluster_regspace  # noqa: E402,F401
+from .api import (assign_to_centers, cluster_kmeans, cluster_mini_batch_kmeans, cluster_regspace,  # noqa: E402,F401
+                  cluster_uniform_time)
 from .clustering import (AssignCenters, KmeansClustering, MiniBatchKmeansClustering,  # noqa: E402,F401
-                         RegularSpaceClustering)
+                         RegularSpaceClustering, UniformTimeClustering)

@@ -5,9 +5,11 @@ cluster_regspace :1953-2055, assign_to_centers :2060-2156, _check_old_chunksize_
 """
 import warnings
 
-from .clustering import AssignCenters, KmeansClustering, MiniBatchKmeansClustering, RegularSpaceClustering
+from .clustering import (AssignCenters, KmeansClustering, MiniBatchKmeansClustering, RegularSpaceClustering,
+                         UniformTimeClustering)
 
-__all__ = ["cluster_kmeans", "cluster_mini_batch_kmeans", "cluster_regspace", "assign_to_centers"]
+__all__ = ["cluster_kmeans", "cluster_mini_batch_kmeans", "cluster_uniform_time", "cluster_regspace",
+           "assign_to_centers"]
 
 _NOTSET = object()
 
@@ -49,6 +51,18 @@ def cluster_mini_batch_kmeans(data=None, k=100, max_iter=10, batch_size=0.2, met
     cs = _check_old_chunksize_arg(chunksize, None, **kwargs)
     res = MiniBatchKmeansClustering(n_clusters=k, max_iter=max_iter, metric=metric, init_strategy=init_strategy,
                                     batch_size=batch_size, n_jobs=n_jobs, skip=skip, clustercenters=clustercenters)
+    if data is not None:
+        res.estimate(data, chunksize=cs)
+    else:
+        res.chunksize = cs
+    return res
+
+
+def cluster_uniform_time(data=None, k=None, stride=1, metric="euclidean", n_jobs=None, chunksize=None, skip=0,
+                         **kwargs):
+    """uniform time clustering (api.py:1870-1949)."""
+    cs = _check_old_chunksize_arg(chunksize, None, **kwargs)
+    res = UniformTimeClustering(k, metric=metric, n_jobs=n_jobs, skip=skip, stride=stride)
     if data is not None:
         res.estimate(data, chunksize=cs)
     else:

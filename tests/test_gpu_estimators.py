@@ -306,3 +306,21 @@ def test_minrmsd_clustering_is_rotation_translation_invariant(b2k):
     km = coor.cluster_kmeans(X, k=n_templates, max_iter=3, metric="minRMSD", fixed_seed=3)
     for t in range(n_templates):
         assert len(np.unique(km.dtrajs[0][truth == t])) == 1
+
+
+def test_uniform_time_clustering(oracle):
+    """uniform_time.py:33-106: centers are frames picked uniformly in time over the concatenated trajectories"""
+    rng = np.random.RandomState(2)
+    trajs = [rng.randn(L, 3).astype(np.float32) for L in (1000, 300, 57)]
+    ut = coor.cluster_uniform_time(trajs, k=20)
+    T, k = 1357, 20
+    next_t = (T // k) // 2
+    idx = np.arange(next_t, T - next_t + 1, (T - 2 * next_t + 1) // k)[:k]
+    allf = np.concatenate(trajs)
+    np.testing.assert_array_equal(ut.clustercenters, allf[idx])
+    assert ut.clustercenters.shape == (20, 3) and ut.n_clusters == 20
+    np.testing.assert_array_equal(np.concatenate(ut.dtrajs), oracle.assign(allf, ut.clustercenters))
+    big = coor.cluster_uniform_time(trajs[2], k=500)            # more clusters than frames -> clipped
+    assert big.n_clusters == 57 and len(big.clustercenters) == 57
+    auto = coor.cluster_uniform_time(trajs, k=None)
+    assert auto.n_clusters == int(np.sqrt(1357))
