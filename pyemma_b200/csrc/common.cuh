@@ -75,6 +75,9 @@ struct b2k_ctx {
     int operand_kernel = 0;   // frame operand builder: 0 per-input-element tile kernel, 1 per-output-piece kernel
     int fallback_mode = 0;    // frames the screen cannot bound: 0 indexed exact tile kernel, 1 CTA-per-frame scan
     int verify_mode = 0;      // wide rows: 0 direct (no staging) verify kernel, 1 shared-memory staged variants
+    int screen_resident_a = 0;  // screen kernel: keep the frame tile in shared memory when the center operand does not fit.
+                                // Off: measured at cfg3 it cuts the L2->SM traffic by 27 % but leaves room for only 3 ring
+                                // stages of center k-blocks -- 13.0 ms against 11.0 ms for the 4-stage streaming mode
     int screen_group = 0;     // centers per candidate group of the screen (0: automatic; 8, 4, 2)
     int rmsd_kernel = 0;      // 0: slab-streaming QCP kernel, 1: whole-row tile kernel
     int cost_kernel = 0;      // 0: quad kernel for wide rows, 1: the shared-memory staged variant

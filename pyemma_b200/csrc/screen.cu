@@ -393,6 +393,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// one non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -484,6 +496,8 @@ struct GemmArgs {
     int nk16;           // K=16 MMA steps that carry data
     int d, terms;
     int resident;       // 1: the whole center operand B' stays in shared memory, only frame tiles stream
+                        // 2: the FRAME tile (all k-blocks) stays while its center tiles stream: A is read once per
+                        //    frame tile instead of once per center tile (L2->SM traffic, the limiter of mid-size rows)
     int n_stages;       // pipeline stages
     int stage_bytes;    // resident: n_kblocks*A_BYTES (a frame tile, full K); streaming: A_BYTES+B_BYTES (one k-block)
     int bres_bytes;     // resident: bytes of B' in shared memory
@@ -494,6 +508,7 @@ struct GemmArgs {
 };
 
 static constexpr int MAX_STAGES = 8;
+static constexpr int MAX_A_KBLOCKS = 8;
 static constexpr int EPI_WARPS = 8;                    // 2 column halves x 4 TMEM lane quarters
 static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-9 epilogue
 static constexpr int HALF_CHUNKS = TILE_N / CHUNK / 2;  // chunks of one accumulator stage handled by one epilogue warp
@@ -501,6 +516,7 @@ static constexpr int HALF_CHUNKS = TILE_N / CHUNK / 2;  // chunks of one accumul
 // small shared-memory block behind the operand tiles
 struct GemmSmemTail {
     uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2], bfull_bar;
+    uint64_t afull_bar[MAX_A_KBLOCKS], aempty_bar[MAX_A_KBLOCKS];  // resident-A mode: one pair per k-block of the frame tile
     uint32_t tmem_slot, pad[3];
     uint32_t list_id[2][LIST_CAP][TILE_M];
     float list_v[2][LIST_CAP][TILE_M];
@@ -588,6 +604,7 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int s = 0; s < g.n_stages; ++s) { mbar_init(&T->full_bar[s], 1); mbar_init(&T->empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&T->tfull_bar[s], 1); mbar_init(&T->tempty_bar[s], EPI_WARPS); }
         mbar_init(&T->bfull_bar, 1);
+        for (int kb = 0; kb < MAX_A_KBLOCKS; ++kb) { mbar_init(&T->afull_bar[kb], 1); mbar_init(&T->aempty_bar[kb], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -605,7 +622,42 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            if (g.resident) {
+            if (g.resident == 2) {
+                // resident-A: two independent load streams polled by this one thread.  A: k-block kb of the frame
+                // tile is refilled as soon as the last center tile of the previous frame tile has consumed it (while
+                // that tile's remaining MMAs still run).  B: center k-blocks through the ring, running ahead into the
+                // next frame tile -- neither stream ever waits for the other.
+                int a_tile = blockIdx.x, a_kb = 0;
+                uint32_t a_phase = 0;
+                int b_tile = blockIdx.x, b_nt = 0, b_kb = 0;
+                bool a_done = a_tile >= g.n_tiles, b_done = b_tile >= g.n_tiles;
+                while (!a_done || !b_done) {
+                    if (!a_done && mbar_try(&T->aempty_bar[a_kb], a_phase ^ 1)) {
+                        mbar_expect_tx(&T->afull_bar[a_kb], A_BYTES);
+                        tma_load_2d(bres + (size_t)a_kb * A_BYTES, &tmA, &T->afull_bar[a_kb], a_kb * BLOCK_K, a_tile * TILE_M);
+                        if (++a_kb == g.n_kblocks) {
+                            a_kb = 0;
+                            a_phase ^= 1;
+                            a_tile += gridDim.x;
+                            a_done = a_tile >= g.n_tiles;
+                        }
+                    }
+                    if (!b_done && mbar_try(&T->empty_bar[stage], phase ^ 1)) {
+                        mbar_expect_tx(&T->full_bar[stage], B_BYTES);
+                        tma_load_2d(tiles + (size_t)stage * g.stage_bytes, &tmB, &T->full_bar[stage], b_kb * BLOCK_K,
+                                    b_nt * TILE_N);
+                        if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+                        if (++b_kb == g.n_kblocks) {
+                            b_kb = 0;
+                            if (++b_nt == g.n_ntiles) {
+                                b_nt = 0;
+                                b_tile += gridDim.x;
+                                b_done = b_tile >= g.n_tiles;
+                            }
+                        }
+                    }
+                }
+            } else if (g.resident) {
                 mbar_expect_tx(&T->bfull_bar, (uint32_t)g.bres_bytes);
                 for (int nt = 0; nt < g.n_ntiles; ++nt)
                     for (int kb = 0; kb < g.n_kblocks; ++kb)
@@ -643,12 +695,13 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
-            if (g.resident) {
+            uint32_t tphase = 0;
+            if (g.resident == 1) {
                 mbar_wait(&T->bfull_bar, 0);
                 tc_fence_after();
             }
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-                if (g.resident) {
+                if (g.resident == 1) {
                     mbar_wait(&T->full_bar[stage], phase);
                     tc_fence_after();
                 }
@@ -659,7 +712,13 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t d_tmem = tmem_base + acc * TILE_N;
                     for (int kb = 0; kb < g.n_kblocks; ++kb) {
                         uint32_t sa, sb;
-                        if (g.resident) {
+                        if (g.resident == 2) {
+                            if (nt == 0) mbar_wait(&T->afull_bar[kb], tphase);
+                            mbar_wait(&T->full_bar[stage], phase);
+                            tc_fence_after();
+                            sa = smem_u32(bres + (size_t)kb * A_BYTES);
+                            sb = smem_u32(tiles + (size_t)stage * g.stage_bytes);
+                        } else if (g.resident) {
                             sa = smem_u32(tiles + (size_t)stage * g.stage_bytes + (size_t)kb * A_BYTES);
                             sb = smem_u32(bres + (size_t)(nt * g.n_kblocks + kb) * B_BYTES);
                         } else {
@@ -676,17 +735,20 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             tc_mma_f16(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc,
                                        (kb | ks) != 0 ? 1u : 0u);
                         }
-                        if (!g.resident) {
+                        if (g.resident != 1) {
                             tc_commit(&T->empty_bar[stage]);  // smem slot free once these MMAs retire
                             if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
                         }
+                        // resident-A: this k-block of the frame tile has met its last center tile
+                        if (g.resident == 2 && nt == g.n_ntiles - 1) tc_commit(&T->aempty_bar[kb]);
                     }
                     tc_commit(&T->tfull_bar[acc]);  // accumulator stage complete
                 }
-                if (g.resident) {
+                if (g.resident == 1) {
                     tc_commit(&T->empty_bar[stage]);  // frame tile consumed by every center tile
                     if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
                 }
+                tphase ^= 1;
             }
         }
     } else {
@@ -1471,7 +1533,7 @@ struct GemmSmemPlan {
     int resident, n_stages, stage_bytes, bres_bytes;
     size_t total;
 };
-static GemmSmemPlan gemm_smem_plan(int k_pad, int Kp, size_t smem_optin) {
+static GemmSmemPlan gemm_smem_plan(int k_pad, int Kp, size_t smem_optin, int allow_resident_a = 1) {
     GemmSmemPlan sp;
     const size_t tail = sizeof(GemmSmemTail) + 1024 /* alignment slack */;
     const size_t b_all = (size_t)k_pad * Kp * 2;            // multiple of B_BYTES
@@ -1482,6 +1544,12 @@ static GemmSmemPlan gemm_smem_plan(int k_pad, int Kp, size_t smem_optin) {
         sp.stage_bytes = (int)a_full;
         sp.n_stages = (int)std::min<size_t>(MAX_STAGES, (smem_optin - tail - b_all) / a_full);
         if (sp.n_stages > 4) sp.n_stages = 4;
+    } else if (allow_resident_a && Kp / BLOCK_K <= MAX_A_KBLOCKS && k_pad / TILE_N >= 2 &&
+               a_full + 2 * (size_t)B_BYTES + tail <= smem_optin) {
+        sp.resident = 2;  // frame tile resident, center k-blocks stream
+        sp.bres_bytes = (int)a_full;
+        sp.stage_bytes = B_BYTES;
+        sp.n_stages = (int)std::min<size_t>(MAX_STAGES, (smem_optin - tail - a_full) / B_BYTES);
     } else {
         sp.resident = 0;
         sp.bres_bytes = 0;
@@ -1685,7 +1753,7 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
     g.prm = p->params;
     g.cand = p->cand;
     g.ncand = p->ncand;
-    const GemmSmemPlan sp = gemm_smem_plan(p->k_pad, p->Kp, ctx->smem_optin);
+    const GemmSmemPlan sp = gemm_smem_plan(p->k_pad, p->Kp, ctx->smem_optin, ctx->screen_resident_a);
     g.resident = sp.resident;
     g.n_stages = sp.n_stages;
     g.stage_bytes = sp.stage_bytes;

@@ -100,6 +100,22 @@ def test_screen_candidate_statistics(b2k, screen_ctx):
     assert chunks < 3.0 and fb < 0.01
 
 
+@pytest.mark.parametrize("n,d,k", [(5000, 64, 2000), (3000, 100, 900), (4000, 33, 3000)])
+def test_screen_resident_frame_tile_mode(b2k, oracle, screen_ctx, n, d, k):
+    """option screen_resident_a: the frame tile stays in shared memory while its center tiles stream (two polled TMA
+    streams, per-k-block barriers) -- same labels as the streaming mode and the oracle"""
+    rng = np.random.RandomState(d + k)
+    X = blobs(rng, n, d, 9)
+    Cn = X[rng.choice(n, k, replace=False)].copy()
+    ref = oracle.assign(X, Cn, n_threads=8)
+    for mode in (1, 0):
+        screen_ctx.set_option("screen_resident_a", mode)
+        try:
+            np.testing.assert_array_equal(b2k.assign(X, Cn), ref, err_msg="screen_resident_a=%d" % mode)
+        finally:
+            screen_ctx.set_option("screen_resident_a", 0)
+
+
 @pytest.mark.parametrize("d,k", [(8, 1500), (64, 2000)])
 def test_screen_list_overflow_goes_to_exact_scan(b2k, oracle, screen_ctx, d, k):
     """centers on a sphere around the frames: hundreds of centers sit within the screen's margin of the best one, the
