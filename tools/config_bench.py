@@ -9,12 +9,10 @@ Run it under `ncu --metrics gpu__time_duration.sum` for the per-kernel split of 
 import argparse
 import ctypes as C
 import json
-import math
 import os
 import sys
 import time
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -221,7 +219,6 @@ def cfg5(ctx, args):
 
 def cfg6(ctx, args):
     """dtraj consumers: count matrix at lag 10 and state histogram of 1e7 metastable labels, k=1000"""
-    from pyemma_b200 import dtraj
     n, k = 10_000_000, 1000
     g = torch.Generator(device=DEV)
     g.manual_seed(6)

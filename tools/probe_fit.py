@@ -1,6 +1,5 @@
 """cluster_kmeans on a pageable host array at cfg2 size: where the wall time goes (gather / Lloyd / dtrajs)."""
 import os, sys, time
-import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import pyemma_b200 as coor

@@ -1,5 +1,7 @@
-import sys, os, ctypes as C, torch
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools')
+import sys, ctypes as C, torch
+import os
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, HERE)
 import config_bench as cb
 from pyemma_b200 import _lib
 ctx = _lib.context(0); ctx.set_stream(torch.cuda.current_stream(cb.DEV).cuda_stream)
