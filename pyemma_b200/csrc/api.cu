@@ -275,6 +275,7 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "screen_terms")) c->screen_terms = (int)value;
     else if (!strcmp(name, "screen_group")) c->screen_group = (int)value;
     else if (!strcmp(name, "screen_resident_a")) c->screen_resident_a = (int)value;
+    else if (!strcmp(name, "screen_cluster")) c->screen_cluster = (int)value;
     else if (!strcmp(name, "verify_mode")) c->verify_mode = (int)value;
     else if (!strcmp(name, "fallback_mode")) c->fallback_mode = (int)value;
     else if (!strcmp(name, "operand_kernel")) c->operand_kernel = (int)value;

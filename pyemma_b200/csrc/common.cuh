@@ -75,6 +75,7 @@ struct b2k_ctx {
     int operand_kernel = 0;   // frame operand builder: 0 per-input-element tile kernel, 1 per-output-piece kernel
     int fallback_mode = 0;    // frames the screen cannot bound: 0 indexed exact tile kernel, 1 CTA-per-frame scan
     int verify_mode = 0;      // wide rows: 0 direct (no staging) verify kernel, 1 shared-memory staged variants
+    int screen_cluster = 0;     // 2: streaming-mode screen kernel as 2-CTA clusters sharing the center tiles (TMA multicast)
     int screen_resident_a = 0;  // screen kernel: keep the frame tile in shared memory when the center operand does not fit.
                                 // Off: measured at cfg3 it cuts the L2->SM traffic by 27 % but leaves room for only 3 ring
                                 // stages of center k-blocks -- 13.0 ms against 11.0 ms for the 4-stage streaming mode

@@ -85,7 +85,7 @@ struct ScreenPlan {
     uint32_t* cand = nullptr;  // [n_pad][CAND_CAP]  chunk id | group mask << 28
     uint8_t* ncand = nullptr;  // [n_pad]  (255: overflow -> exact fallback)
     uint32_t* fb_list = nullptr;  // [n_pad] frames the verify kernels hand to the fallback kernel
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmBh;  // tmBh: center operand in 128-row boxes (one CTA's half of a center tile, cluster mode)
     int64_t prepared_n = -1;
 };
 
@@ -412,6 +412,31 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
         "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// ---- 2-CTA cluster helpers (streaming mode with shared center tiles) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA tile load delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// commit that arrives on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -499,6 +524,8 @@ struct GemmArgs {
                         // 2: the FRAME tile (all k-blocks) stays while its center tiles stream: A is read once per
                         //    frame tile instead of once per center tile (L2->SM traffic, the limiter of mid-size rows)
     int n_stages;       // pipeline stages
+    int cluster2;       // 1: launched as clusters of 2 CTAs (streaming mode): each CTA fetches half of every center
+                        //    k-block and multicasts it to both, halving the center traffic out of L2
     int stage_bytes;    // resident: n_kblocks*A_BYTES (a frame tile, full K); streaming: A_BYTES+B_BYTES (one k-block)
     int bres_bytes;     // resident: bytes of B' in shared memory
     const float* X2;
@@ -588,7 +615,8 @@ __device__ __forceinline__ void scan_chunk(const float (&v)[32], uint32_t chunk_
 // ---- the screen kernel ---------------------------------------------------------------------------------------------
 template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmBh /* center operand, 128-row boxes */, GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     if (!g.prm->valid) return;  // operands unusable: the exact tile kernel takes the whole call (screen_finish_assign)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -597,11 +625,20 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     GemmSmemTail* T = reinterpret_cast<GemmSmemTail*>(tiles + (size_t)g.n_stages * g.stage_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // frame tiles of this CTA: tile = t_first, t_first + t_step, ... (< t_count); in cluster mode the two CTAs of a
+    // pair walk tiles 2*tt and 2*tt+1 in lockstep (a tile index beyond n_tiles is a dummy: zero operand, no output)
+    const uint32_t crank = g.cluster2 ? cluster_ctarank() : 0u;
+    const int t_first = g.cluster2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int t_step = g.cluster2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int t_count = g.cluster2 ? (g.n_tiles + 1) >> 1 : g.n_tiles;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        for (int s = 0; s < g.n_stages; ++s) { mbar_init(&T->full_bar[s], 1); mbar_init(&T->empty_bar[s], 1); }
+        for (int s = 0; s < g.n_stages; ++s) {
+            mbar_init(&T->full_bar[s], 1);
+            mbar_init(&T->empty_bar[s], g.cluster2 ? 2 : 1);  // cluster: the MMA warps of both CTAs release a slot
+        }
         for (int s = 0; s < 2; ++s) { mbar_init(&T->tfull_bar[s], 1); mbar_init(&T->tempty_bar[s], EPI_WARPS); }
         mbar_init(&T->bfull_bar, 1);
         for (int kb = 0; kb < MAX_A_KBLOCKS; ++kb) { mbar_init(&T->afull_bar[kb], 1); mbar_init(&T->aempty_bar[kb], 1); }
@@ -614,6 +651,7 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (g.cluster2) cluster_sync_all();  // the peer's barriers are initialised before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = T->tmem_slot;
 
@@ -672,14 +710,19 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
                 }
             } else {
-                for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+                for (int tt = t_first; tt < t_count; tt += t_step) {
+                    const int tile = g.cluster2 ? 2 * tt + (int)crank : tt;
                     for (int nt = 0; nt < g.n_ntiles; ++nt) {
                         for (int kb = 0; kb < g.n_kblocks; ++kb) {
                             mbar_wait(&T->empty_bar[stage], phase ^ 1);
                             uint8_t* sa = tiles + (size_t)stage * g.stage_bytes;
                             mbar_expect_tx(&T->full_bar[stage], STAGE_BYTES);
                             tma_load_2d(sa, &tmA, &T->full_bar[stage], kb * BLOCK_K, tile * TILE_M);
-                            tma_load_2d(sa + A_BYTES, &tmB, &T->full_bar[stage], kb * BLOCK_K, nt * TILE_N);
+                            if (g.cluster2)  // my half of the center k-block, delivered to both CTAs of the pair
+                                tma_load_2d_mc(sa + A_BYTES + crank * (B_BYTES / 2), &tmBh, &T->full_bar[stage], kb * BLOCK_K,
+                                               nt * TILE_N + (int)crank * (TILE_N / 2), (uint16_t)3);
+                            else
+                                tma_load_2d(sa + A_BYTES, &tmB, &T->full_bar[stage], kb * BLOCK_K, nt * TILE_N);
                             if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -700,7 +743,7 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 mbar_wait(&T->bfull_bar, 0);
                 tc_fence_after();
             }
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+            for (int tt = t_first; tt < t_count; tt += t_step) {
                 if (g.resident == 1) {
                     mbar_wait(&T->full_bar[stage], phase);
                     tc_fence_after();
@@ -736,7 +779,9 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                        (kb | ks) != 0 ? 1u : 0u);
                         }
                         if (g.resident != 1) {
-                            tc_commit(&T->empty_bar[stage]);  // smem slot free once these MMAs retire
+                            // smem slot free once these MMAs retire (cluster: tell both CTAs, either may refill it)
+                            if (g.cluster2) tc_commit_mc(&T->empty_bar[stage], (uint16_t)3);
+                            else tc_commit(&T->empty_bar[stage]);
                             if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
                         }
                         // resident-A: this k-block of the frame tile has met its last center tile
@@ -762,7 +807,8 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t it = 0;
         const float C = g.prm->cmax;
         const int valid_ops = g.prm->valid;
-        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        for (int tt = t_first; tt < t_count; tt += t_step) {
+            const int tile = g.cluster2 ? 2 * tt + (int)crank : tt;
             const int64_t grow = (int64_t)tile * TILE_M + row;
             const float x2 = (grow < g.n) ? g.X2[grow] : 0.f;
             Margin mg;
@@ -847,6 +893,7 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (g.cluster2) cluster_sync_all();  // no CTA leaves while its peer may still write to its shared memory / barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -1610,6 +1657,7 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     }
     int rc = make_tmap(&p->tmA, p->A, (uint64_t)p->n_pad, (uint64_t)p->Kp, TILE_M);
     if (rc == B2K_OK) rc = make_tmap(&p->tmB, p->B, (uint64_t)p->k_pad, (uint64_t)p->Kp, TILE_N);
+    if (rc == B2K_OK) rc = make_tmap(&p->tmBh, p->B, (uint64_t)p->k_pad, (uint64_t)p->Kp, TILE_N / 2);
     if (rc != B2K_OK) { screen_plan_destroy(p); return rc; }
     static PerDeviceOnce attr_set;
     if (attr_set.need(ctx->device)) {
@@ -1765,9 +1813,30 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, st));
     }
-    if (p->cg == 8) screen_gemm_kernel<8><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, g);
-    else if (p->cg == 4) screen_gemm_kernel<4><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, g);
-    else screen_gemm_kernel<2><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, g);
+    g.cluster2 = (ctx->screen_cluster == 2 && sp.resident == 0 && g.n_tiles >= 2 && ctx->sm_count >= 2) ? 1 : 0;
+    if (g.cluster2) {
+        // pairs of CTAs share every center k-block (each fetches half and multicasts it): an even grid of 2-CTA clusters
+        cudaLaunchConfig_t cfg = {};
+        const unsigned pairs = (unsigned)std::min<int64_t>((g.n_tiles + 1) / 2, ctx->sm_count / 2);
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = sp.total;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le;
+        if (p->cg == 8) le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<8>, p->tmA, p->tmB, p->tmBh, g);
+        else if (p->cg == 4) le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<4>, p->tmA, p->tmB, p->tmBh, g);
+        else le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<2>, p->tmA, p->tmB, p->tmBh, g);
+        CUDA_TRY(le);
+    } else if (p->cg == 8) screen_gemm_kernel<8><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+    else if (p->cg == 4) screen_gemm_kernel<4><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+    else screen_gemm_kernel<2><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
     LAUNCH_CHECK();
     if (ctx->profile) {
         CUDA_TRY(cudaEventRecord(ev1, st));

@@ -166,3 +166,19 @@ def test_screen_operand_builders_agree(b2k, oracle, screen_ctx, n, d, k):
         finally:
             screen_ctx.set_option("operand_kernel", 0)
     assert stats[0] == stats[1]
+
+
+@pytest.mark.parametrize("n,d,k", [(20001, 256, 1000), (9000, 100, 2500)])
+def test_screen_cluster_multicast_mode(b2k, oracle, screen_ctx, n, d, k):
+    """option screen_cluster=2: the streaming screen kernel as 2-CTA clusters that share every center k-block through
+    TMA multicast (odd tile counts run a dummy tile in the second CTA) -- same labels as the oracle"""
+    rng = np.random.RandomState(k)
+    X = blobs(rng, n, d, 9)
+    Cn = X[rng.choice(n, k, replace=False)].copy()
+    ref = oracle.assign(X, Cn, n_threads=8)
+    screen_ctx.set_option("screen_resident_a", 0)
+    screen_ctx.set_option("screen_cluster", 2)
+    try:
+        np.testing.assert_array_equal(b2k.assign(X, Cn), ref)
+    finally:
+        screen_ctx.set_option("screen_cluster", 0)
