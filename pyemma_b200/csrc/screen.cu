@@ -613,7 +613,9 @@ __device__ __forceinline__ void scan_chunk(const float (&v)[32], uint32_t chunk_
 }
 
 // ---- the screen kernel ---------------------------------------------------------------------------------------------
-template <int CG>
+// EXP: the experimental operand modes (resident frame tile, 2-CTA multicast) are compiled into a separate instantiation so
+// that the production paths (resident center operand / plain streaming) carry none of their branches.
+template <int CG, bool EXP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmBh /* center operand, 128-row boxes */, GemmArgs g) {
@@ -624,24 +626,30 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint8_t* tiles = smem + g.bres_bytes;       // n_stages * stage_bytes
     GemmSmemTail* T = reinterpret_cast<GemmSmemTail*>(tiles + (size_t)g.n_stages * g.stage_bytes);
 
+    // the EXP=false instantiation is only ever launched with modes 0 and 1: `resident` is a plain flag there
+    const int resident = EXP ? g.resident : (g.resident != 0 ? 1 : 0);
+    const bool cluster2 = EXP && g.cluster2 != 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // frame tiles of this CTA: tile = t_first, t_first + t_step, ... (< t_count); in cluster mode the two CTAs of a
     // pair walk tiles 2*tt and 2*tt+1 in lockstep (a tile index beyond n_tiles is a dummy: zero operand, no output)
-    const uint32_t crank = g.cluster2 ? cluster_ctarank() : 0u;
-    const int t_first = g.cluster2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int t_step = g.cluster2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int t_count = g.cluster2 ? (g.n_tiles + 1) >> 1 : g.n_tiles;
+    const uint32_t crank = cluster2 ? cluster_ctarank() : 0u;
+    // (evaluated at each use: hoisting blockIdx.x into one register shared by all warp roles costs the producer and
+    // MMA-issue threads their uniform-datapath code)
+#define B2K_T_FIRST (cluster2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x)
+#define B2K_T_STEP (cluster2 ? (int)(gridDim.x >> 1) : (int)gridDim.x)
+#define B2K_T_COUNT (cluster2 ? (g.n_tiles + 1) >> 1 : g.n_tiles)
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < g.n_stages; ++s) {
             mbar_init(&T->full_bar[s], 1);
-            mbar_init(&T->empty_bar[s], g.cluster2 ? 2 : 1);  // cluster: the MMA warps of both CTAs release a slot
+            mbar_init(&T->empty_bar[s], cluster2 ? 2 : 1);  // cluster: the MMA warps of both CTAs release a slot
         }
         for (int s = 0; s < 2; ++s) { mbar_init(&T->tfull_bar[s], 1); mbar_init(&T->tempty_bar[s], EPI_WARPS); }
         mbar_init(&T->bfull_bar, 1);
-        for (int kb = 0; kb < MAX_A_KBLOCKS; ++kb) { mbar_init(&T->afull_bar[kb], 1); mbar_init(&T->aempty_bar[kb], 1); }
+        if constexpr (EXP)
+            for (int kb = 0; kb < MAX_A_KBLOCKS; ++kb) { mbar_init(&T->afull_bar[kb], 1); mbar_init(&T->aempty_bar[kb], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -651,7 +659,7 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (g.cluster2) cluster_sync_all();  // the peer's barriers are initialised before anything is sent to them
+    if (cluster2) cluster_sync_all();  // the peer's barriers are initialised before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = T->tmem_slot;
 
@@ -660,7 +668,7 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            if (g.resident == 2) {
+            if (EXP && resident == 2) {
                 // resident-A: two independent load streams polled by this one thread.  A: k-block kb of the frame
                 // tile is refilled as soon as the last center tile of the previous frame tile has consumed it (while
                 // that tile's remaining MMAs still run).  B: center k-blocks through the ring, running ahead into the
@@ -695,7 +703,7 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         }
                     }
                 }
-            } else if (g.resident) {
+            } else if (resident) {
                 mbar_expect_tx(&T->bfull_bar, (uint32_t)g.bres_bytes);
                 for (int nt = 0; nt < g.n_ntiles; ++nt)
                     for (int kb = 0; kb < g.n_kblocks; ++kb)
@@ -710,15 +718,15 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
                 }
             } else {
-                for (int tt = t_first; tt < t_count; tt += t_step) {
-                    const int tile = g.cluster2 ? 2 * tt + (int)crank : tt;
+                for (int tt = B2K_T_FIRST; tt < B2K_T_COUNT; tt += B2K_T_STEP) {
+                    const int tile = cluster2 ? 2 * tt + (int)crank : tt;
                     for (int nt = 0; nt < g.n_ntiles; ++nt) {
                         for (int kb = 0; kb < g.n_kblocks; ++kb) {
                             mbar_wait(&T->empty_bar[stage], phase ^ 1);
                             uint8_t* sa = tiles + (size_t)stage * g.stage_bytes;
                             mbar_expect_tx(&T->full_bar[stage], STAGE_BYTES);
                             tma_load_2d(sa, &tmA, &T->full_bar[stage], kb * BLOCK_K, tile * TILE_M);
-                            if (g.cluster2)  // my half of the center k-block, delivered to both CTAs of the pair
+                            if (cluster2)  // my half of the center k-block, delivered to both CTAs of the pair
                                 tma_load_2d_mc(sa + A_BYTES + crank * (B_BYTES / 2), &tmBh, &T->full_bar[stage], kb * BLOCK_K,
                                                nt * TILE_N + (int)crank * (TILE_N / 2), (uint16_t)3);
                             else
@@ -739,12 +747,12 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             uint32_t phase = 0;
             uint32_t it = 0;
             uint32_t tphase = 0;
-            if (g.resident == 1) {
+            if (resident == 1) {
                 mbar_wait(&T->bfull_bar, 0);
                 tc_fence_after();
             }
-            for (int tt = t_first; tt < t_count; tt += t_step) {
-                if (g.resident == 1) {
+            for (int tt = B2K_T_FIRST; tt < B2K_T_COUNT; tt += B2K_T_STEP) {
+                if (resident == 1) {
                     mbar_wait(&T->full_bar[stage], phase);
                     tc_fence_after();
                 }
@@ -755,13 +763,13 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t d_tmem = tmem_base + acc * TILE_N;
                     for (int kb = 0; kb < g.n_kblocks; ++kb) {
                         uint32_t sa, sb;
-                        if (g.resident == 2) {
+                        if (EXP && resident == 2) {
                             if (nt == 0) mbar_wait(&T->afull_bar[kb], tphase);
                             mbar_wait(&T->full_bar[stage], phase);
                             tc_fence_after();
                             sa = smem_u32(bres + (size_t)kb * A_BYTES);
                             sb = smem_u32(tiles + (size_t)stage * g.stage_bytes);
-                        } else if (g.resident) {
+                        } else if (resident) {
                             sa = smem_u32(tiles + (size_t)stage * g.stage_bytes + (size_t)kb * A_BYTES);
                             sb = smem_u32(bres + (size_t)(nt * g.n_kblocks + kb) * B_BYTES);
                         } else {
@@ -778,18 +786,18 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             tc_mma_f16(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc,
                                        (kb | ks) != 0 ? 1u : 0u);
                         }
-                        if (g.resident != 1) {
+                        if (resident != 1) {
                             // smem slot free once these MMAs retire (cluster: tell both CTAs, either may refill it)
-                            if (g.cluster2) tc_commit_mc(&T->empty_bar[stage], (uint16_t)3);
+                            if (cluster2) tc_commit_mc(&T->empty_bar[stage], (uint16_t)3);
                             else tc_commit(&T->empty_bar[stage]);
                             if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
                         }
                         // resident-A: this k-block of the frame tile has met its last center tile
-                        if (g.resident == 2 && nt == g.n_ntiles - 1) tc_commit(&T->aempty_bar[kb]);
+                        if (EXP && resident == 2 && nt == g.n_ntiles - 1) tc_commit(&T->aempty_bar[kb]);
                     }
                     tc_commit(&T->tfull_bar[acc]);  // accumulator stage complete
                 }
-                if (g.resident == 1) {
+                if (resident == 1) {
                     tc_commit(&T->empty_bar[stage]);  // frame tile consumed by every center tile
                     if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
                 }
@@ -807,8 +815,8 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t it = 0;
         const float C = g.prm->cmax;
         const int valid_ops = g.prm->valid;
-        for (int tt = t_first; tt < t_count; tt += t_step) {
-            const int tile = g.cluster2 ? 2 * tt + (int)crank : tt;
+        for (int tt = B2K_T_FIRST; tt < B2K_T_COUNT; tt += B2K_T_STEP) {
+            const int tile = cluster2 ? 2 * tt + (int)crank : tt;
             const int64_t grow = (int64_t)tile * TILE_M + row;
             const float x2 = (grow < g.n) ? g.X2[grow] : 0.f;
             Margin mg;
@@ -893,7 +901,10 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (g.cluster2) cluster_sync_all();  // no CTA leaves while its peer may still write to its shared memory / barriers
+    if (cluster2) cluster_sync_all();  // no CTA leaves while its peer may still write to its shared memory / barriers
+#undef B2K_T_FIRST
+#undef B2K_T_STEP
+#undef B2K_T_COUNT
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -1661,12 +1672,18 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     if (rc != B2K_OK) { screen_plan_destroy(p); return rc; }
     static PerDeviceOnce attr_set;
     if (attr_set.need(ctx->device)) {
-        cudaError_t ae = cudaFuncSetAttribute(screen_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t ae = cudaFuncSetAttribute(screen_gemm_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)ctx->smem_optin);
         if (ae == cudaSuccess)
-            ae = cudaFuncSetAttribute(screen_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
         if (ae == cudaSuccess)
-            ae = cudaFuncSetAttribute(screen_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+        if (ae == cudaSuccess)
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+        if (ae == cudaSuccess)
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+        if (ae == cudaSuccess)
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
         if (ae != cudaSuccess) { screen_plan_destroy(p); return set_error(B2K_ERR_CUDA, "screen smem attr: %s", cudaGetErrorString(ae)); }
         attr_set.done(ctx->device);
     }
@@ -1830,13 +1847,17 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         cudaError_t le;
-        if (p->cg == 8) le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<8>, p->tmA, p->tmB, p->tmBh, g);
-        else if (p->cg == 4) le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<4>, p->tmA, p->tmB, p->tmBh, g);
-        else le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<2>, p->tmA, p->tmB, p->tmBh, g);
+        if (p->cg == 8) le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<8, true>, p->tmA, p->tmB, p->tmBh, g);
+        else if (p->cg == 4) le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<4, true>, p->tmA, p->tmB, p->tmBh, g);
+        else le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<2, true>, p->tmA, p->tmB, p->tmBh, g);
         CUDA_TRY(le);
-    } else if (p->cg == 8) screen_gemm_kernel<8><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
-    else if (p->cg == 4) screen_gemm_kernel<4><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
-    else screen_gemm_kernel<2><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+    } else if (sp.resident == 2) {
+        if (p->cg == 8) screen_gemm_kernel<8, true><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+        else if (p->cg == 4) screen_gemm_kernel<4, true><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+        else screen_gemm_kernel<2, true><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+    } else if (p->cg == 8) screen_gemm_kernel<8, false><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+    else if (p->cg == 4) screen_gemm_kernel<4, false><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+    else screen_gemm_kernel<2, false><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
     LAUNCH_CHECK();
     if (ctx->profile) {
         CUDA_TRY(cudaEventRecord(ev1, st));
