@@ -87,7 +87,10 @@ int b2k_ctx_sync(b2k_ctx* ctx);
  * pageable -> pinned bounce copy, default 8), "accumulate_mode" (member sums: 0 automatic, 1 one 64-bit
  * RED per frame element, 2 segmented = counting sort by label + warp run sums, 3 per-CTA shared-memory table,
  * 4 tile-sorted = per-tile shared-memory sort + run sums, narrow rows), "own_stream", "profile" (1: time every launch of the
- * tcgen05 screen kernel with CUDA events on the context stream; setting it again clears the record) */
+ * tcgen05 screen kernel with CUDA events on the context stream; setting it again clears the record).
+ * Experimental operand modes of the streaming screen kernel (results identical): "screen_resident_a"
+ * (1: frame tile resident in shared memory), "screen_cluster" (2: 2-CTA clusters with TMA-multicast center tiles,
+ * 3: CTA-pair MMAs, tcgen05 cta_group::2) */
 int b2k_ctx_set_option(b2k_ctx* ctx, const char* name, int64_t value);
 /* stats: "screen_frames", "screen_cand_chunks" (8-center groups re-evaluated exactly), "screen_fallback_frames"
  * of the last screened assign (host-pointer calls: of its last chunk); "screen_gemm_ms_total" and

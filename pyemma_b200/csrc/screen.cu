@@ -437,6 +437,39 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
                  "h"(mask)
                  : "memory");
 }
+// ---- CTA-pair helpers (cta_group::2: one M=256 MMA over the two SMs of a pair, each SM holding its own 128 frame rows
+// and HALF of the center tile; the leader CTA -- rank 0 -- issues every MMA and owns the full / accumulator-empty barriers)
+// TMA tile load into MY shared memory whose completion is signalled on the LEADER's barrier at the same offset
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive on the barrier at this offset in the leader CTA's shared memory
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {  // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -524,8 +557,10 @@ struct GemmArgs {
                         // 2: the FRAME tile (all k-blocks) stays while its center tiles stream: A is read once per
                         //    frame tile instead of once per center tile (L2->SM traffic, the limiter of mid-size rows)
     int n_stages;       // pipeline stages
-    int cluster2;       // 1: launched as clusters of 2 CTAs (streaming mode): each CTA fetches half of every center
-                        //    k-block and multicasts it to both, halving the center traffic out of L2
+    int cluster2;       // launched as clusters of 2 CTAs (streaming mode).  1: each CTA fetches half of every center
+                        //    k-block and multicasts it to both (halves the center traffic out of L2).  2: CTA-pair
+                        //    MMAs (cta_group::2, M=256): each SM keeps only ITS half of the center k-block, so an SM
+                        //    ingests and reads 2/3 of the shared-memory bytes per MMA
     int stage_bytes;    // resident: n_kblocks*A_BYTES (a frame tile, full K); streaming: A_BYTES+B_BYTES (one k-block)
     int bres_bytes;     // resident: bytes of B' in shared memory
     const float* X2;
@@ -613,9 +648,10 @@ __device__ __forceinline__ void scan_chunk(const float (&v)[32], uint32_t chunk_
 }
 
 // ---- the screen kernel ---------------------------------------------------------------------------------------------
-// EXP: the experimental operand modes (resident frame tile, 2-CTA multicast) are compiled into a separate instantiation so
-// that the production paths (resident center operand / plain streaming) carry none of their branches.
-template <int CG, bool EXP>
+// EXP: the experimental operand modes are compiled into separate instantiations so that the production paths (EXP=0:
+// resident center operand / plain streaming) carry none of their branches.  EXP=1: resident frame tile, 2-CTA multicast;
+// EXP=2: CTA-pair MMAs (a kernel containing cta_group::2 instructions can only be launched as clusters).
+template <int CG, int EXP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmBh /* center operand, 128-row boxes */, GemmArgs g) {
@@ -626,9 +662,11 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint8_t* tiles = smem + g.bres_bytes;       // n_stages * stage_bytes
     GemmSmemTail* T = reinterpret_cast<GemmSmemTail*>(tiles + (size_t)g.n_stages * g.stage_bytes);
 
-    // the EXP=false instantiation is only ever launched with modes 0 and 1: `resident` is a plain flag there
-    const int resident = EXP ? g.resident : (g.resident != 0 ? 1 : 0);
-    const bool cluster2 = EXP && g.cluster2 != 0;
+    // only EXP=1 is ever launched with the resident-frame-tile mode (2): elsewhere `resident` is a plain flag
+    const int resident = EXP == 1 ? g.resident : (g.resident != 0 ? 1 : 0);
+    const bool cluster2 = EXP != 0 && g.cluster2 != 0;
+    const bool pair = EXP == 2 && g.cluster2 == 2;  // cta_group::2 MMAs
+    const bool mcast = EXP == 1 && cluster2;        // multicast center tiles, cta_group::1 MMAs
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // frame tiles of this CTA: tile = t_first, t_first + t_step, ... (< t_count); in cluster mode the two CTAs of a
     // pair walk tiles 2*tt and 2*tt+1 in lockstep (a tile index beyond n_tiles is a dummy: zero operand, no output)
@@ -644,18 +682,25 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < g.n_stages; ++s) {
             mbar_init(&T->full_bar[s], 1);
-            mbar_init(&T->empty_bar[s], cluster2 ? 2 : 1);  // cluster: the MMA warps of both CTAs release a slot
+            mbar_init(&T->empty_bar[s], mcast ? 2 : 1);  // multicast mode: the MMA warps of both CTAs release a slot
         }
-        for (int s = 0; s < 2; ++s) { mbar_init(&T->tfull_bar[s], 1); mbar_init(&T->tempty_bar[s], EPI_WARPS); }
+        // pair mode: the leader's MMA thread waits for the epilogue warps of BOTH CTAs
+        for (int s = 0; s < 2; ++s) { mbar_init(&T->tfull_bar[s], 1); mbar_init(&T->tempty_bar[s], pair ? 2 * EPI_WARPS : EPI_WARPS); }
         mbar_init(&T->bfull_bar, 1);
-        if constexpr (EXP)
+        if constexpr (EXP == 1)
             for (int kb = 0; kb < MAX_A_KBLOCKS; ++kb) { mbar_init(&T->afull_bar[kb], 1); mbar_init(&T->aempty_bar[kb], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T->tmem_slot)),
-                     "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (EXP == 2 && pair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T->tmem_slot)),
+                         "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T->tmem_slot)),
+                         "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -668,7 +713,7 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            if (EXP && resident == 2) {
+            if (EXP == 1 && resident == 2) {
                 // resident-A: two independent load streams polled by this one thread.  A: k-block kb of the frame
                 // tile is refilled as soon as the last center tile of the previous frame tile has consumed it (while
                 // that tile's remaining MMAs still run).  B: center k-blocks through the ring, running ahead into the
@@ -724,9 +769,19 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         for (int kb = 0; kb < g.n_kblocks; ++kb) {
                             mbar_wait(&T->empty_bar[stage], phase ^ 1);
                             uint8_t* sa = tiles + (size_t)stage * g.stage_bytes;
+                            if (EXP == 2 && pair) {
+                                // my frame rows + my half of the center k-block into my slot; both CTAs' bytes are
+                                // counted on the leader's barrier (its MMA thread is the only consumer)
+                                if (crank == 0) mbar_expect_tx(&T->full_bar[stage], 2 * (A_BYTES + B_BYTES / 2));
+                                tma_load_2d_pair(sa, &tmA, &T->full_bar[stage], kb * BLOCK_K, tile * TILE_M);
+                                tma_load_2d_pair(sa + A_BYTES, &tmBh, &T->full_bar[stage], kb * BLOCK_K,
+                                                 nt * TILE_N + (int)crank * (TILE_N / 2));
+                                if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+                                continue;
+                            }
                             mbar_expect_tx(&T->full_bar[stage], STAGE_BYTES);
                             tma_load_2d(sa, &tmA, &T->full_bar[stage], kb * BLOCK_K, tile * TILE_M);
-                            if (cluster2)  // my half of the center k-block, delivered to both CTAs of the pair
+                            if (mcast)  // my half of the center k-block, delivered to both CTAs of the pair
                                 tma_load_2d_mc(sa + A_BYTES + crank * (B_BYTES / 2), &tmBh, &T->full_bar[stage], kb * BLOCK_K,
                                                nt * TILE_N + (int)crank * (TILE_N / 2), (uint16_t)3);
                             else
@@ -739,10 +794,10 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=f16, K-major both, N=256, M=128
+        if (lane == 0 && !(EXP == 2 && pair && crank != 0)) {  // pair mode: the leader CTA issues for both
+            // instruction descriptor: D=f32, A=B=f16, K-major both, N=256, M=128 (pair: M=256 over the two CTAs)
             const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TILE_N >> 3) << 17) |
-                                   ((uint32_t)(TILE_M >> 4) << 24);
+                                   ((uint32_t)((pair ? 2 * TILE_M : TILE_M) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
@@ -763,7 +818,7 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t d_tmem = tmem_base + acc * TILE_N;
                     for (int kb = 0; kb < g.n_kblocks; ++kb) {
                         uint32_t sa, sb;
-                        if (EXP && resident == 2) {
+                        if (EXP == 1 && resident == 2) {
                             if (nt == 0) mbar_wait(&T->afull_bar[kb], tphase);
                             mbar_wait(&T->full_bar[stage], phase);
                             tc_fence_after();
@@ -781,6 +836,14 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const uint64_t adesc = make_smem_desc(sa);
                         const uint64_t bdesc = make_smem_desc(sb);
                         const int ksteps = min(BLOCK_K / 16, g.nk16 - kb * (BLOCK_K / 16));
+                        if (EXP == 2 && pair) {
+                            for (int ks = 0; ks < ksteps; ++ks)
+                                tc_mma_f16_pair(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc,
+                                                (kb | ks) != 0 ? 1u : 0u);
+                            tc_commit_pair(&T->empty_bar[stage]);  // both CTAs' slots are free once these retire
+                            if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         for (int ks = 0; ks < ksteps; ++ks) {
                             // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
                             tc_mma_f16(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc,
@@ -788,14 +851,15 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         }
                         if (resident != 1) {
                             // smem slot free once these MMAs retire (cluster: tell both CTAs, either may refill it)
-                            if (cluster2) tc_commit_mc(&T->empty_bar[stage], (uint16_t)3);
+                            if (mcast) tc_commit_mc(&T->empty_bar[stage], (uint16_t)3);
                             else tc_commit(&T->empty_bar[stage]);
                             if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
                         }
                         // resident-A: this k-block of the frame tile has met its last center tile
-                        if (EXP && resident == 2 && nt == g.n_ntiles - 1) tc_commit(&T->aempty_bar[kb]);
+                        if (EXP == 1 && resident == 2 && nt == g.n_ntiles - 1) tc_commit(&T->aempty_bar[kb]);
                     }
-                    tc_commit(&T->tfull_bar[acc]);  // accumulator stage complete
+                    if (EXP == 2 && pair) tc_commit_pair(&T->tfull_bar[acc]);  // each CTA's epilogue reads its own TMEM half
+                    else tc_commit(&T->tfull_bar[acc]);             // accumulator stage complete
                 }
                 if (resident == 1) {
                     tc_commit(&T->empty_bar[stage]);  // frame tile consumed by every center tile
@@ -847,7 +911,10 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         // then start on the next stage while the last chunk is being scanned
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&T->tempty_bar[acc]);
+                        if (lane == 0) {
+                            if (EXP == 2 && pair) mbar_arrive_leader(&T->tempty_bar[acc]);
+                            else mbar_arrive(&T->tempty_bar[acc]);
+                        }
                         if (nt + 1 < g.n_ntiles) {
                             const uint32_t nacc = (it + 1) & 1u, nphase = ((it + 1) >> 1) & 1u;
                             mbar_wait(&T->tfull_bar[nacc], nphase);
@@ -907,7 +974,8 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #undef B2K_T_COUNT
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if (EXP == 2 && pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -1672,18 +1740,24 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     if (rc != B2K_OK) { screen_plan_destroy(p); return rc; }
     static PerDeviceOnce attr_set;
     if (attr_set.need(ctx->device)) {
-        cudaError_t ae = cudaFuncSetAttribute(screen_gemm_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t ae = cudaFuncSetAttribute(screen_gemm_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)ctx->smem_optin);
         if (ae == cudaSuccess)
-            ae = cudaFuncSetAttribute(screen_gemm_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
         if (ae == cudaSuccess)
-            ae = cudaFuncSetAttribute(screen_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
         if (ae == cudaSuccess)
-            ae = cudaFuncSetAttribute(screen_gemm_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
         if (ae == cudaSuccess)
-            ae = cudaFuncSetAttribute(screen_gemm_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
         if (ae == cudaSuccess)
-            ae = cudaFuncSetAttribute(screen_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+        if (ae == cudaSuccess)
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+        if (ae == cudaSuccess)
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+        if (ae == cudaSuccess)
+            ae = cudaFuncSetAttribute(screen_gemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
         if (ae != cudaSuccess) { screen_plan_destroy(p); return set_error(B2K_ERR_CUDA, "screen smem attr: %s", cudaGetErrorString(ae)); }
         attr_set.done(ctx->device);
     }
@@ -1818,7 +1892,19 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
     g.prm = p->params;
     g.cand = p->cand;
     g.ncand = p->ncand;
-    const GemmSmemPlan sp = gemm_smem_plan(p->k_pad, p->Kp, ctx->smem_optin, ctx->screen_resident_a);
+    GemmSmemPlan sp = gemm_smem_plan(p->k_pad, p->Kp, ctx->smem_optin, ctx->screen_resident_a);
+    g.cluster2 = 0;
+    if (sp.resident == 0 && g.n_tiles >= 2 && ctx->sm_count >= 2) {
+        if (ctx->screen_cluster == 2) g.cluster2 = 1;
+        else if (ctx->screen_cluster == 3) {
+            // CTA-pair MMAs: a ring slot holds my frame k-block and my half of the center k-block
+            g.cluster2 = 2;
+            const size_t tail = sizeof(GemmSmemTail) + 1024;
+            sp.stage_bytes = A_BYTES + B_BYTES / 2;
+            sp.n_stages = (int)std::min<size_t>(MAX_STAGES, (ctx->smem_optin - tail) / sp.stage_bytes);
+            sp.total = tail + (size_t)sp.n_stages * sp.stage_bytes;
+        }
+    }
     g.resident = sp.resident;
     g.n_stages = sp.n_stages;
     g.stage_bytes = sp.stage_bytes;
@@ -1830,7 +1916,6 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, st));
     }
-    g.cluster2 = (ctx->screen_cluster == 2 && sp.resident == 0 && g.n_tiles >= 2 && ctx->sm_count >= 2) ? 1 : 0;
     if (g.cluster2) {
         // pairs of CTAs share every center k-block (each fetches half and multicasts it): an even grid of 2-CTA clusters
         cudaLaunchConfig_t cfg = {};
@@ -1847,17 +1932,21 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         cudaError_t le;
-        if (p->cg == 8) le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<8, true>, p->tmA, p->tmB, p->tmBh, g);
-        else if (p->cg == 4) le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<4, true>, p->tmA, p->tmB, p->tmBh, g);
-        else le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<2, true>, p->tmA, p->tmB, p->tmBh, g);
+        if (g.cluster2 == 2) {
+            if (p->cg == 8) le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<8, 2>, p->tmA, p->tmB, p->tmBh, g);
+            else if (p->cg == 4) le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<4, 2>, p->tmA, p->tmB, p->tmBh, g);
+            else le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<2, 2>, p->tmA, p->tmB, p->tmBh, g);
+        } else if (p->cg == 8) le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<8, 1>, p->tmA, p->tmB, p->tmBh, g);
+        else if (p->cg == 4) le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<4, 1>, p->tmA, p->tmB, p->tmBh, g);
+        else le = cudaLaunchKernelEx(&cfg, screen_gemm_kernel<2, 1>, p->tmA, p->tmB, p->tmBh, g);
         CUDA_TRY(le);
     } else if (sp.resident == 2) {
-        if (p->cg == 8) screen_gemm_kernel<8, true><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
-        else if (p->cg == 4) screen_gemm_kernel<4, true><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
-        else screen_gemm_kernel<2, true><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
-    } else if (p->cg == 8) screen_gemm_kernel<8, false><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
-    else if (p->cg == 4) screen_gemm_kernel<4, false><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
-    else screen_gemm_kernel<2, false><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+        if (p->cg == 8) screen_gemm_kernel<8, 1><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+        else if (p->cg == 4) screen_gemm_kernel<4, 1><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+        else screen_gemm_kernel<2, 1><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+    } else if (p->cg == 8) screen_gemm_kernel<8, 0><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+    else if (p->cg == 4) screen_gemm_kernel<4, 0><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
+    else screen_gemm_kernel<2, 0><<<grid, GEMM_THREADS, sp.total, st>>>(p->tmA, p->tmB, p->tmBh, g);
     LAUNCH_CHECK();
     if (ctx->profile) {
         CUDA_TRY(cudaEventRecord(ev1, st));

@@ -168,16 +168,20 @@ def test_screen_operand_builders_agree(b2k, oracle, screen_ctx, n, d, k):
     assert stats[0] == stats[1]
 
 
-@pytest.mark.parametrize("n,d,k", [(20001, 256, 1000), (9000, 100, 2500)])
-def test_screen_cluster_multicast_mode(b2k, oracle, screen_ctx, n, d, k):
-    """option screen_cluster=2: the streaming screen kernel as 2-CTA clusters that share every center k-block through
-    TMA multicast (odd tile counts run a dummy tile in the second CTA) -- same labels as the oracle"""
+@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("n,d,k", [(20001, 256, 1000), (9000, 100, 2500), (4357, 300, 700)])
+def test_screen_cluster_modes(b2k, oracle, screen_ctx, n, d, k, mode):
+    """the streaming screen kernel as 2-CTA clusters (odd tile counts run a dummy tile in the second CTA).
+    screen_cluster=2: the pair shares every center k-block through TMA multicast; screen_cluster=3: CTA-pair MMAs
+    (tcgen05 cta_group::2, M=256: every SM holds its own frame rows and half of the center k-block, the leader CTA
+    issues, commits are multicast, the peer's epilogue releases the accumulators on the leader's barrier) -- same
+    labels as the oracle"""
     rng = np.random.RandomState(k)
     X = blobs(rng, n, d, 9)
     Cn = X[rng.choice(n, k, replace=False)].copy()
     ref = oracle.assign(X, Cn, n_threads=8)
     screen_ctx.set_option("screen_resident_a", 0)
-    screen_ctx.set_option("screen_cluster", 2)
+    screen_ctx.set_option("screen_cluster", mode)
     try:
         np.testing.assert_array_equal(b2k.assign(X, Cn), ref)
     finally:
