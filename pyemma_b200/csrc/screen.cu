@@ -1047,8 +1047,10 @@ __device__ __forceinline__ void verify_stats(unsigned long long groups, unsigned
 // 4 floats of skew per 8-row group, so group g starts at bank (ds*8+4)*g mod 32 -- for ds = 4, 12 (and 8, 16 with
 // the extra skew below) consecutive groups rotate through all eight 16-byte bank groups and the lanes of a warp,
 // which look at unrelated groups, spread over the banks instead of piling onto one.
-template <int DREG>
-__global__ void __launch_bounds__(256) screen_verify_table_kernel(const float* __restrict__ X, int64_t n, int d,
+// CGT = 8: groups of 8 centers get a branch-free, fully unrolled evaluation (the frame and the table are zero padded to
+// DREG columns; a padded column adds (0-0)^2 = +0 to lane 0, which leaves the sum's bits alone), 0: any group size.
+template <int DREG, int CGT>
+__global__ void __launch_bounds__(256, 4) screen_verify_table_kernel(const float* __restrict__ X, int64_t n, int d,
                                                                   const float* __restrict__ Cn, int k,
                                                                   const uint32_t* __restrict__ cand,
                                                                   const uint8_t* __restrict__ ncand,
@@ -1068,6 +1070,7 @@ __global__ void __launch_bounds__(256) screen_verify_table_kernel(const float* _
     }
     __syncthreads();
     const int d4 = d & ~3;
+    const bool full_last = d == DREG;  // d is in (DREG-4, DREG]: the last 4-column block is a full block or a tail
     unsigned long long my_groups = 0, my_fb = 0;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         float xr[DREG];
@@ -1096,6 +1099,32 @@ __global__ void __launch_bounds__(256) screen_verify_table_kernel(const float* _
                     mask &= mask - 1;
                     const int jb = j0 + q * cg;  // first center of the group; a group never crosses an 8-row block
                     const float4* c4 = reinterpret_cast<const float4*>(ctab + (size_t)(jb >> 3) * gstride + (jb & 7) * DS);
+                    my_groups += 1;
+                    if (CGT == 8 && jb + 8 <= k) {
+                        float s8[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            Lanes4 L;
+                            L.init();
+#pragma unroll
+                            for (int e = 0; e < DREG - 4; e += 4) {
+                                const float4 cv = c4[(c * DS + e) >> 2];
+                                L.add4(xr[e], xr[e + 1], xr[e + 2], xr[e + 3], cv.x, cv.y, cv.z, cv.w);
+                            }
+                            const float4 cv = c4[(c * DS + DREG - 4) >> 2];
+                            if (full_last) {
+                                L.add4(xr[DREG - 4], xr[DREG - 3], xr[DREG - 2], xr[DREG - 1], cv.x, cv.y, cv.z, cv.w);
+                            } else {  // 1..3 tail columns into lane 0, in order; the padded ones add +0
+                                L.tail(xr[DREG - 4], cv.x);
+                                L.tail(xr[DREG - 3], cv.y);
+                                L.tail(xr[DREG - 2], cv.z);
+                            }
+                            s8[c] = L.result();
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) am.offer(s8[c], jb + c);
+                        continue;
+                    }
                     const int jn = min(cg, k - jb);
 #pragma unroll 2
                     for (int c = 0; c < cg; ++c) {
@@ -1119,7 +1148,6 @@ __global__ void __launch_bounds__(256) screen_verify_table_kernel(const float* _
                             am.offer(L.result(), jb + c);
                         }
                     }
-                    my_groups += 1;
                 }
             }
         }
@@ -1967,11 +1995,18 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
     do {                                                                                                             \
         static PerDeviceOnce vattr;                                                                                   \
         if (vattr.need(ctx->device)) {                                                                                                \
-            CUDA_TRY(cudaFuncSetAttribute(screen_verify_table_kernel<DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            CUDA_TRY(cudaFuncSetAttribute(screen_verify_table_kernel<DR, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          100 * 1024));                                                              \
+            CUDA_TRY(cudaFuncSetAttribute(screen_verify_table_kernel<DR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           100 * 1024));                                                              \
             vattr.done(ctx->device);                                                                                            \
         }                                                                                                            \
-        screen_verify_table_kernel<DR><<<tgrid, 256, tbytes, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, \
+        if (p->cg == 8 && ctx->verify_mode != 2)                                                                     \
+            screen_verify_table_kernel<DR, 8><<<tgrid, 256, tbytes, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, \
+                                                                   mind, lloyd, p->params, p->fb_list, gstride,     \
+                                                                   p->cg);                                           \
+        else                                                                                                         \
+            screen_verify_table_kernel<DR, 0><<<tgrid, 256, tbytes, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, \
                                                                    mind, lloyd, p->params, p->fb_list, gstride,     \
                                                                    p->cg);                                           \
     } while (0)
