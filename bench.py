@@ -153,6 +153,8 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=2_000_000, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-frames", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
+                    help="b2k_ctx_set_option before the run (experiments; repeatable)")
     ap.add_argument("--engine", default="auto", choices=["auto", "direct", "screen"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
     ap.add_argument("--stage-mb", type=int, default=0, help="pinned staging chunk of the e2e leg in MB (0: library default)")
@@ -180,6 +182,9 @@ def main():
     ctx = _lib.context(local_rank)
     lib = ctx.lib
     ctx.set_option("assign_engine", {"auto": 0, "direct": 1, "screen": 2}[args.engine])
+    for opt in args.option:
+        name, _, val = opt.partition("=")
+        ctx.set_option(name, int(val))
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
 

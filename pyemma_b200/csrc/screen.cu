@@ -1987,7 +1987,7 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         {   // table kernel when the skewed table fits shared memory twice per SM
             const int gstride = GROUP * ds + (((GROUP * ds / 4) & 1) ? 0 : 4);  // odd number of 16-byte units
             const size_t tbytes = (size_t)cdiv(p->k, GROUP) * gstride * 4;
-            if (tbytes <= 100 * 1024) {
+            if (tbytes <= 100 * 1024 && ctx->verify_mode != 3) {
                 const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / tbytes));
                 const unsigned tgrid =
                     (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * per_sm));
@@ -2021,7 +2021,7 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         }
         const int rs = (ds % 8 == 4) ? ds : ds + 4;
         const size_t tab_bytes = (size_t)p->k * rs * 4;
-        const int use_smem = 0;
+        const int use_smem = (ctx->verify_mode == 3 && tab_bytes <= 100 * 1024) ? 1 : 0;  // 8 lanes per frame, table in smem
         const size_t vsmem = use_smem ? tab_bytes : 0;
         const int per_sm = use_smem ? (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(tab_bytes, 1))) : 4;
         const unsigned vgrid =
