@@ -86,7 +86,9 @@ int b2k_ctx_sync(b2k_ctx* ctx);
  * the guard of datasource.py:1067-1075; default 1), "host_copy_threads" (threads of the
  * pageable -> pinned bounce copy, default 8), "accumulate_mode" (member sums: 0 automatic, 1 one 64-bit
  * RED per frame element, 2 segmented = counting sort by label + warp run sums, 3 per-CTA shared-memory table,
- * 4 tile-sorted = per-tile shared-memory sort + run sums, narrow rows), "own_stream", "profile" (1: time every launch of the
+ * 4 tile-sorted = per-tile shared-memory sort + run sums, narrow rows), "cost_kernel" (Lloyd cost pass: 0 automatic --
+ * one-pass kernel for d <= 16, 4-lanes-per-frame kernel above; 1 shared-memory staged wide-row kernel; 2 always two passes),
+ * "own_stream", "profile" (1: time every launch of the
  * tcgen05 screen kernel with CUDA events on the context stream; setting it again clears the record).
  * Experimental operand modes of the streaming screen kernel (results identical): "screen_resident_a"
  * (1: frame tile resident in shared memory), "screen_cluster" (2: 2-CTA clusters with TMA-multicast center tiles,

@@ -660,6 +660,9 @@ B2K_API int b2k_dev_lloyd_cost(b2k_lloyd* s, const float* dC_new, const int32_t*
         B2K_TRY(launch_rmsd_labeled_dist(ctx, s->dX, s->Ga.as<float>(), s->n, s->d, s->pc.C, s->pc.Gb, dlabels,
                                          s->l.as<float>()));
     } else {
+        int fused = 0;  // narrow rows: distances and the integer cost sum in one pass
+        B2K_TRY(launch_cost_fused(ctx, s->dX, s->n, s->d, dC_new, s->k, dlabels, s->scale_cost, slot, &fused));
+        if (fused) return B2K_OK;
         B2K_TRY(launch_labeled_dist(ctx, s->dX, s->n, s->d, dC_new, dlabels, s->l.as<float>()));
     }
     return launch_cost_reduce(ctx, s->l.as<float>(), s->n, s->scale_cost, slot);

@@ -81,7 +81,8 @@ struct b2k_ctx {
                                 // stages of center k-blocks -- 13.0 ms against 11.0 ms for the 4-stage streaming mode
     int screen_group = 0;     // centers per candidate group of the screen (0: automatic; 8, 4, 2)
     int rmsd_kernel = 0;      // 0: slab-streaming QCP kernel, 1: whole-row tile kernel
-    int cost_kernel = 0;      // 0: quad kernel for wide rows, 1: the shared-memory staged variant
+    int cost_kernel = 0;      // 0: quad kernel for wide rows / fused one-pass kernel for narrow rows, 1: the shared-memory
+                              // staged variant (wide rows), 2: always the two-pass path (per-frame distances, then the sum)
     int accumulate_mode = 0;  // 0: automatic (shared-memory table when it fits, else segmented), 1: one RED per
                               // element, 2: segmented (counting sort by label), 3: shared-memory table, 4: tile-sorted
     // stats of the last screen call

@@ -53,6 +53,8 @@ int launch_accumulate(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, con
 int launch_finalize(b2k_ctx* ctx, const int64_t* acc, int k, int d, double inv_scale, const float* old_centers,
                     float* new_centers);
 int launch_cost_reduce(b2k_ctx* ctx, const float* l, int64_t n, double scale, int64_t* acc_slot);
+int launch_cost_fused(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, const int32_t* labels,
+                      double scale, int64_t* acc_slot, int* done);
 int measure_fp32_rate(b2k_ctx* ctx, double* lane_instr_per_s);
 int launch_absmax(b2k_ctx* ctx, const float* X, int64_t count, float* d_out /* device, 1 float, pre-zeroed */);
 int launch_all_finite(b2k_ctx* ctx, const float* X, int64_t count, int* d_flag /* device, pre-set to 1 */);

@@ -403,6 +403,58 @@ __global__ void __launch_bounds__(256) cost_reduce_kernel(const float* __restric
     }
 }
 
+// Narrow rows (d <= 16, center table in shared memory): distance of every frame to ITS center and the fixed-point cost sum in
+// one pass -- the arithmetic of labeled_dist_kernel + cost_reduce_kernel (sqrt, then l*l in fp32, then the exact integer
+// sum), without the round trip of the per-frame distances through HBM.  Frame and table rows are zero padded to DREG
+// columns; a padded column adds (0-0)^2 = +0 to lane 0 of the reference's 4-lane sum, which leaves its bits alone.
+template <int DREG>
+__global__ void __launch_bounds__(256) cost_fused_small_kernel(const float* __restrict__ X, int64_t n, int d,
+                                                               const float* __restrict__ Cn, int k,
+                                                               const int32_t* __restrict__ labels, double scale,
+                                                               unsigned long long* __restrict__ acc_slot) {
+    extern __shared__ __align__(16) float ctab[];  // k rows, stride RS floats = an odd number of 16-byte units
+    __shared__ long long part[8];
+    constexpr int RS = ((DREG / 4) & 1) ? DREG : DREG + 4;
+    for (int t = threadIdx.x; t < k * DREG; t += 256) {
+        const int r = t / DREG, c = t - r * DREG;
+        ctab[r * RS + c] = c < d ? __ldg(Cn + (int64_t)r * d + c) : 0.f;
+    }
+    __syncthreads();
+    const bool full_last = d == DREG;  // d is in (DREG-4, DREG]
+    long long s = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        float xr[DREG];
+#pragma unroll
+        for (int e = 0; e < DREG; ++e) xr[e] = e < d ? __ldg(X + i * d + e) : 0.f;
+        const float4* c4 = reinterpret_cast<const float4*>(ctab + (size_t)labels[i] * RS);
+        Lanes4 L;
+        L.init();
+#pragma unroll
+        for (int e = 0; e < DREG - 4; e += 4) {
+            const float4 cv = c4[e >> 2];
+            L.add4(xr[e], xr[e + 1], xr[e + 2], xr[e + 3], cv.x, cv.y, cv.z, cv.w);
+        }
+        const float4 cv = c4[(DREG - 4) >> 2];
+        if (full_last) {
+            L.add4(xr[DREG - 4], xr[DREG - 3], xr[DREG - 2], xr[DREG - 1], cv.x, cv.y, cv.z, cv.w);
+        } else {
+            L.tail(xr[DREG - 4], cv.x);
+            L.tail(xr[DREG - 3], cv.y);
+            L.tail(xr[DREG - 2], cv.z);
+        }
+        const float li = __fsqrt_rn(L.result());
+        s += __double2ll_rn((double)__fmul_rn(li, li) * scale);
+    }
+    s = warp_sum_ll(s);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        long long t = threadIdx.x < 8 ? part[threadIdx.x] : 0;
+        t = warp_sum_ll(t);
+        if (threadIdx.x == 0) atomicAdd(acc_slot, (unsigned long long)t);
+    }
+}
+
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ X, int64_t count, int* out_bits) {
     float m = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < count; i += (int64_t)gridDim.x * 256) {
@@ -592,6 +644,38 @@ int launch_cost_reduce(b2k_ctx* ctx, const float* l, int64_t n, double scale, in
     if (n <= 0) return B2K_OK;
     cost_reduce_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(l, n, scale, (unsigned long long*)acc_slot);
     LAUNCH_CHECK();
+    return B2K_OK;
+}
+
+// returns B2K_OK with *done = 1 when the fused narrow-row kernel took the job, *done = 0 when the caller has to run the
+// two-pass path (wide rows, table too large for shared memory, labels possibly out of range)
+int launch_cost_fused(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, const int32_t* labels,
+                      double scale, int64_t* acc_slot, int* done) {
+    *done = 0;
+    if (n <= 0 || d > 16 || ctx->cost_kernel == 2) return B2K_OK;
+    const int ds = (d + 3) & ~3;
+    const size_t tbytes = (size_t)k * (((ds / 4) & 1) ? ds : ds + 4) * 4;
+    if (tbytes > 96 * 1024) return B2K_OK;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / tbytes));
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * per_sm));
+#define B2K_COSTF(DR)                                                                                                  \
+    do {                                                                                                               \
+        static PerDeviceOnce cattr;                                                                                    \
+        if (cattr.need(ctx->device)) {                                                                                 \
+            CUDA_TRY(cudaFuncSetAttribute(cost_fused_small_kernel<DR>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                          96 * 1024));                                                                 \
+            cattr.done(ctx->device);                                                                                   \
+        }                                                                                                              \
+        cost_fused_small_kernel<DR><<<grid, 256, tbytes, ctx->stream>>>(X, n, d, C, k, labels, scale,                  \
+                                                                        (unsigned long long*)acc_slot);               \
+    } while (0)
+    if (ds == 4) B2K_COSTF(4);
+    else if (ds == 8) B2K_COSTF(8);
+    else if (ds == 12) B2K_COSTF(12);
+    else B2K_COSTF(16);
+#undef B2K_COSTF
+    LAUNCH_CHECK();
+    *done = 1;
     return B2K_OK;
 }
 

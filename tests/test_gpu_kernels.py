@@ -255,6 +255,29 @@ def test_cost_wide_rows_kernels_agree(b2k, oracle, n, d, k):
     assert abs(float(vals[0]) - float(ref)) <= 2e-7 * float(ref)
 
 
+@pytest.mark.parametrize("n,d,k", [(5000, 1, 7), (7001, 3, 100), (4000, 4, 33), (9000, 7, 500), (20000, 10, 1000),
+                                   (6000, 12, 64), (3000, 13, 20), (5000, 16, 900)])
+def test_cost_narrow_rows_fused_kernel(b2k, oracle, n, d, k):
+    """d <= 16: the one-pass cost kernel (center table in shared memory, zero-padded columns, integer sum in the same
+    kernel) gives the same fixed-point sum as the two-pass path (per-frame distances, then the sum) and matches the
+    oracle's cost."""
+    rng = np.random.RandomState(100 + d)
+    X = blobs(rng, n, d, 6)
+    Cn = X[rng.choice(n, k, replace=False)].copy() + np.float32(0.01)
+    lab = oracle.assign(X, Cn, n_threads=4)
+    ctx = b2k.context()
+    vals = []
+    try:
+        for mode in (0, 2):
+            ctx.set_option("cost_kernel", mode)
+            vals.append(b2k.kmeans_cost(X, Cn, lab))
+    finally:
+        ctx.set_option("cost_kernel", 0)
+    assert vals[0].tobytes() == vals[1].tobytes()
+    ref = oracle.cost(X, Cn, lab, acc="f64")
+    assert abs(float(vals[0]) - float(ref)) <= 2e-7 * float(ref)
+
+
 def test_regspace_multi_piece_chunk(b2k, oracle):
     """a chunk larger than the ~64 MB piece the device pass works on (d=1100 -> 16384-frame pieces): same centers,
     same order as the oracle's single pass; and the max_centers stop still keeps exactly max_centers centers."""
