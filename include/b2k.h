@@ -88,6 +88,7 @@ int b2k_ctx_sync(b2k_ctx* ctx);
  * RED per frame element, 2 segmented = counting sort by label + warp run sums, 3 per-CTA shared-memory table,
  * 4 tile-sorted = per-tile shared-memory sort + run sums, narrow rows), "cost_kernel" (Lloyd cost pass: 0 automatic --
  * one-pass kernel for d <= 16, 4-lanes-per-frame kernel above; 1 shared-memory staged wide-row kernel; 2 always two passes),
+ * "row_vec_max" (widest frame-row load of the narrow-row verify / cost kernels: 4, 2 or 1 floats; default 4),
  * "own_stream", "profile" (1: time every launch of the
  * tcgen05 screen kernel with CUDA events on the context stream; setting it again clears the record).
  * Experimental operand modes of the streaming screen kernel (results identical): "screen_resident_a"

@@ -284,6 +284,7 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "host_copy_threads")) c->host_copy_threads = (int)std::max<int64_t>(1, std::min<int64_t>(value, 32));
     else if (!strcmp(name, "accumulate_mode")) c->accumulate_mode = (int)value;
     else if (!strcmp(name, "cost_kernel")) c->cost_kernel = (int)value;
+    else if (!strcmp(name, "row_vec_max")) c->row_vec_max = (int)value;
     else if (!strcmp(name, "rmsd_kernel")) c->rmsd_kernel = (int)value;
     else if (!strcmp(name, "profile")) {  // (re)start event timing of the screen kernel launches
         for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);

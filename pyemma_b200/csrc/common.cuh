@@ -81,6 +81,7 @@ struct b2k_ctx {
                                 // stages of center k-blocks -- 13.0 ms against 11.0 ms for the 4-stage streaming mode
     int screen_group = 0;     // centers per candidate group of the screen (0: automatic; 8, 4, 2)
     int rmsd_kernel = 0;      // 0: slab-streaming QCP kernel, 1: whole-row tile kernel
+    int row_vec_max = 4;      // widest row load of the narrow-row verify / cost kernels (4, 2 or 1 floats)
     int cost_kernel = 0;      // 0: quad kernel for wide rows / fused one-pass kernel for narrow rows, 1: the shared-memory
                               // staged variant (wide rows), 2: always the two-pass path (per-frame distances, then the sum)
     int accumulate_mode = 0;  // 0: automatic (shared-memory table when it fits, else segmented), 1: one RED per
@@ -133,6 +134,39 @@ struct Lanes4 {
         return __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);  // (0+a0)==a0 exactly
     }
 };
+
+// one frame row (d <= DREG floats) into registers, zero padded to DREG, with the widest loads the row pitch and the
+// base alignment allow (vec = 4: d % 4 == 0 and 16-byte aligned base, 2: d even and 8-byte aligned, else 1).
+// A warp reading 32 consecutive rows touches the same cache lines with every load instruction, so fewer, wider loads
+// cut the L1 wavefronts proportionally.
+__host__ __device__ __forceinline__ int row_load_width(const float* X, int d, int vmax = 4) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(X);
+    if (vmax >= 4 && (d & 3) == 0 && (a & 15) == 0) return 4;
+    if (vmax >= 2 && (d & 1) == 0 && (a & 7) == 0) return 2;
+    return 1;
+}
+template <int DREG>
+__device__ __forceinline__ void load_row_padded(const float* __restrict__ X, int64_t i, int d, int vec, float (&xr)[DREG]) {
+    const float* row = X + i * d;
+    if (vec == 4) {
+#pragma unroll
+        for (int e = 0; e < DREG; e += 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < d) v = __ldg(reinterpret_cast<const float4*>(row + e));
+            xr[e] = v.x; xr[e + 1] = v.y; xr[e + 2] = v.z; xr[e + 3] = v.w;
+        }
+    } else if (vec == 2) {
+#pragma unroll
+        for (int e = 0; e < DREG; e += 2) {
+            float2 v = make_float2(0.f, 0.f);
+            if (e < d) v = __ldg(reinterpret_cast<const float2*>(row + e));
+            xr[e] = v.x; xr[e + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < DREG; ++e) xr[e] = e < d ? __ldg(row + e) : 0.f;
+    }
+}
 
 // generic-pointer version (global or shared), any d
 __device__ __forceinline__ float euclid_sq_exact(const float* __restrict__ x, const float* __restrict__ c, int d) {

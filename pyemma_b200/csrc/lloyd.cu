@@ -411,7 +411,7 @@ template <int DREG>
 __global__ void __launch_bounds__(256) cost_fused_small_kernel(const float* __restrict__ X, int64_t n, int d,
                                                                const float* __restrict__ Cn, int k,
                                                                const int32_t* __restrict__ labels, double scale,
-                                                               unsigned long long* __restrict__ acc_slot) {
+                                                               unsigned long long* __restrict__ acc_slot, int vec) {
     extern __shared__ __align__(16) float ctab[];  // k rows, stride RS floats = an odd number of 16-byte units
     __shared__ long long part[8];
     constexpr int RS = ((DREG / 4) & 1) ? DREG : DREG + 4;
@@ -424,8 +424,7 @@ __global__ void __launch_bounds__(256) cost_fused_small_kernel(const float* __re
     long long s = 0;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         float xr[DREG];
-#pragma unroll
-        for (int e = 0; e < DREG; ++e) xr[e] = e < d ? __ldg(X + i * d + e) : 0.f;
+        load_row_padded<DREG>(X, i, d, vec, xr);
         const float4* c4 = reinterpret_cast<const float4*>(ctab + (size_t)labels[i] * RS);
         Lanes4 L;
         L.init();
@@ -667,7 +666,8 @@ int launch_cost_fused(b2k_ctx* ctx, const float* X, int64_t n, int d, const floa
             cattr.done(ctx->device);                                                                                   \
         }                                                                                                              \
         cost_fused_small_kernel<DR><<<grid, 256, tbytes, ctx->stream>>>(X, n, d, C, k, labels, scale,                  \
-                                                                        (unsigned long long*)acc_slot);               \
+                                                                        (unsigned long long*)acc_slot,                \
+                                                                        row_load_width(X, d, ctx->row_vec_max));      \
     } while (0)
     if (ds == 4) B2K_COSTF(4);
     else if (ds == 8) B2K_COSTF(8);

@@ -1057,7 +1057,8 @@ __global__ void __launch_bounds__(256, 4) screen_verify_table_kernel(const float
                                                                   int32_t* __restrict__ labels,
                                                                   float* __restrict__ mind, int lloyd,
                                                                   ScreenParams* prm, uint32_t* __restrict__ fb_list,
-                                                                  int gstride /* floats per 8-row group */, int cg) {
+                                                                  int gstride /* floats per 8-row group */, int cg,
+                                                                  int vec /* row load width */) {
     extern __shared__ __align__(16) float ctab[];
     const int idb = cand_id_bits(cg);
     const uint32_t idm = cand_id_mask(cg);
@@ -1074,8 +1075,7 @@ __global__ void __launch_bounds__(256, 4) screen_verify_table_kernel(const float
     unsigned long long my_groups = 0, my_fb = 0;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         float xr[DREG];
-#pragma unroll
-        for (int e = 0; e < DREG; ++e) xr[e] = e < d ? __ldg(X + i * d + e) : 0.f;
+        load_row_padded<DREG>(X, i, d, vec, xr);
         const int nc = ncand[i];
         if (nc == 255) {
             fallback_push(prm, fb_list, i);
@@ -2004,11 +2004,11 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         if (p->cg == 8 && ctx->verify_mode != 2)                                                                     \
             screen_verify_table_kernel<DR, 8><<<tgrid, 256, tbytes, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, \
                                                                    mind, lloyd, p->params, p->fb_list, gstride,     \
-                                                                   p->cg);                                           \
+                                                                   p->cg, row_load_width(dX, p->d, ctx->row_vec_max));                                           \
         else                                                                                                         \
             screen_verify_table_kernel<DR, 0><<<tgrid, 256, tbytes, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, \
                                                                    mind, lloyd, p->params, p->fb_list, gstride,     \
-                                                                   p->cg);                                           \
+                                                                   p->cg, row_load_width(dX, p->d, ctx->row_vec_max));                                           \
     } while (0)
                 if (ds == 4) B2K_VTABLE(4);
                 else if (ds == 8) B2K_VTABLE(8);
