@@ -425,7 +425,9 @@ __global__ void __launch_bounds__(256) cost_fused_small_kernel(const float* __re
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         float xr[DREG];
         load_row_padded<DREG>(X, i, d, vec, xr);
-        const float4* c4 = reinterpret_cast<const float4*>(ctab + (size_t)labels[i] * RS);
+        const int32_t a = labels[i];
+        if ((uint32_t)a >= (uint32_t)k) continue;  // caller-supplied labels outside [0, k): no center, no contribution
+        const float4* c4 = reinterpret_cast<const float4*>(ctab + (size_t)a * RS);
         Lanes4 L;
         L.init();
 #pragma unroll
