@@ -55,6 +55,11 @@ def test_kmeans_known_answers():
         T[i * 10000:(i + 1) * 10000] = v
     cl = coor.cluster_kmeans(T, k=4)                         # test_kmeans.py:411-426
     assert sorted(cl.clustercenters[:, 0].tolist()) == [30.0, 60.0, 90.0, 120.0]
+    from test_oracle_kats import _truncated_octahedron, hull_inequalities
+    P = _truncated_octahedron()                              # test_kmeans.py:181-233: k=1 center inside the hull
+    eq = hull_inequalities(P)
+    c = coor.cluster_kmeans(P, k=1).clustercenters[0].astype(np.float64)
+    assert np.all(eq[:, :3] @ c + eq[:, 3] <= 0.0)
 
 
 def test_kmeans_minrmsd_assignment_manual_argmin(b2k):

@@ -33,6 +33,39 @@ def test_kat_k1_cube_corners(oracle):
         np.testing.assert_equal(cen.squeeze(), [0, 0, 0])
 
 
+def _truncated_octahedron(scale=0.7071, seed=3):
+    """24 vertices of a truncated octahedron (all permutations of (0, +-1, +-2)), scaled and rotated: the kind of point
+    set test_kmeans.py:181-233 uses (24 vertices of a convex polytope, k=1)."""
+    pts = set()
+    for perm in itertools.permutations((0.0, 1.0, 2.0)):
+        for s1 in (1.0, -1.0):
+            for s2 in (1.0, -1.0):
+                v = [c * (s1 if c == 1.0 else (s2 if c == 2.0 else 1.0)) for c in perm]
+                pts.add(tuple(v))
+    P = np.array(sorted(pts), np.float64) * scale
+    q, _ = np.linalg.qr(np.random.RandomState(seed).randn(3, 3))
+    return (P @ q.T).astype(np.float32)
+
+
+def hull_inequalities(points):
+    from scipy.spatial import ConvexHull
+    return ConvexHull(points.astype(np.float64)).equations  # rows (a, b): inside <=> a.x + b <= 0
+
+
+def test_kat_k1_center_inside_convex_hull(oracle):
+    # test_kmeans.py:181-233: k=1 on the 24 vertices of a convex polytope -> the center satisfies every facet
+    # inequality of the hull (and is the members' mean, here the origin up to fp32 rounding)
+    X = _truncated_octahedron()
+    assert len(X) == 24
+    eq = hull_inequalities(X)
+    for seed in range(3):
+        c0 = oracle.kmpp_init(X, 1, seed)
+        cen, code, it, _ = oracle.cluster_loop(X, c0, 10, 1e-5)
+        assert cen.shape == (1, 3)
+        assert np.all(eq[:, :3] @ cen[0].astype(np.float64) + eq[:, 3] <= 0.0)
+        np.testing.assert_allclose(cen[0], X.astype(np.float64).mean(0), atol=1e-6)
+
+
 def test_kat_outlier_equilibrium(oracle):
     # test_kmeans.py:168-179
     X = np.array([[1, 1.5, 1], [1, 1, -1], [1, -1, -1], [-1, -1, -1], [-1, 1, 1], [-1, -1, 1], [-1, 1, -1],
