@@ -79,7 +79,7 @@ int b2k_ctx_destroy(b2k_ctx* ctx);
  * private non-blocking stream (the state after b2k_ctx_create). */
 int b2k_ctx_set_stream(b2k_ctx* ctx, void* cuda_stream);
 int b2k_ctx_sync(b2k_ctx* ctx);
-/* options: "assign_engine" (B2K_ENGINE_*), "screen_terms" (1: hi-only fp16 operands, else hi+lo split),
+/* options: "assign_engine" (B2K_ENGINE_*), "screen_terms" (1: hi-only fp16 operands, 2: hi-only for rows of 32+ floats, else hi+lo split),
  * "screen_group" (centers per candidate group the screen hands to the exact verify: 0 automatic, 8, 4 or 2),
  * "stage_bytes" (pinned staging buffer size per slot), "check_finite" (1: the host-pointer
  * assign / stage entry points check every staged chunk on the device and return B2K_ERR_NONFINITE for NaN/inf frames,

@@ -1723,6 +1723,15 @@ bool screen_supported(const b2k_ctx* ctx, int d, int k, int64_t n) {
     return k >= 128 && (int64_t)k * d >= 2048 && n >= 4096;
 }
 
+// operand terms: 3 = hi/lo fp16 split (default: at d=10 hi-only operands leave dozens of candidates per frame), 1 = hi-only
+// (option screen_terms=1), option value 2 = hi-only for wide rows only (d >= 32: tools/terms_study.py expects 1-5 candidates
+// per frame there for a third of the MMA flops -- to be measured, not a default)
+static int screen_term_count(const b2k_ctx* ctx, int d) {
+    if (ctx->screen_terms == 1) return 1;
+    if (ctx->screen_terms == 2 && d >= 32) return 1;
+    return 3;
+}
+
 void screen_plan_destroy(ScreenPlan* p) {
     if (!p) return;
     cudaStreamSynchronize(p->ctx->stream);
@@ -1739,7 +1748,7 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     p->d = d;
     p->k = k;
     p->k_pad = (int)(cdiv(k, TILE_N) * TILE_N);
-    p->terms = ctx->screen_terms == 1 ? 1 : 3;  // hi-only operands leave too many candidates
+    p->terms = screen_term_count(ctx, d);
     // candidate group size: narrow rows (d <= 16) leave the TMEM-read-bound epilogue no slack (measured at 1e7 x 10,
     // k=1000: screen kernel 2.32 / 2.44 / 2.90 ms for groups of 8 / 4 / 2, step time 3.40 / 3.36 / 3.75 ms) -> 8; wide
     // rows are MMA bound and their verify pays 4*d bytes of L2 traffic per candidate center -> 2 (16-bit chunk ids)
@@ -1795,7 +1804,7 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
 
 int screen_plan_acquire(b2k_ctx* ctx, int64_t n, int d, int k, ScreenPlan** out) {
     ScreenPlan* c = static_cast<ScreenPlan*>(ctx->assign_plan);
-    const int terms = ctx->screen_terms == 1 ? 1 : 3;
+    const int terms = screen_term_count(ctx, d);
     const int want_cg = (ctx->screen_group == 8 || ctx->screen_group == 4 || ctx->screen_group == 2) ? ctx->screen_group : 0;
     if (c && c->d == d && c->k == k && c->terms == terms && n <= c->n_cap && (want_cg == 0 || want_cg == c->cg)) {
         c->prepared_n = -1;
