@@ -41,3 +41,17 @@ def test_product_arm_needs_a_gpu():
     r = _run(["--steps", "1", "--warmup", "3", "--no-cpu-baseline"])
     assert r.returncode != 0
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """the driver launches the reference arm like the product arm (torchrun, one process per GPU): rank 0 alone runs it
+    and prints the line, the other ranks exit 0 without work"""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--ref-frames", "20000"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["n_gpus"] == 2 and j["value"] > 0
