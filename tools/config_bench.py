@@ -247,10 +247,15 @@ def main():
     ap.add_argument("--cfg5-frames", type=int, default=1_000_000)
     ap.add_argument("--kmpp-full", action="store_true")
     ap.add_argument("--no-kmpp", action="store_true")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
+                    help="b2k_ctx_set_option before the run (experiments; repeatable)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     ctx = _lib.context(0)
     ctx.set_stream(torch.cuda.current_stream(DEV).cuda_stream)
+    for opt in args.option:
+        name, _, val = opt.partition("=")
+        ctx.set_option(name, int(val))
     fns = {"1": cfg1, "2": cfg2, "3": cfg3, "4": cfg4, "5": cfg5, "6": cfg6}
     results = []
     for c in args.cfg.split(","):
