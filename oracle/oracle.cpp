@@ -14,8 +14,9 @@
 //     (call sites: clustering/src/clustering_module.cpp:21-28)
 // The functions below restate the published algorithms of those packages as recorded
 // in SURVEY.md Appendix A/B, and are pinned against every known-answer test the
-// reference holds for the path (tests/test_oracle_reference_kats.py) and against
-// independent fp64 numpy/Kabsch implementations (tests/test_oracle_numpy.py).
+// reference holds for the path and independent fp64 numpy/Kabsch implementations
+// (tests/test_oracle_kats.py), and against scikit-learn's Lloyd / k-means++ and scipy's
+// Rotation.align_vectors as third-party implementations (tests/test_oracle_independent.py).
 //
 // Build flags are part of the oracle's definition (oracle/Makefile):
 //   g++ -O3 -fopenmp -ffp-contract=off   (no -march; x86-64 baseline, no FMA)

@@ -1,7 +1,7 @@
 """ctypes loader for the CPU oracle -- TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference)
-may import this module.  pyemma_b200/ never does (tests/test_no_oracle_in_product.py
+may import this module.  pyemma_b200/ never does (tests/test_cabi.py::test_product_never_references_oracle
 enforces it).  See oracle.cpp for what is restated and its parity status
 ("parity unpinned upstream": deeptime / mdtraj are absent offline).
 """

@@ -105,6 +105,23 @@ class AbstractClustering:
         self._Y = None
         self.show_progress = False
 
+    # ---- progress reporting (pyemma/_base/progress/reporter.py: _progress_register / _progress_update) --------
+    # The reference drives tqdm bars; here the counters are kept on the estimator (`progress_`: stage ->
+    # [done, total, description]) and an optional user hook `progress_callback(stage, done, total)` is called.
+    def _progress_register(self, amount_of_work, description="", stage=0):
+        if not hasattr(self, "progress_"):
+            self.progress_ = {}
+        self.progress_[stage] = [0, int(amount_of_work), description]
+
+    def _progress_update(self, numerator_increment, stage=0):
+        if not hasattr(self, "progress_") or stage not in self.progress_:
+            return
+        ent = self.progress_[stage]
+        ent[0] += int(numerator_increment)
+        hook = getattr(self, "progress_callback", None)
+        if hook is not None:
+            hook(stage, ent[0], ent[1])
+
     # ---- sklearn-style parameter handling (estimator.py:460-500) ----------------------------
     @classmethod
     def _get_param_names(cls):
@@ -308,7 +325,8 @@ class AbstractClustering:
             raise RuntimeError("no data producer set")
         out = []
         rank, ws = staging.world()
-        if isinstance(src, DataInMemory) and ws > 1:
+        if isinstance(src, DataInMemory) and ws > 1 and getattr(self, "distributed_assign", False):
+            # explicit opt-in: every rank of the torch.distributed job must make this call (it is a collective)
             out = self._get_output_sharded(src, stride, skip, rank, ws)
         elif isinstance(src, DataInMemory):
             for x in src.data:
@@ -325,9 +343,10 @@ class AbstractClustering:
         return out
 
     def _get_output_sharded(self, src, stride, skip, rank, ws):
-        """assign / dtrajs under torchrun: frames are independent, so every rank assigns one contiguous
-        range of the (strided, concatenated) frames and the int32 labels are combined with one all-reduce(sum) over
-        zero-filled buffers; every rank returns the complete dtrajs."""
+        """assign / dtrajs under torchrun, opt-in through `distributed_assign = True`: frames are
+        independent, so every rank assigns one contiguous range of the (strided, concatenated) frames and the int32
+        labels of the shards are combined with ONE all-gather (N/ws labels per rank); every rank returns the complete
+        dtrajs.  A collective: all ranks must call it, and a failure on one rank is raised on all of them."""
         import torch
         import torch.distributed as dist
         views = [x[skip::stride] for x in src.data]
@@ -335,16 +354,22 @@ class AbstractClustering:
         total = int(sum(lengths))
         lo, hi = staging.shard_bounds(total, rank, ws)
         dev = staging.device()
-        flat = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)
-        off = 0
-        for v, L in zip(views, lengths):
-            a, b = max(lo, off), min(hi, off + L)
-            if a < b:
-                lab = self._transform_array(v[a - off:b - off])[:, 0]
-                flat[a:b] = torch.from_numpy(np.ascontiguousarray(lab)).to(dev)
-            off += L
-        dist.all_reduce(flat)
-        host = flat[:total].cpu().numpy()
+        mine = torch.empty(max(hi - lo, 0), dtype=torch.int32, device=dev)
+        err, off = None, 0
+        try:
+            for v, L in zip(views, lengths):
+                a, b = max(lo, off), min(hi, off + L)
+                if a < b:
+                    lab = self._transform_array(v[a - off:b - off])[:, 0]
+                    mine[a - lo:b - lo] = torch.from_numpy(np.ascontiguousarray(lab)).to(dev)
+                off += L
+        except Exception as e:  # keep the collective sequence identical on every rank, then raise everywhere
+            err = e
+        flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()):
+            raise err if err is not None else RuntimeError("sharded assign failed on another rank")
+        host = staging.all_gather_shards(mine, total, rank, ws).cpu().numpy()
         out, off = [], 0
         for L in lengths:
             out.append(host[off:off + L].reshape(-1, 1).copy())

@@ -181,7 +181,10 @@ class KmeansClustering(AbstractClustering):
             if scan == "auto":
                 scan = "serial" if (total_length <= 20000 and ws == 1) else "blocked"
             centers = torch.empty((k, d), dtype=torch.float32, device=dev)
-            cb = self._callback(lambda: None) if self.show_progress else _lib.CALLBACK(0)
+            # kmeans.py:241-249: stage 0 counts the k-means++ picks, stage 1 the Lloyd iterations
+            if self.show_progress:
+                self._progress_register(k, "initialize kmeans++ centers", stage=0)
+            cb = self._callback(lambda: self._progress_update(1, stage=0)) if self.show_progress else _lib.CALLBACK(0)
             if ws > 1:
                 if scan == "serial":
                     raise ValueError("kmpp_scan='serial' follows the frame order of ONE array; sharded (multi-GPU) "
@@ -197,11 +200,19 @@ class KmeansClustering(AbstractClustering):
             self.initial_centers_ = np.array(self.clustercenters, dtype=np.float32)
 
         # ---- Lloyd iterations (deeptime cluster_loop semantics) ----
+        if self.show_progress:
+            self._progress_register(self.max_iter, "kmeans iterations", stage=1)
         try:
             centers, converged, inertias = self._lloyd(ctx, X, centers, k, metric, total_length, rank, ws)
             self.clustercenters = centers.cpu().numpy()
             self._converged = converged
             self.inertias_ = np.asarray(inertias, dtype=np.float32)
+            if stride == 1:
+                # the frames the dtrajs are made of are resident right now: one more device pass against the final
+                # centers (3.5 ms per 1e7 x 10 frames) instead of a second trip of every frame over PCIe when
+                # `.dtrajs` is first read (interface.py:101-106 computes them lazily from the host data)
+                self._dtrajs = self._resident_dtrajs(ctx, X, centers, k, metric, lengths, total_length, rank, ws)
+                self._previous_stride = 1
         finally:
             # kmeans.py:269-284: drop the big array unless the user keeps it for a resume
             if not self.keep_data or self._converged:
@@ -214,6 +225,24 @@ class KmeansClustering(AbstractClustering):
                                 " of %g in %i iterations. Consider increasing max_iter.",
                                 self.tolerance, self.max_iter)
         return self
+
+    def _resident_dtrajs(self, ctx, X, centers, k, metric, lengths, n_total, rank, ws):
+        """labels of the resident shard against `centers` (b2k_dev_assign), all-gathered over the ranks and split per
+        trajectory: the same values AbstractClustering.assign would produce from the host copy of the frames."""
+        n_local, d = X.shape
+        lab = torch.empty(max(n_local, 1), dtype=torch.int32, device=X.device)
+        if n_local:
+            _lib.check(ctx.lib.b2k_dev_assign(ctx.handle, C.c_void_p(X.data_ptr()), n_local, d,
+                                              C.c_void_p(centers.data_ptr()), k, metric, C.c_void_p(lab.data_ptr()), None))
+        lab = lab[:n_local]
+        if ws > 1:
+            lab = staging.all_gather_shards(lab, n_total, rank, ws)
+        host = lab.cpu().numpy()
+        out, off = [], 0
+        for L in lengths:
+            out.append(host[off:off + int(L)].copy())
+            off += int(L)
+        return out
 
     def _callback(self, fn):
         cb = _lib.CALLBACK(lambda _u: fn())
@@ -306,6 +335,10 @@ class KmeansClustering(AbstractClustering):
                 prev = cost
                 if rel <= tol:
                     converged = True
+                elif self.show_progress:
+                    # deeptime cluster_loop calls callback_loop after every iteration that did not converge
+                    # (kmeans.py:246,254-255 registers it as progress stage 1)
+                    self._progress_update(1, stage=1)
                 it += 1
                 if not (it < self.max_iter and not converged):
                     break

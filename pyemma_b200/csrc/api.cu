@@ -223,6 +223,8 @@ B2K_API int b2k_ctx_create(int device, b2k_ctx** out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
+    CUDA_TRY(cudaMalloc(&c->flags, 256));
+    CUDA_TRY(cudaMemset(c->flags, 0, 256));
     for (int s = 0; s < 2; ++s) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream[s], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[s], cudaEventDisableTiming));
@@ -247,6 +249,7 @@ B2K_API int b2k_ctx_destroy(b2k_ctx* c) {
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     for (int i = 0; i < b2k_ctx::N_SLOTS; ++i)
         if (c->slot_ptr[i]) cudaFree(c->slot_ptr[i]);
+    if (c->flags) cudaFree(c->flags);
     if (c->scratch) cudaFree(c->scratch);
     if (c->scratch2) cudaFree(c->scratch2);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -387,14 +390,29 @@ B2K_API int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, 
         B2K_TRY(ga.alloc((size_t)n * 4));
         B2K_TRY(launch_rmsd_center(ctx, dX, n, d, nullptr, ga.as<float>()));
     } else if (ctx->engine != B2K_ENGINE_DIRECT && screen_supported(ctx, d, k, n)) {
+        // the plan (fp16 operand + candidate lists, Kp*2 + ~41 bytes per frame) is sized to what is free: frames beyond
+        // its capacity are assigned piece by piece through the same plan
         ScreenPlan* plan = nullptr;
-        B2K_TRY(screen_plan_acquire(ctx, n, d, k, &plan));
-        int rc = screen_prepare_frames(plan, dX, n);
-        if (rc == B2K_OK) rc = screen_assign(plan, dX, n, dC, dlabels, dmind, 0);
-        ctx->stat_screen_frames = (double)n;
-        ctx->stat_plan = nullptr;
-        ctx->stat_pending = rc == B2K_OK;
-        return rc;
+        int64_t cap = n;
+        int rc = screen_plan_acquire(ctx, cap, d, k, &plan);
+        while (rc == B2K_ERR_NOMEM && cap > (int64_t(1) << 16)) {
+            cap = (cap + 1) / 2;
+            rc = screen_plan_acquire(ctx, cap, d, k, &plan);
+        }
+        if (rc == B2K_OK) {
+            for (int64_t off = 0; off < n && rc == B2K_OK; off += cap) {
+                const int64_t len = std::min(cap, n - off);
+                rc = screen_prepare_frames(plan, dX + off * d, len);
+                if (rc == B2K_OK)
+                    rc = screen_assign(plan, dX + off * d, len, dC, dlabels + off, dmind ? dmind + off : nullptr, 0);
+            }
+            ctx->stat_screen_frames = (double)std::min(cap, n);
+            ctx->stat_plan = nullptr;
+            ctx->stat_pending = rc == B2K_OK;
+            return rc;
+        }
+        if (rc != B2K_ERR_NOMEM) return rc;
+        // not even a 64k-frame plan fits: exact engine below
     }
     B2K_TRY(assign_any(ctx, dX, ga.as<float>(), n, d, pc, k, metric, dlabels, dmind, 0));
     if (pc.mem_c.p || ga.p) CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // temporaries die with this frame
@@ -435,8 +453,7 @@ static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, con
     // there anyway: one flag for the whole call, read at the end
     int* d_finite = nullptr;
     if (ctx->check_finite) {
-        B2K_TRY(ctx->ensure_scratch(64));
-        d_finite = reinterpret_cast<int*>((char*)ctx->scratch + 32);
+        d_finite = ctx->flags + 8;  // dedicated allocation: launch_accumulate may regrow ctx->scratch under us
         const int one = 1;
         CUDA_TRY(cudaMemcpyAsync(d_finite, &one, 4, cudaMemcpyHostToDevice, st));
     }
@@ -578,7 +595,13 @@ B2K_API int b2k_dev_lloyd_create(b2k_ctx* ctx, const float* dX, int64_t n_local,
     if (rc == B2K_OK && metric == B2K_METRIC_EUCLIDEAN && ctx->engine != B2K_ENGINE_DIRECT &&
         screen_supported(ctx, d, k, n_local)) {
         rc = screen_plan_create(ctx, n_local, d, k, &s->plan);
-        if (rc == B2K_OK) rc = screen_prepare_frames(s->plan, dX, n_local);
+        if (rc == B2K_ERR_NOMEM) {
+            // the fp16 screen operand (Kp*2 + ~41 bytes per frame) does not fit next to the frames: the session runs
+            // on the exact CUDA-core engine instead of failing (the reference would still run, kmeans.py:181-200)
+            s->plan = nullptr;
+            rc = B2K_OK;
+        }
+        if (rc == B2K_OK && s->plan) rc = screen_prepare_frames(s->plan, dX, n_local);
     }
     if (rc != B2K_OK) { b2k_dev_lloyd_destroy(s); return rc; }
     *out = s;
@@ -676,10 +699,9 @@ B2K_API double b2k_dev_lloyd_decode_cost(const b2k_lloyd* s, int64_t cost_fixed)
 B2K_API int b2k_dev_absmax(b2k_ctx* ctx, const float* dX, int64_t count, float* out_host) {
     if (!ctx || !out_host) return set_error(B2K_ERR_INVALID_ARG, "absmax: null argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    B2K_TRY(ctx->ensure_scratch(64));
-    CUDA_TRY(cudaMemsetAsync(ctx->scratch, 0, 4, ctx->stream));
-    B2K_TRY(launch_absmax(ctx, dX, count, (float*)ctx->scratch));
-    CUDA_TRY(cudaMemcpyAsync(out_host, ctx->scratch, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->flags, 0, 4, ctx->stream));
+    B2K_TRY(launch_absmax(ctx, dX, count, (float*)ctx->flags));
+    CUDA_TRY(cudaMemcpyAsync(out_host, ctx->flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B2K_OK;
 }
@@ -687,11 +709,10 @@ B2K_API int b2k_dev_absmax(b2k_ctx* ctx, const float* dX, int64_t count, float* 
 B2K_API int b2k_dev_all_finite(b2k_ctx* ctx, const float* dX, int64_t count, int* out_host) {
     if (!ctx || !out_host) return set_error(B2K_ERR_INVALID_ARG, "all_finite: null argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    B2K_TRY(ctx->ensure_scratch(64));
     const int one = 1;
-    CUDA_TRY(cudaMemcpyAsync(ctx->scratch, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
-    B2K_TRY(launch_all_finite(ctx, dX, count, (int*)ctx->scratch));
-    CUDA_TRY(cudaMemcpyAsync(out_host, ctx->scratch, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->flags, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
+    B2K_TRY(launch_all_finite(ctx, dX, count, ctx->flags));
+    CUDA_TRY(cudaMemcpyAsync(out_host, ctx->flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B2K_OK;
 }

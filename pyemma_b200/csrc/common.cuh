@@ -100,6 +100,10 @@ struct b2k_ctx {
     void* slot_ptr[N_SLOTS] = {};
     size_t slot_cap[N_SLOTS] = {};
     int slot(int which, size_t bytes, void** out);
+    // 256 bytes of device flag words, allocated once by b2k_ctx_create and NEVER reallocated (the NaN/inf flag of a
+    // streamed assign lives here across calls that may grow `scratch`): [0] absmax / all_finite / dtraj range flag,
+    // [8] the non-finite flag of stream_assign
+    int* flags = nullptr;
     // generic device scratch (grown on demand)
     void* scratch = nullptr;
     size_t scratch_cap = 0;

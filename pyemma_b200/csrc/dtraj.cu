@@ -69,7 +69,7 @@ static unsigned dgrid(b2k_ctx* ctx, int64_t items) {
 
 static int read_bad(b2k_ctx* ctx, const char* what) {
     int bad = 0;
-    CUDA_TRY(cudaMemcpyAsync(&bad, (char*)ctx->scratch, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&bad, ctx->flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (bad) return set_error(B2K_ERR_INVALID_ARG, "%s: a state index is >= nstates", what);
     return B2K_OK;
@@ -80,13 +80,12 @@ B2K_API int b2k_dev_count_states(b2k_ctx* ctx, const int32_t* dlabels, int64_t n
         return set_error(B2K_ERR_INVALID_ARG, "count_states: bad arguments");
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (n == 0) return B2K_OK;
-    B2K_TRY(ctx->ensure_scratch(64));
-    CUDA_TRY(cudaMemsetAsync(ctx->scratch, 0, 4, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->flags, 0, 4, ctx->stream));
     const int use_smem = nstates <= 12288;
     const unsigned grid = use_smem ? (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 8192), (int64_t)ctx->sm_count * 4))
                                    : dgrid(ctx, n);
     count_states_kernel<<<grid, 256, use_smem ? (size_t)nstates * 4 : 0, ctx->stream>>>(
-        dlabels, n, nstates, (unsigned long long*)dcounts, (int*)ctx->scratch, use_smem);
+        dlabels, n, nstates, (unsigned long long*)dcounts, ctx->flags, use_smem);
     LAUNCH_CHECK();
     return read_bad(ctx, "count_states");
 }
@@ -99,10 +98,9 @@ B2K_API int b2k_dev_count_matrix(b2k_ctx* ctx, const int32_t* dlabels, int64_t n
     if (n <= lag) return B2K_OK;  // a trajectory not longer than the lag contributes nothing
     const int64_t step = sliding ? 1 : lag;
     const int64_t n_pairs = (n - lag - 1) / step + 1;  // t = 0, step, 2 step, ... with t + lag <= n - 1
-    B2K_TRY(ctx->ensure_scratch(64));
-    CUDA_TRY(cudaMemsetAsync(ctx->scratch, 0, 4, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->flags, 0, 4, ctx->stream));
     count_matrix_kernel<<<dgrid(ctx, n_pairs), 256, 0, ctx->stream>>>(dlabels, n_pairs, lag, step, nstates,
-                                                                      (unsigned long long*)dC, (int*)ctx->scratch);
+                                                                      (unsigned long long*)dC, ctx->flags);
     LAUNCH_CHECK();
     return read_bad(ctx, "count_matrix");
 }

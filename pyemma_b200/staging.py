@@ -46,6 +46,19 @@ def shard_bounds(n_total, rank, world_size):
     return lo, min(lo + per, n_total)
 
 
+def all_gather_shards(local, n_total, rank, world_size):
+    """Concatenate the per-rank pieces of a frame-sharded 1-D device tensor (shard_bounds layout) on every rank:
+    one all-gather of ceil(n/ws) elements per rank instead of an all-reduce over a zero-filled length-n buffer."""
+    import torch.distributed as dist
+    lo0, hi0 = shard_bounds(n_total, 0, world_size)
+    per = max(hi0 - lo0, 1)
+    send = torch.zeros(per, dtype=local.dtype, device=local.device)
+    send[:local.numel()] = local
+    recv = torch.empty(per * world_size, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv, send)
+    return recv[:n_total]  # shards are contiguous, equal-sized except the trailing ones: padding only sits at the end
+
+
 class PinnedStager:
     """Two pinned fp32 staging slots + a copy stream."""
 

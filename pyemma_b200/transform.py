@@ -46,8 +46,16 @@ class LinearProjection:
     def project_host_chunk(self, X, out, ctx=None):
         """(n, din) host chunk -> rows of the CUDA tensor `out` (n, dim), through the pinned staging of libb2k"""
         ctx = ctx or _lib.context()
-        X = np.require(X, dtype=np.float32, requirements=["C", "A"])
         md, Wd = self.device_model(out.device)
+        X = np.asarray(X)
+        if X.dtype != np.float32 and md is not None:
+            # fp64 (or integer) features: the reference subtracts the mean in fp64 BEFORE anything is rounded
+            # (_tica_base.py:130-133).  Casting first would lose ~6e-8 |mean| per value, which whitening eigenvectors
+            # amplify for features with a large mean and a small variance -- so the mean leaves on the host in fp64
+            # and the device multiplies the fp32 image of the (small) difference.
+            X = X.astype(np.float64, copy=False) - self.mean
+            md = None
+        X = np.require(X, dtype=np.float32, requirements=["C", "A"])
         _lib.check(ctx.lib.b2k_stage_project(ctx.handle, C.c_void_p(X.ctypes.data), X.shape[0], X.shape[1],
                                              C.c_void_p(md.data_ptr()) if md is not None else None,
                                              C.c_void_p(Wd.data_ptr()), Wd.shape[1], self._dim,
