@@ -79,7 +79,8 @@ int b2k_ctx_destroy(b2k_ctx* ctx);
  * private non-blocking stream (the state after b2k_ctx_create). */
 int b2k_ctx_set_stream(b2k_ctx* ctx, void* cuda_stream);
 int b2k_ctx_sync(b2k_ctx* ctx);
-/* options: "assign_engine" (B2K_ENGINE_*), "screen_terms" (1: hi-only fp16 operands, 2: hi-only for rows of 32+ floats, else hi+lo split),
+/* options: "assign_engine" (B2K_ENGINE_*), "screen_terms" (fp16 operand terms of the tensor-core screen: 3 = hi+lo split of frames and
+ * centers, 2 = split frames x hi-only centers, 1 = hi-only; 0 (default) = measured on a sample per data set for wide rows),
  * "screen_group" (centers per candidate group the screen hands to the exact verify: 0 automatic, 8, 4 or 2),
  * "stage_bytes" (pinned staging buffer size per slot), "check_finite" (1: the host-pointer
  * assign / stage entry points check every staged chunk on the device and return B2K_ERR_NONFINITE for NaN/inf frames,

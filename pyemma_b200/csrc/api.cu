@@ -27,24 +27,6 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
                      int64_t n_total, float* xf, int64_t xf_len, int64_t* xi, b2k_exchange_fn ex, void* exuser,
                      b2k_callback cb, void* user, float* dcenters_out, int64_t* chosen_host);
 
-struct DevMem {
-    void* p = nullptr;
-    size_t cap = 0;
-    ~DevMem() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) {
-        if (p && bytes <= cap) return B2K_OK;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        cap = bytes ? bytes : 16;
-        if (cudaMalloc(&p, cap) != cudaSuccess) {
-            p = nullptr;
-            cap = 0;
-            cudaGetLastError();
-            return set_error(B2K_ERR_NOMEM, "cudaMalloc(%zu bytes) failed", bytes);
-        }
-        return B2K_OK;
-    }
-    template <class T> T* as() const { return (T*)p; }
-};
 
 // pageable host memory -> pinned staging slot.  One memcpy thread moves ~10 GB/s, PCIe Gen5 takes 55: large copies
 // are split over a few threads so that the bounce stays off the critical path (option "host_copy_threads").
@@ -276,6 +258,11 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return set_error(B2K_ERR_INVALID_ARG, "null argument");
     if (!strcmp(name, "assign_engine")) c->engine = (int)value;
     else if (!strcmp(name, "screen_terms")) c->screen_terms = (int)value;
+    else if (!strcmp(name, "probe_max_centers")) c->probe_max_centers = (int)value;
+    else if (!strcmp(name, "probe_min_gflop")) c->probe_min_gflop = (int)value;
+    else if (!strcmp(name, "screen_gather")) c->screen_gather = (int)value;
+    else if (!strcmp(name, "prune_mode")) c->prune_mode = (int)value;
+    else if (!strcmp(name, "prune_resort")) c->prune_resort = (int)value;
     else if (!strcmp(name, "screen_group")) c->screen_group = (int)value;
     else if (!strcmp(name, "screen_resident_a")) c->screen_resident_a = (int)value;
     else if (!strcmp(name, "screen_cluster")) c->screen_cluster = (int)value;
@@ -326,6 +313,12 @@ B2K_API int b2k_ctx_get_stat(b2k_ctx* c, const char* name, double* value) {
     if (!strcmp(name, "screen_cand_chunks")) *value = c->stat_cand_chunks;
     else if (!strcmp(name, "screen_fallback_frames")) *value = c->stat_fallback_frames;
     else if (!strcmp(name, "screen_frames")) *value = c->stat_screen_frames;
+    else if (!strcmp(name, "screen_terms_used")) *value = c->stat_screen_terms;
+    else if (!strcmp(name, "prune_mean_list")) *value = c->stat_prune_mean;
+    else if (!strcmp(name, "prune_steps")) *value = c->stat_prune_steps;
+    else if (!strcmp(name, "prune_sorts")) *value = c->stat_prune_sorts;
+    else if (!strncmp(name, "probe_centers_", 14) && name[14] >= '1' && name[14] <= '3') *value = c->stat_probe_centers[name[14] - '0'];
+    else if (!strncmp(name, "probe_fallback_", 15) && name[15] >= '1' && name[15] <= '3') *value = c->stat_probe_fallback[name[15] - '0'];
     else if (!strcmp(name, "sm_count")) *value = c->sm_count;
     else if (!strcmp(name, "fp32_lane_instr_per_s")) {  // measured now: non-fusable FMUL+FADD chains on every SM
         CUDA_TRY(cudaSetDevice(c->device));
@@ -394,10 +387,12 @@ B2K_API int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, 
         // its capacity are assigned piece by piece through the same plan
         ScreenPlan* plan = nullptr;
         int64_t cap = n;
-        int rc = screen_plan_acquire(ctx, cap, d, k, &plan);
+        int terms = 0;
+        B2K_TRY(screen_choose_terms(ctx, dX, n, d, dC, k, &terms));
+        int rc = screen_plan_acquire(ctx, cap, d, k, terms, &plan);
         while (rc == B2K_ERR_NOMEM && cap > (int64_t(1) << 16)) {
             cap = (cap + 1) / 2;
-            rc = screen_plan_acquire(ctx, cap, d, k, &plan);
+            rc = screen_plan_acquire(ctx, cap, d, k, terms, &plan);
         }
         if (rc == B2K_OK) {
             for (int64_t off = 0; off < n && rc == B2K_OK; off += cap) {
@@ -407,6 +402,7 @@ B2K_API int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, 
                     rc = screen_assign(plan, dX + off * d, len, dC, dlabels + off, dmind ? dmind + off : nullptr, 0);
             }
             ctx->stat_screen_frames = (double)std::min(cap, n);
+            ctx->stat_screen_terms = (double)terms;
             ctx->stat_plan = nullptr;
             ctx->stat_pending = rc == B2K_OK;
             return rc;
@@ -446,7 +442,7 @@ static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, con
     const bool use_screen = metric == B2K_METRIC_EUCLIDEAN && ctx->engine != B2K_ENGINE_DIRECT &&
                             screen_supported(ctx, d, k, cf);
     ScreenPlan* plan = nullptr;
-    if (use_screen) B2K_TRY(screen_plan_acquire(ctx, cf, d, k, &plan));
+    if (use_screen) B2K_TRY(screen_plan_acquire(ctx, cf, d, k, 0, &plan));
     cudaEvent_t ev_k[2];
     for (int s = 0; s < 2; ++s) CUDA_TRY(cudaEventCreateWithFlags(&ev_k[s], cudaEventDisableTiming));
     // NaN / inf guard of the reference's chunk iterator (datasource.py:1067-1075), on the device while the chunk is
@@ -556,6 +552,12 @@ struct b2k_lloyd {
     DevMem l, Ga;
     PreparedCenters pc;
     ScreenPlan* plan = nullptr;
+    bool plan_pending = false;  // the screen plan is built at the first step: its operand term count is chosen with the centers
+    // exact center pruning (prune.cu): after the first step the session works on a copy of the frames sorted by label
+    PruneState* prune = nullptr;
+    bool prune_wanted = false;
+    bool have_labels = false;   // prune_labels() holds the labels of the last step (in the current frame order)
+    int64_t steps = 0, next_sort = 1;
 };
 
 static int ceil_log2_d(double v) {
@@ -594,14 +596,8 @@ B2K_API int b2k_dev_lloyd_create(b2k_ctx* ctx, const float* dX, int64_t n_local,
     }
     if (rc == B2K_OK && metric == B2K_METRIC_EUCLIDEAN && ctx->engine != B2K_ENGINE_DIRECT &&
         screen_supported(ctx, d, k, n_local)) {
-        rc = screen_plan_create(ctx, n_local, d, k, &s->plan);
-        if (rc == B2K_ERR_NOMEM) {
-            // the fp16 screen operand (Kp*2 + ~41 bytes per frame) does not fit next to the frames: the session runs
-            // on the exact CUDA-core engine instead of failing (the reference would still run, kmeans.py:181-200)
-            s->plan = nullptr;
-            rc = B2K_OK;
-        }
-        if (rc == B2K_OK && s->plan) rc = screen_prepare_frames(s->plan, dX, n_local);
+        s->plan_pending = true;
+        s->prune_wanted = prune_supported(ctx, n_local, d, k);
     }
     if (rc != B2K_OK) { b2k_dev_lloyd_destroy(s); return rc; }
     *out = s;
@@ -618,6 +614,7 @@ B2K_API int b2k_dev_lloyd_destroy(b2k_lloyd* s) {
         s->ctx->stat_plan = nullptr;
     }
     if (s->plan) screen_plan_destroy(s->plan);
+    if (s->prune) prune_destroy(s->prune);
     delete s;
     return B2K_OK;
 }
@@ -633,6 +630,12 @@ B2K_API int b2k_stage_lloyd_assign_accumulate(b2k_lloyd* s, const float* X, cons
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaMemsetAsync(dacc, 0, (size_t)((int64_t)s->k * s->d + s->k + 1) * 8, ctx->stream));
     if (s->n == 0) return B2K_OK;
+    // the frame array is rewritten: whatever the session derived from its old content (sorted copy, fp16 operand) is stale
+    if (s->prune) { prune_destroy(s->prune); s->prune = nullptr; }
+    s->have_labels = false;
+    s->steps = 0;
+    s->next_sort = 1;
+    if (s->plan) screen_plan_invalidate_frames(s->plan);
     return stream_assign(ctx, X, s->n, s->d, dcenters, s->k, s->metric, labels_host, 1, dX_out, dlabels_out,
                          lloyd_scale_sum(s), dacc);
 }
@@ -645,9 +648,70 @@ B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaMemsetAsync(dacc, 0, (size_t)b2k_dev_lloyd_acc_len(s) * 8, ctx->stream));
     if (s->n == 0) return B2K_OK;
+    if (s->plan_pending) {
+        s->plan_pending = false;
+        int terms = 0;
+        B2K_TRY(screen_choose_terms(ctx, s->dX, s->n, s->d, dC, s->k, &terms));
+        int rc = screen_plan_create(ctx, s->n, s->d, s->k, terms, &s->plan);
+        if (rc == B2K_ERR_NOMEM) {
+            // the fp16 screen operand (Kp*2 + ~41 bytes per frame) does not fit next to the frames: the session runs
+            // on the exact CUDA-core engine instead of failing (the reference would still run, kmeans.py:181-200)
+            s->plan = nullptr;
+            rc = B2K_OK;
+        }
+        if (rc == B2K_OK && s->plan) rc = screen_prepare_frames(s->plan, s->dX, s->n);
+        if (rc != B2K_OK) return rc;
+    }
+    if (s->plan && s->prune_wanted) {
+        // (re)sort by the labels of the previous step when the schedule says so: steps 1, 2, 4, 8, ... or every prune_resort
+        if (s->prune && s->have_labels && s->steps >= s->next_sort) {
+            B2K_TRY(prune_sort(s->prune, s->dX, prune_labels(s->prune)));
+            screen_plan_invalidate_frames(s->plan);
+            s->next_sort = ctx->prune_resort > 0 ? s->steps + ctx->prune_resort : s->steps * 2;
+            ctx->stat_prune_sorts += 1;
+        }
+        if (s->prune && prune_sorted(s->prune)) {
+            PruneState* pr = s->prune;
+            double mean = 0;
+            int mx = 0, ov = 0;
+            B2K_TRY(prune_lists(pr, dC, &mean, &mx, &ov));
+            ctx->stat_prune_mean = mean;
+            // the listed screen drains mean (padded) columns per frame, the full one k rounded up to 256
+            if (ov == 0 && (mean <= 0.6 * (double)(cdiv(s->k, 256) * 256) || ctx->prune_mode == 3)) {
+                B2K_TRY(screen_assign_listed(s->plan, prune_frames(pr), s->n, dC, prune_tlist(pr), prune_tcount(pr),
+                                             prune_lcap(pr), prune_labels(pr), 1));
+                ctx->stat_prune_steps += 1;
+            } else {  // the lists would not pay: every center for every tile, still on the sorted frames
+                B2K_TRY(screen_assign(s->plan, prune_frames(pr), s->n, dC, prune_labels(pr), nullptr, 1));
+            }
+            ctx->stat_screen_frames = (double)s->n;
+            ctx->stat_screen_terms = (double)screen_plan_terms(s->plan);
+            ctx->stat_plan = s->plan;
+            ctx->stat_pending = true;
+            s->have_labels = true;
+            s->steps += 1;
+            B2K_TRY(prune_scatter_labels(pr, dlabels));
+            return launch_accumulate(ctx, prune_frames(pr), s->n, s->d, s->k, prune_labels(pr), s->scale_sum, dacc);
+        }
+    }
     if (s->plan) {
         B2K_TRY(screen_assign(s->plan, s->dX, s->n, dC, dlabels, nullptr, 1));
+        s->steps += 1;
+        if (s->prune_wanted && !s->prune) {
+            // first step done: keep its labels; the frames are sorted by them at the start of the next step (a session
+            // that stops after one iteration never pays for the sort)
+            if (prune_create(ctx, s->n, s->d, s->k, &s->prune) != B2K_OK) {
+                cudaGetLastError();
+                s->prune = nullptr;
+                s->prune_wanted = false;  // no room for the sorted copy: the session stays on the unsorted path
+            }
+        }
+        if (s->prune && !prune_sorted(s->prune)) {
+            CUDA_TRY(cudaMemcpyAsync(prune_labels(s->prune), dlabels, (size_t)s->n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            s->have_labels = true;
+        }
         ctx->stat_screen_frames = (double)s->n;
+        ctx->stat_screen_terms = (double)screen_plan_terms(s->plan);
         ctx->stat_plan = s->plan;
         ctx->stat_pending = true;
     } else {
@@ -679,15 +743,22 @@ B2K_API int b2k_dev_lloyd_cost(b2k_lloyd* s, const float* dC_new, const int32_t*
     int64_t* slot = dacc + (int64_t)s->k * s->d + s->k;
     CUDA_TRY(cudaMemsetAsync(slot, 0, 8, ctx->stream));
     if (s->n == 0) return B2K_OK;
+    const float* fX = s->dX;
+    if (s->prune && prune_sorted(s->prune) && s->have_labels) {
+        // the session works on its sorted copy of the frames: the labels of the last step are there in the same order
+        // (the cost is an exact integer sum, so the order of the frames does not change a bit of it)
+        fX = prune_frames(s->prune);
+        dlabels = prune_labels(s->prune);
+    }
     if (s->metric == B2K_METRIC_MINRMSD) {
         B2K_TRY(s->pc.prepare(ctx, dC_new, s->k, s->d, s->metric));
         B2K_TRY(launch_rmsd_labeled_dist(ctx, s->dX, s->Ga.as<float>(), s->n, s->d, s->pc.C, s->pc.Gb, dlabels,
                                          s->l.as<float>()));
     } else {
         int fused = 0;  // narrow rows: distances and the integer cost sum in one pass
-        B2K_TRY(launch_cost_fused(ctx, s->dX, s->n, s->d, dC_new, s->k, dlabels, s->scale_cost, slot, &fused));
+        B2K_TRY(launch_cost_fused(ctx, fX, s->n, s->d, dC_new, s->k, dlabels, s->scale_cost, slot, &fused));
         if (fused) return B2K_OK;
-        B2K_TRY(launch_labeled_dist(ctx, s->dX, s->n, s->d, dC_new, dlabels, s->l.as<float>()));
+        B2K_TRY(launch_labeled_dist(ctx, fX, s->n, s->d, dC_new, dlabels, s->l.as<float>()));
     }
     return launch_cost_reduce(ctx, s->l.as<float>(), s->n, s->scale_cost, slot);
 }

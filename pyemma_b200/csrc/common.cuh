@@ -40,6 +40,26 @@ int set_error(int code, const char* fmt, ...);
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// owning device allocation (freed with the scope)
+struct DevMem {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~DevMem() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        if (p && bytes <= cap) return B2K_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cap = bytes ? bytes : 16;
+        if (cudaMalloc(&p, cap) != cudaSuccess) {
+            p = nullptr;
+            cap = 0;
+            cudaGetLastError();
+            return set_error(B2K_ERR_NOMEM, "cudaMalloc(%zu bytes) failed", bytes);
+        }
+        return B2K_OK;
+    }
+    template <class T> T* as() const { return (T*)p; }
+};
+
 // cudaFuncSetAttribute is per device: one-time kernel attribute setup is tracked per device ordinal
 struct PerDeviceOnce {
     std::atomic<unsigned long long> mask{0};
@@ -68,7 +88,11 @@ struct b2k_ctx {
     std::vector<cudaEvent_t> prof_events;  // start/stop pairs on `stream`
     // options
     int engine = B2K_ENGINE_AUTO;
-    int screen_terms = 0;
+    int screen_terms = 0;       // 1..3: operand terms of the screen forced, 0: measured per data set (screen_choose_terms)
+    int probe_min_gflop = 1000; // ... and only for jobs of at least this many algorithmic GFLOP (2 n k d) per pass
+    int probe_max_centers = 12; // the term probe accepts a count that leaves at most this many candidate centers per frame
+    double stat_probe_centers[4] = {0, 0, 0, 0}, stat_probe_fallback[4] = {0, 0, 0, 0};  // last probe, per term count
+    double stat_screen_terms = 0;  // term count of the last screened call
     int check_finite = 1;       // host-pointer assign entry points reject NaN/inf frames (B2K_ERR_NONFINITE)
     int host_copy_threads = 8;  // threads of the pageable -> pinned bounce copy (1e7 x 10 frames: 32.7 ms with 1, 18.2 ms with 8)
     int kmpp_prune = 1;       // k-means++ (blocked, euclidean): skip candidate distances the triangle inequality decides
@@ -79,6 +103,12 @@ struct b2k_ctx {
     int screen_resident_a = 0;  // screen kernel: keep the frame tile in shared memory when the center operand does not fit.
                                 // Off: measured at cfg3 it cuts the L2->SM traffic by 27 % but leaves room for only 3 ring
                                 // stages of center k-blocks -- 13.0 ms against 11.0 ms for the 4-stage streaming mode
+    int prune_mode = 1;       // Lloyd sessions: 1 sort the frames by label after the first iteration and screen every tile
+                              // against its own center list (exact), 0 never, 2 also for small jobs, 3 listed screen even
+                              // when the lists exclude nothing (tests)
+    int screen_gather = 0;    // listed screen: 0 cp.async gather warps, 1 TMA tile::gather4
+    int prune_resort = 0;     // re-sort schedule: 0 at iterations 1, 2, 4, 8, ... ; n > 0 every n iterations
+    double stat_prune_mean = 0, stat_prune_steps = 0, stat_prune_sorts = 0;  // mean list length of the last pruned step
     int screen_group = 0;     // centers per candidate group of the screen (0: automatic; 8, 4, 2)
     int rmsd_kernel = 0;      // 0: slab-streaming QCP kernel, 1: whole-row tile kernel
     int row_vec_max = 4;      // widest row load of the narrow-row verify / cost kernels (4, 2 or 1 floats)

@@ -55,16 +55,23 @@ int launch_finalize(b2k_ctx* ctx, const int64_t* acc, int k, int d, double inv_s
 int launch_cost_reduce(b2k_ctx* ctx, const float* l, int64_t n, double scale, int64_t* acc_slot);
 int launch_cost_fused(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, const int32_t* labels,
                       double scale, int64_t* acc_slot, int* done);
+// counting sort of the frame indices by label (labels outside [0, k) are left out; seg[k] = frames sorted)
+int launch_label_sort(b2k_ctx* ctx, const int32_t* labels, int64_t n, int k, uint32_t* seg /* k+1 */, uint32_t* perm /* n */);
 int measure_fp32_rate(b2k_ctx* ctx, double* lane_instr_per_s);
 int launch_absmax(b2k_ctx* ctx, const float* X, int64_t count, float* d_out /* device, 1 float, pre-zeroed */);
 int launch_all_finite(b2k_ctx* ctx, const float* X, int64_t count, int* d_flag /* device, pre-set to 1 */);
 
 // ---- screen.cu (tcgen05 distance screen + exact verify) -------------------------------------
 struct ScreenPlan;
-int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** out);
+// terms: 1..3, 0 = the context's default (option screen_terms, else 3)
+int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, int terms, ScreenPlan** out);
+// operand term count for this data set and these centers (measured on a sample when option screen_terms is 0)
+int screen_choose_terms(b2k_ctx* ctx, const float* dX, int64_t n, int d, const float* dC, int k, int* terms_out);
+int screen_plan_terms(const ScreenPlan* p);
+void screen_plan_invalidate_frames(ScreenPlan* p);  // the frame array changed (re-sorted): rebuild the operand at the next assign
 void screen_plan_destroy(ScreenPlan* p);
 // plan cached in the context for one-shot / chunked assignment (reused while d, k match and n fits)
-int screen_plan_acquire(b2k_ctx* ctx, int64_t n, int d, int k, ScreenPlan** out);
+int screen_plan_acquire(b2k_ctx* ctx, int64_t n, int d, int k, int terms, ScreenPlan** out);
 void screen_plan_release_cached(b2k_ctx* ctx);
 // (re)build the frame operand for n frames at dX (done once per dataset / chunk)
 int screen_prepare_frames(ScreenPlan* p, const float* dX, int64_t n);
@@ -73,5 +80,23 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dcente
                   int lloyd);
 int screen_read_stats(ScreenPlan* p, double* cand_chunks, double* fallback_frames);
 bool screen_supported(const b2k_ctx* ctx, int d, int k, int64_t n);
+
+// ---- prune.cu (frames sorted by label, per-tile center lists: exact triangle-inequality pruning) --------------
+struct PruneState;
+bool prune_supported(const b2k_ctx* ctx, int64_t n, int d, int k);
+int prune_create(b2k_ctx* ctx, int64_t n, int d, int k, PruneState** out);
+void prune_destroy(PruneState* p);
+int prune_sort(PruneState* p, const float* X, const int32_t* labels_current_order);
+int prune_lists(PruneState* p, const float* dC, double* mean_count, int* max_count, int* overflow_tiles);
+int prune_scatter_labels(PruneState* p, int32_t* out_original_order);
+const float* prune_frames(const PruneState* p);   // frames in sorted order
+int32_t* prune_labels(PruneState* p);             // labels in sorted order (written by the assign, read by the sort)
+const uint16_t* prune_tlist(const PruneState* p);
+const uint32_t* prune_tcount(const PruneState* p);
+int prune_lcap(const PruneState* p);
+bool prune_sorted(const PruneState* p);
+// screen + verify over per-tile center lists (frames = the plan's prepared frames, in sorted order)
+int screen_assign_listed(ScreenPlan* p, const float* dX, int64_t n, const float* dcenters, const uint16_t* tlist,
+                         const uint32_t* tcount, int lcap, int32_t* labels, int lloyd);
 
 }  // namespace b2k

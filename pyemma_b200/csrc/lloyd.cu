@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(1024) seg_scan_kernel(const uint32_t* __restri
         const uint32_t c = hist[j];
         seg[j] = run;
         cursor[j] = run;
-        if (c) atomicAdd(acc_counts + j, (unsigned long long)c);
+        if (c && acc_counts) atomicAdd(acc_counts + j, (unsigned long long)c);
         run += c;
     }
     if (threadIdx.x == 1023) seg[k] = part[1023];
@@ -628,6 +628,39 @@ int launch_accumulate(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, con
     else
         accumulate_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(X, n, d, k, labels, scale,
                                                                              (unsigned long long*)acc);
+    LAUNCH_CHECK();
+    return B2K_OK;
+}
+
+// stable counting sort of the frame indices by label: perm[seg[a] .. seg[a+1]) = frames with label a, ascending;
+// frames whose label is outside [0, k) are left out (seg[k] = number of sorted frames)
+int launch_label_sort(b2k_ctx* ctx, const int32_t* labels, int64_t n, int k, uint32_t* seg, uint32_t* perm) {
+    if (n <= 0 || n >= (int64_t(1) << 32) - 1 || k > SEG_TABLE_MAX)
+        return set_error(B2K_ERR_INVALID_ARG, "label sort: unsupported size");
+    cudaStream_t st = ctx->stream;
+    B2K_TRY(ctx->ensure_scratch((size_t)(2 * k + 8) * 4 + 64));
+    uint32_t* hist = reinterpret_cast<uint32_t*>((char*)ctx->scratch + 64);
+    uint32_t* cursor = hist + k;
+    int n_cta = (int)std::min<int64_t>(std::min<int64_t>(cdiv(n, 4096), (int64_t)ctx->sm_count * 4),
+                                       std::max<int64_t>(1, (int64_t(8) << 20) / k));
+    if (n_cta < 1) n_cta = 1;
+    const int64_t per_cta = cdiv(cdiv(n, n_cta), 256) * 256;
+    n_cta = (int)cdiv(n, per_cta);
+    B2K_TRY(ctx->ensure_scratch2((size_t)n_cta * k * 4));
+    uint32_t* hist2 = reinterpret_cast<uint32_t*>(ctx->scratch2);
+    static PerDeviceOnce attr_set;
+    if (attr_set.need(ctx->device)) {
+        CUDA_TRY(cudaFuncSetAttribute(seg_hist2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_TABLE_MAX * 4));
+        CUDA_TRY(cudaFuncSetAttribute(seg_scatter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_TABLE_MAX * 4));
+        attr_set.done(ctx->device);
+    }
+    seg_hist2_kernel<<<n_cta, 256, (size_t)k * 4, st>>>(labels, n, k, per_cta, hist2);
+    LAUNCH_CHECK();
+    seg_colscan_kernel<<<(unsigned)cdiv(k, 256), 256, 0, st>>>(hist2, n_cta, k, hist);
+    LAUNCH_CHECK();
+    seg_scan_kernel<<<1, 1024, 0, st>>>(hist, k, seg, cursor, nullptr);
+    LAUNCH_CHECK();
+    seg_scatter2_kernel<<<n_cta, 256, (size_t)k * 4, st>>>(labels, n, k, per_cta, hist2, seg, perm);
     LAUNCH_CHECK();
     return B2K_OK;
 }

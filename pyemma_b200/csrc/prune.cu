@@ -1,0 +1,421 @@
+// prune.cu -- exact center pruning for the Lloyd iterations of a session (K2p).
+//
+// deeptime's kmeans.cluster (pyemma/coordinates/clustering/kmeans.py:254-258) evaluates all N x k distances in every
+// iteration.  Most of them cannot matter: after the first iteration the frames are kept in HBM SORTED BY LABEL, so a
+// tile of 128 consecutive frames lives in a small ball B(p_t, R_t) (p_t = tile mean, R_t = max distance to it, both
+// computed once per sort).  For a center c_j and the center c_b nearest to p_t the triangle inequality gives, for
+// every frame x of the tile,
+//        |x - c_j| >= |c_j - p_t| - R_t          |x - c_b| <= |c_b - p_t| + R_t
+// so j cannot be the frame's nearest center when |c_j - p_t| > |c_b - p_t| + 2 R_t.  Per iteration one small kernel
+// writes the list of surviving centers of every tile (ascending center index, padded with a dummy row); the tensor-
+// core screen (screen.cu: screen_gemm_listed_kernel) gathers exactly those rows of the center operand with TMA
+// tile::gather4 and the exact verify resolves list positions back to center indices.  The bound carries a relative
+// slack of 1e-4 -- three orders of magnitude above every fp32 rounding on the path (the reference's own distance has
+// a relative error of (d/4+9) 2^-24) -- so a pruned center is STRICTLY farther than c_b in the reference's arithmetic
+// as well: labels, member sums and costs are bit-identical to the unpruned iteration (tests/test_gpu_prune.py).
+//
+// Wide rows (the k x d center table does not fit shared memory) use the same bound through the center-center
+// distances: with a = the label of the tile's first frame, |c_j - p_t| >= |c_j - c_a| - |c_a - p_t|, so j is pruned
+// when |c_j - c_a| > 2 (|c_a - p_t| + R_t): O(k^2 d + n_tiles (d + k)) work instead of O(n_tiles k d).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b2k {
+
+static constexpr int PT = 128;          // frames per tile (= the screen kernel's TILE_M)
+static constexpr float PRUNE_SLACK = 1e-4f;
+
+struct PruneStats {  // device
+    unsigned long long total;  // sum of the padded list lengths
+    unsigned int max_count;    // longest list
+    unsigned int overflow;     // tiles whose list did not fit lcap
+};
+
+// Xs[p][:] = X[perm[p]][:]
+template <typename V>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const V* __restrict__ X, const uint32_t* __restrict__ perm,
+                                                          int64_t n, int dv, V* __restrict__ Xs) {
+    const int64_t total = n * dv;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+        const int64_t p = t / dv;
+        const int e = (int)(t - p * dv);
+        Xs[t] = __ldg(X + (int64_t)perm[p] * dv + e);
+    }
+}
+
+__global__ void __launch_bounds__(256) compose_perm_kernel(const uint32_t* __restrict__ perm_old,
+                                                           const uint32_t* __restrict__ sigma, int64_t n,
+                                                           uint32_t* __restrict__ perm_new) {
+    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < n; p += (int64_t)gridDim.x * 256)
+        perm_new[p] = perm_old[sigma[p]];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gather_values_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx,
+                                                            int64_t n, T* __restrict__ dst) {
+    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < n; p += (int64_t)gridDim.x * 256) dst[p] = src[idx[p]];
+}
+
+__global__ void __launch_bounds__(256) scatter_labels_kernel(const int32_t* __restrict__ labels_s,
+                                                             const uint32_t* __restrict__ perm, int64_t n,
+                                                             int32_t* __restrict__ out) {
+    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < n; p += (int64_t)gridDim.x * 256)
+        out[perm[p]] = labels_s[p];
+}
+
+// one CTA (128 threads) per tile: mean (fixed summation order) and radius of the tile's frames
+__global__ void __launch_bounds__(PT) tile_meta_kernel(const float* __restrict__ Xs, int64_t n, int d,
+                                                       float* __restrict__ tmean, float* __restrict__ trad) {
+    extern __shared__ float sm[];  // [4][d] partial sums, then [d] mean
+    float* part = sm;
+    float* mean = sm + 4 * d;
+    __shared__ float red[PT / 32];
+    const int64_t tile = blockIdx.x;
+    const int64_t row0 = tile * PT;
+    const int rows = (int)min((int64_t)PT, n - row0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int e = lane; e < d; e += 32) {
+        float s = 0.f;
+        const int r0 = warp * 32, r1 = min(rows, r0 + 32);
+        for (int r = r0; r < r1; ++r) s += __ldg(Xs + (row0 + r) * d + e);
+        part[warp * d + e] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < d; e += PT) {
+        const float m = (((part[e] + part[d + e]) + part[2 * d + e]) + part[3 * d + e]) / (float)rows;
+        mean[e] = m;
+        tmean[tile * d + e] = m;
+    }
+    __syncthreads();
+    float r2 = 0.f;
+    if ((int)threadIdx.x < rows) {
+        const float* x = Xs + (row0 + threadIdx.x) * d;
+        for (int e = 0; e < d; ++e) { const float t = __ldg(x + e) - mean[e]; r2 = fmaf(t, t, r2); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+    if (lane == 0) red[warp] = r2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float m2 = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+        // NaN/inf frames: the radius becomes NaN/inf and every comparison below keeps every center
+        trad[tile] = sqrtf(m2) * (1.f + 1e-5f);
+    }
+}
+
+__device__ __forceinline__ void warp_stats(PruneStats* st, unsigned int padded, bool overflow) {
+    atomicAdd(&st->total, (unsigned long long)padded);
+    atomicMax(&st->max_count, padded);
+    if (overflow) atomicAdd(&st->overflow, 1u);
+}
+
+// narrow rows: the center table (row stride ds floats, 16-byte aligned) sits in shared memory; one warp per tile.
+// pass 1: dmin = min_j |c_j - p_t|; pass 2: keep j unless |c_j - p_t| > dmin + 2 R_t (+ slack), ascending j.
+template <int DS>
+__global__ void __launch_bounds__(256, 4) tile_lists_direct_kernel(const float* __restrict__ C, int k, int d,
+                                                                const float* __restrict__ tmean,
+                                                                const float* __restrict__ trad, int n_tiles, int lcap,
+                                                                int pad_to, uint16_t dummy, uint16_t* __restrict__ tlist,
+                                                                uint32_t* __restrict__ tcount, PruneStats* st) {
+    extern __shared__ __align__(16) float ctab[];  // [k][DS]
+    for (int t = threadIdx.x; t < k * DS; t += 256) {
+        const int r = t / DS, c = t - r * DS;
+        ctab[t] = c < d ? __ldg(C + (int64_t)r * d + c) : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5, n_warps = (gridDim.x * 256) >> 5;
+    for (int tile = warp_global; tile < n_tiles; tile += n_warps) {
+        float m[DS];
+#pragma unroll
+        for (int e = 0; e < DS; ++e) m[e] = e < d ? __ldg(tmean + (int64_t)tile * d + e) : 0.f;
+        const float R = __ldg(trad + tile);
+        auto dist2 = [&](int j) {
+            const float4* row = reinterpret_cast<const float4*>(ctab + (size_t)j * DS);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent chains
+#pragma unroll
+            for (int e = 0; e < DS; e += 4) {
+                const float4 c = row[e >> 2];
+                float t = c.x - m[e]; s0 = fmaf(t, t, s0);
+                t = c.y - m[e + 1]; s1 = fmaf(t, t, s1);
+                t = c.z - m[e + 2]; s2 = fmaf(t, t, s2);
+                t = c.w - m[e + 3]; s3 = fmaf(t, t, s3);
+            }
+            return (s0 + s1) + (s2 + s3);
+        };
+        // k <= 1024: every lane keeps its (up to 32) squared distances between the two passes
+        constexpr int RMAX = 32;
+        const bool cached = k <= 32 * RMAX;
+        float dd[RMAX];
+        float best = __int_as_float(0x7f800000);
+        if (cached) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const int j = r * 32 + lane;
+                dd[r] = (r * 32 < k) ? dist2(min(j, k - 1)) : __int_as_float(0x7f800000);
+                if (j < k) best = fminf(best, dd[r]);
+            }
+        } else {
+            for (int j = lane; j < k; j += 32) best = fminf(best, dist2(j));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        // keep unless D_j > thr  <=>  keep unless D_j^2 > thr^2 (both sides >= 0); NaN anywhere keeps the center
+        const float thr = (sqrtf(best) + 2.f * R) * (1.f + PRUNE_SLACK) + 1e-30f;
+        const float thr2 = thr * thr;
+        uint16_t* out = tlist + (size_t)tile * lcap;
+        int count = 0;
+        if (cached) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                if (r * 32 < k) {
+                    const int j = r * 32 + lane;
+                    const bool keep = j < k && !(dd[r] > thr2);
+                    const unsigned b = __ballot_sync(0xffffffffu, keep);
+                    const int pos = count + __popc(b & ((1u << lane) - 1u));
+                    if (keep && pos < lcap) out[pos] = (uint16_t)j;
+                    count += __popc(b);
+                }
+            }
+        } else {
+            for (int j0 = 0; j0 < k; j0 += 32) {
+                const int j = j0 + lane;
+                const bool keep = j < k && !(dist2(min(j, k - 1)) > thr2);
+                const unsigned b = __ballot_sync(0xffffffffu, keep);
+                const int pos = count + __popc(b & ((1u << lane) - 1u));
+                if (keep && pos < lcap) out[pos] = (uint16_t)j;
+                count += __popc(b);
+            }
+        }
+        const bool overflow = count > lcap;
+        int padded = overflow ? lcap : (count + pad_to - 1) / pad_to * pad_to;
+        if (padded > lcap) padded = lcap;
+        for (int pos = count + lane; pos < padded; pos += 32) out[pos] = dummy;
+        if (lane == 0) {
+            tcount[tile] = overflow ? 0xffffffffu : (uint32_t)padded;
+            warp_stats(st, (unsigned int)padded, overflow);
+        }
+    }
+}
+
+// cc[a][j] = |c_a - c_j| (fp32, any order: the consumer's slack covers it); one warp per (a, j-block of 32)
+__global__ void __launch_bounds__(256) center_dist_kernel(const float* __restrict__ C, int k, int d, float* __restrict__ cc) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int jb = (k + 31) / 32;
+    if (warp >= (int64_t)k * jb) return;
+    const int a = (int)(warp / jb), j0 = (int)(warp % jb) * 32;
+    const float* ca = C + (int64_t)a * d;
+    // lanes stride the dimension; the 32 centers of the block one after the other (coalesced row reads)
+    for (int jj = 0; jj < 32; ++jj) {
+        const int j = j0 + jj;
+        if (j >= k) break;
+        const float* cj = C + (int64_t)j * d;
+        float s = 0.f;
+        for (int e = lane; e < d; e += 32) { const float t = __ldg(ca + e) - __ldg(cj + e); s = fmaf(t, t, s); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) cc[(int64_t)a * k + j] = sqrtf(s);
+    }
+}
+
+// wide rows: one warp per tile; a = label of the tile's first frame, delta = |c_a - p_t|;
+// keep j unless cc[a][j] > 2 (delta + R_t) (+ slack)
+__global__ void __launch_bounds__(256) tile_lists_cc_kernel(const float* __restrict__ C, int k, int d,
+                                                            const float* __restrict__ cc,
+                                                            const int32_t* __restrict__ labels_s, int64_t n,
+                                                            const float* __restrict__ tmean,
+                                                            const float* __restrict__ trad, int n_tiles, int lcap,
+                                                            int pad_to, uint16_t dummy, uint16_t* __restrict__ tlist,
+                                                            uint32_t* __restrict__ tcount, PruneStats* st) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5, n_warps = (gridDim.x * 256) >> 5;
+    for (int tile = warp_global; tile < n_tiles; tile += n_warps) {
+        int a = __ldg(labels_s + (int64_t)tile * PT);
+        if (a < 0 || a >= k) a = 0;
+        const float* ca = C + (int64_t)a * d;
+        const float* m = tmean + (int64_t)tile * d;
+        float s = 0.f;
+        for (int e = lane; e < d; e += 32) { const float t = __ldg(ca + e) - __ldg(m + e); s = fmaf(t, t, s); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float delta = sqrtf(s) * (1.f + 1e-5f);
+        const float thr = 2.f * (delta + __ldg(trad + tile)) * (1.f + PRUNE_SLACK) + 1e-30f;
+        const float* row = cc + (int64_t)a * k;
+        uint16_t* out = tlist + (size_t)tile * lcap;
+        int count = 0;
+        for (int j0 = 0; j0 < k; j0 += 32) {
+            const int j = j0 + lane;
+            const bool keep = j < k && !(__ldg(row + min(j, k - 1)) > thr);
+            const unsigned b = __ballot_sync(0xffffffffu, keep);
+            const int pos = count + __popc(b & ((1u << lane) - 1u));
+            if (keep && pos < lcap) out[pos] = (uint16_t)j;
+            count += __popc(b);
+        }
+        const bool overflow = count > lcap;
+        int padded = overflow ? lcap : (count + pad_to - 1) / pad_to * pad_to;
+        if (padded > lcap) padded = lcap;
+        for (int pos = count + lane; pos < padded; pos += 32) out[pos] = dummy;
+        if (lane == 0) {
+            tcount[tile] = overflow ? 0xffffffffu : (uint32_t)padded;
+            warp_stats(st, (unsigned int)padded, overflow);
+        }
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+struct PruneState {
+    b2k_ctx* ctx = nullptr;
+    int64_t n = 0;
+    int d = 0, k = 0, n_tiles = 0, lcap = 0, pad_to = 64;
+    DevMem Xs, perm, perm2, sigma, seg, labels_s, labels_t, tmean, trad, tlist, tcount, stats, cc;
+    bool sorted = false;
+};
+
+static unsigned grid_cap(b2k_ctx* ctx, int64_t items, int per_block, int per_sm = 8) {
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(items, per_block), (int64_t)ctx->sm_count * per_sm));
+}
+
+bool prune_supported(const b2k_ctx* ctx, int64_t n, int d, int k) {
+    if (ctx->prune_mode == 0) return false;
+    // 16-bit center ids in the lists, the counting sort's shared-memory label table, at least a few tiles per SM
+    if (k < 64 || k > 49152 || n >= (int64_t(1) << 32) - 1) return false;
+    if (ctx->prune_mode >= 2) return n >= 2 * PT;  // tests: small jobs too (3: listed screen even when the lists are full)
+    return n >= (int64_t)ctx->sm_count * PT * 8 && k >= 256;
+}
+
+int prune_create(b2k_ctx* ctx, int64_t n, int d, int k, PruneState** out) {
+    PruneState* p = new PruneState();
+    p->ctx = ctx; p->n = n; p->d = d; p->k = k;
+    p->n_tiles = (int)cdiv(n, PT);
+    p->lcap = (int)std::min<int64_t>(1024, cdiv(k, 64) * 64);
+    const int64_t n_pad = (int64_t)p->n_tiles * PT;
+    int rc = p->Xs.alloc((size_t)n_pad * d * 4);
+    if (rc == B2K_OK) rc = p->perm.alloc((size_t)n * 4);
+    if (rc == B2K_OK) rc = p->perm2.alloc((size_t)n * 4);
+    if (rc == B2K_OK) rc = p->sigma.alloc((size_t)n * 4);
+    if (rc == B2K_OK) rc = p->seg.alloc((size_t)(k + 2) * 4);
+    if (rc == B2K_OK) rc = p->labels_s.alloc((size_t)n_pad * 4);
+    if (rc == B2K_OK) rc = p->labels_t.alloc((size_t)n_pad * 4);
+    if (rc == B2K_OK) rc = p->tmean.alloc((size_t)p->n_tiles * d * 4);
+    if (rc == B2K_OK) rc = p->trad.alloc((size_t)p->n_tiles * 4);
+    if (rc == B2K_OK) rc = p->tlist.alloc((size_t)p->n_tiles * p->lcap * 2);
+    if (rc == B2K_OK) rc = p->tcount.alloc((size_t)p->n_tiles * 4);
+    if (rc == B2K_OK) rc = p->stats.alloc(sizeof(PruneStats));
+    if (rc != B2K_OK) { delete p; return rc; }
+    *out = p;
+    return B2K_OK;
+}
+
+void prune_destroy(PruneState* p) {
+    if (!p) return;
+    cudaStreamSynchronize(p->ctx->stream);
+    delete p;
+}
+
+const float* prune_frames(const PruneState* p) { return p->Xs.as<float>(); }
+int32_t* prune_labels(PruneState* p) { return p->labels_s.as<int32_t>(); }
+const uint16_t* prune_tlist(const PruneState* p) { return p->tlist.as<uint16_t>(); }
+const uint32_t* prune_tcount(const PruneState* p) { return p->tcount.as<uint32_t>(); }
+int prune_lcap(const PruneState* p) { return p->lcap; }
+bool prune_sorted(const PruneState* p) { return p->sorted; }
+
+// (re)sort: `labels` are in the CURRENT order of the session's frames (original order before the first sort, sorted
+// order afterwards); X is always the caller's original array
+int prune_sort(PruneState* p, const float* X, const int32_t* labels) {
+    b2k_ctx* ctx = p->ctx;
+    cudaStream_t st = ctx->stream;
+    const int64_t n = p->n;
+    uint32_t* sigma = p->sigma.as<uint32_t>();
+    // a frame without a label in [0, k) would drop out of the sort: Lloyd assigns always label every frame
+    B2K_TRY(launch_label_sort(ctx, labels, n, p->k, p->seg.as<uint32_t>(), sigma));
+    if (p->sorted) {
+        compose_perm_kernel<<<grid_cap(ctx, n, 256), 256, 0, st>>>(p->perm.as<uint32_t>(), sigma, n, p->perm2.as<uint32_t>());
+        LAUNCH_CHECK();
+        std::swap(p->perm.p, p->perm2.p);
+        std::swap(p->perm.cap, p->perm2.cap);
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(p->perm.p, sigma, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    // labels in the new order (the first frame of a tile names the tile's reference center)
+    gather_values_kernel<int32_t><<<grid_cap(ctx, n, 256), 256, 0, st>>>(labels, sigma, n, p->labels_t.as<int32_t>());
+    LAUNCH_CHECK();
+    std::swap(p->labels_s.p, p->labels_t.p);
+    std::swap(p->labels_s.cap, p->labels_t.cap);
+    const uint32_t* perm = p->perm.as<uint32_t>();
+    float* Xs = p->Xs.as<float>();
+    if (p->d % 4 == 0 && ((uintptr_t)X & 15) == 0)
+        gather_rows_kernel<float4><<<grid_cap(ctx, n * (p->d / 4), 256, 16), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(X), perm, n, p->d / 4, reinterpret_cast<float4*>(Xs));
+    else if (p->d % 2 == 0 && ((uintptr_t)X & 7) == 0)
+        gather_rows_kernel<float2><<<grid_cap(ctx, n * (p->d / 2), 256, 16), 256, 0, st>>>(
+            reinterpret_cast<const float2*>(X), perm, n, p->d / 2, reinterpret_cast<float2*>(Xs));
+    else
+        gather_rows_kernel<float><<<grid_cap(ctx, n * p->d, 256, 16), 256, 0, st>>>(X, perm, n, p->d, Xs);
+    LAUNCH_CHECK();
+    tile_meta_kernel<<<(unsigned)p->n_tiles, PT, (size_t)5 * p->d * 4, st>>>(Xs, n, p->d, p->tmean.as<float>(),
+                                                                          p->trad.as<float>());
+    LAUNCH_CHECK();
+    p->sorted = true;
+    return B2K_OK;
+}
+
+// per-iteration center lists; stats come back to the host (one 16-byte read + sync): the caller decides whether the
+// pruned screen is worth running this iteration
+int prune_lists(PruneState* p, const float* dC, double* mean_count, int* max_count, int* overflow_tiles) {
+    b2k_ctx* ctx = p->ctx;
+    cudaStream_t st = ctx->stream;
+    PruneStats* ds = p->stats.as<PruneStats>();
+    CUDA_TRY(cudaMemsetAsync(ds, 0, sizeof(PruneStats), st));
+    const int k_pad = (int)(cdiv(p->k, 256) * 256);
+    const uint16_t dummy = (uint16_t)k_pad;  // a -inf row behind the center operand (screen_centers_kernel)
+    const int ds4 = (p->d + 3) & ~3;
+    const size_t tab = (size_t)p->k * ds4 * 4;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(tab, 1)));
+    const unsigned grid = grid_cap(ctx, p->n_tiles, 8, per_sm);
+    if (p->d <= 16 && tab <= 96 * 1024) {
+#define B2K_TL(DS)                                                                                                    \
+    do {                                                                                                              \
+        static PerDeviceOnce at;                                                                                      \
+        if (at.need(ctx->device)) {                                                                                   \
+            CUDA_TRY(cudaFuncSetAttribute(tile_lists_direct_kernel<DS>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          96 * 1024));                                                                \
+            at.done(ctx->device);                                                                                     \
+        }                                                                                                             \
+        tile_lists_direct_kernel<DS><<<grid, 256, tab, st>>>(dC, p->k, p->d, p->tmean.as<float>(), p->trad.as<float>(), \
+                                                             p->n_tiles, p->lcap, p->pad_to, dummy,                   \
+                                                             p->tlist.as<uint16_t>(), p->tcount.as<uint32_t>(), ds);  \
+    } while (0)
+        if (ds4 == 4) B2K_TL(4);
+        else if (ds4 == 8) B2K_TL(8);
+        else if (ds4 == 12) B2K_TL(12);
+        else B2K_TL(16);
+#undef B2K_TL
+        LAUNCH_CHECK();
+    } else {
+        B2K_TRY(p->cc.alloc((size_t)p->k * p->k * 4));
+        const int64_t warps = (int64_t)p->k * cdiv(p->k, 32);
+        center_dist_kernel<<<(unsigned)cdiv(warps, 8), 256, 0, st>>>(dC, p->k, p->d, p->cc.as<float>());
+        LAUNCH_CHECK();
+        tile_lists_cc_kernel<<<grid_cap(ctx, p->n_tiles, 8, 8), 256, 0, st>>>(
+            dC, p->k, p->d, p->cc.as<float>(), p->labels_s.as<int32_t>(), p->n, p->tmean.as<float>(), p->trad.as<float>(),
+            p->n_tiles, p->lcap, p->pad_to, dummy, p->tlist.as<uint16_t>(), p->tcount.as<uint32_t>(), ds);
+        LAUNCH_CHECK();
+    }
+    PruneStats h;
+    CUDA_TRY(cudaMemcpyAsync(&h, ds, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *mean_count = (double)h.total / (double)std::max(p->n_tiles, 1);
+    *max_count = (int)h.max_count;
+    *overflow_tiles = (int)h.overflow;
+    return B2K_OK;
+}
+
+int prune_scatter_labels(PruneState* p, int32_t* out) {
+    scatter_labels_kernel<<<grid_cap(p->ctx, p->n, 256, 16), 256, 0, p->ctx->stream>>>(
+        p->labels_s.as<int32_t>(), p->perm.as<uint32_t>(), p->n, out);
+    LAUNCH_CHECK();
+    return B2K_OK;
+}
+
+}  // namespace b2k

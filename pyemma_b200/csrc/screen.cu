@@ -67,9 +67,11 @@ struct ScreenParams {  // device resident; written by the prep kernels, read by 
     float xmax2_raw;   // max_i |x_i - mu|^2 over the prepared frames
     float cmax2_raw;   // max_j |c_j - mu|^2 at prepare time
     float cmax2_now;   // max_j |c~_j|^2 of the current B' operand
+    float cl2_now;     // max_j |c~_j - hi(c~_j)|^2 of the current B' operand (what a hi-only center operand drops)
     int valid;         // 0: operands unusable -> every frame takes the exact fallback
     unsigned long long cand_chunks, fallback_frames;  // statistics of the last verify
     unsigned int fb_count, fb_pad;                    // frames handed to the exact fallback kernel
+    float cl;          // upper bound of max_j |c~_j - hi(c~_j)|
 };
 
 struct ScreenPlan {
@@ -80,12 +82,16 @@ struct ScreenPlan {
     __half* A = nullptr;       // [n_pad][Kp]
     __half* B = nullptr;       // [k_pad][Kp]
     float* X2 = nullptr;       // [n_pad] |x~|^2
+    float* XL = nullptr;       // [n_pad] upper bound of |x~ - hi(x~)| (terms < 3: what a hi-only frame operand drops)
     float* mu = nullptr;       // [d]
     ScreenParams* params = nullptr;
     uint32_t* cand = nullptr;  // [n_pad][CAND_CAP]  chunk id | group mask << 28
     uint8_t* ncand = nullptr;  // [n_pad]  (255: overflow -> exact fallback)
     uint32_t* fb_list = nullptr;  // [n_pad] frames the verify kernels hand to the fallback kernel
     CUtensorMap tmA, tmB, tmBh;  // tmBh: center operand in 128-row boxes (one CTA's half of a center tile, cluster mode)
+    CUtensorMap tmBg;            // center operand in single-row boxes: the source of tile::gather4 loads (listed screen)
+    int k_rows = 0;              // rows of B: k_pad + 8, the rows from k on carry a -inf bias (never candidates); row k_pad
+                                 // is the padding id of the per-tile center lists
     int64_t prepared_n = -1;
 };
 
@@ -105,6 +111,7 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 static int make_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    // (box_rows = 1: the descriptor of tile::gather4 loads -- one row of the gathered dimension, BLOCK_K contiguous columns)
     PFN_encodeTiled enc = get_encode();
     if (!enc) return set_error(B2K_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     cuuint64_t dims[2] = {cols, rows};
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(256) screen_frames_kernel(const float* __restr
         cst[q] = 0.f;
         if (c < ones0) {
             const int ps = (c >= 2 * d) ? 2 : (c >= d ? 1 : 0);  // physical segment; the hi.hi products come LAST
-            seg[q] = (terms == 3) ? (ps == 2 ? 0 : ps + 1) : 0;
+            seg[q] = (terms == 3) ? (ps == 2 ? 0 : ps + 1) : (terms == 2 ? (ps == 0 ? 2 : 0) : 0);
             dim[q] = c - ps * d;
             muv[q] = __ldg(mu + dim[q]);
         } else if (c < ones0 + 3) {
@@ -287,6 +294,9 @@ __global__ void __launch_bounds__(256) screen_frames_tile_kernel(const float* __
                 out[e] = __float2half_rn(h16_ftz(hi * 0.03125f));
                 out[d + e] = __float2half_rn(h16_ftz(__fsub_rn(xt, hi) * 32.f));
                 out[2 * d + e] = __float2half_rn(hi);
+            } else if (terms == 2) {
+                out[e] = __float2half_rn(h16_ftz(__fsub_rn(xt, hi) * 32.f));
+                out[d + e] = __float2half_rn(hi);
             } else {
                 out[e] = __float2half_rn(hi);
             }
@@ -312,13 +322,28 @@ template <int LPR>
 __global__ void __launch_bounds__(256) screen_x2_kernel(const float* __restrict__ X, int64_t n, int64_t n_pad, int d,
                                                         const float* __restrict__ mu,
                                                         const ScreenParams* __restrict__ prm,
-                                                        float* __restrict__ X2) {
+                                                        float* __restrict__ X2, float* __restrict__ XL) {
     const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPR;  // n_pad is a multiple of 128: whole warps
     if (i >= n_pad) return;
-    float s = row_sqnorm<LPR>(X + (i < n ? i : 0) * d, mu, d, prm->sigma, threadIdx.x % LPR);
+    const float* row = X + (i < n ? i : 0) * d;
+    const int sub = threadIdx.x % LPR;
+    float s = row_sqnorm<LPR>(row, mu, d, prm->sigma, sub);
     if (i >= n) s = 0.f;
     else if (!(s < 3.0e38f)) s = __int_as_float(0x7f800000);  // NaN/inf frame -> flagged by the epilogue
-    if (threadIdx.x % LPR == 0) X2[i] = s;
+    if (sub == 0) X2[i] = s;
+    if (XL) {
+        // |x~ - hi(x~)|: the part of the frame a hi-only operand does not carry (flushed values included), rounded up
+        const float sigma = prm->sigma;
+        float l = 0.f;
+        for (int e = sub; e < d; e += LPR) {
+            const float xt = __fmul_rn(__fsub_rn(__ldg(row + e), __ldg(mu + e)), sigma);
+            const float t = __fsub_rn(xt, h16_ftz(xt));
+            l += t * t;
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        if (sub == 0) XL[i] = (i < n && l < 3.0e38f) ? sqrtf(l * (1.f + (d + 4) * 1.2e-7f)) * 1.000001f : 0.f;
+    }
 }
 
 // B' rows (one thread per center): [c_hi | (c_lo | c_hi) | -b1 -b2 -b3 | 0..]; rows >= k: bias -inf
@@ -335,15 +360,20 @@ __global__ void __launch_bounds__(128) screen_centers_kernel(const float* __rest
         return;
     }
     const float sigma = prm->sigma;
-    float s = 0.f;
+    float s = 0.f, sl = 0.f;
     for (int e = 0; e < d; ++e) {
         const float ct = __fmul_rn(__fsub_rn(C[(int64_t)j * d + e], mu[e]), sigma);
         s += ct * ct;
         const float hi = h16_ftz(ct);
+        const float lo = __fsub_rn(ct, hi);
+        sl += lo * lo;
         if (terms == 3) {
-            row[e] = __float2half_rn(h16_ftz(__fsub_rn(ct, hi) * 32.f));
+            row[e] = __float2half_rn(h16_ftz(lo * 32.f));
             row[d + e] = __float2half_rn(h16_ftz(hi * 0.03125f));
             row[2 * d + e] = __float2half_rn(hi);
+        } else if (terms == 2) {
+            row[e] = __float2half_rn(h16_ftz(hi * 0.03125f));
+            row[d + e] = __float2half_rn(hi);
         } else {
             row[e] = __float2half_rn(hi);
         }
@@ -360,12 +390,14 @@ __global__ void __launch_bounds__(128) screen_centers_kernel(const float* __rest
     row[ones0 + 2] = __float2half_rn(-b3);
     for (int c = ones0 + 3; c < Kp; ++c) row[c] = __float2half_rn(0.f);
     atomicMax((int*)&prm->cmax2_now, __float_as_int(s));
+    atomicMax((int*)&prm->cl2_now, __float_as_int(sl));
 }
 
 __global__ void screen_finish_centers_kernel(ScreenParams* p, int d) {
     // upper bound of max |c~| (the fp32 evaluation above is within (d+2) ulp)
     const float c2 = p->cmax2_now * (1.f + (d + 4) * 1.2e-7f);
     p->cmax = sqrtf(c2) * 1.000001f;
+    p->cl = sqrtf(p->cl2_now * (1.f + (d + 4) * 1.2e-7f)) * 1.000001f;
     if (!(p->cmax <= CMAX_LIMIT)) p->valid = 0;  // centers moved outside the scaled range
 }
 
@@ -517,25 +549,38 @@ __device__ __forceinline__ void tmem_ld_fence(float (&v)[32]) {
                           "+f"(v[e + 6]), "+f"(v[e + 7])::"memory");
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- margin ----------------------------------------------------------------------------------------------------
 struct Margin {
     float a, r, x2;
-    __device__ __forceinline__ void init(float x2_, float C, int d, int nk16, int terms) {
+    // xl, CL: upper bounds of |x~ - hi(x~)| (this frame) and max_j |c~_j - hi(c~_j)| -- the parts a hi-only operand does
+    // not carry, MEASURED by the operand builders (flushed values included), so the Cauchy-Schwarz bounds
+    //   terms=1:  |x.c - x_hi.c_hi| <= |x_lo| |c| + |x_hi| |c_lo|      terms=2:  |x.c - x.c_hi| <= |x| |c_lo|
+    // use the data's actual rounding residues (~2^-12.3 of the norms) instead of the worst case 2^-11 per side.
+    __device__ __forceinline__ void init(float x2_, float xl, float C, float CL, int d, int nk16, int terms) {
         const float u = 5.9604645e-8f;
         const float gam = (0.25f * d + 9.f) * u * 1.01f;
         const float rho = 2.f * gam + 4.9e-7f;
         const float X = sqrtf(x2_) * (1.f + 2.f * gam);
         const float R = X + C;
         const float d1 = 2.1f * u * R * R;
-        const float erep = (terms == 3) ? 3.01f * 2.3841858e-7f : (2.f * 4.8828125e-4f + 2.4e-7f) * 1.01f;
+        // rounding of the scaled lo segments (terms=3: x_lo, c_lo and the dropped lo.lo; terms=2: x_lo)
+        const float erep = (terms == 3) ? 3.01f * 2.3841858e-7f : (terms == 2 ? 1.01f * 2.3841858e-7f : 0.f);
+        const float edrop = (terms == 3) ? 0.f : (terms == 2 ? 1.001f * X * CL : 1.001f * (xl * C + 1.0005f * X * CL));
         // K=16 steps whose addends/partial sums are of full magnitude: from the step that holds the first
-        // hi.hi column (2d for terms=3, 0 for terms=1) to the end; the earlier ones see sums <= 2^-10 X C
-        const int nk_lo = (terms == 3) ? (2 * d) / 16 : 0;
+        // hi.hi column (2d for terms=3, d for terms=2, 0 for terms=1) to the end; the earlier ones see sums <= 2^-10 X C
+        const int nk_lo = (terms == 3) ? (2 * d) / 16 : (terms == 2 ? d / 16 : 0);
         const float eacc = ((float)((nk16 - nk_lo) * 17) + (float)(nk_lo * 17) * 9.8e-4f) * 1.1920929e-7f;
         // values flushed to zero by the operand builder: per element <= (2^-19+2^-20)(|x_e|+|c_e|) with the
-        // scaled lo segments (terms=3), <= 2^-14 (|x_e|+|c_e|) with the hi segment alone (terms=1)
-        const float eflush = (terms == 3) ? 2.9e-6f : 6.2e-5f;
-        const float d2 = erep * X * C + eflush * sqrtf((float)d) * R + eacc * (1.01f * X * C + 0.5f * C * C) +
+        // scaled lo segments (terms=3, 2); with the hi segment alone (terms=1) the flushed values are part of xl / CL
+        const float eflush = (terms == 1) ? 0.f : 2.9e-6f;
+        const float d2 = erep * X * C + edrop + eflush * sqrtf((float)d) * R + eacc * (1.01f * X * C + 0.5f * C * C) +
                          (gam + 1.2e-10f) * 0.5f * C * C + 4e-9f;
         a = (2.f * d2 + d1) * 1.01f;
         r = 0.5f * rho * 1.01f;
@@ -564,6 +609,7 @@ struct GemmArgs {
     int stage_bytes;    // resident: n_kblocks*A_BYTES (a frame tile, full K); streaming: A_BYTES+B_BYTES (one k-block)
     int bres_bytes;     // resident: bytes of B' in shared memory
     const float* X2;
+    const float* XL;    // terms < 3
     const ScreenParams* prm;
     uint32_t* cand;
     uint8_t* ncand;
@@ -877,14 +923,15 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t* lid = &T->list_id[h][0][row];
         float* lv = &T->list_v[h][0][row];
         uint32_t it = 0;
-        const float C = g.prm->cmax;
+        const float C = g.prm->cmax, CL = g.prm->cl;
         const int valid_ops = g.prm->valid;
         for (int tt = B2K_T_FIRST; tt < B2K_T_COUNT; tt += B2K_T_STEP) {
             const int tile = cluster2 ? 2 * tt + (int)crank : tt;
             const int64_t grow = (int64_t)tile * TILE_M + row;
             const float x2 = (grow < g.n) ? g.X2[grow] : 0.f;
+            const float xl = (g.terms != 3 && grow < g.n) ? g.XL[grow] : 0.f;
             Margin mg;
-            mg.init(x2, C, g.d, g.nk16, g.terms);
+            mg.init(x2, xl, C, CL, g.d, g.nk16, g.terms);
             RowScan rs;
             rs.init();
             float va[32], vb[32];
@@ -976,6 +1023,355 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tc_fence_after();
         if (EXP == 2 && pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+
+// ---- the screen kernel over per-tile center lists (prune.cu) --------------------------------------------------------
+// Same roles as above in streaming mode, but frame tile t meets only the centers of ITS list: per pass of <= 256 list
+// entries the producer thread fetches the frame k-block with one tiled TMA load, four GATHER warps copy the listed rows
+// of the center operand (L2 resident) into the stage with 16-byte cp.async, writing the SWIZZLE_128B K-major layout a
+// tiled TMA load would produce (chunk c of row r at c ^ (r & 7)) and publishing it to the async proxy
+// (fence.proxy.async) before they arrive on the stage's barrier; the MMA thread issues M=128 x N=rows instructions, and
+// the two column halves of the epilogue take alternate 32-column chunks (list lengths are multiples of 64, so both always
+// have work).  A candidate entry's chunk id counts 32-entry chunks of the LIST; the listed verify kernels map list
+// positions back to center indices.  (gather = 1 fetches the rows with TMA tile::gather4 instead -- four rows per
+// instruction: correct, but measured 1.43 ms against the cp.async gather at 1e7 x 10, k=1000, ~160 listed centers per
+// tile: one gather4 costs the TMA unit ~130 cycles, 40 of them per tile are the whole kernel.)
+struct ListArgs {
+    const uint16_t* tlist;   // [n_tiles][lcap] center ids, ascending, padded with the id of a -inf row
+    const uint32_t* tcount;  // [n_tiles] padded list lengths (multiples of 64, <= lcap)
+    const __half* B;         // center operand [k_rows][Kp]
+    int lcap, Kp;
+    int gather;              // 0: cp.async gather warps, 1: TMA tile::gather4
+};
+static constexpr int GATHER_WARPS = 4;
+static constexpr int LISTED_THREADS = GEMM_THREADS + GATHER_WARPS * 32;
+
+__device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* tm, uint64_t* bar, int col, int r0, int r1, int r2,
+                                            int r3) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+        "%7}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        : "memory");
+}
+
+template <int CG>
+__global__ void __launch_bounds__(LISTED_THREADS, 1)
+screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBg, GemmArgs g,
+                          ListArgs la) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if (!g.prm->valid) return;
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    GemmSmemTail* T = reinterpret_cast<GemmSmemTail*>(tiles + (size_t)g.n_stages * STAGE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBg) : "memory");
+        // a stage is full when the frame tile has landed (the producer's expect_tx arrival + TMA bytes) and every gather
+        // warp has published its rows
+        for (int s = 0; s < g.n_stages; ++s) {
+            mbar_init(&T->full_bar[s], la.gather == 0 ? 1 + GATHER_WARPS : 1);
+            mbar_init(&T->empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) { mbar_init(&T->tfull_bar[s], 1); mbar_init(&T->tempty_bar[s], EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T->tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = T->tmem_slot;
+
+    if (warp >= GEMM_THREADS / 32) {
+        // ===== gather warps: listed rows of B' -> stage, 16 bytes per cp.async, one pass behind in signalling so that two
+        // stages' copies are in flight =====
+        if (la.gather == 0) {
+            const int gt = (int)threadIdx.x - GEMM_THREADS;  // 0 .. 127
+            const int chunk = gt & 7;                        // 16-byte chunk of a 128-byte row piece
+            const int r0 = (gt >> 3) * 16;                   // this thread's 16 consecutive list rows of a pass
+            const size_t row_bytes = (size_t)la.Kp * 2;
+            const uint8_t* Bb = reinterpret_cast<const uint8_t*>(la.B) + (size_t)(chunk << 4);
+            int stage = 0, prev_stage = -1;
+            uint32_t phase = 0;
+            // the per-tile metadata (list length, this thread's 16 ids of the first pass) is requested one tile ahead:
+            // a dependent global load per tile on this path would cost more than the tile's whole copy
+            int tile = blockIdx.x;
+            int cnt = tile < g.n_tiles ? (int)__ldg(la.tcount + tile) : 0;
+            uint4 ia = make_uint4(0u, 0u, 0u, 0u), ib = ia;
+            if (tile < g.n_tiles && r0 < la.lcap) {  // (r0 + 16 <= lcap: both are multiples of 16)
+                const uint4* src = reinterpret_cast<const uint4*>(la.tlist + (size_t)tile * la.lcap + r0);
+                ia = __ldg(src);
+                ib = __ldg(src + 1);
+            }
+            for (; tile < g.n_tiles; tile += gridDim.x) {
+                const int ntile = tile + (int)gridDim.x;
+                int ncnt = 0;
+                uint4 na = make_uint4(0u, 0u, 0u, 0u), nb = na;
+                if (ntile < g.n_tiles) {
+                    ncnt = (int)__ldg(la.tcount + ntile);
+                    if (r0 < la.lcap) {
+                        const uint4* src = reinterpret_cast<const uint4*>(la.tlist + (size_t)ntile * la.lcap + r0);
+                        na = __ldg(src);
+                        nb = __ldg(src + 1);
+                    }
+                }
+                const uint16_t* tl = la.tlist + (size_t)tile * la.lcap;
+                for (int p0 = 0; p0 < cnt; p0 += TILE_N) {
+                    const int rows = min(TILE_N, cnt - p0);
+                    if (p0 > 0 && p0 + r0 < la.lcap) {  // later passes of a long list: fetched here
+                        const uint4* src = reinterpret_cast<const uint4*>(tl + p0 + r0);
+                        ia = __ldg(src);
+                        ib = __ldg(src + 1);
+                    }
+                    const uint32_t w[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+                    for (int kb = 0; kb < g.n_kblocks; ++kb) {
+                        if (lane == 0) mbar_wait(&T->empty_bar[stage], phase ^ 1);
+                        __syncwarp();
+                        uint8_t* sb = tiles + (size_t)stage * STAGE_BYTES + A_BYTES;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int r = r0 + i;
+                            if (r < rows) {
+                                const uint32_t j = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu);
+                                cp_async16(sb + (size_t)r * 128 + (size_t)((chunk ^ (r & 7)) << 4),
+                                           Bb + (size_t)j * row_bytes + (size_t)kb * 128);
+                            }
+                        }
+                        cp_async_commit();
+                        if (prev_stage >= 0) {
+                            cp_async_wait<1>();
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&T->full_bar[prev_stage]);
+                        }
+                        prev_stage = stage;
+                        if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                cnt = ncnt;
+                ia = na;
+                ib = nb;
+            }
+            if (prev_stage >= 0) {
+                cp_async_wait<0>();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&T->full_bar[prev_stage]);
+            }
+        }
+    } else if (warp == 0 && la.gather == 0) {
+        // ===== producer (cp.async gather mode): the frame k-blocks =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int tile = blockIdx.x;
+            int cnt = tile < g.n_tiles ? (int)__ldg(la.tcount + tile) : 0;
+            for (; tile < g.n_tiles; tile += gridDim.x) {
+                const int ntile = tile + (int)gridDim.x;
+                const int ncnt = ntile < g.n_tiles ? (int)__ldg(la.tcount + ntile) : 0;  // one tile ahead
+                for (int p0 = 0; p0 < cnt; p0 += TILE_N) {
+                    for (int kb = 0; kb < g.n_kblocks; ++kb) {
+                        mbar_wait(&T->empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&T->full_bar[stage], (uint32_t)A_BYTES);
+                        tma_load_2d(tiles + (size_t)stage * STAGE_BYTES, &tmA, &T->full_bar[stage], kb * BLOCK_K, tile * TILE_M);
+                        if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                cnt = ncnt;
+            }
+        }
+    } else if (warp == 0) {
+        // ===== producer (gather4 mode): the whole warp issues (lane l owns list rows 8l .. 8l+7 of a pass) =====
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+            const int cnt = (int)la.tcount[tile];
+            const uint16_t* tl = la.tlist + (size_t)tile * la.lcap;
+            for (int p0 = 0; p0 < cnt; p0 += TILE_N) {
+                const int rows = min(TILE_N, cnt - p0);
+                const bool mine = 8 * lane < rows;
+                uint4 iv = make_uint4(0u, 0u, 0u, 0u);
+                if (mine) iv = __ldg(reinterpret_cast<const uint4*>(tl + p0 + 8 * lane));
+                for (int kb = 0; kb < g.n_kblocks; ++kb) {
+                    uint8_t* sa = tiles + (size_t)stage * STAGE_BYTES;
+                    if (lane == 0) {
+                        mbar_wait(&T->empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&T->full_bar[stage], (uint32_t)(A_BYTES + rows * (BLOCK_K * 2)));
+                        tma_load_2d(sa, &tmA, &T->full_bar[stage], kb * BLOCK_K, tile * TILE_M);
+                    }
+                    __syncwarp();
+                    if (mine) {
+                        uint8_t* sb = sa + A_BYTES + (size_t)(8 * lane) * (BLOCK_K * 2);
+                        tma_gather4(sb, &tmBg, &T->full_bar[stage], kb * BLOCK_K, (int)(iv.x & 0xffffu), (int)(iv.x >> 16),
+                                    (int)(iv.y & 0xffffu), (int)(iv.y >> 16));
+                        tma_gather4(sb + 4 * (BLOCK_K * 2), &tmBg, &T->full_bar[stage], kb * BLOCK_K, (int)(iv.z & 0xffffu),
+                                    (int)(iv.z >> 16), (int)(iv.w & 0xffffu), (int)(iv.w >> 16));
+                    }
+                    if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, it = 0;
+            int tile = blockIdx.x;
+            int cnt = tile < g.n_tiles ? (int)__ldg(la.tcount + tile) : 0;
+            int ncnt = 0;
+            for (; tile < g.n_tiles; tile += gridDim.x, cnt = ncnt) {
+                const int ntile = tile + (int)gridDim.x;
+                ncnt = ntile < g.n_tiles ? (int)__ldg(la.tcount + ntile) : 0;  // one tile ahead
+                for (int p0 = 0; p0 < cnt; p0 += TILE_N, ++it) {
+                    const int rows = min(TILE_N, cnt - p0);
+                    // instruction descriptor: D=f32, A=B=f16, K-major both, N=rows, M=128
+                    const uint32_t idesc = (1u << 4) | ((uint32_t)(rows >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+                    const uint32_t acc = it & 1u, accphase = (it >> 1) & 1u;
+                    mbar_wait(&T->tempty_bar[acc], accphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * TILE_N;
+                    for (int kb = 0; kb < g.n_kblocks; ++kb) {
+                        mbar_wait(&T->full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
+                        const uint64_t adesc = make_smem_desc(sa);
+                        const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+                        const int ksteps = min(BLOCK_K / 16, g.nk16 - kb * (BLOCK_K / 16));
+                        for (int ks = 0; ks < ksteps; ++ks)
+                            tc_mma_f16(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc,
+                                       (kb | ks) != 0 ? 1u : 0u);
+                        tc_commit(&T->empty_bar[stage]);
+                        if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(&T->tfull_bar[acc]);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: one frame (TMEM lane) per thread, column half h takes the chunks h, h+2, ... of every pass =====
+        const int q = warp & 3;
+        const int h = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t* lid = &T->list_id[h][0][row];
+        float* lv = &T->list_v[h][0][row];
+        const float C = g.prm->cmax, CL = g.prm->cl;
+        const int valid_ops = g.prm->valid;
+        uint32_t it = 0;
+        float va[32], vb[32];
+        bool par = false;       // the buffer that holds (or receives) the current chunk: false = va
+        bool primed = false;    // the first chunk of the current pass was already requested by the previous pass
+        // per-tile metadata one tile ahead (see the gather warps)
+        int tile = blockIdx.x;
+        int cnt = 0, ncnt = 0;
+        float x2 = 0.f, xl = 0.f, nx2 = 0.f, nxl = 0.f;
+        if (tile < g.n_tiles) {
+            cnt = (int)__ldg(la.tcount + tile);
+            const int64_t gr = (int64_t)tile * TILE_M + row;
+            if (gr < g.n) { x2 = __ldg(g.X2 + gr); if (g.terms != 3) xl = __ldg(g.XL + gr); }
+        }
+        for (; tile < g.n_tiles; tile += gridDim.x, cnt = ncnt, x2 = nx2, xl = nxl) {
+            const int64_t grow = (int64_t)tile * TILE_M + row;
+            const int next_tile = tile + (int)gridDim.x;
+            ncnt = 0; nx2 = 0.f; nxl = 0.f;
+            if (next_tile < g.n_tiles) {
+                ncnt = (int)__ldg(la.tcount + next_tile);
+                const int64_t gr = (int64_t)next_tile * TILE_M + row;
+                if (gr < g.n) { nx2 = __ldg(g.X2 + gr); if (g.terms != 3) nxl = __ldg(g.XL + gr); }
+            }
+            Margin mg;
+            mg.init(x2, xl, C, CL, g.d, g.nk16, g.terms);
+            RowScan rs;
+            rs.init();
+            for (int p0 = 0; p0 < cnt; p0 += TILE_N, ++it) {
+                const int nmine = min(TILE_N, cnt - p0) / (2 * CHUNK);   // my chunks of this pass (>= 1)
+                const uint32_t acc = it & 1u;
+                const uint32_t taddr = lane_addr + acc * TILE_N + (uint32_t)(h * CHUNK);
+                const uint32_t cbase = (uint32_t)(p0 / CHUNK + h);
+                if (!primed) {
+                    mbar_wait(&T->tfull_bar[acc], (it >> 1) & 1u);
+                    tc_fence_after();
+                    if (par) tmem_ld32(taddr, vb); else tmem_ld32(taddr, va);
+                }
+                primed = false;
+                // is there a pass after this one (same tile or the CTA's next tile)?
+                const bool more = (p0 + TILE_N < cnt) || ncnt != 0;
+                for (int i = 0; i < nmine; ++i) {
+                    tmem_ld_wait();
+                    if (par) tmem_ld_fence(vb); else tmem_ld_fence(va);
+                    if (i + 1 < nmine) {
+                        if (par) tmem_ld32(taddr + (uint32_t)((i + 1) * 2 * CHUNK), va);
+                        else tmem_ld32(taddr + (uint32_t)((i + 1) * 2 * CHUNK), vb);
+                    } else {
+                        // my last load of this accumulator stage has landed: hand it back, then request the first chunk
+                        // of the next pass while this one is scanned
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&T->tempty_bar[acc]);
+                        if (more) {
+                            const uint32_t nit = it + 1, nacc = nit & 1u;
+                            mbar_wait(&T->tfull_bar[nacc], (nit >> 1) & 1u);
+                            tc_fence_after();
+                            const uint32_t naddr = lane_addr + nacc * TILE_N + (uint32_t)(h * CHUNK);
+                            if (par) tmem_ld32(naddr, va); else tmem_ld32(naddr, vb);
+                            primed = true;
+                        }
+                    }
+                    if (par) scan_chunk<CG>(vb, cbase + (uint32_t)(2 * i), rs, mg, lid, lv);
+                    else scan_chunk<CG>(va, cbase + (uint32_t)(2 * i), rs, mg, lid, lv);
+                    par = !par;
+                }
+            }
+            // ---- merge the two column halves of this frame (as in screen_gemm_kernel) ----
+            T->half_m[h][row] = rs.m;
+            named_bar_sync(1, EPI_WARPS * 32);
+            const float m = fmaxf(T->half_m[0][row], T->half_m[1][row]);
+            const float thr = mg.threshold(m);
+            {
+                int kept = 0;
+                for (int t = 0; t < rs.cnt; ++t) {
+                    if (lv[t * TILE_M] >= thr) {
+                        if (kept < CAND_CAP) T->out_id[h][kept][row] = lid[t * TILE_M];
+                        ++kept;
+                    }
+                }
+                if (rs.overflow || kept > CAND_CAP) kept = CAND_CAP + 1;
+                T->out_n[h][row] = (uint32_t)kept;
+            }
+            named_bar_sync(2, EPI_WARPS * 32);
+            if (h == 0 && grow < g.n) {
+                const int n0 = (int)T->out_n[0][row], n1 = (int)T->out_n[1][row];
+                uint32_t ids[CAND_CAP] = {0, 0, 0, 0, 0, 0, 0, 0};
+                int kept = n0 + n1;
+                bool overflow = n0 > CAND_CAP || n1 > CAND_CAP || kept > CAND_CAP || kept == 0 || !(m > -3.0e38f) ||
+                                !valid_ops || !(x2 < 3.0e38f);
+                if (!overflow) {
+                    int a = 0, b = 0;
+                    for (int w = 0; w < kept; ++w) {
+                        const uint32_t ia = a < n0 ? T->out_id[0][a][row] : 0xffffffffu;
+                        const uint32_t ib = b < n1 ? T->out_id[1][b][row] : 0xffffffffu;
+                        if (a < n0 && (b >= n1 || (ia & cand_id_mask(CG)) < (ib & cand_id_mask(CG)))) { ids[w] = ia; ++a; }
+                        else { ids[w] = ib; ++b; }
+                    }
+                }
+                uint4* cout = reinterpret_cast<uint4*>(g.cand + grow * CAND_CAP);
+                cout[0] = make_uint4(ids[0], ids[1], ids[2], ids[3]);
+                if (kept > 4 && !overflow) cout[1] = make_uint4(ids[4], ids[5], ids[6], ids[7]);
+                g.ncand[grow] = overflow ? (uint8_t)255 : (uint8_t)kept;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -1157,6 +1553,118 @@ __global__ void __launch_bounds__(256, 4) screen_verify_table_kernel(const float
     verify_stats(my_groups, my_fb, prm);
 }
 
+
+// the same for the listed screen (prune.cu): a candidate group is `cg` consecutive POSITIONS of the frame tile's center
+// list; the ids are ascending along the list, so the scan order (lowest index wins ties) is unchanged.  Consecutive
+// frames belong to the same tile and mostly share candidate groups, so the lanes of a warp read the same table rows
+// (shared-memory broadcasts) where the unsorted kernel above serialises on bank conflicts.
+template <int DREG>
+__global__ void __launch_bounds__(256, 4) screen_verify_table_listed_kernel(
+    const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Cn, int k, const uint32_t* __restrict__ cand,
+    const uint8_t* __restrict__ ncand, const uint16_t* __restrict__ tlist, int lcap, int32_t* __restrict__ labels, int lloyd,
+    ScreenParams* prm, uint32_t* __restrict__ fb_list, int gstride, int cg, int vec) {
+    extern __shared__ __align__(16) float ctab[];
+    const int idb = cand_id_bits(cg);
+    const uint32_t idm = cand_id_mask(cg);
+    if (!prm->valid) return;
+    constexpr int DS = DREG;
+    const int n_groups = (k + GROUP - 1) / GROUP;
+    for (int t = threadIdx.x; t < n_groups * GROUP * DS; t += 256) {
+        const int r = t / DS, c = t - r * DS;
+        ctab[(r >> 3) * gstride + (r & 7) * DS + c] = (r < k && c < d) ? __ldg(Cn + (int64_t)r * d + c) : 0.f;
+    }
+    __syncthreads();
+    const bool full_last = d == DREG;
+    unsigned long long my_groups = 0, my_fb = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        float xr[DREG];
+        load_row_padded<DREG>(X, i, d, vec, xr);
+        const int nc = ncand[i];
+        if (nc == 255) {
+            fallback_push(prm, fb_list, i);
+            my_fb += 1;
+            continue;
+        }
+        const uint16_t* tl = tlist + (size_t)(i / TILE_M) * lcap;
+        const uint4* cp = reinterpret_cast<const uint4*>(cand + i * CAND_CAP);
+        const uint4 p0 = cp[0];
+        uint4 p1 = make_uint4(0, 0, 0, 0);
+        if (nc > 4) p1 = cp[1];
+        const uint32_t ent[CAND_CAP] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        ArgMin am;
+        am.init();
+#pragma unroll
+        for (int t = 0; t < CAND_CAP; ++t) {
+            if (t < nc) {
+                const int pos0 = (int)(ent[t] & idm) * CHUNK;
+                uint32_t mask = ent[t] >> idb;
+                while (mask) {
+                    const int q = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int pb = pos0 + q * cg;
+                    my_groups += 1;
+                    if (cg == 8) {
+                        // 8 ids with one 16-byte load; branch-free unrolled evaluation (a padding id reads row k-1 and is
+                        // dropped before the argmin)
+                        const uint4 iv = __ldg(reinterpret_cast<const uint4*>(tl + pb));
+                        const int ids[8] = {(int)(iv.x & 0xffffu), (int)(iv.x >> 16), (int)(iv.y & 0xffffu), (int)(iv.y >> 16),
+                                            (int)(iv.z & 0xffffu), (int)(iv.z >> 16), (int)(iv.w & 0xffffu), (int)(iv.w >> 16)};
+                        float s8[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int j = min(ids[c], k - 1);
+                            const float4* c4 = reinterpret_cast<const float4*>(ctab + (size_t)(j >> 3) * gstride + (j & 7) * DS);
+                            Lanes4 L;
+                            L.init();
+#pragma unroll
+                            for (int e = 0; e < DREG - 4; e += 4) {
+                                const float4 cv = c4[e >> 2];
+                                L.add4(xr[e], xr[e + 1], xr[e + 2], xr[e + 3], cv.x, cv.y, cv.z, cv.w);
+                            }
+                            const float4 cv = c4[(DREG - 4) >> 2];
+                            if (full_last) {
+                                L.add4(xr[DREG - 4], xr[DREG - 3], xr[DREG - 2], xr[DREG - 1], cv.x, cv.y, cv.z, cv.w);
+                            } else {
+                                L.tail(xr[DREG - 4], cv.x);
+                                L.tail(xr[DREG - 3], cv.y);
+                                L.tail(xr[DREG - 2], cv.z);
+                            }
+                            s8[c] = L.result();
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (ids[c] < k) am.offer(s8[c], ids[c]);
+                        continue;
+                    }
+                    for (int c = 0; c < cg; ++c) {
+                        const int j = (int)__ldg(tl + pb + c);
+                        if (j >= k) continue;  // list padding
+                        const float4* c4 = reinterpret_cast<const float4*>(ctab + (size_t)(j >> 3) * gstride + (j & 7) * DS);
+                        Lanes4 L;
+                        L.init();
+#pragma unroll
+                        for (int e = 0; e < DREG - 4; e += 4) {
+                            const float4 cv = c4[e >> 2];
+                            L.add4(xr[e], xr[e + 1], xr[e + 2], xr[e + 3], cv.x, cv.y, cv.z, cv.w);
+                        }
+                        const float4 cv = c4[(DREG - 4) >> 2];
+                        if (full_last) {
+                            L.add4(xr[DREG - 4], xr[DREG - 3], xr[DREG - 2], xr[DREG - 1], cv.x, cv.y, cv.z, cv.w);
+                        } else {  // 1..3 tail columns into lane 0, in order; the padded ones add +0
+                            L.tail(xr[DREG - 4], cv.x);
+                            L.tail(xr[DREG - 3], cv.y);
+                            L.tail(xr[DREG - 2], cv.z);
+                        }
+                        am.offer(L.result(), j);
+                    }
+                }
+            }
+        }
+        labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
+    }
+    verify_stats(my_groups, my_fb, prm);
+}
+
 // d <= 16, table too large for shared memory: 8 lanes per frame (4 frames per warp), lane `sub` evaluates center `sub` of every candidate group
 // with the frame in registers; the center table sits in shared memory when it fits (row stride rs = 4 mod 8
 // floats: the 8 rows of a group then cover all 32 banks, so a 16-byte load per lane is conflict free).
@@ -1283,12 +1791,6 @@ static constexpr int VC_FRAME = GROUP * VC_ROW;                // floats per fra
 static constexpr int VC_STAGE = 4 * VC_FRAME + 4 * 32;         // + the 4 frame slabs
 static constexpr int VC_WARP_FLOATS = 2 * VC_STAGE;
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(256) screen_verify_stream_kernel(const float* __restrict__ X, int64_t n, int d,
                                                                    const float* __restrict__ Cn, int k,
@@ -1580,7 +2082,9 @@ __global__ void __launch_bounds__(256) screen_verify_direct_kernel(const float* 
                                                                    int32_t* __restrict__ labels,
                                                                    float* __restrict__ mind, int lloyd,
                                                                    ScreenParams* prm, uint32_t* __restrict__ fb_list,
-                                                                   int cg) {
+                                                                   int cg, const uint16_t* __restrict__ tlist /* per-tile
+                                                                   center lists (candidate groups count list positions) or
+                                                                   null */, int lcap) {
     if (!prm->valid) return;
     const int lane = threadIdx.x & 31;
     const int sub = lane & 7, slot = lane >> 3;
@@ -1597,6 +2101,7 @@ __global__ void __launch_bounds__(256) screen_verify_direct_kernel(const float* 
         const int nc = live ? (int)ncand[i] : 0;
         uint32_t ent = 0;
         if (live && nc != 255 && sub < nc) ent = cand[i * CAND_CAP + sub];
+        const uint16_t* tl = tlist ? tlist + (size_t)((live ? i : 0) / TILE_M) * lcap : nullptr;
         const int pc = __popc(ent >> idb);
         int off = pc;  // inclusive scan over the 8 lanes of the frame
 #pragma unroll
@@ -1626,7 +2131,8 @@ __global__ void __launch_bounds__(256) screen_verify_direct_kernel(const float* 
                 }
                 if (gi >= total) g = -1;
             }
-            const int j = g >= 0 ? g * cg + within : -1;
+            int j = g >= 0 ? g * cg + within : -1;
+            if (tl && j >= 0) j = (int)__ldg(tl + j);  // list position -> center id (the padding id is >= k)
             if (j >= 0 && j < k) {
                 const float* cr = Cn + (int64_t)j * d;
                 Lanes4 L;
@@ -1723,24 +2229,22 @@ bool screen_supported(const b2k_ctx* ctx, int d, int k, int64_t n) {
     return k >= 128 && (int64_t)k * d >= 2048 && n >= 4096;
 }
 
-// operand terms: 3 = hi/lo fp16 split (default: at d=10 hi-only operands leave dozens of candidates per frame), 1 = hi-only
-// (option screen_terms=1), option value 2 = hi-only for wide rows only (d >= 32: tools/terms_study.py expects 1-5 candidates
-// per frame there for a third of the MMA flops -- to be measured, not a default)
-static int screen_term_count(const b2k_ctx* ctx, int d) {
-    if (ctx->screen_terms == 1) return 1;
-    if (ctx->screen_terms == 2 && d >= 32) return 1;
-    return 3;
+// operand terms (MMA K = terms*d + 3): 3 = hi/lo fp16 split of frames and centers, 2 = split frames against hi-only
+// centers, 1 = hi-only both.  Fewer terms issue fewer MMA flops and leave a wider margin, i.e. more candidates for the exact
+// verify; option screen_terms forces 1/2/3, 0 lets screen_choose_terms measure the candidate counts on a sample.
+static int screen_default_terms(const b2k_ctx* ctx) {
+    return (ctx->screen_terms >= 1 && ctx->screen_terms <= 3) ? ctx->screen_terms : 3;
 }
 
 void screen_plan_destroy(ScreenPlan* p) {
     if (!p) return;
     cudaStreamSynchronize(p->ctx->stream);
-    cudaFree(p->A); cudaFree(p->B); cudaFree(p->X2); cudaFree(p->mu); cudaFree(p->params); cudaFree(p->cand);
+    cudaFree(p->A); cudaFree(p->B); cudaFree(p->X2); cudaFree(p->XL); cudaFree(p->mu); cudaFree(p->params); cudaFree(p->cand);
     cudaFree(p->ncand); cudaFree(p->fb_list);
     delete p;
 }
 
-int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** out) {
+int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, int terms, ScreenPlan** out) {
     ScreenPlan* p = new ScreenPlan();
     p->ctx = ctx;
     p->n_cap = n_cap;
@@ -1748,7 +2252,7 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     p->d = d;
     p->k = k;
     p->k_pad = (int)(cdiv(k, TILE_N) * TILE_N);
-    p->terms = screen_term_count(ctx, d);
+    p->terms = (terms >= 1 && terms <= 3) ? terms : screen_default_terms(ctx);
     // candidate group size: narrow rows (d <= 16) leave the TMEM-read-bound epilogue no slack (measured at 1e7 x 10,
     // k=1000: screen kernel 2.32 / 2.44 / 2.90 ms for groups of 8 / 4 / 2, step time 3.40 / 3.36 / 3.75 ms) -> 8; wide
     // rows are MMA bound and their verify pays 4*d bytes of L2 traffic per candidate center -> 2 (16-bit chunk ids)
@@ -1759,8 +2263,10 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     p->Kp = (int)(cdiv(p->Kc, BLOCK_K) * BLOCK_K);
     p->nk16 = (int)cdiv(p->Kc, 16);
     cudaError_t e = cudaMalloc(&p->A, (size_t)p->n_pad * p->Kp * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&p->B, (size_t)p->k_pad * p->Kp * 2);
+    p->k_rows = p->k_pad + 8;
+    if (e == cudaSuccess) e = cudaMalloc(&p->B, (size_t)p->k_rows * p->Kp * 2);
     if (e == cudaSuccess) e = cudaMalloc(&p->X2, (size_t)p->n_pad * 4);
+    if (e == cudaSuccess && p->terms != 3) e = cudaMalloc(&p->XL, (size_t)p->n_pad * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->mu, (size_t)d * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->params, sizeof(ScreenParams));
     if (e == cudaSuccess) e = cudaMalloc(&p->cand, (size_t)p->n_pad * CAND_CAP * 4);
@@ -1772,8 +2278,9 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
         return set_error(B2K_ERR_NOMEM, "screen plan: %s", cudaGetErrorString(e));
     }
     int rc = make_tmap(&p->tmA, p->A, (uint64_t)p->n_pad, (uint64_t)p->Kp, TILE_M);
-    if (rc == B2K_OK) rc = make_tmap(&p->tmB, p->B, (uint64_t)p->k_pad, (uint64_t)p->Kp, TILE_N);
-    if (rc == B2K_OK) rc = make_tmap(&p->tmBh, p->B, (uint64_t)p->k_pad, (uint64_t)p->Kp, TILE_N / 2);
+    if (rc == B2K_OK) rc = make_tmap(&p->tmB, p->B, (uint64_t)p->k_rows, (uint64_t)p->Kp, TILE_N);
+    if (rc == B2K_OK) rc = make_tmap(&p->tmBh, p->B, (uint64_t)p->k_rows, (uint64_t)p->Kp, TILE_N / 2);
+    if (rc == B2K_OK) rc = make_tmap(&p->tmBg, p->B, (uint64_t)p->k_rows, (uint64_t)p->Kp, 1);
     if (rc != B2K_OK) { screen_plan_destroy(p); return rc; }
     static PerDeviceOnce attr_set;
     if (attr_set.need(ctx->device)) {
@@ -1802,9 +2309,9 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, ScreenPlan** o
     return B2K_OK;
 }
 
-int screen_plan_acquire(b2k_ctx* ctx, int64_t n, int d, int k, ScreenPlan** out) {
+int screen_plan_acquire(b2k_ctx* ctx, int64_t n, int d, int k, int terms, ScreenPlan** out) {
     ScreenPlan* c = static_cast<ScreenPlan*>(ctx->assign_plan);
-    const int terms = screen_term_count(ctx, d);
+    if (terms < 1 || terms > 3) terms = screen_default_terms(ctx);
     const int want_cg = (ctx->screen_group == 8 || ctx->screen_group == 4 || ctx->screen_group == 2) ? ctx->screen_group : 0;
     if (c && c->d == d && c->k == k && c->terms == terms && n <= c->n_cap && (want_cg == 0 || want_cg == c->cg)) {
         c->prepared_n = -1;
@@ -1812,7 +2319,7 @@ int screen_plan_acquire(b2k_ctx* ctx, int64_t n, int d, int k, ScreenPlan** out)
         return B2K_OK;
     }
     screen_plan_release_cached(ctx);
-    B2K_TRY(screen_plan_create(ctx, n, d, k, &c));
+    B2K_TRY(screen_plan_create(ctx, n, d, k, terms, &c));
     ctx->assign_plan = c;
     *out = c;
     return B2K_OK;
@@ -1869,11 +2376,11 @@ int screen_prepare_frames_with_centers(ScreenPlan* p, const float* dX, int64_t n
     }
     LAUNCH_CHECK();
     if (p->d <= 16)
-        screen_x2_kernel<1><<<(unsigned)cdiv(n_pad_now, 256), 256, 0, st>>>(dX, n, n_pad_now, p->d, p->mu, p->params, p->X2);
+        screen_x2_kernel<1><<<(unsigned)cdiv(n_pad_now, 256), 256, 0, st>>>(dX, n, n_pad_now, p->d, p->mu, p->params, p->X2, p->XL);
     else if (p->d <= 128)
-        screen_x2_kernel<8><<<(unsigned)cdiv(n_pad_now, 32), 256, 0, st>>>(dX, n, n_pad_now, p->d, p->mu, p->params, p->X2);
+        screen_x2_kernel<8><<<(unsigned)cdiv(n_pad_now, 32), 256, 0, st>>>(dX, n, n_pad_now, p->d, p->mu, p->params, p->X2, p->XL);
     else
-        screen_x2_kernel<32><<<(unsigned)cdiv(n_pad_now, 8), 256, 0, st>>>(dX, n, n_pad_now, p->d, p->mu, p->params, p->X2);
+        screen_x2_kernel<32><<<(unsigned)cdiv(n_pad_now, 8), 256, 0, st>>>(dX, n, n_pad_now, p->d, p->mu, p->params, p->X2, p->XL);
     LAUNCH_CHECK();
     p->prepared_n = n;
     return B2K_OK;
@@ -1910,10 +2417,10 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
     cudaStream_t st = ctx->stream;
     if (p->prepared_n != n) B2K_TRY(screen_prepare_frames_with_centers(p, dX, n, dC));
     // center operand for the current centers
-    CUDA_TRY(cudaMemsetAsync(&p->params->cmax2_now, 0, 4, st));
+    CUDA_TRY(cudaMemsetAsync(&p->params->cmax2_now, 0, 8, st));  // cmax2_now, cl2_now
     CUDA_TRY(cudaMemsetAsync(&p->params->cand_chunks, 0, 24, st));
-    screen_centers_kernel<<<(unsigned)cdiv(p->k_pad, 128), 128, 0, st>>>(dC, p->k, p->k_pad, p->d, p->terms, p->Kp,
-                                                                         p->mu, p->params, p->B);
+    screen_centers_kernel<<<(unsigned)cdiv(p->k_rows, 128), 128, 0, st>>>(dC, p->k, p->k_rows, p->d, p->terms, p->Kp,
+                                                                          p->mu, p->params, p->B);
     LAUNCH_CHECK();
     screen_finish_centers_kernel<<<1, 1, 0, st>>>(p->params, p->d);
     LAUNCH_CHECK();
@@ -1926,6 +2433,7 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
     g.d = p->d;
     g.terms = p->terms;
     g.X2 = p->X2;
+    g.XL = p->XL;
     g.prm = p->params;
     g.cand = p->cand;
     g.ncand = p->ncand;
@@ -2057,10 +2565,10 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         const unsigned dgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 32), (int64_t)ctx->sm_count * 8));
         if (vec)
             screen_verify_direct_kernel<true><<<dgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind,
-                                                                     lloyd, p->params, p->fb_list, p->cg);
+                                                                     lloyd, p->params, p->fb_list, p->cg, nullptr, 0);
         else
             screen_verify_direct_kernel<false><<<dgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind,
-                                                                      lloyd, p->params, p->fb_list, p->cg);
+                                                                      lloyd, p->params, p->fb_list, p->cg, nullptr, 0);
     } else {
         if (p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0) {
             const size_t tsmem = (size_t)8 * VC_WARP_FLOATS * 4;
@@ -2092,6 +2600,149 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
     LAUNCH_CHECK();
     return screen_finish_assign(p, dX, n, dC, labels, mind, lloyd);
 }
+
+// Term count for a data set: forced by option screen_terms, 3 for narrow rows / small jobs (their screen kernel is not
+// MMA bound), otherwise MEASURED: the screen + verify run on a sample of the frames (four contiguous blocks spread over the
+// array) with 1 and then 2 terms, and the first count whose candidate lists stay short is taken.  Labels are exact with any
+// count; only the split of the work between the tensor pipe and the exact verify changes.
+int screen_choose_terms(b2k_ctx* ctx, const float* dX, int64_t n, int d, const float* dC, int k, int* terms_out) {
+    *terms_out = screen_default_terms(ctx);
+    if (ctx->screen_terms >= 1 && ctx->screen_terms <= 3) return B2K_OK;
+    // the probe costs a few milliseconds: only jobs whose 3-term screen takes ~10 ms or more are worth it
+    if (d < 32 || n < 65536 || 2.0 * (double)n * k * d < 1e9 * (double)ctx->probe_min_gflop || !screen_supported(ctx, d, k, n))
+        return B2K_OK;
+    const int64_t blk = 8192, nblk = 4, m = blk * nblk;
+    DevMem xs, ls;
+    if (xs.alloc((size_t)m * d * 4) != B2K_OK || ls.alloc((size_t)m * 4) != B2K_OK) { cudaGetLastError(); return B2K_OK; }
+    for (int64_t b = 0; b < nblk; ++b) {
+        const int64_t off = (n - blk) * b / (nblk - 1);
+        CUDA_TRY(cudaMemcpyAsync(xs.as<float>() + b * blk * d, dX + off * d, (size_t)blk * d * 4, cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+    }
+    const int cg = (ctx->screen_group == 8 || ctx->screen_group == 4 || ctx->screen_group == 2) ? ctx->screen_group : 2;
+    for (int t = 1; t <= 2; ++t) {
+        ScreenPlan* tp = nullptr;
+        if (screen_plan_create(ctx, m, d, k, t, &tp) != B2K_OK) { cudaGetLastError(); break; }
+        int rc = screen_assign(tp, xs.as<float>(), m, dC, ls.as<int32_t>(), nullptr, 0);
+        double groups = 0, fb = 0;
+        if (rc == B2K_OK) rc = screen_read_stats(tp, &groups, &fb);
+        screen_plan_destroy(tp);
+        if (rc != B2K_OK) return rc;
+        ctx->stat_probe_centers[t] = groups * cg / (double)m;
+        ctx->stat_probe_fallback[t] = fb / (double)m;
+        // a candidate center costs the verify ~4d bytes of L2 traffic, a dropped term saves k*d MMA flops per frame
+        if (fb <= 0.002 * m && groups * cg <= (double)ctx->probe_max_centers * m) { *terms_out = t; break; }
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B2K_OK;
+}
+
+
+// Listed screen (prune.cu): the plan's frames are the session's SORTED frames; tile t meets the centers tlist[t][0 .. tcount[t]).
+// Labels come out in the frames' (sorted) order.
+int screen_assign_listed(ScreenPlan* p, const float* dX, int64_t n, const float* dC, const uint16_t* tlist,
+                         const uint32_t* tcount, int lcap, int32_t* labels, int lloyd) {
+    b2k_ctx* ctx = p->ctx;
+    cudaStream_t st = ctx->stream;
+    if (p->prepared_n != n) B2K_TRY(screen_prepare_frames_with_centers(p, dX, n, dC));
+    CUDA_TRY(cudaMemsetAsync(&p->params->cmax2_now, 0, 8, st));
+    CUDA_TRY(cudaMemsetAsync(&p->params->cand_chunks, 0, 24, st));
+    screen_centers_kernel<<<(unsigned)cdiv(p->k_rows, 128), 128, 0, st>>>(dC, p->k, p->k_rows, p->d, p->terms, p->Kp,
+                                                                          p->mu, p->params, p->B);
+    LAUNCH_CHECK();
+    screen_finish_centers_kernel<<<1, 1, 0, st>>>(p->params, p->d);
+    LAUNCH_CHECK();
+    GemmArgs g;
+    g.n = n;
+    g.n_tiles = (int)cdiv(n, TILE_M);
+    g.n_ntiles = 0;
+    g.n_kblocks = p->Kp / BLOCK_K;
+    g.nk16 = p->nk16;
+    g.d = p->d;
+    g.terms = p->terms;
+    g.X2 = p->X2;
+    g.XL = p->XL;
+    g.prm = p->params;
+    g.cand = p->cand;
+    g.ncand = p->ncand;
+    g.resident = 0;
+    g.cluster2 = 0;
+    g.bres_bytes = 0;
+    g.stage_bytes = STAGE_BYTES;
+    const size_t tail = sizeof(GemmSmemTail) + 1024;
+    g.n_stages = (int)std::min<size_t>(MAX_STAGES, (ctx->smem_optin - tail) / STAGE_BYTES);
+    const size_t smem = tail + (size_t)g.n_stages * STAGE_BYTES;
+    ListArgs la;
+    la.tlist = tlist;
+    la.tcount = tcount;
+    la.lcap = lcap;
+    la.B = p->B;
+    la.Kp = p->Kp;
+    la.gather = ctx->screen_gather;
+    static PerDeviceOnce attr_set;
+    if (attr_set.need(ctx->device)) {
+        CUDA_TRY(cudaFuncSetAttribute(screen_gemm_listed_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(screen_gemm_listed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(screen_gemm_listed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        attr_set.done(ctx->device);
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>(g.n_tiles, ctx->sm_count);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->profile) {
+        CUDA_TRY(cudaEventCreate(&ev0));
+        CUDA_TRY(cudaEventCreate(&ev1));
+        CUDA_TRY(cudaEventRecord(ev0, st));
+    }
+    if (p->cg == 8) screen_gemm_listed_kernel<8><<<grid, LISTED_THREADS, smem, st>>>(p->tmA, p->tmBg, g, la);
+    else if (p->cg == 4) screen_gemm_listed_kernel<4><<<grid, LISTED_THREADS, smem, st>>>(p->tmA, p->tmBg, g, la);
+    else screen_gemm_listed_kernel<2><<<grid, LISTED_THREADS, smem, st>>>(p->tmA, p->tmBg, g, la);
+    LAUNCH_CHECK();
+    if (ctx->profile) {
+        CUDA_TRY(cudaEventRecord(ev1, st));
+        ctx->prof_events.push_back(ev0);
+        ctx->prof_events.push_back(ev1);
+    }
+    const int ds = (p->d + 3) & ~3;
+    const int gstride = GROUP * ds + (((GROUP * ds / 4) & 1) ? 0 : 4);
+    const size_t tbytes = (size_t)cdiv(p->k, GROUP) * gstride * 4;
+    if (p->d <= 16 && tbytes <= 100 * 1024) {
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / tbytes));
+        const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * per_sm));
+#define B2K_VTL(DR)                                                                                                          \
+    do {                                                                                                                     \
+        static PerDeviceOnce vattr;                                                                                          \
+        if (vattr.need(ctx->device)) {                                                                                       \
+            CUDA_TRY(cudaFuncSetAttribute(screen_verify_table_listed_kernel<DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          100 * 1024));                                                                      \
+            vattr.done(ctx->device);                                                                                         \
+        }                                                                                                                    \
+        screen_verify_table_listed_kernel<DR><<<tgrid, 256, tbytes, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, tlist,   \
+                                                                          lcap, labels, lloyd, p->params, p->fb_list,        \
+                                                                          gstride, p->cg,                                    \
+                                                                          row_load_width(dX, p->d, ctx->row_vec_max));       \
+    } while (0)
+        if (ds == 4) B2K_VTL(4);
+        else if (ds == 8) B2K_VTL(8);
+        else if (ds == 12) B2K_VTL(12);
+        else B2K_VTL(16);
+#undef B2K_VTL
+    } else {
+        const bool vec = p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0;
+        const unsigned dgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 32), (int64_t)ctx->sm_count * 8));
+        if (vec)
+            screen_verify_direct_kernel<true><<<dgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, nullptr,
+                                                                     lloyd, p->params, p->fb_list, p->cg, tlist, lcap);
+        else
+            screen_verify_direct_kernel<false><<<dgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, nullptr,
+                                                                      lloyd, p->params, p->fb_list, p->cg, tlist, lcap);
+    }
+    LAUNCH_CHECK();
+    return screen_finish_assign(p, dX, n, dC, labels, nullptr, lloyd);
+}
+
+void screen_plan_invalidate_frames(ScreenPlan* p) { if (p) p->prepared_n = -1; }
+
+int screen_plan_terms(const ScreenPlan* p) { return p ? p->terms : 0; }
 
 int screen_read_stats(ScreenPlan* p, double* cand_chunks, double* fallback_frames) {
     ScreenParams h;

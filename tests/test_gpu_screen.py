@@ -23,8 +23,8 @@ def screen_ctx(b2k):
 
 
 SHAPES = [(5000, 2, 100, 0), (20000, 10, 1000, 1), (20000, 10, 1000, 3), (4096, 3, 257, 0), (3000, 16, 300, 0),
-          (6000, 17, 513, 0), (5000, 64, 2000, 3), (5000, 64, 2000, 1), (2500, 256, 1000, 3), (1000, 300, 64, 0),
-          (129, 5, 40, 0)]
+          (6000, 17, 513, 0), (5000, 64, 2000, 3), (5000, 64, 2000, 1), (5000, 64, 2000, 2), (2500, 256, 1000, 3),
+          (2500, 256, 1000, 2), (2500, 256, 1000, 1), (20000, 10, 1000, 2), (1000, 300, 64, 0), (129, 5, 40, 0)]
 
 
 @pytest.mark.parametrize("n,d,k,terms", SHAPES)
@@ -41,6 +41,29 @@ def test_screen_assign_bit_exact(b2k, oracle, screen_ctx, n, d, k, terms):
             screen_ctx.set_option("verify_mode", vmode)
             got = b2k.assign(X, C)
             np.testing.assert_array_equal(got, ref, err_msg="screen_group=%d verify_mode=%d" % (group, vmode))
+
+
+def test_screen_measured_term_count(b2k, oracle, screen_ctx):
+    """option screen_terms=0: a Lloyd session on wide rows measures the candidate counts of 1 and 2 operand terms on a
+    sample and picks one; whatever it picks, the labels -- and therefore the exact member sums -- do not change"""
+    rng = np.random.RandomState(11)
+    X = blobs(rng, 100_000, 256, 40, spread=3.0, sigma=1.0)
+    C0 = X[rng.choice(len(X), 5000, replace=False)].copy()
+    res = {}
+    screen_ctx.set_option("probe_min_gflop", 100)   # the probe is meant for jobs of >= 1 TFLOP per pass: lower the bar
+    try:
+        for terms in (0, 3):
+            screen_ctx.set_option("screen_terms", terms)
+            res[terms] = b2k.kmeans_cluster_loop(X, C0, 2, 0.0)
+            used = int(screen_ctx.get_stat("screen_terms_used"))
+            assert used == 3 if terms == 3 else used in (1, 2, 3)
+    finally:
+        screen_ctx.set_option("probe_min_gflop", 1000)
+    assert screen_ctx.get_stat("probe_centers_1") > 0          # the probe ran
+    np.testing.assert_array_equal(res[0][0], res[3][0])        # centers bit-identical
+    np.testing.assert_array_equal(res[0][3], res[3][3])        # inertias too
+    rc, rcode, rit, rin = oracle.cluster_loop(X, C0, 2, 0.0, n_threads=16, acc="f64")
+    assert np.abs(res[0][0] - rc).max() <= 1e-5 * np.abs(rc).max()
 
 
 def test_screen_offset_data_and_ties(b2k, oracle, screen_ctx):

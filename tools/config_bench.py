@@ -92,6 +92,8 @@ def lloyd_and_assign(ctx, X, k, reps, label):
     gemm_ms = ctx.get_stat("screen_gemm_ms_total") if gl else None
     groups = ctx.get_stat("screen_cand_chunks")
     fb = ctx.get_stat("screen_fallback_frames")
+    terms_used = ctx.get_stat("screen_terms_used")
+    probe = {t: [ctx.get_stat("probe_centers_%d" % t), ctx.get_stat("probe_fallback_%d" % t)] for t in (1, 2)}
     ctx.set_option("profile", 0)
     lib.b2k_dev_lloyd_destroy(sess)
 
@@ -103,7 +105,7 @@ def lloyd_and_assign(ctx, X, k, reps, label):
     out = {"cfg": label, "n": n, "d": d, "k": k, "lloyd_ms_per_iter": ms_step, "lloyd_frames_per_s": n / ms_step * 1e3,
            "assign_ms_cold_plan": ms_assign, "assign_frames_per_s": n / ms_assign * 1e3,
            "screen_gemm_ms_per_iter": gemm_ms, "cand_groups_per_frame": groups / n if gl else None,
-           "fallback_frames": fb,
+           "fallback_frames": fb, "terms_used": terms_used, "probe_centers_fallback": probe,
            "tensor_frac_step": flops / (ms_step * 1e-3) / 1e12 / TF,
            "tensor_frac_gemm": (flops / (gemm_ms * 1e-3) / 1e12 / TF) if gemm_ms else None,
            "cost_first_last": [costs[0], costs[-1]]}
