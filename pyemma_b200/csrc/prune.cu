@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) tile_lists_cc_kernel(const float* __restr
 struct PruneState {
     b2k_ctx* ctx = nullptr;
     int64_t n = 0;
-    int d = 0, k = 0, n_tiles = 0, lcap = 0, pad_to = 64;
+    int d = 0, k = 0, n_tiles = 0, lcap = 0, pad_to = 32;
     DevMem Xs, perm, perm2, sigma, seg, labels_s, labels_t, tmean, trad, tlist, tcount, stats, cc;
     bool sorted = false;
 };

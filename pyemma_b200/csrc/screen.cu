@@ -1076,7 +1076,7 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             mbar_init(&T->full_bar[s], la.gather == 0 ? 1 + GATHER_WARPS : 1);
             mbar_init(&T->empty_bar[s], 1);
         }
-        for (int s = 0; s < 2; ++s) { mbar_init(&T->tfull_bar[s], 1); mbar_init(&T->tempty_bar[s], EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&T->tfull_bar[s], 1); mbar_init(&T->tempty_bar[s], EPI_WARPS / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1221,18 +1221,22 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         // ===== MMA issuer =====
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0, it = 0;
+            uint32_t phase = 0;
+            uint32_t uses[2] = {0u, 0u};  // passes each accumulator stage has carried
+            uint32_t seq = 0;             // tile sequence number of this CTA: stage (and epilogue team) seq & 1
             int tile = blockIdx.x;
             int cnt = tile < g.n_tiles ? (int)__ldg(la.tcount + tile) : 0;
             int ncnt = 0;
-            for (; tile < g.n_tiles; tile += gridDim.x, cnt = ncnt) {
+            for (; tile < g.n_tiles; tile += gridDim.x, cnt = ncnt, ++seq) {
                 const int ntile = tile + (int)gridDim.x;
                 ncnt = ntile < g.n_tiles ? (int)__ldg(la.tcount + ntile) : 0;  // one tile ahead
-                for (int p0 = 0; p0 < cnt; p0 += TILE_N, ++it) {
+                const uint32_t acc = seq & 1u;
+                for (int p0 = 0; p0 < cnt; p0 += TILE_N) {
                     const int rows = min(TILE_N, cnt - p0);
                     // instruction descriptor: D=f32, A=B=f16, K-major both, N=rows, M=128
                     const uint32_t idesc = (1u << 4) | ((uint32_t)(rows >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-                    const uint32_t acc = it & 1u, accphase = (it >> 1) & 1u;
+                    const uint32_t accphase = (acc ? uses[1] : uses[0]) & 1u;
+                    if (acc) ++uses[1]; else ++uses[0];
                     mbar_wait(&T->tempty_bar[acc], accphase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * TILE_N;
@@ -1254,21 +1258,24 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             }
         }
     } else {
-        // ===== epilogue: one frame (TMEM lane) per thread, column half h takes the chunks h, h+2, ... of every pass =====
+        // ===== epilogue: two TEAMS of four warps (one per TMEM lane quarter).  Team t owns accumulator stage t and
+        // every second tile of this CTA: one thread scans ALL chunks of its frame, so there are no column halves to
+        // merge and no barrier between the eight warps; while one team finishes a tile (threshold, candidate entries,
+        // stores) and waits for its stage to be refilled, the other one keeps the TMEM read port busy. =====
         const int q = warp & 3;
-        const int h = (warp - 2) >> 2;
+        const int team = (warp - 2) >> 2;
         const int row = q * 32 + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint32_t* lid = &T->list_id[h][0][row];
-        float* lv = &T->list_v[h][0][row];
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(team * TILE_N);
+        uint32_t* lid = &T->list_id[team][0][row];
+        float* lv = &T->list_v[team][0][row];
         const float C = g.prm->cmax, CL = g.prm->cl;
         const int valid_ops = g.prm->valid;
-        uint32_t it = 0;
+        uint32_t uses = 0;  // passes this team's accumulator stage has carried
         float va[32], vb[32];
-        bool par = false;       // the buffer that holds (or receives) the current chunk: false = va
-        bool primed = false;    // the first chunk of the current pass was already requested by the previous pass
+        bool par = false;   // the buffer that holds (or receives) the current chunk: false = va
+        const int tstep = 2 * (int)gridDim.x;
+        int tile = blockIdx.x + team * (int)gridDim.x;
         // per-tile metadata one tile ahead (see the gather warps)
-        int tile = blockIdx.x;
         int cnt = 0, ncnt = 0;
         float x2 = 0.f, xl = 0.f, nx2 = 0.f, nxl = 0.f;
         if (tile < g.n_tiles) {
@@ -1276,9 +1283,9 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             const int64_t gr = (int64_t)tile * TILE_M + row;
             if (gr < g.n) { x2 = __ldg(g.X2 + gr); if (g.terms != 3) xl = __ldg(g.XL + gr); }
         }
-        for (; tile < g.n_tiles; tile += gridDim.x, cnt = ncnt, x2 = nx2, xl = nxl) {
+        for (; tile < g.n_tiles; tile += tstep, cnt = ncnt, x2 = nx2, xl = nxl) {
             const int64_t grow = (int64_t)tile * TILE_M + row;
-            const int next_tile = tile + (int)gridDim.x;
+            const int next_tile = tile + tstep;
             ncnt = 0; nx2 = 0.f; nxl = 0.f;
             if (next_tile < g.n_tiles) {
                 ncnt = (int)__ldg(la.tcount + next_tile);
@@ -1289,77 +1296,45 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             mg.init(x2, xl, C, CL, g.d, g.nk16, g.terms);
             RowScan rs;
             rs.init();
-            for (int p0 = 0; p0 < cnt; p0 += TILE_N, ++it) {
-                const int nmine = min(TILE_N, cnt - p0) / (2 * CHUNK);   // my chunks of this pass (>= 1)
-                const uint32_t acc = it & 1u;
-                const uint32_t taddr = lane_addr + acc * TILE_N + (uint32_t)(h * CHUNK);
-                const uint32_t cbase = (uint32_t)(p0 / CHUNK + h);
-                if (!primed) {
-                    mbar_wait(&T->tfull_bar[acc], (it >> 1) & 1u);
-                    tc_fence_after();
-                    if (par) tmem_ld32(taddr, vb); else tmem_ld32(taddr, va);
-                }
-                primed = false;
-                // is there a pass after this one (same tile or the CTA's next tile)?
-                const bool more = (p0 + TILE_N < cnt) || ncnt != 0;
-                for (int i = 0; i < nmine; ++i) {
+            for (int p0 = 0; p0 < cnt; p0 += TILE_N, ++uses) {
+                const int nch = min(TILE_N, cnt - p0) / CHUNK;   // >= 1
+                const uint32_t cbase = (uint32_t)(p0 / CHUNK);
+                mbar_wait(&T->tfull_bar[team], uses & 1u);
+                tc_fence_after();
+                if (par) tmem_ld32(taddr0, vb); else tmem_ld32(taddr0, va);
+                for (int c = 0; c < nch; ++c) {
                     tmem_ld_wait();
                     if (par) tmem_ld_fence(vb); else tmem_ld_fence(va);
-                    if (i + 1 < nmine) {
-                        if (par) tmem_ld32(taddr + (uint32_t)((i + 1) * 2 * CHUNK), va);
-                        else tmem_ld32(taddr + (uint32_t)((i + 1) * 2 * CHUNK), vb);
+                    if (c + 1 < nch) {
+                        if (par) tmem_ld32(taddr0 + (uint32_t)((c + 1) * CHUNK), va);
+                        else tmem_ld32(taddr0 + (uint32_t)((c + 1) * CHUNK), vb);
                     } else {
-                        // my last load of this accumulator stage has landed: hand it back, then request the first chunk
-                        // of the next pass while this one is scanned
+                        // the last load of this pass has landed: the MMA thread may refill the stage
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&T->tempty_bar[acc]);
-                        if (more) {
-                            const uint32_t nit = it + 1, nacc = nit & 1u;
-                            mbar_wait(&T->tfull_bar[nacc], (nit >> 1) & 1u);
-                            tc_fence_after();
-                            const uint32_t naddr = lane_addr + nacc * TILE_N + (uint32_t)(h * CHUNK);
-                            if (par) tmem_ld32(naddr, va); else tmem_ld32(naddr, vb);
-                            primed = true;
-                        }
+                        if (lane == 0) mbar_arrive(&T->tempty_bar[team]);
                     }
-                    if (par) scan_chunk<CG>(vb, cbase + (uint32_t)(2 * i), rs, mg, lid, lv);
-                    else scan_chunk<CG>(va, cbase + (uint32_t)(2 * i), rs, mg, lid, lv);
+                    if (par) scan_chunk<CG>(vb, cbase + (uint32_t)c, rs, mg, lid, lv);
+                    else scan_chunk<CG>(va, cbase + (uint32_t)c, rs, mg, lid, lv);
                     par = !par;
                 }
             }
-            // ---- merge the two column halves of this frame (as in screen_gemm_kernel) ----
-            T->half_m[h][row] = rs.m;
-            named_bar_sync(1, EPI_WARPS * 32);
-            const float m = fmaxf(T->half_m[0][row], T->half_m[1][row]);
-            const float thr = mg.threshold(m);
-            {
+            if (grow < g.n) {
+                // entries still above the final threshold, in scan (= ascending chunk) order
+                const float thr = rs.thr;
+                uint32_t ids[CAND_CAP] = {0, 0, 0, 0, 0, 0, 0, 0};
                 int kept = 0;
                 for (int t = 0; t < rs.cnt; ++t) {
                     if (lv[t * TILE_M] >= thr) {
-                        if (kept < CAND_CAP) T->out_id[h][kept][row] = lid[t * TILE_M];
+                        const uint32_t e = lid[t * TILE_M];
+#pragma unroll
+                        for (int w = 0; w < CAND_CAP; ++w)
+                            if (w == kept) ids[w] = e;
                         ++kept;
                     }
                 }
-                if (rs.overflow || kept > CAND_CAP) kept = CAND_CAP + 1;
-                T->out_n[h][row] = (uint32_t)kept;
-            }
-            named_bar_sync(2, EPI_WARPS * 32);
-            if (h == 0 && grow < g.n) {
-                const int n0 = (int)T->out_n[0][row], n1 = (int)T->out_n[1][row];
-                uint32_t ids[CAND_CAP] = {0, 0, 0, 0, 0, 0, 0, 0};
-                int kept = n0 + n1;
-                bool overflow = n0 > CAND_CAP || n1 > CAND_CAP || kept > CAND_CAP || kept == 0 || !(m > -3.0e38f) ||
-                                !valid_ops || !(x2 < 3.0e38f);
-                if (!overflow) {
-                    int a = 0, b = 0;
-                    for (int w = 0; w < kept; ++w) {
-                        const uint32_t ia = a < n0 ? T->out_id[0][a][row] : 0xffffffffu;
-                        const uint32_t ib = b < n1 ? T->out_id[1][b][row] : 0xffffffffu;
-                        if (a < n0 && (b >= n1 || (ia & cand_id_mask(CG)) < (ib & cand_id_mask(CG)))) { ids[w] = ia; ++a; }
-                        else { ids[w] = ib; ++b; }
-                    }
-                }
+                const bool overflow = rs.overflow || kept > CAND_CAP || kept == 0 || !(rs.m > -3.0e38f) || !valid_ops ||
+                                      !(x2 < 3.0e38f);
                 uint4* cout = reinterpret_cast<uint4*>(g.cand + grow * CAND_CAP);
                 cout[0] = make_uint4(ids[0], ids[1], ids[2], ids[3]);
                 if (kept > 4 && !overflow) cout[1] = make_uint4(ids[4], ids[5], ids[6], ids[7]);
