@@ -157,6 +157,13 @@ int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dcenters, int32_t
  * and its member sums are added to acc while the next chunk is on the bus; labels also go to labels_host if given */
 int b2k_stage_lloyd_assign_accumulate(b2k_lloyd* s, const float* X, const float* dcenters, float* dX_out,
                                       int32_t* dlabels_out, int32_t* labels_host_or_null, int64_t* dacc);
+/* Out-of-core tier (the reference spills to a host memmap when the array does not fit, kmeans.py:181-200): create the
+ * session with dX = NULL, keep the frames in (pinned) host memory and run ONE pass per iteration.  Per chunk: if
+ * have_prev, the cost of the previous labels (dlabels_io on entry) against dcenters -- the cost of the iteration that
+ * produced dcenters -- is added to the cost slot; the chunk is assigned (dlabels_io on exit, labels_host if given); its
+ * member sums and counts are added to acc.  acc and cost are bit-identical to the resident calls'. */
+int b2k_stage_lloyd_pass(b2k_lloyd* s, const float* X, const float* dcenters, int32_t* dlabels_io, int have_prev,
+                         int32_t* labels_host_or_null, int64_t* dacc);
 /* acc <- local sums+counts for GIVEN labels (e.g. those b2k_stage_assign produced); cost slot zeroed */
 int b2k_dev_lloyd_accumulate(b2k_lloyd* s, const int32_t* dlabels, int64_t* dacc);
 /* new centers from (all-reduced) acc; count==0 keeps old */

@@ -101,6 +101,7 @@ def load():
         L.b2k_dev_kmeans_init_centers_kmpp_sharded.argtypes = [vp, vp, i64, i32, i32, C.c_int, i64, i64, i64, vp, i64, vp,
                                                                EXCHANGE, vp, CALLBACK, vp, vp, vp]
         L.b2k_stage_lloyd_assign_accumulate.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.b2k_stage_lloyd_pass.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
         L.b2k_upload.argtypes = [vp, vp, vp, i64]
         L.b2k_dev_project.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, vp]
         L.b2k_stage_project.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, vp]

@@ -14,6 +14,7 @@ What changes:
 """
 import ctypes as C
 import math
+import os
 import random
 
 import numpy as np
@@ -97,12 +98,27 @@ class KmeansClustering(AbstractClustering):
         lengths = iterable.trajectory_lengths(stride=stride, skip=self.skip)
         total = int(np.sum(lengths))
         need = total * iterable.dimension() * 4 // ws
+        if self.init_strategy == "kmeans++" and not self._check_resume_iteration():
+            # k-means++ scratch next to the frames: m = 2+ln k distance rows, D^2, labels, candidate masks
+            need += (total // ws) * 4 * (6 + int(math.log(max(int(self.n_clusters or 1), 1))))
         free, _tot = torch.cuda.mem_get_info(staging.device())
-        if need > free * 0.9:
-            # kmeans.py:181-200 falls back to a host memmap; there is no slower tier below HBM here
-            self.logger.warning("K-means failed to load all the data (%d bytes required, %d available) into HBM. "
-                                "Consider using a larger stride or more GPUs.", need, free)
-            raise MemoryError()
+        budget = int(os.environ.get("B2K_HBM_BUDGET_BYTES", "0")) or int(free * 0.9)
+        self._host_frames = None
+        if need > budget:
+            # kmeans.py:181-200 spills to a host memmap (oom_strategy='memmap'); here the tier below HBM is pinned host
+            # memory: the frames stay there and pass through the device once per Lloyd iteration (_lloyd_out_of_core)
+            if self.oom_strategy != "memmap":
+                self.logger.warning("K-means failed to load all the data (%d bytes required, %d available) into HBM. "
+                                    "Consider using a larger stride or more GPUs.", need, budget)
+                raise MemoryError()
+            self.logger.warning("K-means: %d bytes do not fit the HBM budget of %d bytes; the frames stay in pinned host "
+                                "memory and are streamed through the device every iteration.", need, budget)
+            X, n_total, lo = staging.gather_frames(iterable, stride=stride, skip=self.skip, chunksize=self.chunksize,
+                                                   rank=rank, world_size=ws, to_host=True)
+            self._host_frames, self._dev_frames = X, None
+            self._dev_n_total, self._dev_lo = n_total, lo
+            self._in_memory_chunks_set = False
+            return
         X, n_total, lo = staging.gather_frames(iterable, stride=stride, skip=self.skip, chunksize=self.chunksize,
                                                rank=rank, world_size=ws)
         self._dev_frames, self._dev_n_total, self._dev_lo = X, n_total, lo
@@ -145,6 +161,8 @@ class KmeansClustering(AbstractClustering):
         if not resume and self.init_strategy == "uniform":
             self.initial_centers_ = self._uniform_picks(iterable)
         self._gather(iterable)
+        if getattr(self, "_host_frames", None) is not None:
+            return self._estimate_out_of_core(iterable, lengths, total_length, resume, stride)
         X = self._dev_frames
         n_local, d = X.shape
         k = int(self.n_clusters)
@@ -218,6 +236,115 @@ class KmeansClustering(AbstractClustering):
             if not self.keep_data or self._converged:
                 self._dev_frames = None
                 self._in_memory_chunks_set = False
+        if self._converged:
+            self.logger.debug("Cluster centers converged after %i steps.", len(self.inertias_))
+        else:
+            self.logger.warning("Algorithm did not reach convergence criterion"
+                                " of %g in %i iterations. Consider increasing max_iter.",
+                                self.tolerance, self.max_iter)
+        return self
+
+    # ---- the tier below HBM -------------------------------------------------------------------------------------------
+    def _estimate_out_of_core(self, iterable, lengths, total_length, resume, stride):
+        """Lloyd iterations over frames that stay in pinned host memory (kmeans.py:181-200 runs the same loop over a host
+        memmap).  One pass over PCIe per iteration (b2k_stage_lloyd_pass: the cost of iteration i is taken during the
+        pass of iteration i+1, when its labels and centers meet the frames again), every sum an exact integer, so
+        centers, inertias, iteration count and dtrajs are bit-identical to the resident path.  k-means++ seeding needs
+        k passes over all frames; out of core it runs on the largest strided subset of the frames that fits HBM
+        (logged: the reference would seed on all frames)."""
+        import torch.distributed as dist
+        hx = self._host_frames
+        n_local, d = hx.shape
+        k = int(self.n_clusters)
+        if k > total_length:
+            raise ValueError("n_clusters=%d larger than the number of frames %d" % (k, total_length))
+        rank, ws = staging.world()
+        ctx = _lib.context()
+        dev = staging.device(ctx)
+        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        metric = _lib.metric_id(self.metric)
+        lib = ctx.lib
+        hnp = hx.numpy()
+        absmax = 0.0
+        for a in range(0, n_local, 1 << 20):
+            blk = hnp[a:a + (1 << 20)]
+            if not np.isfinite(blk).all():
+                raise _lib.InvalidDataInStreamException("Found invalid values (NaN/inf) in the input frames")
+            absmax = max(absmax, float(np.abs(blk).max()))
+        if resume:
+            centers = torch.from_numpy(np.array(self.clustercenters, dtype=np.float32)).to(dev)
+        elif self.init_strategy == "uniform":
+            centers = torch.from_numpy(self.initial_centers_).to(dev)
+        else:
+            if ws > 1:
+                raise NotImplementedError("out-of-core k-means++ seeding is single-GPU; pass clustercenters or use more GPUs")
+            free, _tot = torch.cuda.mem_get_info(dev)
+            budget = int(os.environ.get("B2K_HBM_BUDGET_BYTES", "0")) or int(free * 0.9)
+            per_frame = 4 * d + 4 * (6 + int(math.log(max(k, 1))))
+            sub = max(1, -(-n_local * per_frame // max(budget, per_frame * k)))
+            self.logger.warning("out-of-core k-means++: seeding on every %d-th frame (%d frames)", sub, len(hnp[::sub]))
+            Xs = torch.from_numpy(np.ascontiguousarray(hnp[::sub])).to(dev)
+            centers = torch.empty((k, d), dtype=torch.float32, device=dev)
+            _lib.check(lib.b2k_dev_kmeans_init_centers_kmpp(
+                ctx.handle, C.c_void_p(Xs.data_ptr()), Xs.shape[0], d, k, metric, int(self.fixed_seed), _lib.KMPP_BLOCKED,
+                _lib.CALLBACK(0), None, C.c_void_p(centers.data_ptr()), None))
+            del Xs
+            self.initial_centers_ = centers.cpu().numpy()
+        if resume:
+            self.initial_centers_ = np.array(self.clustercenters, dtype=np.float32)
+        am = torch.tensor([absmax, float(centers.abs().max())], dtype=torch.float32, device=dev)
+        if ws > 1:
+            dist.all_reduce(am, op=dist.ReduceOp.MAX)
+        sess = C.c_void_p()
+        _lib.check(lib.b2k_dev_lloyd_create(ctx.handle, None, n_local, d, k, metric, total_length, C.c_float(float(am.max())),
+                                            C.byref(sess)))
+        try:
+            acc_len = int(lib.b2k_dev_lloyd_acc_len(sess))
+            acc = torch.zeros(acc_len, dtype=torch.int64, device=dev)
+            labels = torch.empty(max(n_local, 1), dtype=torch.int32, device=dev)
+            cur = centers.contiguous().clone()
+            nxt = torch.empty_like(cur)
+            it, converged, prev, have_prev = 0, False, np.float32(0), 0
+            inertias = []
+            tol = np.float32(self.tolerance)
+            while True:
+                _lib.check(lib.b2k_stage_lloyd_pass(sess, C.c_void_p(hx.data_ptr()), C.c_void_p(cur.data_ptr()),
+                                                    C.c_void_p(labels.data_ptr()), have_prev, None, C.c_void_p(acc.data_ptr())))
+                if ws > 1:
+                    dist.all_reduce(acc)
+                if have_prev:  # this pass measured the cost of the iteration that produced `cur`
+                    cost = np.float32(lib.b2k_dev_lloyd_decode_cost(sess, int(acc[acc_len - 1].item())))
+                    inertias.append(cost)
+                    rel = np.float32(abs(cost - prev) / cost) if cost != 0 else np.float32(0)
+                    prev = cost
+                    if rel <= tol:
+                        converged = True
+                    elif self.show_progress:
+                        self._progress_update(1, stage=1)
+                    it += 1
+                    if not (it < self.max_iter and not converged):
+                        break  # `labels` = the assignment to the final centers `cur`: the dtrajs
+                _lib.check(lib.b2k_dev_lloyd_finalize(sess, C.c_void_p(acc.data_ptr()), C.c_void_p(cur.data_ptr()),
+                                                      C.c_void_p(nxt.data_ptr())))
+                cur, nxt = nxt, cur
+                have_prev = 1
+        finally:
+            lib.b2k_dev_lloyd_destroy(sess)
+        self.clustercenters = cur.cpu().numpy()
+        self._converged = converged
+        self.inertias_ = np.asarray(inertias, dtype=np.float32)
+        if stride == 1:
+            lab = labels[:n_local]
+            if ws > 1:
+                lab = staging.all_gather_shards(lab, total_length, rank, ws)
+            host = lab.cpu().numpy()
+            out, off = [], 0
+            for L in lengths:
+                out.append(host[off:off + int(L)].copy())
+                off += int(L)
+            self._dtrajs = out
+            self._previous_stride = 1
+        self._host_frames = None
         if self._converged:
             self.logger.debug("Cluster centers converged after %i steps.", len(self.inertias_))
         else:

@@ -261,8 +261,10 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "probe_max_centers")) c->probe_max_centers = (int)value;
     else if (!strcmp(name, "probe_min_gflop")) c->probe_min_gflop = (int)value;
     else if (!strcmp(name, "screen_gather")) c->screen_gather = (int)value;
+    else if (!strcmp(name, "rmsd_abandon")) c->rmsd_abandon = (int)value;
     else if (!strcmp(name, "prune_mode")) c->prune_mode = (int)value;
     else if (!strcmp(name, "prune_resort")) c->prune_resort = (int)value;
+    else if (!strcmp(name, "prune_unit_shift")) c->prune_unit_shift = (int)value;
     else if (!strcmp(name, "screen_group")) c->screen_group = (int)value;
     else if (!strcmp(name, "screen_resident_a")) c->screen_resident_a = (int)value;
     else if (!strcmp(name, "screen_cluster")) c->screen_cluster = (int)value;
@@ -380,8 +382,14 @@ B2K_API int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, 
     B2K_TRY(pc.prepare(ctx, dC, k, d, metric));
     DevMem ga;
     if (metric == B2K_METRIC_MINRMSD) {
-        B2K_TRY(ga.alloc((size_t)n * 4));
-        B2K_TRY(launch_rmsd_center(ctx, dX, n, d, nullptr, ga.as<float>()));
+        // traces of the centred frames: a grow-only slot of the context (no allocation per call)
+        B2K_TRY(ctx->slot(b2k_ctx::SLOT_CHUNK_G0, (size_t)n * 4, &ga.p));
+        float* ga_slot = (float*)ga.p;
+        ga.p = nullptr;  // not owned: ~DevMem must not free a slot
+        B2K_TRY(launch_rmsd_center(ctx, dX, n, d, nullptr, ga_slot));
+        B2K_TRY(assign_any(ctx, dX, ga_slot, n, d, pc, k, metric, dlabels, dmind, 0));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the centred centers (pc) die with this frame
+        return B2K_OK;
     } else if (ctx->engine != B2K_ENGINE_DIRECT && screen_supported(ctx, d, k, n)) {
         // the plan (fp16 operand + candidate lists, Kp*2 + ~41 bytes per frame) is sized to what is free: frames beyond
         // its capacity are assigned piece by piece through the same plan
@@ -419,9 +427,13 @@ B2K_API int b2k_dev_assign(b2k_ctx* ctx, const float* dX, int64_t n, int32_t d, 
 // chunk c (compute stream) and the D2H of chunk c-1's labels.  With dX_keep / dL_keep the chunks (and their
 // labels) additionally stay resident in one device array, which is how b2k_kmeans_cluster gets its frames
 // into HBM while the assignment of the first chunks is already running.
+// dprev / cost_slot (out-of-core Lloyd pass): before a chunk is assigned, the squared distances of its frames to the
+// centers their PREVIOUS labels (dprev, device, n ints; may alias dL_keep) name are added to *cost_slot (exact integer
+// sum, cost_scale) -- the cost of the previous iteration, taken while the frames are on the device anyway.
 static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, const float* dC, int32_t k, int metric,
                          int32_t* labels, int lloyd, float* dX_keep, int32_t* dL_keep, double acc_scale = 0.0,
-                         int64_t* dacc = nullptr) {
+                         int64_t* dacc = nullptr, const int32_t* dprev = nullptr, double cost_scale = 0.0,
+                         int64_t* cost_slot = nullptr) {
     cudaStream_t st = ctx->stream;
     PreparedCenters pc;
     B2K_TRY(pc.prepare(ctx, dC, k, d, metric));
@@ -439,6 +451,8 @@ static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, con
         if (!dL_keep) B2K_TRY(ctx->slot(b2k_ctx::SLOT_CHUNK_L0 + s, (size_t)cf * 4, (void**)&dL[s]));
         if (metric == B2K_METRIC_MINRMSD) B2K_TRY(ctx->slot(b2k_ctx::SLOT_CHUNK_G0 + s, (size_t)cf * 4, (void**)&dG[s]));
     }
+    float* dist_buf = nullptr;  // per-frame distances of the cost pass (wide rows / minRMSD)
+    if (cost_slot) B2K_TRY(ctx->slot(b2k_ctx::SLOT_LABELS, (size_t)cf * 4, (void**)&dist_buf));
     const bool use_screen = metric == B2K_METRIC_EUCLIDEAN && ctx->engine != B2K_ENGINE_DIRECT &&
                             screen_supported(ctx, d, k, cf);
     ScreenPlan* plan = nullptr;
@@ -473,12 +487,27 @@ static int stream_assign(b2k_ctx* ctx, const float* X, int64_t n, int32_t d, con
         cudaStreamWaitEvent(st, ctx->ev_h2d[s], 0);
         if (d_finite) rc = launch_all_finite(ctx, dx, len * d, d_finite);
         if (rc != B2K_OK) break;
+        if (metric == B2K_METRIC_MINRMSD) rc = launch_rmsd_center(ctx, dx, len, d, nullptr, dG[s]);
+        if (rc == B2K_OK && cost_slot) {  // cost of the previous labels against these centers, before dl is overwritten
+            const int32_t* pl = dprev + off;
+            if (metric == B2K_METRIC_MINRMSD) {
+                rc = launch_rmsd_labeled_dist(ctx, dx, dG[s], len, d, pc.C, pc.Gb, pl, dist_buf);
+                if (rc == B2K_OK) rc = launch_cost_reduce(ctx, dist_buf, len, cost_scale, cost_slot);
+            } else {
+                int fused = 0;
+                rc = launch_cost_fused(ctx, dx, len, d, dC, k, pl, cost_scale, cost_slot, &fused);
+                if (rc == B2K_OK && !fused) {
+                    rc = launch_labeled_dist(ctx, dx, len, d, dC, pl, dist_buf);
+                    if (rc == B2K_OK) rc = launch_cost_reduce(ctx, dist_buf, len, cost_scale, cost_slot);
+                }
+            }
+        }
+        if (rc != B2K_OK) break;
         if (use_screen) {
             rc = screen_prepare_frames(plan, dx, len);
             if (rc == B2K_OK) rc = screen_assign(plan, dx, len, dC, dl, nullptr, lloyd);
         } else {
-            if (metric == B2K_METRIC_MINRMSD) rc = launch_rmsd_center(ctx, dx, len, d, nullptr, dG[s]);
-            if (rc == B2K_OK) rc = assign_any(ctx, dx, dG[s], len, d, pc, k, metric, dl, nullptr, lloyd);
+            rc = assign_any(ctx, dx, dG[s], len, d, pc, k, metric, dl, nullptr, lloyd);
         }
         // member sums of this chunk while the next one is on the bus (exact integer sums: any chunking gives the same bits)
         if (rc == B2K_OK && dacc) rc = launch_accumulate(ctx, dx, len, d, k, dl, acc_scale, dacc);
@@ -578,8 +607,9 @@ static void lloyd_scales(float absmax_global, int64_t n_total, int d, int* q_sum
 
 B2K_API int b2k_dev_lloyd_create(b2k_ctx* ctx, const float* dX, int64_t n_local, int32_t d, int32_t k, int metric,
                                  int64_t n_total, float absmax_global, b2k_lloyd** out) {
-    if (!ctx || !out || n_local < 0 || d < 1 || k < 1 || n_total < n_local || (n_local > 0 && !dX))
+    if (!ctx || !out || n_local < 0 || d < 1 || k < 1 || n_total < n_local)
         return set_error(B2K_ERR_INVALID_ARG, "lloyd_create: bad arguments");
+    const bool staged_only = n_local > 0 && !dX;  // out-of-core session: only b2k_stage_lloyd_pass / finalize / decode_cost
     if (!std::isfinite(absmax_global))
         return set_error(B2K_ERR_NONFINITE, "lloyd_create: data contains NaN or inf");
     B2K_TRY(check_metric_dim(metric, d));
@@ -589,12 +619,12 @@ B2K_API int b2k_dev_lloyd_create(b2k_ctx* ctx, const float* dX, int64_t n_local,
     lloyd_scales(absmax_global, n_total, d, &s->q_sum, &s->q_cost);
     s->scale_sum = std::ldexp(1.0, s->q_sum);
     s->scale_cost = std::ldexp(1.0, s->q_cost);
-    int rc = s->l.alloc((size_t)std::max<int64_t>(n_local, 1) * 4);
-    if (rc == B2K_OK && metric == B2K_METRIC_MINRMSD) {
+    int rc = staged_only ? B2K_OK : s->l.alloc((size_t)std::max<int64_t>(n_local, 1) * 4);
+    if (rc == B2K_OK && metric == B2K_METRIC_MINRMSD && !staged_only) {
         rc = s->Ga.alloc((size_t)std::max<int64_t>(n_local, 1) * 4);
         if (rc == B2K_OK) rc = launch_rmsd_center(ctx, dX, n_local, d, nullptr, s->Ga.as<float>());
     }
-    if (rc == B2K_OK && metric == B2K_METRIC_EUCLIDEAN && ctx->engine != B2K_ENGINE_DIRECT &&
+    if (rc == B2K_OK && !staged_only && metric == B2K_METRIC_EUCLIDEAN && ctx->engine != B2K_ENGINE_DIRECT &&
         screen_supported(ctx, d, k, n_local)) {
         s->plan_pending = true;
         s->prune_wanted = prune_supported(ctx, n_local, d, k);
@@ -640,10 +670,30 @@ B2K_API int b2k_stage_lloyd_assign_accumulate(b2k_lloyd* s, const float* X, cons
                          lloyd_scale_sum(s), dacc);
 }
 
+// Out-of-core Lloyd pass (the tier below HBM; the reference spills to a host memmap, kmeans.py:181-200): the session was
+// created with dX = NULL, the frames live in (pinned) host memory and only pass through the two chunk slots.  One pass
+// per iteration: for every chunk (a) if have_prev, the cost of the PREVIOUS labels (dlabels_io on entry) against
+// dcenters -- i.e. the cost of the iteration that produced dcenters -- goes to the cost slot, (b) the chunk is assigned
+// (dlabels_io on exit, labels_host if given), (c) its member sums and counts are added to acc.  All sums are exact
+// integers: acc and cost are bit-identical to the resident session's.
+B2K_API int b2k_stage_lloyd_pass(b2k_lloyd* s, const float* X, const float* dcenters, int32_t* dlabels_io, int have_prev,
+                                 int32_t* labels_host, int64_t* dacc) {
+    if (!s || !dcenters || !dacc || (s->n > 0 && (!X || !dlabels_io)))
+        return set_error(B2K_ERR_INVALID_ARG, "stage_lloyd_pass: null argument");
+    b2k_ctx* ctx = s->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int64_t len = (int64_t)s->k * s->d + s->k + 1;
+    CUDA_TRY(cudaMemsetAsync(dacc, 0, (size_t)len * 8, ctx->stream));
+    if (s->n == 0) return B2K_OK;
+    return stream_assign(ctx, X, s->n, s->d, dcenters, s->k, s->metric, labels_host, 1, nullptr, dlabels_io, s->scale_sum,
+                         dacc, have_prev ? dlabels_io : nullptr, s->scale_cost, have_prev ? dacc + (len - 1) : nullptr);
+}
+
 B2K_API int64_t b2k_dev_lloyd_acc_len(const b2k_lloyd* s) { return s ? (int64_t)s->k * s->d + s->k + 1 : 0; }
 
 B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32_t* dlabels, int64_t* dacc) {
     if (!s || !dC || !dacc || (s->n > 0 && !dlabels)) return set_error(B2K_ERR_INVALID_ARG, "lloyd step: null argument");
+    if (s->n > 0 && !s->dX) return set_error(B2K_ERR_INVALID_ARG, "lloyd step: out-of-core session (use b2k_stage_lloyd_pass)");
     b2k_ctx* ctx = s->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaMemsetAsync(dacc, 0, (size_t)b2k_dev_lloyd_acc_len(s) * 8, ctx->stream));
@@ -665,7 +715,7 @@ B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32
     if (s->plan && s->prune_wanted) {
         // (re)sort by the labels of the previous step when the schedule says so: steps 1, 2, 4, 8, ... or every prune_resort
         if (s->prune && s->have_labels && s->steps >= s->next_sort) {
-            B2K_TRY(prune_sort(s->prune, s->dX, prune_labels(s->prune)));
+            B2K_TRY(prune_sort(s->prune, s->dX, prune_labels(s->prune), dC));
             screen_plan_invalidate_frames(s->plan);
             s->next_sort = ctx->prune_resort > 0 ? s->steps + ctx->prune_resort : s->steps * 2;
             ctx->stat_prune_sorts += 1;
@@ -679,7 +729,7 @@ B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32
             // the listed screen drains mean (padded) columns per frame, the full one k rounded up to 256
             if (ov == 0 && (mean <= 0.6 * (double)(cdiv(s->k, 256) * 256) || ctx->prune_mode == 3)) {
                 B2K_TRY(screen_assign_listed(s->plan, prune_frames(pr), s->n, dC, prune_tlist(pr), prune_tcount(pr),
-                                             prune_lcap(pr), prune_labels(pr), 1));
+                                             prune_lcap(pr), prune_unit_shift(pr), prune_labels(pr), 1));
                 ctx->stat_prune_steps += 1;
             } else {  // the lists would not pay: every center for every tile, still on the sorted frames
                 B2K_TRY(screen_assign(s->plan, prune_frames(pr), s->n, dC, prune_labels(pr), nullptr, 1));
@@ -723,6 +773,7 @@ B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32
 
 B2K_API int b2k_dev_lloyd_accumulate(b2k_lloyd* s, const int32_t* dlabels, int64_t* dacc) {
     if (!s || !dacc || (s->n > 0 && !dlabels)) return set_error(B2K_ERR_INVALID_ARG, "lloyd accumulate: null argument");
+    if (s->n > 0 && !s->dX) return set_error(B2K_ERR_INVALID_ARG, "lloyd accumulate: out-of-core session");
     b2k_ctx* ctx = s->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaMemsetAsync(dacc, 0, (size_t)b2k_dev_lloyd_acc_len(s) * 8, ctx->stream));
@@ -738,6 +789,7 @@ B2K_API int b2k_dev_lloyd_finalize(b2k_lloyd* s, const int64_t* dacc, const floa
 
 B2K_API int b2k_dev_lloyd_cost(b2k_lloyd* s, const float* dC_new, const int32_t* dlabels, int64_t* dacc) {
     if (!s || !dC_new || !dacc) return set_error(B2K_ERR_INVALID_ARG, "lloyd cost: null argument");
+    if (s->n > 0 && !s->dX) return set_error(B2K_ERR_INVALID_ARG, "lloyd cost: out-of-core session (b2k_stage_lloyd_pass measures it)");
     b2k_ctx* ctx = s->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
     int64_t* slot = dacc + (int64_t)s->k * s->d + s->k;

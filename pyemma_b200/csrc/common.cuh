@@ -107,9 +107,12 @@ struct b2k_ctx {
                               // against its own center list (exact), 0 never, 2 also for small jobs, 3 listed screen even
                               // when the lists exclude nothing (tests)
     int screen_gather = 0;    // listed screen: 0 cp.async gather warps, 1 TMA tile::gather4
+    int prune_unit_shift = -1; // 1 << shift consecutive 128-frame tiles share one center list (list kernel cost against list
+                              // length: measured at 1e7 x 10, k=1000 step 1.93 / 1.87 / 1.88 / 2.01 ms for shift 0..3); -1: 1 for narrow rows, else 0
     int prune_resort = 0;     // re-sort schedule: 0 at iterations 1, 2, 4, 8, ... ; n > 0 every n iterations
     double stat_prune_mean = 0, stat_prune_steps = 0, stat_prune_sorts = 0;  // mean list length of the last pruned step
     int screen_group = 0;     // centers per candidate group of the screen (0: automatic; 8, 4, 2)
+    int rmsd_abandon = 1;     // minRMSD argmin: abandon pairs whose msd lower bound already exceeds the frame's best (exact)
     int rmsd_kernel = 0;      // 0: slab-streaming QCP kernel, 1: whole-row tile kernel
     int row_vec_max = 4;      // widest row load of the narrow-row verify / cost kernels (4, 2 or 1 floats)
     int cost_kernel = 0;      // 0: quad kernel for wide rows / fused one-pass kernel for narrow rows, 1: the shared-memory

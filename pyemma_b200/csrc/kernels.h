@@ -86,7 +86,7 @@ struct PruneState;
 bool prune_supported(const b2k_ctx* ctx, int64_t n, int d, int k);
 int prune_create(b2k_ctx* ctx, int64_t n, int d, int k, PruneState** out);
 void prune_destroy(PruneState* p);
-int prune_sort(PruneState* p, const float* X, const int32_t* labels_current_order);
+int prune_sort(PruneState* p, const float* X, const int32_t* labels_current_order, const float* dC);
 int prune_lists(PruneState* p, const float* dC, double* mean_count, int* max_count, int* overflow_tiles);
 int prune_scatter_labels(PruneState* p, int32_t* out_original_order);
 const float* prune_frames(const PruneState* p);   // frames in sorted order
@@ -94,9 +94,10 @@ int32_t* prune_labels(PruneState* p);             // labels in sorted order (wri
 const uint16_t* prune_tlist(const PruneState* p);
 const uint32_t* prune_tcount(const PruneState* p);
 int prune_lcap(const PruneState* p);
+int prune_unit_shift(const PruneState* p);  // 1 << shift consecutive 128-frame tiles share one list
 bool prune_sorted(const PruneState* p);
 // screen + verify over per-tile center lists (frames = the plan's prepared frames, in sorted order)
 int screen_assign_listed(ScreenPlan* p, const float* dX, int64_t n, const float* dcenters, const uint16_t* tlist,
-                         const uint32_t* tcount, int lcap, int32_t* labels, int lloyd);
+                         const uint32_t* tcount, int lcap, int unit_shift, int32_t* labels, int lloyd);
 
 }  // namespace b2k

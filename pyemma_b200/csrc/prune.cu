@@ -19,6 +19,7 @@
 // when |c_j - c_a| > 2 (|c_a - p_t| + R_t): O(k^2 d + n_tiles (d + k)) work instead of O(n_tiles k d).
 #include "common.cuh"
 #include "kernels.h"
+#include <algorithm>
 
 namespace b2k {
 
@@ -63,20 +64,57 @@ __global__ void __launch_bounds__(256) scatter_labels_kernel(const int32_t* __re
         out[perm[p]] = labels_s[p];
 }
 
-// one CTA (128 threads) per tile: mean (fixed summation order) and radius of the tile's frames
-__global__ void __launch_bounds__(PT) tile_meta_kernel(const float* __restrict__ Xs, int64_t n, int d,
+// key[i] = rank[label[i]]: the frames are sorted by the RANK of their label in a kd-tree order of the centers, so that
+// labels next to each other in the sorted array are neighbours in space and a tile that straddles two labels stays compact
+__global__ void __launch_bounds__(256) label_rank_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ rank,
+                                                         int64_t n, int k, int32_t* __restrict__ keys) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const int32_t a = labels[i];
+        keys[i] = (a >= 0 && a < k) ? __ldg(rank + a) : 0;
+    }
+}
+
+// kd-tree leaf order of the centers (host; k is a few thousand): split the widest dimension at its median, recurse
+static void kd_order(const float* C, int d, int* idx, int lo, int hi) {
+    if (hi - lo <= 1) return;
+    int best = 0;
+    float spread = -1.f;
+    for (int e = 0; e < d; ++e) {
+        float mn = C[(size_t)idx[lo] * d + e], mx = mn;
+        for (int t = lo + 1; t < hi; ++t) {
+            const float v = C[(size_t)idx[t] * d + e];
+            mn = std::min(mn, v);
+            mx = std::max(mx, v);
+        }
+        if (mx - mn > spread) { spread = mx - mn; best = e; }
+    }
+    if (!(spread > 0.f)) return;  // identical (or non-finite) centers: any order
+    const int mid = (lo + hi) / 2;
+    std::nth_element(idx + lo, idx + mid, idx + hi, [&](int a, int b) {
+        const float va = C[(size_t)a * d + best], vb = C[(size_t)b * d + best];
+        return va < vb || (va == vb && a < b);
+    });
+    kd_order(C, d, idx, lo, mid);
+    kd_order(C, d, idx, mid, hi);
+}
+
+// one CTA (128 threads) per LIST UNIT (S = 1 << sshift consecutive tiles share one center list): mean (fixed summation
+// order) and radius of the unit's frames
+__global__ void __launch_bounds__(PT) tile_meta_kernel(const float* __restrict__ Xs, int64_t n, int d, int sshift,
                                                        float* __restrict__ tmean, float* __restrict__ trad) {
     extern __shared__ float sm[];  // [4][d] partial sums, then [d] mean
     float* part = sm;
     float* mean = sm + 4 * d;
     __shared__ float red[PT / 32];
-    const int64_t tile = blockIdx.x;
-    const int64_t row0 = tile * PT;
-    const int rows = (int)min((int64_t)PT, n - row0);
+    const int64_t unit = blockIdx.x;
+    const int urows = PT << sshift;
+    const int64_t row0 = unit * urows;
+    const int rows = (int)min((int64_t)urows, n - row0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_warp = urows / 4;
     for (int e = lane; e < d; e += 32) {
         float s = 0.f;
-        const int r0 = warp * 32, r1 = min(rows, r0 + 32);
+        const int r0 = warp * per_warp, r1 = min(rows, r0 + per_warp);
         for (int r = r0; r < r1; ++r) s += __ldg(Xs + (row0 + r) * d + e);
         part[warp * d + e] = s;
     }
@@ -84,22 +122,28 @@ __global__ void __launch_bounds__(PT) tile_meta_kernel(const float* __restrict__
     for (int e = threadIdx.x; e < d; e += PT) {
         const float m = (((part[e] + part[d + e]) + part[2 * d + e]) + part[3 * d + e]) / (float)rows;
         mean[e] = m;
-        tmean[tile * d + e] = m;
+        tmean[unit * d + e] = m;
     }
     __syncthreads();
     float r2 = 0.f;
-    if ((int)threadIdx.x < rows) {
-        const float* x = Xs + (row0 + threadIdx.x) * d;
-        for (int e = 0; e < d; ++e) { const float t = __ldg(x + e) - mean[e]; r2 = fmaf(t, t, r2); }
+    for (int r = threadIdx.x; r < rows; r += PT) {
+        const float* x = Xs + (row0 + r) * d;
+        float q = 0.f;
+        for (int e = 0; e < d; ++e) { const float t = __ldg(x + e) - mean[e]; q = fmaf(t, t, q); }
+        r2 = fmaxf(r2, q);
+        if (!(q == q)) r2 = q;  // NaN frame: keep every center (comparisons with NaN are false)
     }
+    const bool bad = !(r2 == r2);
+    const unsigned anybad = __ballot_sync(0xffffffffu, bad);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
-    if (lane == 0) red[warp] = r2;
+    if (lane == 0) red[warp] = anybad ? __int_as_float(0x7fc00000) : r2;
     __syncthreads();
     if (threadIdx.x == 0) {
-        const float m2 = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-        // NaN/inf frames: the radius becomes NaN/inf and every comparison below keeps every center
-        trad[tile] = sqrtf(m2) * (1.f + 1e-5f);
+        float m2 = 0.f;
+        bool nan = false;
+        for (int w = 0; w < PT / 32; ++w) { if (!(red[w] == red[w])) nan = true; m2 = fmaxf(m2, red[w]); }
+        trad[unit] = nan ? __int_as_float(0x7fc00000) : sqrtf(m2) * (1.f + 1e-5f);
     }
 }
 
@@ -223,7 +267,7 @@ __global__ void __launch_bounds__(256) center_dist_kernel(const float* __restric
 // keep j unless cc[a][j] > 2 (delta + R_t) (+ slack)
 __global__ void __launch_bounds__(256) tile_lists_cc_kernel(const float* __restrict__ C, int k, int d,
                                                             const float* __restrict__ cc,
-                                                            const int32_t* __restrict__ labels_s, int64_t n,
+                                                            const int32_t* __restrict__ labels_s, int64_t n, int sshift,
                                                             const float* __restrict__ tmean,
                                                             const float* __restrict__ trad, int n_tiles, int lcap,
                                                             int pad_to, uint16_t dummy, uint16_t* __restrict__ tlist,
@@ -231,7 +275,7 @@ __global__ void __launch_bounds__(256) tile_lists_cc_kernel(const float* __restr
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5, n_warps = (gridDim.x * 256) >> 5;
     for (int tile = warp_global; tile < n_tiles; tile += n_warps) {
-        int a = __ldg(labels_s + (int64_t)tile * PT);
+        int a = __ldg(labels_s + ((int64_t)tile * PT << sshift));
         if (a < 0 || a >= k) a = 0;
         const float* ca = C + (int64_t)a * d;
         const float* m = tmean + (int64_t)tile * d;
@@ -268,7 +312,10 @@ struct PruneState {
     b2k_ctx* ctx = nullptr;
     int64_t n = 0;
     int d = 0, k = 0, n_tiles = 0, lcap = 0, pad_to = 32;
-    DevMem Xs, perm, perm2, sigma, seg, labels_s, labels_t, tmean, trad, tlist, tcount, stats, cc;
+    int sshift = 0, n_units = 0;  // 1 << sshift tiles share one center list
+    DevMem Xs, perm, perm2, sigma, seg, labels_s, labels_t, tmean, trad, tlist, tcount, stats, cc, rank;
+    std::vector<float> hC;
+    std::vector<int> hidx, hrank;
     bool sorted = false;
 };
 
@@ -288,7 +335,10 @@ int prune_create(b2k_ctx* ctx, int64_t n, int d, int k, PruneState** out) {
     PruneState* p = new PruneState();
     p->ctx = ctx; p->n = n; p->d = d; p->k = k;
     p->n_tiles = (int)cdiv(n, PT);
-    p->lcap = (int)std::min<int64_t>(1024, cdiv(k, 64) * 64);
+    p->sshift = ctx->prune_unit_shift < 0 ? (d <= 16 ? 1 : 0) : std::min(4, ctx->prune_unit_shift);
+    p->n_units = (int)cdiv(n, (int64_t)PT << p->sshift);
+    // room for every center (k <= 8192): a unit the bound cannot help simply lists them all, no special case downstream
+    p->lcap = (int)std::min<int64_t>(8192, cdiv(k, 64) * 64);
     const int64_t n_pad = (int64_t)p->n_tiles * PT;
     int rc = p->Xs.alloc((size_t)n_pad * d * 4);
     if (rc == B2K_OK) rc = p->perm.alloc((size_t)n * 4);
@@ -297,11 +347,12 @@ int prune_create(b2k_ctx* ctx, int64_t n, int d, int k, PruneState** out) {
     if (rc == B2K_OK) rc = p->seg.alloc((size_t)(k + 2) * 4);
     if (rc == B2K_OK) rc = p->labels_s.alloc((size_t)n_pad * 4);
     if (rc == B2K_OK) rc = p->labels_t.alloc((size_t)n_pad * 4);
-    if (rc == B2K_OK) rc = p->tmean.alloc((size_t)p->n_tiles * d * 4);
-    if (rc == B2K_OK) rc = p->trad.alloc((size_t)p->n_tiles * 4);
-    if (rc == B2K_OK) rc = p->tlist.alloc((size_t)p->n_tiles * p->lcap * 2);
-    if (rc == B2K_OK) rc = p->tcount.alloc((size_t)p->n_tiles * 4);
+    if (rc == B2K_OK) rc = p->tmean.alloc((size_t)p->n_units * d * 4);
+    if (rc == B2K_OK) rc = p->trad.alloc((size_t)p->n_units * 4);
+    if (rc == B2K_OK) rc = p->tlist.alloc((size_t)p->n_units * p->lcap * 2);
+    if (rc == B2K_OK) rc = p->tcount.alloc((size_t)p->n_units * 4);
     if (rc == B2K_OK) rc = p->stats.alloc(sizeof(PruneStats));
+    if (rc == B2K_OK) rc = p->rank.alloc((size_t)k * 4);
     if (rc != B2K_OK) { delete p; return rc; }
     *out = p;
     return B2K_OK;
@@ -318,17 +369,32 @@ int32_t* prune_labels(PruneState* p) { return p->labels_s.as<int32_t>(); }
 const uint16_t* prune_tlist(const PruneState* p) { return p->tlist.as<uint16_t>(); }
 const uint32_t* prune_tcount(const PruneState* p) { return p->tcount.as<uint32_t>(); }
 int prune_lcap(const PruneState* p) { return p->lcap; }
+int prune_unit_shift(const PruneState* p) { return p->sshift; }
 bool prune_sorted(const PruneState* p) { return p->sorted; }
 
 // (re)sort: `labels` are in the CURRENT order of the session's frames (original order before the first sort, sorted
 // order afterwards); X is always the caller's original array
-int prune_sort(PruneState* p, const float* X, const int32_t* labels) {
+int prune_sort(PruneState* p, const float* X, const int32_t* labels, const float* dC) {
     b2k_ctx* ctx = p->ctx;
     cudaStream_t st = ctx->stream;
     const int64_t n = p->n;
     uint32_t* sigma = p->sigma.as<uint32_t>();
-    // a frame without a label in [0, k) would drop out of the sort: Lloyd assigns always label every frame
-    B2K_TRY(launch_label_sort(ctx, labels, n, p->k, p->seg.as<uint32_t>(), sigma));
+    // rank of every label in the kd order of the current centers (host: k*d floats down, k ints up)
+    p->hC.resize((size_t)p->k * p->d);
+    p->hidx.resize(p->k);
+    p->hrank.resize(p->k);
+    CUDA_TRY(cudaMemcpyAsync(p->hC.data(), dC, (size_t)p->k * p->d * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int j = 0; j < p->k; ++j) p->hidx[j] = j;
+    kd_order(p->hC.data(), p->d, p->hidx.data(), 0, p->k);
+    for (int r = 0; r < p->k; ++r) p->hrank[p->hidx[r]] = r;
+    CUDA_TRY(cudaMemcpyAsync(p->rank.p, p->hrank.data(), (size_t)p->k * 4, cudaMemcpyHostToDevice, st));
+    int32_t* keys = p->labels_t.as<int32_t>();  // free until the labels are gathered below
+    label_rank_kernel<<<grid_cap(ctx, n, 256), 256, 0, st>>>(labels, p->rank.as<int32_t>(), n, p->k, keys);
+    LAUNCH_CHECK();
+    // (a frame without a label in [0, k) would drop out of the sort: Lloyd assigns always label every frame)
+    B2K_TRY(launch_label_sort(ctx, keys, n, p->k, p->seg.as<uint32_t>(), sigma));
+    CUDA_TRY(cudaStreamSynchronize(st));  // hrank is reused by the next sort
     if (p->sorted) {
         compose_perm_kernel<<<grid_cap(ctx, n, 256), 256, 0, st>>>(p->perm.as<uint32_t>(), sigma, n, p->perm2.as<uint32_t>());
         LAUNCH_CHECK();
@@ -353,7 +419,7 @@ int prune_sort(PruneState* p, const float* X, const int32_t* labels) {
     else
         gather_rows_kernel<float><<<grid_cap(ctx, n * p->d, 256, 16), 256, 0, st>>>(X, perm, n, p->d, Xs);
     LAUNCH_CHECK();
-    tile_meta_kernel<<<(unsigned)p->n_tiles, PT, (size_t)5 * p->d * 4, st>>>(Xs, n, p->d, p->tmean.as<float>(),
+    tile_meta_kernel<<<(unsigned)p->n_units, PT, (size_t)5 * p->d * 4, st>>>(Xs, n, p->d, p->sshift, p->tmean.as<float>(),
                                                                           p->trad.as<float>());
     LAUNCH_CHECK();
     p->sorted = true;
@@ -372,7 +438,7 @@ int prune_lists(PruneState* p, const float* dC, double* mean_count, int* max_cou
     const int ds4 = (p->d + 3) & ~3;
     const size_t tab = (size_t)p->k * ds4 * 4;
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(tab, 1)));
-    const unsigned grid = grid_cap(ctx, p->n_tiles, 8, per_sm);
+    const unsigned grid = grid_cap(ctx, p->n_units, 8, per_sm);
     if (p->d <= 16 && tab <= 96 * 1024) {
 #define B2K_TL(DS)                                                                                                    \
     do {                                                                                                              \
@@ -383,7 +449,7 @@ int prune_lists(PruneState* p, const float* dC, double* mean_count, int* max_cou
             at.done(ctx->device);                                                                                     \
         }                                                                                                             \
         tile_lists_direct_kernel<DS><<<grid, 256, tab, st>>>(dC, p->k, p->d, p->tmean.as<float>(), p->trad.as<float>(), \
-                                                             p->n_tiles, p->lcap, p->pad_to, dummy,                   \
+                                                             p->n_units, p->lcap, p->pad_to, dummy,                   \
                                                              p->tlist.as<uint16_t>(), p->tcount.as<uint32_t>(), ds);  \
     } while (0)
         if (ds4 == 4) B2K_TL(4);
@@ -397,15 +463,15 @@ int prune_lists(PruneState* p, const float* dC, double* mean_count, int* max_cou
         const int64_t warps = (int64_t)p->k * cdiv(p->k, 32);
         center_dist_kernel<<<(unsigned)cdiv(warps, 8), 256, 0, st>>>(dC, p->k, p->d, p->cc.as<float>());
         LAUNCH_CHECK();
-        tile_lists_cc_kernel<<<grid_cap(ctx, p->n_tiles, 8, 8), 256, 0, st>>>(
-            dC, p->k, p->d, p->cc.as<float>(), p->labels_s.as<int32_t>(), p->n, p->tmean.as<float>(), p->trad.as<float>(),
-            p->n_tiles, p->lcap, p->pad_to, dummy, p->tlist.as<uint16_t>(), p->tcount.as<uint32_t>(), ds);
+        tile_lists_cc_kernel<<<grid_cap(ctx, p->n_units, 8, 8), 256, 0, st>>>(
+            dC, p->k, p->d, p->cc.as<float>(), p->labels_s.as<int32_t>(), p->n, p->sshift, p->tmean.as<float>(),
+            p->trad.as<float>(), p->n_units, p->lcap, p->pad_to, dummy, p->tlist.as<uint16_t>(), p->tcount.as<uint32_t>(), ds);
         LAUNCH_CHECK();
     }
     PruneStats h;
     CUDA_TRY(cudaMemcpyAsync(&h, ds, sizeof(h), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    *mean_count = (double)h.total / (double)std::max(p->n_tiles, 1);
+    *mean_count = (double)h.total / (double)std::max(p->n_units, 1);
     *max_count = (int)h.max_count;
     *overflow_tiles = (int)h.overflow;
     return B2K_OK;

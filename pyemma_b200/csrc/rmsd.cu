@@ -22,7 +22,26 @@ namespace b2k {
 #define DA(a, b) __dadd_rn((a), (b))
 #define DS(a, b) __dsub_rn((a), (b))
 
-__device__ __forceinline__ float qcp_msd(const float* Mf, float Ga, float Gb, int n_atoms) {
+// `bound` (argmin callers; +inf: none): the frame's best squared distance so far.  A pair that provably cannot beat it is
+// abandoned and reported as +inf -- it would lose the argmin anyway, and the winner's (and every near-tie's) arithmetic is
+// untouched, so labels and distances keep their bits.  Two exits, both LOWER bounds of the pair's msd:
+//  (1) before the quartic: lambda_max = max over rotations of tr(R^T M) <= s1+s2+s3 <= sqrt(3) |M|_F
+//  (2) inside the Newton loop: started at (Ga+Gb)/2 >= lambda_max, the iterates of this convex, increasing branch of the
+//      quartic decrease monotonically towards lambda_max, so (Ga+Gb-2 lam_t)/N never exceeds the final msd.
+// The slack (1e-5 relative + 1e-6 (Ga+Gb)/N absolute) is orders of magnitude above the fp32 / fp64 rounding of either side.
+__device__ __forceinline__ float qcp_msd(const float* Mf, float Ga, float Gb, int n_atoms,
+                                         float bound = 3.402823466e+38f) {
+    const bool bounded = bound < 3.0e38f;
+    float cut = 0.f;
+    if (bounded) {
+        const float gs = Ga + Gb;
+        cut = bound * 1.00001f + 1e-6f * gs / (float)n_atoms;
+        float f = 0.f;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) f = fmaf(Mf[e], Mf[e], f);
+        const float r = sqrtf(3.f * f) * 1.000001f;
+        if ((gs - 2.f * r) * (1.f - 1e-6f) / (float)n_atoms > cut) return 3.402823466e+38f;
+    }
     const double Sxx = Mf[0], Sxy = Mf[1], Sxz = Mf[2];
     const double Syx = Mf[3], Syy = Mf[4], Syz = Mf[5];
     const double Szx = Mf[6], Szy = Mf[7], Szz = Mf[8];
@@ -66,6 +85,7 @@ __device__ __forceinline__ float qcp_msd(const float* Mf, float Ga, float Gb, in
         if (den == 0.0) break;
         lam = DS(lam, __ddiv_rn(num, den));
         if (fabs(DS(lam, old)) < fabs(DM(1e-11, lam))) break;
+        if (bounded && (Gs - 2.0 * lam) > (double)cut * (double)n_atoms) return 3.402823466e+38f;
     }
     double msd = __ddiv_rn(DS(Gs, DM(2.0, lam)), (double)n_atoms);
     if (!(msd > 0.0)) msd = 0.0;
@@ -276,7 +296,7 @@ __device__ __forceinline__ void rs_cp16(float* dst, const float* src) {
                  : "memory");
 }
 
-template <int MODE, int CPT, bool ALIGNED>
+template <int MODE, int CPT, bool ALIGNED, bool ABANDON = true>
 __global__ void __launch_bounds__(256, 2) rmsd_slab_kernel(const float* __restrict__ X, const float* __restrict__ Ga,
                                                            int64_t n, int d, const float* __restrict__ Cc,
                                                            const float* __restrict__ Gb, int k,
@@ -287,7 +307,9 @@ __global__ void __launch_bounds__(256, 2) rmsd_slab_kernel(const float* __restri
     __shared__ __align__(16) float sm[2 * STAGE];
     __shared__ float red_s[256];
     __shared__ int32_t red_j[256];
+    __shared__ int best_bits[32];  // per frame: float bits of the best squared distance any warp has seen (monotone)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid < 32) best_bits[tid] = 0x7f800000;
     const int64_t base = (int64_t)blockIdx.x * 32;
     const int n_atoms = d / 3;
     const int n_slabs = (n_atoms + RS_ATOMS - 1) / RS_ATOMS;
@@ -392,9 +414,15 @@ __global__ void __launch_bounds__(256, 2) rmsd_slab_kernel(const float* __restri
                 if (j < k && fvalid) {
                     float M[9];
                     cov[c].finish(M);
-                    const float s = qcp_msd(M, ga, Gb[j], n_atoms);
-                    if (MODE == MODE_ARGMIN) am.offer(s, j);
-                    else out[(int64_t)j * n + fi] = __fsqrt_rn(s);
+                    if (MODE == MODE_ARGMIN) {
+                        // (a stale bound only abandons less; the first barrier of the loop ordered the initialisation)
+                        const float bound = ABANDON ? __int_as_float(*(volatile int*)&best_bits[lane]) : 3.402823466e+38f;
+                        const float s = qcp_msd(M, ga, Gb[j], n_atoms, bound);
+                        am.offer(s, j);
+                        if (ABANDON && s < bound) atomicMin(&best_bits[lane], __float_as_int(s));  // s >= 0: int order = float order
+                    } else {
+                        out[(int64_t)j * n + fi] = __fsqrt_rn(qcp_msd(M, ga, Gb[j], n_atoms));
+                    }
                 }
             }
         }
@@ -441,8 +469,23 @@ static int launch_rtile(b2k_ctx* ctx, const float* X, const float* Ga, int64_t n
     if (ctx->rmsd_kernel != 1 && n >= 32) {
         const unsigned grid = (unsigned)cdiv(n, 32);
         const bool al = (d % 4 == 0) && ((((uintptr_t)X) | ((uintptr_t)Cc)) & 15) == 0;
-#define B2K_RS(MODE_, CPT_, AL_) \
-    rmsd_slab_kernel<MODE_, CPT_, AL_><<<grid, 256, 0, ctx->stream>>>(X, Ga, n, d, Cc, Gb, k, labels, out, lloyd)
+// (two CTAs of ~40 KB static shared memory per SM: ask for the maximum shared-memory carve-out instead of leaving the
+//  L1 / shared split of each launch to the driver's heuristic)
+#define B2K_RS(MODE_, CPT_, AL_)                                                                                          \
+    do {                                                                                                                  \
+        static PerDeviceOnce carve;                                                                                       \
+        if (carve.need(ctx->device)) {                                                                                    \
+            CUDA_TRY(cudaFuncSetAttribute(rmsd_slab_kernel<MODE_, CPT_, AL_, true>,                                       \
+                                          cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+            CUDA_TRY(cudaFuncSetAttribute(rmsd_slab_kernel<MODE_, CPT_, AL_, false>,                                      \
+                                          cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+            carve.done(ctx->device);                                                                                      \
+        }                                                                                                                 \
+        if (ctx->rmsd_abandon)                                                                                            \
+            rmsd_slab_kernel<MODE_, CPT_, AL_, true><<<grid, 256, 0, ctx->stream>>>(X, Ga, n, d, Cc, Gb, k, labels, out, lloyd); \
+        else                                                                                                              \
+            rmsd_slab_kernel<MODE_, CPT_, AL_, false><<<grid, 256, 0, ctx->stream>>>(X, Ga, n, d, Cc, Gb, k, labels, out, lloyd); \
+    } while (0)
         if (mode == MODE_ARGMIN) {
             if (k > 8) { if (al) B2K_RS(MODE_ARGMIN, 2, true); else B2K_RS(MODE_ARGMIN, 2, false); }
             else { if (al) B2K_RS(MODE_ARGMIN, 1, true); else B2K_RS(MODE_ARGMIN, 1, false); }

@@ -1043,6 +1043,7 @@ struct ListArgs {
     const uint32_t* tcount;  // [n_tiles] padded list lengths (multiples of 64, <= lcap)
     const __half* B;         // center operand [k_rows][Kp]
     int lcap, Kp;
+    int ushift;              // list unit of frame tile t: t >> ushift
     int gather;              // 0: cp.async gather warps, 1: TMA tile::gather4
 };
 static constexpr int GATHER_WARPS = 4;
@@ -1102,10 +1103,10 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             // the per-tile metadata (list length, this thread's 16 ids of the first pass) is requested one tile ahead:
             // a dependent global load per tile on this path would cost more than the tile's whole copy
             int tile = blockIdx.x;
-            int cnt = tile < g.n_tiles ? (int)__ldg(la.tcount + tile) : 0;
+            int cnt = tile < g.n_tiles ? (int)__ldg(la.tcount + (tile >> la.ushift)) : 0;
             uint4 ia = make_uint4(0u, 0u, 0u, 0u), ib = ia;
             if (tile < g.n_tiles && r0 < la.lcap) {  // (r0 + 16 <= lcap: both are multiples of 16)
-                const uint4* src = reinterpret_cast<const uint4*>(la.tlist + (size_t)tile * la.lcap + r0);
+                const uint4* src = reinterpret_cast<const uint4*>(la.tlist + (size_t)(tile >> la.ushift) * la.lcap + r0);
                 ia = __ldg(src);
                 ib = __ldg(src + 1);
             }
@@ -1114,14 +1115,14 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                 int ncnt = 0;
                 uint4 na = make_uint4(0u, 0u, 0u, 0u), nb = na;
                 if (ntile < g.n_tiles) {
-                    ncnt = (int)__ldg(la.tcount + ntile);
+                    ncnt = (int)__ldg(la.tcount + (ntile >> la.ushift));
                     if (r0 < la.lcap) {
-                        const uint4* src = reinterpret_cast<const uint4*>(la.tlist + (size_t)ntile * la.lcap + r0);
+                        const uint4* src = reinterpret_cast<const uint4*>(la.tlist + (size_t)(ntile >> la.ushift) * la.lcap + r0);
                         na = __ldg(src);
                         nb = __ldg(src + 1);
                     }
                 }
-                const uint16_t* tl = la.tlist + (size_t)tile * la.lcap;
+                const uint16_t* tl = la.tlist + (size_t)(tile >> la.ushift) * la.lcap;
                 for (int p0 = 0; p0 < cnt; p0 += TILE_N) {
                     const int rows = min(TILE_N, cnt - p0);
                     if (p0 > 0 && p0 + r0 < la.lcap) {  // later passes of a long list: fetched here
@@ -1171,10 +1172,10 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             int stage = 0;
             uint32_t phase = 0;
             int tile = blockIdx.x;
-            int cnt = tile < g.n_tiles ? (int)__ldg(la.tcount + tile) : 0;
+            int cnt = tile < g.n_tiles ? (int)__ldg(la.tcount + (tile >> la.ushift)) : 0;
             for (; tile < g.n_tiles; tile += gridDim.x) {
                 const int ntile = tile + (int)gridDim.x;
-                const int ncnt = ntile < g.n_tiles ? (int)__ldg(la.tcount + ntile) : 0;  // one tile ahead
+                const int ncnt = ntile < g.n_tiles ? (int)__ldg(la.tcount + (ntile >> la.ushift)) : 0;  // one tile ahead
                 for (int p0 = 0; p0 < cnt; p0 += TILE_N) {
                     for (int kb = 0; kb < g.n_kblocks; ++kb) {
                         mbar_wait(&T->empty_bar[stage], phase ^ 1);
@@ -1191,8 +1192,8 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-            const int cnt = (int)la.tcount[tile];
-            const uint16_t* tl = la.tlist + (size_t)tile * la.lcap;
+            const int cnt = (int)la.tcount[tile >> la.ushift];
+            const uint16_t* tl = la.tlist + (size_t)(tile >> la.ushift) * la.lcap;
             for (int p0 = 0; p0 < cnt; p0 += TILE_N) {
                 const int rows = min(TILE_N, cnt - p0);
                 const bool mine = 8 * lane < rows;
@@ -1225,11 +1226,11 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             uint32_t uses[2] = {0u, 0u};  // passes each accumulator stage has carried
             uint32_t seq = 0;             // tile sequence number of this CTA: stage (and epilogue team) seq & 1
             int tile = blockIdx.x;
-            int cnt = tile < g.n_tiles ? (int)__ldg(la.tcount + tile) : 0;
+            int cnt = tile < g.n_tiles ? (int)__ldg(la.tcount + (tile >> la.ushift)) : 0;
             int ncnt = 0;
             for (; tile < g.n_tiles; tile += gridDim.x, cnt = ncnt, ++seq) {
                 const int ntile = tile + (int)gridDim.x;
-                ncnt = ntile < g.n_tiles ? (int)__ldg(la.tcount + ntile) : 0;  // one tile ahead
+                ncnt = ntile < g.n_tiles ? (int)__ldg(la.tcount + (ntile >> la.ushift)) : 0;  // one tile ahead
                 const uint32_t acc = seq & 1u;
                 for (int p0 = 0; p0 < cnt; p0 += TILE_N) {
                     const int rows = min(TILE_N, cnt - p0);
@@ -1279,7 +1280,7 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         int cnt = 0, ncnt = 0;
         float x2 = 0.f, xl = 0.f, nx2 = 0.f, nxl = 0.f;
         if (tile < g.n_tiles) {
-            cnt = (int)__ldg(la.tcount + tile);
+            cnt = (int)__ldg(la.tcount + (tile >> la.ushift));
             const int64_t gr = (int64_t)tile * TILE_M + row;
             if (gr < g.n) { x2 = __ldg(g.X2 + gr); if (g.terms != 3) xl = __ldg(g.XL + gr); }
         }
@@ -1288,7 +1289,7 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             const int next_tile = tile + tstep;
             ncnt = 0; nx2 = 0.f; nxl = 0.f;
             if (next_tile < g.n_tiles) {
-                ncnt = (int)__ldg(la.tcount + next_tile);
+                ncnt = (int)__ldg(la.tcount + (next_tile >> la.ushift));
                 const int64_t gr = (int64_t)next_tile * TILE_M + row;
                 if (gr < g.n) { nx2 = __ldg(g.X2 + gr); if (g.terms != 3) nxl = __ldg(g.XL + gr); }
             }
@@ -1536,8 +1537,8 @@ __global__ void __launch_bounds__(256, 4) screen_verify_table_kernel(const float
 template <int DREG>
 __global__ void __launch_bounds__(256, 4) screen_verify_table_listed_kernel(
     const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Cn, int k, const uint32_t* __restrict__ cand,
-    const uint8_t* __restrict__ ncand, const uint16_t* __restrict__ tlist, int lcap, int32_t* __restrict__ labels, int lloyd,
-    ScreenParams* prm, uint32_t* __restrict__ fb_list, int gstride, int cg, int vec) {
+    const uint8_t* __restrict__ ncand, const uint16_t* __restrict__ tlist, int lcap, int unit_frames,
+    int32_t* __restrict__ labels, int lloyd, ScreenParams* prm, uint32_t* __restrict__ fb_list, int gstride, int cg, int vec) {
     extern __shared__ __align__(16) float ctab[];
     const int idb = cand_id_bits(cg);
     const uint32_t idm = cand_id_mask(cg);
@@ -1560,7 +1561,7 @@ __global__ void __launch_bounds__(256, 4) screen_verify_table_listed_kernel(
             my_fb += 1;
             continue;
         }
-        const uint16_t* tl = tlist + (size_t)(i / TILE_M) * lcap;
+        const uint16_t* tl = tlist + (size_t)(i / unit_frames) * lcap;
         const uint4* cp = reinterpret_cast<const uint4*>(cand + i * CAND_CAP);
         const uint4 p0 = cp[0];
         uint4 p1 = make_uint4(0, 0, 0, 0);
@@ -1636,6 +1637,207 @@ __global__ void __launch_bounds__(256, 4) screen_verify_table_listed_kernel(
             }
         }
         labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
+    }
+    verify_stats(my_groups, my_fb, prm);
+}
+
+
+// ---- listed verify for wide rows (d > 16, d % 4 == 0): one CTA per 128-frame tile ---------------------------------------
+// The frames of a tile are neighbours in space (sorted by label), so their candidate centers are a handful of list
+// positions that most of the 128 frames share.  The CTA marks the positions its frames need in a shared bitmap, copies
+// exactly those center rows into shared memory once (a few KB from L2 per tile instead of 4*d bytes per frame and
+// candidate), and every thread then walks ITS frame row once per four candidates: the row streams through registers
+// (16-byte loads), the center rows come out of shared memory (lanes of a warp mostly read the same row: broadcast), and
+// every (frame, center) sum stays one thread's sequential Lanes4 sum in the reference order.
+static constexpr int VT_CMAX = 16;        // candidate centers a thread keeps; frames with more take the exact fallback
+static constexpr int VT_WORDS = 8192 / 32;  // bitmap over list positions (lcap <= 8192)
+
+__global__ void __launch_bounds__(TILE_M) screen_verify_tile_listed_kernel(
+    const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Cn, int k, const uint32_t* __restrict__ cand,
+    const uint8_t* __restrict__ ncand, const uint16_t* __restrict__ tlist, int lcap, int ushift, int32_t* __restrict__ labels,
+    int lloyd, ScreenParams* prm, uint32_t* __restrict__ fb_list, int cg, int batch /* center rows per shared batch */) {
+    extern __shared__ __align__(16) float vts[];  // [batch][d + 4] center rows
+    __shared__ uint32_t bits[VT_WORDS];
+    __shared__ uint16_t pre[VT_WORDS];            // set bits below word w
+    __shared__ uint16_t slot_pos[1024];           // list position of slot s (first 1024 slots; more -> fallback below)
+    __shared__ int s_total;
+    if (!prm->valid) return;
+    const int idb = cand_id_bits(cg);
+    const uint32_t idm = cand_id_mask(cg);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rs = d + 4;
+    const int nwords = (lcap + 31) >> 5;
+    const int64_t n_tiles = (n + TILE_M - 1) / TILE_M;
+    unsigned long long my_groups = 0, my_fb = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i = tile * TILE_M + tid;
+        const bool live = i < n;
+        const uint16_t* tl = tlist + (size_t)(tile >> ushift) * lcap;
+        for (int w = tid; w < nwords; w += TILE_M) bits[w] = 0u;
+        __syncthreads();
+        // ---- my candidate list positions (ascending) ----
+        int nc = live ? (int)ncand[i] : 0;
+        uint16_t cpos[VT_CMAX];
+        int ncs = 0;
+        bool fb = live && nc == 255;
+        if (live && nc != 255) {
+            const uint4* cp = reinterpret_cast<const uint4*>(cand + i * CAND_CAP);
+            const uint4 p0 = cp[0];
+            uint4 p1 = make_uint4(0, 0, 0, 0);
+            if (nc > 4) p1 = cp[1];
+            const uint32_t ent[CAND_CAP] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (int t = 0; t < CAND_CAP; ++t) {
+                if (t < nc) {
+                    const int pos0 = (int)(ent[t] & idm) * CHUNK;
+                    uint32_t mask = ent[t] >> idb;
+                    while (mask) {
+                        const int q = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        my_groups += 1;
+                        for (int c = 0; c < cg; ++c) {
+                            const int pos = pos0 + q * cg + c;
+                            if (ncs < VT_CMAX) {
+#pragma unroll
+                                for (int u = 0; u < VT_CMAX; ++u)
+                                    if (u == ncs) cpos[u] = (uint16_t)pos;
+                            }
+                            ++ncs;
+                        }
+                    }
+                }
+            }
+            if (ncs > VT_CMAX) { fb = true; ncs = 0; }
+        }
+#pragma unroll
+        for (int u = 0; u < VT_CMAX; ++u)
+            if (u < ncs) atomicOr(&bits[cpos[u] >> 5], 1u << (cpos[u] & 31));
+        __syncthreads();
+        // ---- prefix over the bitmap words (warp 0), slot -> position table ----
+        if (warp == 0) {
+            int run = 0;
+            for (int w0 = 0; w0 < nwords; w0 += 32) {
+                const int w = w0 + lane;
+                const int c = w < nwords ? __popc(bits[w]) : 0;
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (w < nwords) pre[w] = (uint16_t)(run + inc - c);
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) s_total = run;
+        }
+        __syncthreads();
+        const int total = s_total;
+        for (int w = tid; w < nwords; w += TILE_M) {
+            uint32_t b = bits[w];
+            int sidx = pre[w];
+            while (b) {
+                const int bit = __ffs(b) - 1;
+                b &= b - 1;
+                if (sidx < 1024) slot_pos[sidx] = (uint16_t)(w * 32 + bit);
+                ++sidx;
+            }
+        }
+        if (total > 1024) { if (!fb && live && nc != 255) fb = true; ncs = 0; }  // (never seen: 128 frames x 16 centers = 2048 at most)
+        __syncthreads();
+        // my candidates as (slot, center id)
+        uint16_t cslot[VT_CMAX];
+#pragma unroll
+        for (int u = 0; u < VT_CMAX; ++u) {
+            cslot[u] = 0;
+            if (u < ncs) {
+                const int pos = cpos[u];
+                cslot[u] = (uint16_t)(pre[pos >> 5] + __popc(bits[pos >> 5] & ((1u << (pos & 31)) - 1u)));
+            }
+        }
+        ArgMin am;
+        am.init();
+        const float4* x4 = reinterpret_cast<const float4*>(X + (live ? i : 0) * d);
+        const int nv = d >> 2;
+        int cur = 0;  // my next candidate (slots ascend with u)
+        for (int b0 = 0; b0 < min(total, 1024); b0 += batch) {
+            const int bn = min(batch, min(total, 1024) - b0);
+            __syncthreads();  // the previous batch has been consumed
+            // copy the batch's center rows (a padding id -- >= k -- leaves its row untouched: it is never offered)
+            for (int t = tid; t < bn * nv; t += TILE_M) {
+                const int r = t / nv, c = t - r * nv;
+                const int j = (int)tl[slot_pos[b0 + r]];
+                if (j < k) *reinterpret_cast<float4*>(vts + (size_t)r * rs + c * 4) =
+                    __ldg(reinterpret_cast<const float4*>(Cn + (int64_t)j * d) + c);
+            }
+            __syncthreads();
+            auto slot_at = [&](int idx) {  // cslot[idx] without dynamic register indexing
+                int v = 0x7fffffff;
+#pragma unroll
+                for (int u = 0; u < VT_CMAX; ++u)
+                    if (u == idx) v = (int)cslot[u];
+                return v;
+            };
+            while (cur < ncs && slot_at(cur) < b0 + bn) {
+                // up to four candidates of this batch at a time: the frame row is read once for all of them
+                int cnt4 = 0;
+                int sl[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int u = 0; u < VT_CMAX; ++u) {
+                    if (u >= cur && u < ncs && cnt4 < 4 && (int)cslot[u] < b0 + bn) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q == cnt4) sl[q] = (int)cslot[u] - b0;
+                        ++cnt4;
+                    }
+                }
+                Lanes4 L0, L1, L2, L3;
+                L0.init(); L1.init(); L2.init(); L3.init();
+                const float4* c0 = reinterpret_cast<const float4*>(vts + (size_t)sl[0] * rs);
+                const float4* c1 = reinterpret_cast<const float4*>(vts + (size_t)sl[1] * rs);
+                const float4* c2 = reinterpret_cast<const float4*>(vts + (size_t)sl[2] * rs);
+                const float4* c3 = reinterpret_cast<const float4*>(vts + (size_t)sl[3] * rs);
+                int t = 0;
+                for (; t + 4 <= nv; t += 4) {  // four 16-byte loads of the frame row in flight per thread
+                    float4 xv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) xv[u] = __ldg(x4 + t + u);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 a = c0[t + u];
+                        L0.add4(xv[u].x, xv[u].y, xv[u].z, xv[u].w, a.x, a.y, a.z, a.w);
+                        if (cnt4 > 1) { const float4 b = c1[t + u]; L1.add4(xv[u].x, xv[u].y, xv[u].z, xv[u].w, b.x, b.y, b.z, b.w); }
+                        if (cnt4 > 2) { const float4 c = c2[t + u]; L2.add4(xv[u].x, xv[u].y, xv[u].z, xv[u].w, c.x, c.y, c.z, c.w); }
+                        if (cnt4 > 3) { const float4 e = c3[t + u]; L3.add4(xv[u].x, xv[u].y, xv[u].z, xv[u].w, e.x, e.y, e.z, e.w); }
+                    }
+                }
+                for (; t < nv; ++t) {
+                    const float4 xv = __ldg(x4 + t);
+                    const float4 a = c0[t];
+                    L0.add4(xv.x, xv.y, xv.z, xv.w, a.x, a.y, a.z, a.w);
+                    if (cnt4 > 1) { const float4 b = c1[t]; L1.add4(xv.x, xv.y, xv.z, xv.w, b.x, b.y, b.z, b.w); }
+                    if (cnt4 > 2) { const float4 c = c2[t]; L2.add4(xv.x, xv.y, xv.z, xv.w, c.x, c.y, c.z, c.w); }
+                    if (cnt4 > 3) { const float4 e = c3[t]; L3.add4(xv.x, xv.y, xv.z, xv.w, e.x, e.y, e.z, e.w); }
+                }
+                const float res[4] = {L0.result(), L1.result(), L2.result(), L3.result()};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < cnt4) {
+                        const int j = (int)tl[slot_pos[b0 + sl[q]]];
+                        if (j < k) am.offer(res[q], j);
+                    }
+                }
+                cur += cnt4;
+            }
+        }
+        if (live) {
+            if (fb) {
+                fallback_push(prm, fb_list, i);
+                my_fb += 1;
+            } else {
+                labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
+            }
+        }
+        __syncthreads();  // bits / slot tables are rewritten by the next tile
     }
     verify_stats(my_groups, my_fb, prm);
 }
@@ -2059,7 +2261,7 @@ __global__ void __launch_bounds__(256) screen_verify_direct_kernel(const float* 
                                                                    ScreenParams* prm, uint32_t* __restrict__ fb_list,
                                                                    int cg, const uint16_t* __restrict__ tlist /* per-tile
                                                                    center lists (candidate groups count list positions) or
-                                                                   null */, int lcap) {
+                                                                   null */, int lcap, int unit_frames /* frames per list */) {
     if (!prm->valid) return;
     const int lane = threadIdx.x & 31;
     const int sub = lane & 7, slot = lane >> 3;
@@ -2076,7 +2278,7 @@ __global__ void __launch_bounds__(256) screen_verify_direct_kernel(const float* 
         const int nc = live ? (int)ncand[i] : 0;
         uint32_t ent = 0;
         if (live && nc != 255 && sub < nc) ent = cand[i * CAND_CAP + sub];
-        const uint16_t* tl = tlist ? tlist + (size_t)((live ? i : 0) / TILE_M) * lcap : nullptr;
+        const uint16_t* tl = tlist ? tlist + (size_t)((live ? i : 0) / unit_frames) * lcap : nullptr;
         const int pc = __popc(ent >> idb);
         int off = pc;  // inclusive scan over the 8 lanes of the frame
 #pragma unroll
@@ -2540,10 +2742,10 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         const unsigned dgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 32), (int64_t)ctx->sm_count * 8));
         if (vec)
             screen_verify_direct_kernel<true><<<dgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind,
-                                                                     lloyd, p->params, p->fb_list, p->cg, nullptr, 0);
+                                                                     lloyd, p->params, p->fb_list, p->cg, nullptr, 0, TILE_M);
         else
             screen_verify_direct_kernel<false><<<dgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, mind,
-                                                                      lloyd, p->params, p->fb_list, p->cg, nullptr, 0);
+                                                                      lloyd, p->params, p->fb_list, p->cg, nullptr, 0, TILE_M);
     } else {
         if (p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0) {
             const size_t tsmem = (size_t)8 * VC_WARP_FLOATS * 4;
@@ -2616,7 +2818,7 @@ int screen_choose_terms(b2k_ctx* ctx, const float* dX, int64_t n, int d, const f
 // Listed screen (prune.cu): the plan's frames are the session's SORTED frames; tile t meets the centers tlist[t][0 .. tcount[t]).
 // Labels come out in the frames' (sorted) order.
 int screen_assign_listed(ScreenPlan* p, const float* dX, int64_t n, const float* dC, const uint16_t* tlist,
-                         const uint32_t* tcount, int lcap, int32_t* labels, int lloyd) {
+                         const uint32_t* tcount, int lcap, int unit_shift, int32_t* labels, int lloyd) {
     b2k_ctx* ctx = p->ctx;
     cudaStream_t st = ctx->stream;
     if (p->prepared_n != n) B2K_TRY(screen_prepare_frames_with_centers(p, dX, n, dC));
@@ -2653,6 +2855,7 @@ int screen_assign_listed(ScreenPlan* p, const float* dX, int64_t n, const float*
     la.lcap = lcap;
     la.B = p->B;
     la.Kp = p->Kp;
+    la.ushift = unit_shift;
     la.gather = ctx->screen_gather;
     static PerDeviceOnce attr_set;
     if (attr_set.need(ctx->device)) {
@@ -2692,7 +2895,7 @@ int screen_assign_listed(ScreenPlan* p, const float* dX, int64_t n, const float*
             vattr.done(ctx->device);                                                                                         \
         }                                                                                                                    \
         screen_verify_table_listed_kernel<DR><<<tgrid, 256, tbytes, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, tlist,   \
-                                                                          lcap, labels, lloyd, p->params, p->fb_list,        \
+                                                                          lcap, TILE_M << unit_shift, labels, lloyd, p->params, p->fb_list, \
                                                                           gstride, p->cg,                                    \
                                                                           row_load_width(dX, p->d, ctx->row_vec_max));       \
     } while (0)
@@ -2701,15 +2904,31 @@ int screen_assign_listed(ScreenPlan* p, const float* dX, int64_t n, const float*
         else if (ds == 12) B2K_VTL(12);
         else B2K_VTL(16);
 #undef B2K_VTL
+    } else if (ctx->verify_mode != 2 && p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0 && lcap <= 8192 &&
+               (size_t)(p->d + 4) * 4 * 8 <= 64 * 1024) {
+        // tile verify: the center rows a tile needs are staged once in shared memory
+        const int rs = p->d + 4;
+        // a small batch (a tile rarely needs more than a dozen rows): ~9 KB of shared memory per CTA keeps 12+ CTAs per SM
+        const int batch = (int)std::max<size_t>(8, std::min<size_t>(32, (9 * 1024) / ((size_t)rs * 4)));
+        const size_t vsm = (size_t)batch * rs * 4;
+        static PerDeviceOnce vattr;
+        if (vattr.need(ctx->device)) {
+            CUDA_TRY(cudaFuncSetAttribute(screen_verify_tile_listed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            vattr.done(ctx->device);
+        }
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / (vsm + 4096)));
+        const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, TILE_M), (int64_t)ctx->sm_count * per_sm));
+        screen_verify_tile_listed_kernel<<<tgrid, TILE_M, vsm, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, tlist, lcap,
+                                                                     unit_shift, labels, lloyd, p->params, p->fb_list, p->cg, batch);
     } else {
         const bool vec = p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0;
         const unsigned dgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 32), (int64_t)ctx->sm_count * 8));
         if (vec)
             screen_verify_direct_kernel<true><<<dgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, nullptr,
-                                                                     lloyd, p->params, p->fb_list, p->cg, tlist, lcap);
+                                                                     lloyd, p->params, p->fb_list, p->cg, tlist, lcap, TILE_M << unit_shift);
         else
             screen_verify_direct_kernel<false><<<dgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, labels, nullptr,
-                                                                      lloyd, p->params, p->fb_list, p->cg, tlist, lcap);
+                                                                      lloyd, p->params, p->fb_list, p->cg, tlist, lcap, TILE_M << unit_shift);
     }
     LAUNCH_CHECK();
     return screen_finish_assign(p, dX, n, dC, labels, nullptr, lloyd);

@@ -91,8 +91,9 @@ class PinnedStager:
         self.stream.synchronize()
 
 
-def gather_frames(source, stride=1, skip=0, chunksize=None, ctx=None, rank=0, world_size=1, progress=None):
-    """All (strided, skipped) frames of `source` owned by this rank as ONE fp32 (n_local, d) CUDA tensor.
+def gather_frames(source, stride=1, skip=0, chunksize=None, ctx=None, rank=0, world_size=1, progress=None, to_host=False):
+    """All (strided, skipped) frames of `source` owned by this rank as ONE fp32 (n_local, d) CUDA tensor -- or, with
+    to_host (the tier below HBM), as one PINNED host tensor that the library streams through the device.
 
     Returns (tensor, n_total, lo) where lo is the global index of the first local frame."""
     dev = device(ctx)
@@ -101,6 +102,24 @@ def gather_frames(source, stride=1, skip=0, chunksize=None, ctx=None, rank=0, wo
     n_total = int(np.sum(lengths))
     lo, hi = shard_bounds(n_total, rank, world_size)
     n_local = hi - lo
+    if to_host:
+        out = torch.empty((n_local, d), dtype=torch.float32, pin_memory=True)
+        view = out.numpy()
+        if getattr(source, "project_host_chunk", None) is not None:
+            raise NotImplementedError("fused projection sources need the resident path")
+        cs = source.chunksize if chunksize is None else chunksize
+        t = 0
+        with source.iterator(stride=stride, skip=skip, chunk=cs, return_trajindex=True) as it:
+            for _itraj, X in it:
+                a, b = t, t + len(X)
+                t = b
+                if progress is not None:
+                    progress()
+                if b <= lo or a >= hi:
+                    continue
+                xa, xb = max(a, lo) - a, min(b, hi) - a
+                np.copyto(view[a + xa - lo:a + xb - lo], X[xa:xb], casting="unsafe")
+        return out, n_total, lo
     out = torch.empty((n_local, d), dtype=torch.float32, device=dev)
     cs = source.chunksize if chunksize is None else chunksize
     stage_rows = max(1, min(n_local if n_local else 1, (64 << 20) // max(4 * d, 1)))

@@ -329,3 +329,40 @@ def test_uniform_time_clustering(oracle):
     assert big.n_clusters == 57 and len(big.clustercenters) == 57
     auto = coor.cluster_uniform_time(trajs, k=None)
     assert auto.n_clusters == int(np.sqrt(1357))
+
+
+# ---- the tier below HBM (reference: host memmap, kmeans.py:181-200) ---------------------------------------------------
+@pytest.mark.parametrize("metric,d", [("euclidean", 10), ("euclidean", 40), ("minRMSD", 30)])
+def test_out_of_core_kmeans_is_bit_identical(monkeypatch, oracle, metric, d):
+    """with a tiny artificial HBM budget the frames stay in pinned host memory and pass through the device once per
+    iteration (b2k_stage_lloyd_pass); centers, inertias, iteration count and dtrajs equal the resident fit bit for bit"""
+    from pyemma_b200 import _lib
+    rng = np.random.RandomState(31)
+    n, k = 60_000, 150
+    cen = rng.uniform(-4, 4, size=(9, d))
+    X = (cen[rng.randint(0, 9, n)] + 0.6 * rng.randn(n, d)).astype(np.float32)
+    trajs = [X[:25_000], X[25_000:25_100], X[25_100:]]
+    C0 = X[rng.choice(n, k, replace=False)].copy()
+    resident = coor.cluster_kmeans(trajs, k=k, max_iter=7, clustercenters=C0.copy(), metric=metric, tolerance=1e-7)
+    ctx = _lib.context()
+    ctx.set_option("stage_bytes", 1 << 19)      # a few thousand frames per chunk: many chunks per pass
+    monkeypatch.setenv("B2K_HBM_BUDGET_BYTES", str(n * d * 4 // 3))
+    try:
+        ooc = coor.cluster_kmeans(trajs, k=k, max_iter=7, clustercenters=C0.copy(), metric=metric, tolerance=1e-7)
+    finally:
+        ctx.set_option("stage_bytes", 64 << 20)
+    np.testing.assert_array_equal(ooc.clustercenters, resident.clustercenters)
+    np.testing.assert_array_equal(ooc.inertias_, resident.inertias_)
+    assert ooc.converged == resident.converged and len(ooc.inertias_) == len(resident.inertias_)
+    for a, b in zip(ooc.dtrajs, resident.dtrajs):
+        np.testing.assert_array_equal(a, b)
+    ref = oracle.assign(X, ooc.clustercenters, metric, n_threads=8)
+    np.testing.assert_array_equal(np.concatenate(ooc.dtrajs), ref)
+    # k-means++ seeding out of core runs on a strided subset that fits the budget: a valid fit, centers are frames
+    km = coor.cluster_kmeans(trajs, k=20, max_iter=3, fixed_seed=7, metric=metric)
+    assert km.clustercenters.shape == (20, d) and np.isfinite(km.clustercenters).all()
+    assert all((km.initial_centers_[i] == X).all(axis=1).any() for i in range(20))
+    monkeypatch.setenv("B2K_HBM_BUDGET_BYTES", "1000")
+    with pytest.raises(MemoryError):
+        from pyemma_b200.clustering import KmeansClustering
+        KmeansClustering(20, max_iter=2, clustercenters=C0[:20].copy(), oom_strategy="raise").estimate(trajs)

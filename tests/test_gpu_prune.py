@@ -75,7 +75,7 @@ def test_pruned_session_is_bit_identical(b2k, oracle, n, d, k, nb, mode, resort)
     before = b2k.context().get_stat("prune_steps")
     got, cen1, stats = run_session(b2k, X, C0, steps, {"assign_engine": b2k.ENGINE_SCREEN, "prune_mode": mode,
                                                        "prune_resort": resort})
-    if k <= 1024:   # (longer lists than the 1024-entry capacity: the session uses the full screen on the sorted frames)
+    if k <= 8192:   # (lists longer than the 8192-entry capacity: the session uses the full screen on the sorted frames)
         assert stats["prune_steps"] - before >= steps - 2, stats     # iterations 2.. ran on per-tile center lists
     if mode == 2:
         assert stats["prune_mean_list"] <= 0.6 * ((k + 255) // 256 * 256)   # the lists (padded to 64) did exclude centers

@@ -20,7 +20,7 @@ ap.add_argument("--steps", type=int, default=12)
 ap.add_argument("--option", action="append", default=[])
 args = ap.parse_args()
 bench.select_workload(args.workload)
-n = args.frames or bench.FRAMES_PER_GPU
+n = args.frames or bench.W["n"]
 dev = torch.device("cuda", 0)
 ctx = _lib.context(0)
 lib = ctx.lib
@@ -30,7 +30,7 @@ for opt in args.option:
     name, _, val = opt.partition("=")
     ctx.set_option(name, int(val))
 X = bench.synth_device(n, 0, dev)
-D, K = bench.D, bench.K
+D, K = bench.W["d"], bench.W["k"]
 cur = X[:K].clone()
 nxt = torch.empty_like(cur)
 absmax = C.c_float(0)
