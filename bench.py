@@ -138,35 +138,44 @@ def conformations(n, n_atoms, n_templates, seed, noise=0.05):
     return out
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe): ONE `nvidia-smi -lms <period>` child
+    process started before the region and read back after it.  Every query -- from a thread of this process, through NVML
+    or from a child -- holds up kernel launches on this system for ~0.1 s (measured on the launch-bound cfg1 fit: 10.2 ms
+    without sampling, 13.9 / 24.7 ms with 7 / 11 samples in the region), so the launch-bound workload samples once a
+    second and the kernel-bound ones four times."""
 
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
-
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.1)
+
+    def __init__(self, index, period_ms=250):
+        self.index, self.proc, self.period_ms = index, None, int(period_ms)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=6)
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i] == "Active"})
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            rows = [[c.strip() for c in l.split(",")] for l in out.splitlines() if l.strip()]
+        sm = sorted(int(r[0]) for r in rows if r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
+        reasons = sorted({self.NAMES[i] for r in rows for i in range(4) if len(r) > 2 + i and r[2 + i] == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(rows), "source": "nvidia-smi -lms %d (child process)" % self.period_ms}
 
 
 # ---------------------------------------------------------------------------------------------- CPU oracle legs
@@ -547,9 +556,11 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank, 1000 if W["kind"] == "fit" else 250) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.3)  # the child is up (and has taken its first sample) before the timed region starts
+        barrier()
     ctx.set_option("profile", 1)
     l0 = _lib.launch_count()
     if W["kind"] == "fit":
@@ -586,25 +597,59 @@ def main():
         pass
     gemm_launches = ctx.get_stat("screen_gemm_launches")
     gemm_ms = ctx.get_stat("screen_gemm_ms_total") / gemm_launches if gemm_launches else None
+    classes = {}
+    for cls in ("verify", "sums", "cost", "lists"):
+        cn = ctx.get_stat("prof_n_" + cls)
+        if cn:
+            classes[cls] = ctx.get_stat("prof_ms_" + cls) / args.steps
     ctx.set_option("profile", 0)
     if W["kind"] == "lloyd" and gemm_ms:
+        step_ms = total_ms / args.steps
         flops = 2.0 * K * D * n  # algorithmic: SURVEY 8d "2*k*d flop per frame" x frames per launch
-        achieved_tf = flops / (gemm_ms * 1e-3) / 1e12
         pruned = ctx.get_stat("prune_steps") > 0
+        mean_list = ctx.get_stat("prune_mean_list")
+        terms = ctx.get_stat("screen_terms_used")
+        kc = terms * D + 3
+        k_eff = -(-kc // 16) * 16
+        cols = mean_list if pruned else -(-K // 256) * 256
+        issued = 2.0 * cols * k_eff * n  # MMA flops the kernel really issues (listed centers x operand columns)
+        breakdown = dict(classes)
+        breakdown["screen"] = gemm_ms * gemm_launches / args.steps
+        breakdown["other"] = max(step_ms - sum(breakdown.values()), 0.0)
+        extra["step_breakdown_ms"] = breakdown
         extra["pruning"] = {
-            "active": bool(pruned), "mean_centers_per_tile_list": ctx.get_stat("prune_mean_list"), "k": K,
-            "sorts": ctx.get_stat("prune_sorts"),
+            "active": bool(pruned), "mean_centers_per_tile_list": mean_list, "k": K, "sorts": ctx.get_stat("prune_sorts"),
             "note": ("after its first iteration the session keeps the frames sorted by label; every 128-frame tile is "
                      "screened against the centers the triangle inequality cannot exclude (exact: labels, sums and "
-                     "costs are bit-identical to the unpruned iteration, tests/test_gpu_prune.py).  Algorithmic flops "
-                     "stay 2*k*d per frame; the first (unpruned) iteration is reported as first_iteration_ms")}
-        roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved_tf / peak_tf, "traffic": traffic,
-                    "kernel": "b2k::screen_gemm_%skernel (tcgen05 distance screen, %d launches timed with CUDA events inside "
-                              "the timed region)" % ("listed_" if pruned else "", int(gemm_launches)),
-                    "kernel_ms": gemm_ms, "peak_source": "bf16_tflops_sustained, " + src,
-                    "algorithmic_flops_per_launch": flops, "operand_terms": ctx.get_stat("screen_terms_used"),
-                    "step_frac": flops / (total_ms / args.steps * 1e-3) / 1e12 / peak_tf}
+                     "costs are bit-identical to the unpruned iteration, tests/test_gpu_prune.py); the first (unpruned) "
+                     "iteration is reported as first_iteration_ms")}
+        dominant = max(breakdown, key=lambda c: breakdown[c] if c != "other" else -1.0)
+        screen_roof = {"bound": "tensor", "achieved": flops / (gemm_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                       "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak_tf, "traffic": traffic,
+                       "kernel": "b2k::screen_gemm_%skernel (tcgen05 distance screen, %d launches timed with CUDA events "
+                                 "inside the timed region)" % ("listed_" if pruned else "", int(gemm_launches)),
+                       "kernel_ms": gemm_ms, "peak_source": "bf16_tflops_sustained, " + src,
+                       "algorithmic_flops_per_launch": flops, "operand_terms": terms,
+                       "issued_mma_flops_per_launch": issued, "issued_frac": issued / (gemm_ms * 1e-3) / 1e12 / peak_tf,
+                       "hbm": {"bytes_per_launch": n * (-(-kc // 64) * 64) * 2.0,
+                               "achieved_gbs": n * (-(-kc // 64) * 64) * 2.0 / (gemm_ms * 1e-3) / 1e9, "peak_gbs": peak_hbm},
+                       "note": ("achieved = SURVEY 8d algorithmic flops (2*k*d per frame) / kernel time: with exact pruning "
+                                "the kernel only meets the listed centers, so this can exceed what the MMA pipe issues "
+                                "(issued_frac) and, on clustered wide-row data, the dense tensor peak itself")
+                               if pruned else "3-term fp16 operand split issues 3x the algorithmic flops"}
+        if dominant == "screen":
+            roofline = screen_roof
+        else:
+            # an HBM-streaming kernel leads the step: 4d+4 algorithmic bytes per frame (the frame row and its label)
+            kms = breakdown[dominant]
+            gbs = n * (4.0 * D + 4) / (kms * 1e-3) / 1e9
+            names = {"verify": "exact verify of the screen's candidates (screen_verify_*_kernel + exact fallback)",
+                     "sums": "member sums (seg_* counting sort + seg_sum_kernel)", "cost": "cost (labeled distances + integer sum)",
+                     "lists": "per-tile center lists (prune.cu)"}
+            roofline = {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
+                        "traffic": None, "kernel": names[dominant], "kernel_ms": kms, "peak_source": "hbm_gbs, " + src,
+                        "algorithmic_bytes_per_launch": n * (4.0 * D + 4), "screen_kernel": screen_roof}
+        roofline["step_frac"] = flops / (step_ms * 1e-3) / 1e12 / peak_tf
     elif W["kind"] == "lloyd":
         achieved_tf = 2.0 * K * D * n / (total_ms / args.steps * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
@@ -678,6 +723,23 @@ def main():
 
     if W["kind"] == "lloyd":
         lib.b2k_dev_lloyd_destroy(sess)
+        if ws == 1:
+            # the same iteration without pruning (what the first iteration of every session costs, setup excluded)
+            ctx.set_option("prune_mode", 0)
+            sess = C.c_void_p()
+            _lib.check(lib.b2k_dev_lloyd_create(ctx.handle, C.c_void_p(X.data_ptr()), n, D, K, _lib.EUCLIDEAN, n * ws,
+                                                C.c_float(float(am.item())), C.byref(sess)))
+            step()
+            torch.cuda.synchronize(dev)
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record(stream)
+            for _ in range(3):
+                step()
+            u1.record(stream)
+            torch.cuda.synchronize(dev)
+            extra["unpruned_iteration_ms"] = u0.elapsed_time(u1) / 3
+            lib.b2k_dev_lloyd_destroy(sess)
+            ctx.set_option("prune_mode", 1)
     if rank == 0:
         line = {
             "metric": metric_text(), "value": value, "unit": "frames/s", "n_gpus": ws, "steps": args.steps,

@@ -229,6 +229,7 @@ B2K_API int b2k_ctx_destroy(b2k_ctx* c) {
     }
     screen_plan_release_cached(c);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+    for (auto& v : c->prof_class) for (cudaEvent_t e : v) cudaEventDestroy(e);
     for (int i = 0; i < b2k_ctx::N_SLOTS; ++i)
         if (c->slot_ptr[i]) cudaFree(c->slot_ptr[i]);
     if (c->flags) cudaFree(c->flags);
@@ -261,7 +262,9 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "probe_max_centers")) c->probe_max_centers = (int)value;
     else if (!strcmp(name, "probe_min_gflop")) c->probe_min_gflop = (int)value;
     else if (!strcmp(name, "screen_gather")) c->screen_gather = (int)value;
+    else if (!strcmp(name, "screen_decide")) c->screen_decide = (int)value;
     else if (!strcmp(name, "rmsd_abandon")) c->rmsd_abandon = (int)value;
+    else if (!strcmp(name, "kmpp_async")) c->kmpp_async = (int)value;
     else if (!strcmp(name, "prune_mode")) c->prune_mode = (int)value;
     else if (!strcmp(name, "prune_resort")) c->prune_resort = (int)value;
     else if (!strcmp(name, "prune_unit_shift")) c->prune_unit_shift = (int)value;
@@ -281,6 +284,7 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "profile")) {  // (re)start event timing of the screen kernel launches
         for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
         c->prof_events.clear();
+        for (auto& v : c->prof_class) { for (cudaEvent_t e : v) cudaEventDestroy(e); v.clear(); }
         c->profile = value != 0;
     }
     else if (!strcmp(name, "stage_bytes")) c->stage_bytes = (size_t)std::max<int64_t>(value, 1 << 16);
@@ -312,10 +316,30 @@ B2K_API int b2k_ctx_get_stat(b2k_ctx* c, const char* name, double* value) {
         *value = !strcmp(name, "screen_gemm_ms_total") ? total : (double)(c->prof_events.size() / 2);
         return B2K_OK;
     }
+    if (!strncmp(name, "prof_ms_", 8) || !strncmp(name, "prof_n_", 7)) {
+        const bool want_ms = name[5] == 'm';
+        const char* cls = name + (want_ms ? 8 : 7);
+        static const char* names[b2k_ctx::PROF_N] = {"verify", "sums", "cost", "lists"};
+        for (int k = 0; k < b2k_ctx::PROF_N; ++k) {
+            if (strcmp(cls, names[k])) continue;
+            auto& v = c->prof_class[k];
+            double total = 0;
+            for (size_t i = 0; i + 1 < v.size(); i += 2) {
+                CUDA_TRY(cudaEventSynchronize(v[i + 1]));
+                float ms = 0.f;
+                CUDA_TRY(cudaEventElapsedTime(&ms, v[i], v[i + 1]));
+                total += ms;
+            }
+            *value = want_ms ? total : (double)(v.size() / 2);
+            return B2K_OK;
+        }
+        return set_error(B2K_ERR_INVALID_ARG, "unknown stat '%s'", name);
+    }
     if (!strcmp(name, "screen_cand_chunks")) *value = c->stat_cand_chunks;
     else if (!strcmp(name, "screen_fallback_frames")) *value = c->stat_fallback_frames;
     else if (!strcmp(name, "screen_frames")) *value = c->stat_screen_frames;
     else if (!strcmp(name, "screen_terms_used")) *value = c->stat_screen_terms;
+    else if (!strcmp(name, "kmpp_async_fallbacks")) *value = c->stat_kmpp_async_fallbacks;
     else if (!strcmp(name, "prune_mean_list")) *value = c->stat_prune_mean;
     else if (!strcmp(name, "prune_steps")) *value = c->stat_prune_steps;
     else if (!strcmp(name, "prune_sorts")) *value = c->stat_prune_sorts;
@@ -795,6 +819,7 @@ B2K_API int b2k_dev_lloyd_cost(b2k_lloyd* s, const float* dC_new, const int32_t*
     int64_t* slot = dacc + (int64_t)s->k * s->d + s->k;
     CUDA_TRY(cudaMemsetAsync(slot, 0, 8, ctx->stream));
     if (s->n == 0) return B2K_OK;
+    ProfScope prof(ctx, b2k_ctx::PROF_COST);
     const float* fX = s->dX;
     if (s->prune && prune_sorted(s->prune) && s->have_labels) {
         // the session works on its sorted copy of the frames: the labels of the last step are there in the same order

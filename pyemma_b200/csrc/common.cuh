@@ -86,6 +86,9 @@ struct b2k_ctx {
     // optional CUDA-event timing of the screen kernel launches (option "profile", stats "screen_gemm_ms_*")
     int profile = 0;
     std::vector<cudaEvent_t> prof_events;  // start/stop pairs on `stream`
+    // the other kernels of a Lloyd step, timed the same way (ProfScope below; stats "prof_ms_<class>", "prof_n_<class>")
+    enum { PROF_VERIFY = 0, PROF_SUMS, PROF_COST, PROF_LISTS, PROF_N };
+    std::vector<cudaEvent_t> prof_class[PROF_N];
     // options
     int engine = B2K_ENGINE_AUTO;
     int screen_terms = 0;       // 1..3: operand terms of the screen forced, 0: measured per data set (screen_choose_terms)
@@ -95,6 +98,8 @@ struct b2k_ctx {
     double stat_screen_terms = 0;  // term count of the last screened call
     int check_finite = 1;       // host-pointer assign entry points reject NaN/inf frames (B2K_ERR_NONFINITE)
     int host_copy_threads = 8;  // threads of the pageable -> pinned bounce copy (1e7 x 10 frames: 32.7 ms with 1, 18.2 ms with 8)
+    double stat_kmpp_async_fallbacks = 0;
+    int kmpp_async = 1;       // k-means++ (blocked, one GPU, no callback): rounds are queued without a host round trip each
     int kmpp_prune = 1;       // k-means++ (blocked, euclidean): skip candidate distances the triangle inequality decides
     int operand_kernel = 0;   // frame operand builder: 0 per-input-element tile kernel, 1 per-output-piece kernel
     int fallback_mode = 0;    // frames the screen cannot bound: 0 indexed exact tile kernel, 1 CTA-per-frame scan
@@ -106,6 +111,10 @@ struct b2k_ctx {
     int prune_mode = 1;       // Lloyd sessions: 1 sort the frames by label after the first iteration and screen every tile
                               // against its own center list (exact), 0 never, 2 also for small jobs, 3 listed screen even
                               // when the lists exclude nothing (tests)
+    int screen_decide = 0;    // listed screen: frames with a single possible center (one candidate chunk, its runner-up below the
+                              // threshold) skip the exact verify.  Off: 99.4 % of the cfg2 frames and 58 % of the cfg3 frames are
+                              // decided, but finding the runner-up costs the instruction-bound epilogue more (screen kernel 0.79 ->
+                              // 1.10 ms at cfg2) than the verify saves (0.36 -> ~0.1 ms)
     int screen_gather = 0;    // listed screen: 0 cp.async gather warps, 1 TMA tile::gather4
     int prune_unit_shift = -1; // 1 << shift consecutive 128-frame tiles share one center list (list kernel cost against list
                               // length: measured at 1e7 x 10, k=1000 step 1.93 / 1.87 / 1.88 / 2.01 ms for shift 0..3); -1: 1 for narrow rows, else 0
@@ -145,6 +154,28 @@ struct b2k_ctx {
     size_t scratch2_cap = 0;
     int ensure_scratch2(size_t bytes);
 };
+
+namespace b2k {
+// CUDA-event pair around a group of launches on ctx->stream when option "profile" is on (no cost otherwise)
+struct ProfScope {
+    b2k_ctx* ctx;
+    int cls;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(b2k_ctx* c, int k) : ctx(c), cls(k) {
+        if (!ctx->profile) return;
+        cudaEvent_t e0 = nullptr;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e1 = nullptr; return; }
+        cudaEventRecord(e0, ctx->stream);
+        ctx->prof_class[cls].push_back(e0);
+    }
+    ~ProfScope() {
+        if (!e1) return;
+        cudaEventRecord(e1, ctx->stream);
+        ctx->prof_class[cls].push_back(e1);
+    }
+};
+}  // namespace b2k
+
 
 // ---- device helpers: the exact fp32 arithmetic of the reference path -------------------------
 namespace b2k {

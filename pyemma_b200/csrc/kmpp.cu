@@ -142,6 +142,47 @@ __global__ void kmpp_update_kernel(float* __restrict__ D, const unsigned char* _
     if (delta) delta[i] = dl;
 }
 
+// The same update with the accepted candidate read from the device state: the host does not wait for the round's result
+// (kmpp_run_blocked, asynchronous rounds).  *fail != 0: an earlier round found no candidate -> the run is repeated with
+// the synchronous loop, whatever happens here is discarded.
+__global__ void kmpp_update_dev_kernel(float* __restrict__ D, const unsigned char* __restrict__ taken, int64_t n,
+                                       const float* __restrict__ cd, const KmppState* __restrict__ st, int src_is_sqrt,
+                                       int32_t* __restrict__ assigned, int32_t center_index,
+                                       const uint16_t* __restrict__ framemask, const int* __restrict__ fail) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || *fail) return;
+    const int jbit = st->jbest;
+    if (jbit < 0) return;
+    const float* src = cd + (size_t)jbit * n;
+    if (!taken[i] && (!framemask || ((framemask[i] >> jbit) & 1u))) {
+        float dd = src[i];
+        if (src_is_sqrt) dd = __fmul_rn(dd, dd);
+        const float old = D[i];
+        if (dd < old) {
+            D[i] = dd;
+            if (assigned) assigned[i] = center_index;
+        }
+    }
+}
+
+__global__ void kmpp_commit_dev_kernel(const KmppState* __restrict__ st, long long lo, int64_t n_local,
+                                       const float* __restrict__ rows, int d, unsigned char* __restrict__ taken,
+                                       float* __restrict__ center_out, long long* __restrict__ chosen_out, int* fail) {
+    const long long best = st->best;
+    const int jbest = st->jbest;
+    if (best < 0 || jbest < 0) {
+        if (threadIdx.x == 0) *fail = 1;
+        return;
+    }
+    const float* row = rows + (size_t)jbest * d;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) center_out[e] = row[e];
+    if (threadIdx.x == 0) {
+        *chosen_out = best;
+        const long long b = best - lo;
+        if (b >= 0 && b < n_local) taken[b] = 1;
+    }
+}
+
 // Rc[j][a] = lower bound of |center_a - candidate_j| (fp64 sum, rounded down): one warp per (a, j)
 __global__ void __launch_bounds__(256) kmpp_center_cand_dist_kernel(const float* __restrict__ centers, int found,
                                                                     const float* __restrict__ rows, int m, int d,
@@ -878,6 +919,17 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
     T.lv[5] = bL25.as<float>(); T.len[5] = n25g;
     T.lv[6] = bL30.as<float>(); T.len[6] = n30g;
 
+    // Asynchronous rounds (single GPU, no progress callback): the accepted candidate stays on the device -- commit and D2
+    // update read it from the state -- so the host queues round after round without waiting; the picks come back once at
+    // the end.  A round without a usable candidate (the reference's "take the next available point") raises a device flag
+    // and the whole seeding is repeated with the synchronous loop below.
+    const bool async_rounds = !ex && !cb && ctx->kmpp_async != 0 && n > 0;
+    DevBuf bChosen, bFail;
+    if (async_rounds) {
+        B2K_TRY(bChosen.alloc((size_t)k * 8));
+        B2K_TRY(bFail.alloc(16));
+        CUDA_TRY(cudaMemsetAsync(bFail.p, 0, 16, st));
+    }
     KmppState hs;
     for (int found = 1; found < k; ++found) {
         const float* ur = bU.as<float>() + (size_t)(found - 1) * m;
@@ -935,6 +987,18 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         }
         kmpp_select_kernel<<<1, 32, 0, st>>>(S, pots, m, taken, n);
         LAUNCH_CHECK();
+        if (async_rounds) {
+            kmpp_commit_dev_kernel<<<1, 128, 0, st>>>(S, lo, n, rows, d, taken, dcenters_out + (size_t)found * d,
+                                                      bChosen.as<long long>() + found, bFail.as<int>());
+            LAUNCH_CHECK();
+            if (found + 1 < k) {
+                kmpp_update_dev_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(
+                    D, taken, n, cd, S, prune ? 1 : 0, prune ? bAssigned.as<int32_t>() : nullptr, found,
+                    prune ? bFrameMask.as<uint16_t>() : nullptr, bFail.as<int>());
+                LAUNCH_CHECK();
+            }
+            continue;
+        }
         CUDA_TRY(cudaMemcpyAsync(&hs, S, sizeof(KmppState), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         long long best = hs.best;
@@ -973,6 +1037,22 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
                                                                            prune ? bAssigned.as<int32_t>() : nullptr, found);
                 LAUNCH_CHECK();
             }
+        }
+    }
+    if (async_rounds) {
+        int fail = 0;
+        CUDA_TRY(cudaMemcpyAsync(&fail, bFail.p, 4, cudaMemcpyDeviceToHost, st));
+        if (k > 1)
+            CUDA_TRY(cudaMemcpyAsync(chosen.data() + 1, bChosen.as<long long>() + 1, (size_t)(k - 1) * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (fail) {  // rare: repeat with the synchronous loop, which handles the fallback pick on the host
+            ctx->stat_kmpp_async_fallbacks += 1;
+            const int keep = ctx->kmpp_async;
+            ctx->kmpp_async = 0;
+            const int rc = kmpp_run_blocked(ctx, dX, n, d, k, metric, seed, lo, n_total, xf, xf_len, xi, ex, exuser, cb, user,
+                                            dcenters_out, chosen_host);
+            ctx->kmpp_async = keep;
+            return rc;
         }
     }
     CUDA_TRY(cudaStreamSynchronize(st));

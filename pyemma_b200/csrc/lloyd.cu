@@ -523,6 +523,7 @@ static unsigned grid_for(b2k_ctx* ctx, int64_t work_items, int per_block) {
 int launch_accumulate(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, const int32_t* labels, double scale,
                       int64_t* acc) {
     if (n <= 0) return B2K_OK;
+    ProfScope prof(ctx, b2k_ctx::PROF_SUMS);
     const int64_t total = n * d;
     const size_t table_bytes = ((size_t)2 * k * d + k) * 4;
     // automatic: the table kernel only in the launch-latency regime (one kernel instead of four); measured at

@@ -433,6 +433,7 @@ int prune_lists(PruneState* p, const float* dC, double* mean_count, int* max_cou
     cudaStream_t st = ctx->stream;
     PruneStats* ds = p->stats.as<PruneStats>();
     CUDA_TRY(cudaMemsetAsync(ds, 0, sizeof(PruneStats), st));
+    ProfScope* prof = new ProfScope(ctx, b2k_ctx::PROF_LISTS);
     const int k_pad = (int)(cdiv(p->k, 256) * 256);
     const uint16_t dummy = (uint16_t)k_pad;  // a -inf row behind the center operand (screen_centers_kernel)
     const int ds4 = (p->d + 3) & ~3;
@@ -468,6 +469,7 @@ int prune_lists(PruneState* p, const float* dC, double* mean_count, int* max_cou
             p->trad.as<float>(), p->n_units, p->lcap, p->pad_to, dummy, p->tlist.as<uint16_t>(), p->tcount.as<uint32_t>(), ds);
         LAUNCH_CHECK();
     }
+    delete prof;
     PruneStats h;
     CUDA_TRY(cudaMemcpyAsync(&h, ds, sizeof(h), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

@@ -642,15 +642,23 @@ struct RowScan {
     float m, thr;
     int cnt;
     bool overflow;
+    // TRACK (listed screen): the column that holds the running maximum and the second largest score of ITS chunk.  If at
+    // the end only that chunk is a candidate and its second score is below the final threshold, exactly one center can
+    // be the reference's argmin: the frame is DECIDED by the screen and needs no exact evaluation (NCAND_DECIDED).
+    float best_v2;
+    uint32_t best_pos;
     __device__ __forceinline__ void init() {
         m = __int_as_float(0xff800000);
         thr = m;
         cnt = 0;
         overflow = false;
+        best_v2 = m;
+        best_pos = 0;
     }
 };
+static constexpr int NCAND_DECIDED = 254;  // ncand value: cand[0] is the list position of the only possible center
 
-template <int CG>
+template <int CG, bool TRACK = false>
 __device__ __forceinline__ void scan_chunk(const float (&v)[32], uint32_t chunk_id, RowScan& rs, const Margin& mg,
                                            uint32_t* lid, float* lv /* this thread's column of the list arrays */) {
     constexpr int NG = CHUNK / CG;
@@ -669,7 +677,23 @@ __device__ __forceinline__ void scan_chunk(const float (&v)[32], uint32_t chunk_
     float cm = (NG % 3 == 1) ? gm[NG - 1] : fmaxf(gm[NG - 2], gm[NG - 1]);
 #pragma unroll
     for (int q = 0; q < nt; ++q) cm = fmaxf(cm, t3[q]);
-    if (cm > rs.m) { rs.m = cm; rs.thr = mg.threshold(cm); }
+    if (cm > rs.m) {
+        rs.m = cm;
+        rs.thr = mg.threshold(cm);
+        if (TRACK) {  // a few times per frame: argmax column and runner-up of the chunk that now holds the maximum
+            float m1 = v[0], m2 = __int_as_float(0xff800000);
+            uint32_t c1 = 0;
+#pragma unroll
+            for (int e = 1; e < CHUNK; ++e) {
+                const bool gt = v[e] > m1;
+                m2 = gt ? m1 : fmaxf(m2, v[e]);  // an equal score counts as a second candidate
+                c1 = gt ? (uint32_t)e : c1;
+                m1 = gt ? v[e] : m1;
+            }
+            rs.best_v2 = m2;
+            rs.best_pos = chunk_id * CHUNK + c1;
+        }
+    }
     if (cm >= rs.thr) {
         // groups below the CURRENT threshold can never pass the final (higher) one
         uint32_t mask = 0;
@@ -1044,6 +1068,7 @@ struct ListArgs {
     const __half* B;         // center operand [k_rows][Kp]
     int lcap, Kp;
     int ushift;              // list unit of frame tile t: t >> ushift
+    int decide;              // 1: frames with a single possible center are settled by the screen (NCAND_DECIDED)
     int gather;              // 0: cp.async gather warps, 1: TMA tile::gather4
 };
 static constexpr int GATHER_WARPS = 4;
@@ -1058,7 +1083,7 @@ __device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* tm, ui
         : "memory");
 }
 
-template <int CG>
+template <int CG, bool DECIDE>
 __global__ void __launch_bounds__(LISTED_THREADS, 1)
 screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBg, GemmArgs g,
                           ListArgs la) {
@@ -1315,8 +1340,8 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&T->tempty_bar[team]);
                     }
-                    if (par) scan_chunk<CG>(vb, cbase + (uint32_t)c, rs, mg, lid, lv);
-                    else scan_chunk<CG>(va, cbase + (uint32_t)c, rs, mg, lid, lv);
+                    if (par) scan_chunk<CG, DECIDE>(vb, cbase + (uint32_t)c, rs, mg, lid, lv);
+                    else scan_chunk<CG, DECIDE>(va, cbase + (uint32_t)c, rs, mg, lid, lv);
                     par = !par;
                 }
             }
@@ -1336,10 +1361,14 @@ screen_gemm_listed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                 }
                 const bool overflow = rs.overflow || kept > CAND_CAP || kept == 0 || !(rs.m > -3.0e38f) || !valid_ops ||
                                       !(x2 < 3.0e38f);
+                // one candidate chunk (the one that holds the maximum) and no second score of it within the margin:
+                // only one center can be the argmin
+                const bool decided = DECIDE && !overflow && kept == 1 && rs.best_v2 < thr;
+                if (decided) ids[0] = rs.best_pos;
                 uint4* cout = reinterpret_cast<uint4*>(g.cand + grow * CAND_CAP);
                 cout[0] = make_uint4(ids[0], ids[1], ids[2], ids[3]);
                 if (kept > 4 && !overflow) cout[1] = make_uint4(ids[4], ids[5], ids[6], ids[7]);
-                g.ncand[grow] = overflow ? (uint8_t)255 : (uint8_t)kept;
+                g.ncand[grow] = overflow ? (uint8_t)255 : (decided ? (uint8_t)NCAND_DECIDED : (uint8_t)kept);
             }
         }
     }
@@ -1553,8 +1582,6 @@ __global__ void __launch_bounds__(256, 4) screen_verify_table_listed_kernel(
     const bool full_last = d == DREG;
     unsigned long long my_groups = 0, my_fb = 0;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        float xr[DREG];
-        load_row_padded<DREG>(X, i, d, vec, xr);
         const int nc = ncand[i];
         if (nc == 255) {
             fallback_push(prm, fb_list, i);
@@ -1562,6 +1589,14 @@ __global__ void __launch_bounds__(256, 4) screen_verify_table_listed_kernel(
             continue;
         }
         const uint16_t* tl = tlist + (size_t)(i / unit_frames) * lcap;
+        if (nc == NCAND_DECIDED) {  // settled by the screen: no distance to evaluate, the frame row is not even read
+            const int j = (int)__ldg(tl + cand[i * CAND_CAP]);
+            if (j < k) labels[i] = j;
+            else { fallback_push(prm, fb_list, i); my_fb += 1; }
+            continue;
+        }
+        float xr[DREG];
+        load_row_padded<DREG>(X, i, d, vec, xr);
         const uint4* cp = reinterpret_cast<const uint4*>(cand + i * CAND_CAP);
         const uint4 p0 = cp[0];
         uint4 p1 = make_uint4(0, 0, 0, 0);
@@ -1649,10 +1684,17 @@ __global__ void __launch_bounds__(256, 4) screen_verify_table_listed_kernel(
 // candidate), and every thread then walks ITS frame row once per four candidates: the row streams through registers
 // (16-byte loads), the center rows come out of shared memory (lanes of a warp mostly read the same row: broadcast), and
 // every (frame, center) sum stays one thread's sequential Lanes4 sum in the reference order.
+// (Measured at 1.25e7 x 64, k=2000, Lloyd step: 7.3 ms with this kernel, 7.8 ms with the 8-lanes-per-frame direct kernel,
+//  9.6 ms with a variant that streamed the tile's frame rows through shared memory by cp.async one slab ahead at 2 CTAs
+//  per SM -- every one of them is bound by the chain of dependent loads per tile / frame group (candidate entries -> list
+//  ids -> rows), not by bandwidth: 3.6 GB at 1.2 TB/s.  profiles/r02_notes.md)
+#ifndef B2K_VT_MINBLOCKS
+#define B2K_VT_MINBLOCKS 8  // register cap: measured Lloyd step at cfg3 7.9 / 7.3 / 7.1 ms for 4 / 6 / 8 CTAs per SM
+#endif
 static constexpr int VT_CMAX = 16;        // candidate centers a thread keeps; frames with more take the exact fallback
 static constexpr int VT_WORDS = 8192 / 32;  // bitmap over list positions (lcap <= 8192)
 
-__global__ void __launch_bounds__(TILE_M) screen_verify_tile_listed_kernel(
+__global__ void __launch_bounds__(TILE_M, B2K_VT_MINBLOCKS) screen_verify_tile_listed_kernel(
     const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Cn, int k, const uint32_t* __restrict__ cand,
     const uint8_t* __restrict__ ncand, const uint16_t* __restrict__ tlist, int lcap, int ushift, int32_t* __restrict__ labels,
     int lloyd, ScreenParams* prm, uint32_t* __restrict__ fb_list, int cg, int batch /* center rows per shared batch */) {
@@ -1680,6 +1722,12 @@ __global__ void __launch_bounds__(TILE_M) screen_verify_tile_listed_kernel(
         uint16_t cpos[VT_CMAX];
         int ncs = 0;
         bool fb = live && nc == 255;
+        int decided_j = -1;
+        if (live && nc == NCAND_DECIDED) {  // settled by the screen
+            decided_j = (int)__ldg(tl + cand[i * CAND_CAP]);
+            if (decided_j >= k) { decided_j = -1; fb = true; }
+            nc = 255;  // nothing to evaluate
+        }
         if (live && nc != 255) {
             const uint4* cp = reinterpret_cast<const uint4*>(cand + i * CAND_CAP);
             const uint4 p0 = cp[0];
@@ -1833,6 +1881,8 @@ __global__ void __launch_bounds__(TILE_M) screen_verify_tile_listed_kernel(
             if (fb) {
                 fallback_push(prm, fb_list, i);
                 my_fb += 1;
+            } else if (decided_j >= 0) {
+                labels[i] = decided_j;
             } else {
                 labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
             }
@@ -2275,10 +2325,19 @@ __global__ void __launch_bounds__(256) screen_verify_direct_kernel(const float* 
     for (int64_t base = warp_global * 4; base < n; base += n_warps * 4) {
         const int64_t i = base + slot;
         const bool live = i < n;
-        const int nc = live ? (int)ncand[i] : 0;
+        int nc = live ? (int)ncand[i] : 0;
+        const uint16_t* tl = tlist ? tlist + (size_t)((live ? i : 0) / unit_frames) * lcap : nullptr;
+        if (nc == NCAND_DECIDED) {  // settled by the listed screen (tl is set): no evaluation
+            const int j = (int)__ldg(tl + cand[i * CAND_CAP]);
+            if (sub == 0) {
+                if (j < k) labels[i] = j;
+                else { fallback_push(prm, fb_list, i); my_fb += 1; }
+            }
+            nc = 0;
+        }
+        const bool skip_out = live && ncand[i] == NCAND_DECIDED;
         uint32_t ent = 0;
         if (live && nc != 255 && sub < nc) ent = cand[i * CAND_CAP + sub];
-        const uint16_t* tl = tlist ? tlist + (size_t)((live ? i : 0) / unit_frames) * lcap : nullptr;
         const int pc = __popc(ent >> idb);
         int off = pc;  // inclusive scan over the 8 lanes of the frame
 #pragma unroll
@@ -2356,7 +2415,7 @@ __global__ void __launch_bounds__(256) screen_verify_direct_kernel(const float* 
             const int32_t jo = __shfl_xor_sync(0xffffffffu, am.j, o);
             am.merge(so, jo);
         }
-        if (live && sub == 0 && nc != 255) {
+        if (live && sub == 0 && nc != 255 && !skip_out) {
             labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
             if (mind) mind[i] = am.j >= 0 ? __fsqrt_rn(am.s) : 3.402823466e+38f;
         }
@@ -2676,6 +2735,7 @@ int screen_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, in
         ctx->prof_events.push_back(ev1);
     }
     // verify (persistent grids)
+    ProfScope prof_verify(ctx, b2k_ctx::PROF_VERIFY);
     if (p->d <= 16) {
         const int ds = (p->d + 3) & ~3;
         {   // table kernel when the skewed table fits shared memory twice per SM
@@ -2856,12 +2916,16 @@ int screen_assign_listed(ScreenPlan* p, const float* dX, int64_t n, const float*
     la.B = p->B;
     la.Kp = p->Kp;
     la.ushift = unit_shift;
+    la.decide = ctx->screen_decide;
     la.gather = ctx->screen_gather;
     static PerDeviceOnce attr_set;
     if (attr_set.need(ctx->device)) {
-        CUDA_TRY(cudaFuncSetAttribute(screen_gemm_listed_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-        CUDA_TRY(cudaFuncSetAttribute(screen_gemm_listed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-        CUDA_TRY(cudaFuncSetAttribute(screen_gemm_listed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(screen_gemm_listed_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(screen_gemm_listed_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(screen_gemm_listed_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(screen_gemm_listed_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(screen_gemm_listed_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(screen_gemm_listed_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
         attr_set.done(ctx->device);
     }
     const unsigned grid = (unsigned)std::min<int64_t>(g.n_tiles, ctx->sm_count);
@@ -2871,15 +2935,20 @@ int screen_assign_listed(ScreenPlan* p, const float* dX, int64_t n, const float*
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, st));
     }
-    if (p->cg == 8) screen_gemm_listed_kernel<8><<<grid, LISTED_THREADS, smem, st>>>(p->tmA, p->tmBg, g, la);
-    else if (p->cg == 4) screen_gemm_listed_kernel<4><<<grid, LISTED_THREADS, smem, st>>>(p->tmA, p->tmBg, g, la);
-    else screen_gemm_listed_kernel<2><<<grid, LISTED_THREADS, smem, st>>>(p->tmA, p->tmBg, g, la);
+    if (ctx->screen_decide) {
+        if (p->cg == 8) screen_gemm_listed_kernel<8, true><<<grid, LISTED_THREADS, smem, st>>>(p->tmA, p->tmBg, g, la);
+        else if (p->cg == 4) screen_gemm_listed_kernel<4, true><<<grid, LISTED_THREADS, smem, st>>>(p->tmA, p->tmBg, g, la);
+        else screen_gemm_listed_kernel<2, true><<<grid, LISTED_THREADS, smem, st>>>(p->tmA, p->tmBg, g, la);
+    } else if (p->cg == 8) screen_gemm_listed_kernel<8, false><<<grid, LISTED_THREADS, smem, st>>>(p->tmA, p->tmBg, g, la);
+    else if (p->cg == 4) screen_gemm_listed_kernel<4, false><<<grid, LISTED_THREADS, smem, st>>>(p->tmA, p->tmBg, g, la);
+    else screen_gemm_listed_kernel<2, false><<<grid, LISTED_THREADS, smem, st>>>(p->tmA, p->tmBg, g, la);
     LAUNCH_CHECK();
     if (ctx->profile) {
         CUDA_TRY(cudaEventRecord(ev1, st));
         ctx->prof_events.push_back(ev0);
         ctx->prof_events.push_back(ev1);
     }
+    ProfScope prof_verify(ctx, b2k_ctx::PROF_VERIFY);
     const int ds = (p->d + 3) & ~3;
     const int gstride = GROUP * ds + (((GROUP * ds / 4) & 1) ? 0 : 4);
     const size_t tbytes = (size_t)cdiv(p->k, GROUP) * gstride * 4;

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""k-means++ timing probe: python tools/kmpp_probe.py N D K [serial|blocked]  (device-resident frames, one GPU)."""
+"""k-means++ seeding time on resident frames: asynchronous rounds against the synchronous loop."""
 import ctypes as C
 import os
 import sys
@@ -7,26 +7,50 @@ import time
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
 from pyemma_b200 import _lib  # noqa: E402
 
-n, d, k = int(float(sys.argv[1])), int(sys.argv[2]), int(sys.argv[3])
-scan = sys.argv[4] if len(sys.argv) > 4 else "blocked"
+n, d, k = (int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (100000, 2, 100)))
 dev = torch.device("cuda", 0)
-g = torch.Generator(device=dev)
-g.manual_seed(4)
-means = torch.randn((200, d), generator=g, device=dev) * 5
-X = torch.randn((n, d), generator=g, device=dev) + means[torch.randint(0, 200, (n,), generator=g, device=dev)]
 ctx = _lib.context(0)
+lib = ctx.lib
 ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+if d == 2:
+    X = torch.from_numpy(bench.three_well(n, 1)).to(dev)
+else:
+    bench.W = dict(bench.WORKLOADS["cfg4"], name="cfg4", d=d)
+    X = bench.synth_device(n, 0, dev)
 cen = torch.empty((k, d), dtype=torch.float32, device=dev)
-for rep in range(2):
+chosen = (C.c_int64 * k)()
+res = {}
+for mode in (1, 0, 1, 0):
+    ctx.set_option("kmpp_async", mode)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    _lib.check(ctx.lib.b2k_dev_kmeans_init_centers_kmpp(ctx.handle, C.c_void_p(X.data_ptr()), n, d, k, 0, 42,
-                                                        _lib.KMPP_SERIAL if scan == "serial" else _lib.KMPP_BLOCKED,
-                                                        _lib.CALLBACK(0), None, C.c_void_p(cen.data_ptr()), None))
+    reps = 3
+    for _ in range(reps):
+        _lib.check(lib.b2k_dev_kmeans_init_centers_kmpp(ctx.handle, C.c_void_p(X.data_ptr()), n, d, k, 0, 42, _lib.KMPP_BLOCKED,
+                                                        _lib.CALLBACK(0), None, C.c_void_p(cen.data_ptr()), chosen))
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    print("kmpp n=%d d=%d k=%d %s: %.3f s, %.3f ms/round, hbm-algorithmic %.1f GB/s" %
-          (n, d, k, scan, dt, dt / max(k - 1, 1) * 1e3, (k - 1) * n * (4 * d + 8) / dt / 1e9), flush=True)
+    dt = (time.perf_counter() - t0) / reps
+    res[mode] = list(chosen)
+    print("async=%d  %.2f ms per seeding (%.1f us per round)  fallbacks so far %d" % (mode, dt * 1e3, dt / k * 1e6, ctx.get_stat("kmpp_async_fallbacks")))
+print("picks identical:", res[0] == res[1])
+# the Lloyd loop that follows the seeding in a fit (cfg1: 10 iterations)
+code, iters = C.c_int(0), C.c_int(0)
+inert = (C.c_float * 16)()
+for mode in (1, 0, 1, 0):
+    ctx.set_option("kmpp_async", mode)
+    for what in ("seed+loop", "loop only"):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            if what == "seed+loop":
+                _lib.check(lib.b2k_dev_kmeans_init_centers_kmpp(ctx.handle, C.c_void_p(X.data_ptr()), n, d, k, 0, 42, _lib.KMPP_BLOCKED,
+                                                                _lib.CALLBACK(0), None, C.c_void_p(cen.data_ptr()), None))
+            _lib.check(lib.b2k_dev_kmeans_cluster_loop(ctx.handle, C.c_void_p(X.data_ptr()), n, d, C.c_void_p(cen.data_ptr()), k, 0, 10,
+                                                       C.c_float(1e-5), _lib.CALLBACK(0), None, C.byref(code), C.byref(iters), inert, 16, None))
+        torch.cuda.synchronize()
+        print("async=%d  %-10s %.2f ms (%d iterations)" % (mode, what, (time.perf_counter() - t0) / 3 * 1e3, iters.value))
