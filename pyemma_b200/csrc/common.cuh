@@ -99,7 +99,8 @@ struct b2k_ctx {
     int check_finite = 1;       // host-pointer assign entry points reject NaN/inf frames (B2K_ERR_NONFINITE)
     int host_copy_threads = 8;  // threads of the pageable -> pinned bounce copy (1e7 x 10 frames: 32.7 ms with 1, 18.2 ms with 8)
     double stat_kmpp_async_fallbacks = 0;
-    int kmpp_async = 1;       // k-means++ (blocked, one GPU, no callback): rounds are queued without a host round trip each
+    int kmpp_async = 2;       // k-means++ (blocked, one GPU, no callback): 1 rounds are queued without a host round trip each,
+                              // 2 (default) additionally replayed from one captured CUDA graph, 0 synchronous loop
     int kmpp_prune = 1;       // k-means++ (blocked, euclidean): skip candidate distances the triangle inequality decides
     int operand_kernel = 0;   // frame operand builder: 0 per-input-element tile kernel, 1 per-output-piece kernel
     int fallback_mode = 0;    // frames the screen cannot bound: 0 indexed exact tile kernel, 1 CTA-per-frame scan

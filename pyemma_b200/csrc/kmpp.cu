@@ -80,6 +80,7 @@ struct KmppState {
     long long best;  // frame index of the accepted center
     int jbest;       // which candidate (-1: fallback "first non-taken frame")
     float delta_sum;
+    int round;       // asynchronous rounds: centers found so far (the device-side loop counter a CUDA graph replays on)
 };
 
 __global__ void kmpp_square_init_kernel(const float* __restrict__ v, int64_t n, int64_t first, float* __restrict__ D,
@@ -147,10 +148,11 @@ __global__ void kmpp_update_kernel(float* __restrict__ D, const unsigned char* _
 // the synchronous loop, whatever happens here is discarded.
 __global__ void kmpp_update_dev_kernel(float* __restrict__ D, const unsigned char* __restrict__ taken, int64_t n,
                                        const float* __restrict__ cd, const KmppState* __restrict__ st, int src_is_sqrt,
-                                       int32_t* __restrict__ assigned, int32_t center_index,
-                                       const uint16_t* __restrict__ framemask, const int* __restrict__ fail) {
+                                       int32_t* __restrict__ assigned, const uint16_t* __restrict__ framemask,
+                                       const int* __restrict__ fail) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || *fail) return;
+    const int32_t center_index = st->round - 1;  // the commit kernel before this one advanced the counter
     const int jbit = st->jbest;
     if (jbit < 0) return;
     const float* src = cd + (size_t)jbit * n;
@@ -165,30 +167,40 @@ __global__ void kmpp_update_dev_kernel(float* __restrict__ D, const unsigned cha
     }
 }
 
-__global__ void kmpp_commit_dev_kernel(const KmppState* __restrict__ st, long long lo, int64_t n_local,
-                                       const float* __restrict__ rows, int d, unsigned char* __restrict__ taken,
-                                       float* __restrict__ center_out, long long* __restrict__ chosen_out, int* fail) {
+__global__ void kmpp_commit_dev_kernel(KmppState* st, long long lo, int64_t n_local, const float* __restrict__ rows, int d,
+                                       unsigned char* __restrict__ taken, float* __restrict__ centers,
+                                       long long* __restrict__ chosen, int* fail, int k) {
     const long long best = st->best;
     const int jbest = st->jbest;
+    const int found = st->round;  // this round's center index
+    __syncthreads();              // every thread has read the counter before thread 0 advances it
+    if (found >= k) return;       // (a graph replayed once too often: nothing left to pick)
     if (best < 0 || jbest < 0) {
-        if (threadIdx.x == 0) *fail = 1;
+        if (threadIdx.x == 0) { *fail = 1; st->round = found + 1; }
         return;
     }
     const float* row = rows + (size_t)jbest * d;
+    float* center_out = centers + (size_t)found * d;
     for (int e = threadIdx.x; e < d; e += blockDim.x) center_out[e] = row[e];
     if (threadIdx.x == 0) {
-        *chosen_out = best;
+        chosen[found] = best;
         const long long b = best - lo;
         if (b >= 0 && b < n_local) taken[b] = 1;
+        st->round = found + 1;
     }
 }
+
+__global__ void kmpp_set_round_kernel(KmppState* st, int round) { st->round = round; }
 
 // Rc[j][a] = lower bound of |center_a - candidate_j| (fp64 sum, rounded down): one warp per (a, j)
 __global__ void __launch_bounds__(256) kmpp_center_cand_dist_kernel(const float* __restrict__ centers, int found,
                                                                     const float* __restrict__ rows, int m, int d,
-                                                                    float* __restrict__ Rc, int rc_stride) {
-    const int w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= found * m) return;
+                                                                    float* __restrict__ Rc, int rc_stride,
+                                                                    const KmppState* __restrict__ st = nullptr) {
+    if (st) found = st->round;  // asynchronous rounds: a fixed grid strides over the found x m pairs
+    const int lane = threadIdx.x & 31;
+    const int n_w = (gridDim.x * 256) >> 5;
+    for (int w = (blockIdx.x * 256 + threadIdx.x) >> 5; w < found * m; w += n_w) {
     const int a = w / m, j = w - a * m;
     const float* c = centers + (size_t)a * d;
     const float* r = rows + (size_t)j * d;
@@ -204,6 +216,7 @@ __global__ void __launch_bounds__(256) kmpp_center_cand_dist_kernel(const float*
         float f = (float)R;
         if ((double)f > R) f = nextafterf(f, 0.f);  // never above the true distance
         Rc[(size_t)a * rc_stride + j] = (s == s) ? f : 0.f;  // [center][candidate]; NaN data: no pruning
+    }
     }
 }
 
@@ -364,8 +377,9 @@ __global__ void kmpp_tree_pick_kernel(TreeLevels T, const unsigned char* __restr
 // r = root*u <= root always goes left there, so the walk equals the one from H; phase B (the owner of that node)
 // finishes the descent in its shard.
 __global__ void kmpp_pick_top_kernel(TreeLevels T, int Hs, KmppState* st, const float* __restrict__ u, int m,
-                                     long long* __restrict__ node10, float* __restrict__ resid) {
+                                     long long* __restrict__ node10, float* __restrict__ resid, int by_round = 0) {
     __shared__ float root;
+    if (by_round) u += (size_t)(st->round - 1) * m;  // this round's uniforms (the host does not pass a per-round pointer)
     if (threadIdx.x == 0) {
         root = tree_node_sum(T, nullptr, Hs, 0);
         st->dist_sum = root;
@@ -930,9 +944,27 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         B2K_TRY(bFail.alloc(16));
         CUDA_TRY(cudaMemsetAsync(bFail.p, 0, 16, st));
     }
+    if (async_rounds) {
+        kmpp_set_round_kernel<<<1, 1, 0, st>>>(S, 1);
+        LAUNCH_CHECK();
+    }
+    // Asynchronous rounds are identical launches (every per-round quantity lives in the device state), so from the third
+    // round on they are replayed from ONE captured CUDA graph: ~15 kernel nodes per graph launch instead of ~15 launches.
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    bool capturing = false;
     KmppState hs;
     for (int found = 1; found < k; ++found) {
-        const float* ur = bU.as<float>() + (size_t)(found - 1) * m;
+        if (async_rounds && gexec) {
+            CUDA_TRY(cudaGraphLaunch(gexec, st));
+            g_launches.fetch_add(1);
+            continue;
+        }
+        if (async_rounds && ctx->kmpp_async == 2 && found == 2 && k > 3) {
+            capturing = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (!capturing) cudaGetLastError();
+        }
+        const float* ur = async_rounds ? bU.as<float>() : bU.as<float>() + (size_t)(found - 1) * m;
         // ---- tree over D: local heights 5 and 10, [sum] height 10, replicated upper levels ----
         float* l10 = ex ? xf : bL10g.as<float>();
         if (ex) CUDA_TRY(cudaMemsetAsync(xf, 0, (size_t)n10g * 4, st));
@@ -946,7 +978,7 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         }
         B2K_TRY(tree_top(bL10g.as<float>(), 1, bL15.as<float>(), bL20.as<float>(), bL25.as<float>(), bL30.as<float>()));
         // ---- candidates ----
-        kmpp_pick_top_kernel<<<1, 32, 0, st>>>(T, Hs, S, ur, m, bNode.as<long long>(), bResid.as<float>());
+        kmpp_pick_top_kernel<<<1, 32, 0, st>>>(T, Hs, S, ur, m, bNode.as<long long>(), bResid.as<float>(), async_rounds ? 1 : 0);
         LAUNCH_CHECK();
         kmpp_pick_leaf_kernel<<<1, 32, 0, st>>>(T, taken, n, node_lo, lo, bNode.as<long long>(), bResid.as<float>(), m, xil);
         LAUNCH_CHECK();
@@ -957,8 +989,12 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         // ---- potentials ----
         if (prune && n > 0) {
             // distances of the m candidates to the `found` centers chosen so far, then the pruned distance rows
-            kmpp_center_cand_dist_kernel<<<(unsigned)cdiv((int64_t)found * m * 32, 256), 256, 0, st>>>(
-                dcenters_out, found, rows, m, d, bRc.as<float>(), rc_stride);
+            if (async_rounds)  // fixed grid, `found` read from the device state
+                kmpp_center_cand_dist_kernel<<<(unsigned)std::min<int64_t>(cdiv((int64_t)k * m * 32, 256), ctx->sm_count * 8), 256, 0,
+                                               st>>>(dcenters_out, found, rows, m, d, bRc.as<float>(), rc_stride, S);
+            else
+                kmpp_center_cand_dist_kernel<<<(unsigned)cdiv((int64_t)found * m * 32, 256), 256, 0, st>>>(
+                    dcenters_out, found, rows, m, d, bRc.as<float>(), rc_stride);
             LAUNCH_CHECK();
             B2K_TRY(launch_dist_rows_pruned(ctx, dX, n, d, rows, m, cd, D, bAssigned.as<int32_t>(), taken,
                                             bRc.as<float>(), rc_stride, bList.as<uint32_t>(), bMasks.as<uint32_t>(),
@@ -988,14 +1024,27 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         kmpp_select_kernel<<<1, 32, 0, st>>>(S, pots, m, taken, n);
         LAUNCH_CHECK();
         if (async_rounds) {
-            kmpp_commit_dev_kernel<<<1, 128, 0, st>>>(S, lo, n, rows, d, taken, dcenters_out + (size_t)found * d,
-                                                      bChosen.as<long long>() + found, bFail.as<int>());
+            kmpp_commit_dev_kernel<<<1, 128, 0, st>>>(S, lo, n, rows, d, taken, dcenters_out, bChosen.as<long long>(),
+                                                      bFail.as<int>(), k);
             LAUNCH_CHECK();
-            if (found + 1 < k) {
-                kmpp_update_dev_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(
-                    D, taken, n, cd, S, prune ? 1 : 0, prune ? bAssigned.as<int32_t>() : nullptr, found,
-                    prune ? bFrameMask.as<uint16_t>() : nullptr, bFail.as<int>());
-                LAUNCH_CHECK();
+            // (also after the last pick: the D2 update is then unused, but every round stays the same launch sequence)
+            kmpp_update_dev_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(
+                D, taken, n, cd, S, prune ? 1 : 0, prune ? bAssigned.as<int32_t>() : nullptr,
+                prune ? bFrameMask.as<uint16_t>() : nullptr, bFail.as<int>());
+            LAUNCH_CHECK();
+            if (capturing) {
+                capturing = false;
+                if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph &&
+                    cudaGraphInstantiate(&gexec, graph, 0) == cudaSuccess) {
+                    CUDA_TRY(cudaGraphLaunch(gexec, st));  // the captured round itself has not run yet
+                    g_launches.fetch_add(1);
+                } else {
+                    cudaGetLastError();
+                    if (graph) cudaGraphDestroy(graph);
+                    graph = nullptr;
+                    gexec = nullptr;
+                    return set_error(B2K_ERR_CUDA, "k-means++: graph capture of a round failed");
+                }
             }
             continue;
         }
@@ -1041,6 +1090,11 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
     }
     if (async_rounds) {
         int fail = 0;
+        if (gexec) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            cudaGraphExecDestroy(gexec);
+            cudaGraphDestroy(graph);
+        }
         CUDA_TRY(cudaMemcpyAsync(&fail, bFail.p, 4, cudaMemcpyDeviceToHost, st));
         if (k > 1)
             CUDA_TRY(cudaMemcpyAsync(chosen.data() + 1, bChosen.as<long long>() + 1, (size_t)(k - 1) * 8, cudaMemcpyDeviceToHost, st));

@@ -25,7 +25,7 @@ else:
 cen = torch.empty((k, d), dtype=torch.float32, device=dev)
 chosen = (C.c_int64 * k)()
 res = {}
-for mode in (1, 0, 1, 0):
+for mode in (2, 1, 0, 2, 1, 0):
     ctx.set_option("kmpp_async", mode)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -37,11 +37,11 @@ for mode in (1, 0, 1, 0):
     dt = (time.perf_counter() - t0) / reps
     res[mode] = list(chosen)
     print("async=%d  %.2f ms per seeding (%.1f us per round)  fallbacks so far %d" % (mode, dt * 1e3, dt / k * 1e6, ctx.get_stat("kmpp_async_fallbacks")))
-print("picks identical:", res[0] == res[1])
+print("picks identical:", res[0] == res[1] == res[2])
 # the Lloyd loop that follows the seeding in a fit (cfg1: 10 iterations)
 code, iters = C.c_int(0), C.c_int(0)
 inert = (C.c_float * 16)()
-for mode in (1, 0, 1, 0):
+for mode in (2, 0):
     ctx.set_option("kmpp_async", mode)
     for what in ("seed+loop", "loop only"):
         torch.cuda.synchronize()
