@@ -326,6 +326,18 @@ def distributed_parity(ctx, dist, rank, ws, dev):
     dist.all_gather(parts, lab)
     dtraj = torch.cat(parts).cpu().numpy()
     centers = cur.cpu().numpy()
+    # --- sharded metric='minRMSD' assign: 4096 conformations of 20 atoms against 64 of them ---
+    Y = conformations(4096, 20, 12, 9)
+    Cy = Y[::64].copy()
+    ylo, yhi = rank * (4096 // ws), (4096 if rank == ws - 1 else (rank + 1) * (4096 // ws))
+    dY, dCy = torch.from_numpy(Y[ylo:yhi]).to(dev), torch.from_numpy(Cy).to(dev)
+    ylab = torch.empty(yhi - ylo, dtype=torch.int32, device=dev)
+    _lib.check(lib.b2k_dev_assign(ctx.handle, C.c_void_p(dY.data_ptr()), yhi - ylo, 60, C.c_void_p(dCy.data_ptr()), 64, 1,
+                                  C.c_void_p(ylab.data_ptr()), None))
+    ysizes = [4096 // ws] * (ws - 1) + [4096 - (4096 // ws) * (ws - 1)]
+    yparts = [torch.empty(s, dtype=torch.int32, device=dev) for s in ysizes]
+    dist.all_gather(yparts, ylab)
+    ydtraj = torch.cat(yparts).cpu().numpy()
     if rank != 0:
         return None
     from oracle import oracle as O
@@ -339,7 +351,8 @@ def distributed_parity(ctx, dist, rank, ws, dev):
             "kmpp_picks": bool(np.array_equal(picks, ridx)), "kmpp_picks_sha1": h(picks), "oracle_picks_sha1": h(ridx),
             "centers_max_rel_err_vs_f64_oracle": float(np.abs(centers - rcen).max() / np.abs(rcen).max()),
             "centers": bool(np.abs(centers - rcen).max() <= 1e-5 * np.abs(rcen).max()),
-            "dtrajs": bool(np.array_equal(dtraj, rdtraj)), "dtrajs_sha1": h(dtraj), "oracle_dtrajs_sha1": h(rdtraj)}
+            "dtrajs": bool(np.array_equal(dtraj, rdtraj)), "dtrajs_sha1": h(dtraj), "oracle_dtrajs_sha1": h(rdtraj),
+            "minrmsd_dtrajs": bool(np.array_equal(ydtraj, O.assign(Y, Cy, "minRMSD", n_threads=os.cpu_count() or 1)))}
 
 
 # ---------------------------------------------------------------------------------------------- main
@@ -560,7 +573,7 @@ def main():
     if sampler:
         sampler.start()
         time.sleep(0.3)  # the child is up (and has taken its first sample) before the timed region starts
-        barrier()
+    barrier()            # every rank (the sampler only runs on rank 0)
     ctx.set_option("profile", 1)
     l0 = _lib.launch_count()
     if W["kind"] == "fit":
@@ -688,6 +701,33 @@ def main():
         extra["kmeans_pp"] = {"frames": kn, "k": K, "seconds": dtk, "ms_per_round": dtk / K * 1e3,
                               "hbm_frac_naive": float(K) * kn * (4 * D + 8) / dtk / 1e9 / peak_hbm,
                               "note": "exact triangle-inequality pruning skips most frame reads, so the naive-traffic fraction may exceed 1"}
+
+    if W["name"] == "cfg4" and ws > 1:
+        # sharded k-means++: the frames of all ranks, 300 rounds timed (4 small all-reduces per round)
+        kk = 300
+        nf = int(lib.b2k_kmpp_exchange_floats(n * ws, D, kk))
+        xf = torch.zeros(max(nf, 1), dtype=torch.float32, device=dev)
+        xi = torch.zeros(32, dtype=torch.int64, device=dev)
+        ops = {0: dist.ReduceOp.SUM, 1: dist.ReduceOp.MAX, 2: dist.ReduceOp.MIN}
+
+        def exchange(_user, which, count, op):
+            try:
+                dist.all_reduce((xf if which == 0 else xi)[:count], op=ops[op])
+                stream.synchronize()
+                return 0
+            except Exception:
+                return 1
+
+        fn = _lib.EXCHANGE(exchange)
+        cenk = torch.empty((kk, D), dtype=torch.float32, device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        _lib.check(lib.b2k_dev_kmeans_init_centers_kmpp_sharded(
+            ctx.handle, C.c_void_p(X.data_ptr()), n, D, kk, 0, 42, rank * n, n * ws, C.c_void_p(xf.data_ptr()), xf.numel(),
+            C.c_void_p(xi.data_ptr()), fn, None, _lib.CALLBACK(0), None, C.c_void_p(cenk.data_ptr()), None))
+        barrier()
+        dtk = time.perf_counter() - t0
+        extra["kmeans_pp_sharded"] = {"frames_total": n * ws, "k": kk, "seconds": dtk, "ms_per_round": dtk / kk * 1e3}
 
     # ---------------------------------------------------------------- e2e: host buffers, copies inside the timed region
     if args.stage_mb > 0:
