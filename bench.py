@@ -602,12 +602,13 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_hbm = peaks.get("hbm_gbs", 6500.0)
     src = ("measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)")
-    traffic = None
-    try:
+    traffic_by_class = {}
+    try:  # measured DRAM bytes per launch (ncu --set full) of the kernel classes captured for this exact shape, else null
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tr.get("%s n=%d d=%d k=%d" % (W["name"], n, D, K), {}).get("dram_bytes_per_launch")
+        traffic_by_class = tr.get("%s n=%d d=%d k=%d" % (W["name"], n, D, K), {})
     except Exception:
         pass
+    traffic = traffic_by_class.get("screen")
     gemm_launches = ctx.get_stat("screen_gemm_launches")
     gemm_ms = ctx.get_stat("screen_gemm_ms_total") / gemm_launches if gemm_launches else None
     classes = {}
@@ -660,7 +661,8 @@ def main():
                      "sums": "member sums (seg_* counting sort + seg_sum_kernel)", "cost": "cost (labeled distances + integer sum)",
                      "lists": "per-tile center lists (prune.cu)"}
             roofline = {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
-                        "traffic": None, "kernel": names[dominant], "kernel_ms": kms, "peak_source": "hbm_gbs, " + src,
+                        "traffic": traffic_by_class.get(dominant), "kernel": names[dominant], "kernel_ms": kms,
+                        "peak_source": "hbm_gbs, " + src,
                         "algorithmic_bytes_per_launch": n * (4.0 * D + 4), "screen_kernel": screen_roof}
         roofline["step_frac"] = flops / (step_ms * 1e-3) / 1e12 / peak_tf
     elif W["kind"] == "lloyd":
