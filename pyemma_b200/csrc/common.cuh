@@ -103,7 +103,8 @@ struct b2k_ctx {
                               // 2 (default) additionally replayed from one captured CUDA graph, 0 synchronous loop
     int kmpp_prune = 1;       // k-means++ (blocked, euclidean): skip candidate distances the triangle inequality decides
     int operand_kernel = 0;   // frame operand builder: 0 per-input-element tile kernel, 1 per-output-piece kernel
-    int fallback_mode = 0;    // frames the screen cannot bound: 0 indexed exact tile kernel, 1 CTA-per-frame scan
+    int fallback_mode = 0;    // frames the screen cannot bound: 0 by queue length (< 256: CTA-per-frame scan, else the indexed
+                              // exact tile kernel), 1 always CTA per frame, 2 always the tile kernel
     int verify_mode = 0;      // wide rows: 0 direct (no staging) verify kernel, 1 shared-memory staged variants
     int screen_cluster = 0;     // 2: streaming-mode screen kernel as 2-CTA clusters sharing the center tiles (TMA multicast)
     int screen_resident_a = 0;  // screen kernel: keep the frame tile in shared memory when the center operand does not fit.

@@ -192,10 +192,11 @@ __global__ void __launch_bounds__(128) tile_indexed_kernel(const float* __restri
                                                            const unsigned int* __restrict__ count_dev,
                                                            const int* __restrict__ run_if_nonzero,
                                                            int32_t* __restrict__ labels, float* __restrict__ mind,
-                                                           int lloyd) {
+                                                           int lloyd, unsigned int min_count) {
     extern __shared__ __align__(16) float sm[];
     if (run_if_nonzero && *run_if_nonzero == 0) return;
     const unsigned int count = *count_dev;
+    if (count < min_count) return;  // a handful of frames: the CTA-per-frame scan takes them (screen.cu)
     float* xs = sm;
     float* cs = sm + (size_t)cfg.FB * cfg.xstride;
     float* red_s = cs + (size_t)cfg.KT * cfg.ds;
@@ -707,7 +708,7 @@ static int launch_tile_gated(b2k_ctx* ctx, const float* X, int64_t n, int d, con
 
 int launch_tile_indexed(b2k_ctx* ctx, const float* X, int d, const float* C, int k, const uint32_t* row_index,
                         const unsigned int* count_dev, const int* run_if_nonzero, int32_t* labels, float* mind,
-                        int lloyd) {
+                        int lloyd, unsigned int min_count) {
     if (k <= 0) return B2K_OK;
     const size_t budget = std::min<size_t>(ctx->smem_optin, 100 * 1024);  // two CTAs per SM
     TileCfg cfg = tile_cfg(d, k, budget);
@@ -720,7 +721,7 @@ int launch_tile_indexed(b2k_ctx* ctx, const float* X, int d, const float* C, int
         attr_set.done(ctx->device);
     }
     tile_indexed_kernel<<<ctx->sm_count * 2, 128, cfg.smem, ctx->stream>>>(X, d, C, k, cfg, row_index, count_dev,
-                                                                          run_if_nonzero, labels, mind, lloyd);
+                                                                          run_if_nonzero, labels, mind, lloyd, min_count);
     LAUNCH_CHECK();
     return B2K_OK;
 }

@@ -17,7 +17,7 @@ int launch_tile(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, 
 // exact argmin for the frames row_index[0 .. *count_dev) (device-side count; skipped when *run_if_nonzero == 0)
 int launch_tile_indexed(b2k_ctx* ctx, const float* X, int d, const float* C, int k, const uint32_t* row_index,
                         const unsigned int* count_dev, const int* run_if_nonzero, int32_t* labels, float* mind,
-                        int lloyd);
+                        int lloyd, unsigned int min_count = 0 /* the kernel returns at once for shorter lists */);
 // out[j][i] = sqrt(dist2(x_i, rows_j)), j < m
 int launch_dist_rows(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* rows, int m, float* out);
 // same with the k-means++ triangle-inequality pruning (exact.cu DistRowsPrune); D == null: no pruning

@@ -242,25 +242,50 @@ __global__ void __launch_bounds__(256, 4) tile_lists_direct_kernel(const float* 
     }
 }
 
-// cc[a][j] = |c_a - c_j| (fp32, any order: the consumer's slack covers it); one warp per (a, j-block of 32)
+// cc[a][j] = |c_a - c_j| (fp32 differences, any order: the consumer's slack covers it).  32 x 32 output blocks of the upper
+// triangle, the d-range walked in shared-memory slabs of 32 columns; 256 threads, 2 x 2 outputs each; the mirror block is
+// written from the same sums (round 2's first version -- one warp per row and 32 columns, rows straight from L2 -- took
+// 3.0 ms per step at k=5000, d=256)
 __global__ void __launch_bounds__(256) center_dist_kernel(const float* __restrict__ C, int k, int d, float* __restrict__ cc) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
-    const int jb = (k + 31) / 32;
-    if (warp >= (int64_t)k * jb) return;
-    const int a = (int)(warp / jb), j0 = (int)(warp % jb) * 32;
-    const float* ca = C + (int64_t)a * d;
-    // lanes stride the dimension; the 32 centers of the block one after the other (coalesced row reads)
-    for (int jj = 0; jj < 32; ++jj) {
-        const int j = j0 + jj;
-        if (j >= k) break;
-        const float* cj = C + (int64_t)j * d;
-        float s = 0.f;
-        for (int e = lane; e < d; e += 32) { const float t = __ldg(ca + e) - __ldg(cj + e); s = fmaf(t, t, s); }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) cc[(int64_t)a * k + j] = sqrtf(s);
+    __shared__ float As[32][33], Bs[32][33];
+    // linear block index -> (bi <= bj)
+    const int nb = (k + 31) / 32;
+    int bi = 0, rem = blockIdx.x;
+    while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
+    const int bj = bi + rem;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+    for (int e0 = 0; e0 < d; e0 += 32) {
+        for (int t = threadIdx.x; t < 32 * 32; t += 256) {
+            const int r = t >> 5, c = t & 31;
+            const int ra = bi * 32 + r, rb = bj * 32 + r;
+            As[r][c] = (ra < k && e0 + c < d) ? __ldg(C + (int64_t)ra * d + e0 + c) : 0.f;
+            Bs[r][c] = (rb < k && e0 + c < d) ? __ldg(C + (int64_t)rb * d + e0 + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) {
+            const float a0 = As[2 * ty][c], a1 = As[2 * ty + 1][c];
+            const float b0 = Bs[2 * tx][c], b1 = Bs[2 * tx + 1][c];
+            float t = a0 - b0; s00 = fmaf(t, t, s00);
+            t = a0 - b1; s01 = fmaf(t, t, s01);
+            t = a1 - b0; s10 = fmaf(t, t, s10);
+            t = a1 - b1; s11 = fmaf(t, t, s11);
+        }
+        __syncthreads();
     }
+    const int a0 = bi * 32 + 2 * ty, j0 = bj * 32 + 2 * tx;
+    const float v[2][2] = {{sqrtf(s00), sqrtf(s01)}, {sqrtf(s10), sqrtf(s11)}};
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const int a = a0 + u, j = j0 + w;
+            if (a < k && j < k) {
+                cc[(int64_t)a * k + j] = v[u][w];
+                cc[(int64_t)j * k + a] = v[u][w];
+            }
+        }
 }
 
 // wide rows: one warp per tile; a = label of the tile's first frame, delta = |c_a - p_t|;
@@ -461,8 +486,8 @@ int prune_lists(PruneState* p, const float* dC, double* mean_count, int* max_cou
         LAUNCH_CHECK();
     } else {
         B2K_TRY(p->cc.alloc((size_t)p->k * p->k * 4));
-        const int64_t warps = (int64_t)p->k * cdiv(p->k, 32);
-        center_dist_kernel<<<(unsigned)cdiv(warps, 8), 256, 0, st>>>(dC, p->k, p->d, p->cc.as<float>());
+        const int64_t nb = cdiv(p->k, 32);
+        center_dist_kernel<<<(unsigned)(nb * (nb + 1) / 2), 256, 0, st>>>(dC, p->k, p->d, p->cc.as<float>());
         LAUNCH_CHECK();
         tile_lists_cc_kernel<<<grid_cap(ctx, p->n_units, 8, 8), 256, 0, st>>>(
             dC, p->k, p->d, p->cc.as<float>(), p->labels_s.as<int32_t>(), p->n, p->sshift, p->tmean.as<float>(),

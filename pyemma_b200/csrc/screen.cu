@@ -1398,13 +1398,14 @@ __global__ void __launch_bounds__(256) screen_fallback_kernel(const float* __res
                                                               const uint32_t* __restrict__ fb_list,
                                                               const ScreenParams* __restrict__ prm,
                                                               int32_t* __restrict__ labels, float* __restrict__ mind,
-                                                              int lloyd) {
+                                                              int lloyd, unsigned int max_count) {
     extern __shared__ __align__(16) float fsm[];
     float* xs = fsm;                                   // [d]
     float* red_s = fsm + ((d + 3) & ~3);               // [256]
     int32_t* red_j = reinterpret_cast<int32_t*>(red_s + 256);
     if (!prm->valid) return;  // the whole call went to the exact tile kernel instead
     const unsigned int count = prm->fb_count;
+    if (count >= max_count) return;  // a long queue: the register-tiled kernel takes it
     for (unsigned int b = blockIdx.x; b < count; b += gridDim.x) {
         const int64_t i = fb_list[b];
         __syncthreads();
@@ -1888,6 +1889,140 @@ __global__ void __launch_bounds__(TILE_M, B2K_VT_MINBLOCKS) screen_verify_tile_l
             }
         }
         __syncthreads();  // bits / slot tables are rewritten by the next tile
+    }
+    verify_stats(my_groups, my_fb, prm);
+}
+
+
+// ---- listed verify for wide rows, one THREAD per frame (d % 4 == 0) -------------------------------------------------
+// The 8-lanes-per-frame kernels keep 4 frames per warp in flight and, with ~2.6 candidate centers per frame, 5 of 8 lanes
+// idle; the tile kernel serialises a tile behind half a dozen barriers.  Sorted frames make the plain mapping the best
+// one: a lane owns a frame, streams its row once per four candidates (32 bytes per load step: whole sectors) and reads the
+// candidates' center rows through L1 -- the 32 lanes of a warp are neighbours in space and mostly name the same handful
+// of centers, so those loads are broadcasts that hit L1.  32 frames per warp in flight, no shared memory, no barrier; every
+// (frame, center) sum is still one thread's sequential Lanes4 sum in the reference order.
+#ifndef B2K_VF_MINBLOCKS
+#define B2K_VF_MINBLOCKS 4  // measured Lloyd step at cfg3: 6.27 / 6.16 / 7.24 / 7.96 ms for 3 / 4 / 5 / 6 CTAs of 256 threads per SM
+#endif
+__global__ void __launch_bounds__(256, B2K_VF_MINBLOCKS) screen_verify_frame_listed_kernel(
+    const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Cn, int k, const uint32_t* __restrict__ cand,
+    const uint8_t* __restrict__ ncand, const uint16_t* __restrict__ tlist, int lcap, int unit_frames,
+    int32_t* __restrict__ labels, int lloyd, ScreenParams* prm, uint32_t* __restrict__ fb_list, int cg) {
+    if (!prm->valid) return;
+    const int idb = cand_id_bits(cg);
+    const uint32_t idm = cand_id_mask(cg);
+    const int nv = d >> 2;
+    unsigned long long my_groups = 0, my_fb = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const int nc = ncand[i];
+        if (nc == 255) {
+            fallback_push(prm, fb_list, i);
+            my_fb += 1;
+            continue;
+        }
+        const uint16_t* tl = tlist + (size_t)(i / unit_frames) * lcap;
+        if (nc == NCAND_DECIDED) {
+            const int j = (int)__ldg(tl + cand[i * CAND_CAP]);
+            if (j < k) labels[i] = j;
+            else { fallback_push(prm, fb_list, i); my_fb += 1; }
+            continue;
+        }
+        const uint4* cp = reinterpret_cast<const uint4*>(cand + i * CAND_CAP);
+        const uint4 p0 = cp[0];
+        uint4 p1 = make_uint4(0, 0, 0, 0);
+        if (nc > 4) p1 = cp[1];
+        const uint32_t ent[CAND_CAP] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        const float4* x4 = reinterpret_cast<const float4*>(X + i * d);
+        ArgMin am;
+        am.init();
+        // walk the candidate centers in ascending list order, four at a time
+        int t = 0;            // entry
+        uint32_t mask = nc > 0 ? ent[0] >> idb : 0u;
+        int sub = 0;          // center inside the current group
+        int q = mask ? __ffs(mask) - 1 : 0;
+        bool more = nc > 0 && mask != 0;
+        while (more) {
+            int js[4] = {0, 0, 0, 0};
+            int cnt4 = 0;
+            while (more && cnt4 < 4) {
+                uint32_t e = ent[0];
+#pragma unroll
+                for (int u = 1; u < CAND_CAP; ++u)
+                    if (u == t) e = ent[u];
+                const int pos = (int)(e & idm) * CHUNK + q * cg + sub;
+                const int j = (int)__ldg(tl + pos);
+                if (j < k) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (u == cnt4) js[u] = j;
+                    ++cnt4;
+                }
+                // advance: next center of the group, next group of the entry, next entry
+                if (++sub == cg) {
+                    sub = 0;
+                    my_groups += 1;
+                    mask &= mask - 1;
+                    if (mask) {
+                        q = __ffs(mask) - 1;
+                    } else {
+                        ++t;
+                        more = false;
+                        while (t < nc) {
+                            uint32_t e2 = ent[0];
+#pragma unroll
+                            for (int u = 1; u < CAND_CAP; ++u)
+                                if (u == t) e2 = ent[u];
+                            mask = e2 >> idb;
+                            if (mask) { q = __ffs(mask) - 1; more = true; break; }
+                            ++t;
+                        }
+                    }
+                }
+            }
+            if (cnt4 == 0) break;
+            const float4* c0 = reinterpret_cast<const float4*>(Cn + (int64_t)js[0] * d);
+            const float4* c1 = reinterpret_cast<const float4*>(Cn + (int64_t)js[1] * d);
+            const float4* c2 = reinterpret_cast<const float4*>(Cn + (int64_t)js[2] * d);
+            const float4* c3 = reinterpret_cast<const float4*>(Cn + (int64_t)js[3] * d);
+            Lanes4 L0, L1, L2, L3;
+            L0.init(); L1.init(); L2.init(); L3.init();
+            int v = 0;
+            for (; v + 2 <= nv; v += 2) {
+                const float4 xa = __ldg(x4 + v), xb = __ldg(x4 + v + 1);
+                {
+                    const float4 a = __ldg(c0 + v), b = __ldg(c0 + v + 1);
+                    L0.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w);
+                    L0.add4(xb.x, xb.y, xb.z, xb.w, b.x, b.y, b.z, b.w);
+                }
+                if (cnt4 > 1) {
+                    const float4 a = __ldg(c1 + v), b = __ldg(c1 + v + 1);
+                    L1.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w);
+                    L1.add4(xb.x, xb.y, xb.z, xb.w, b.x, b.y, b.z, b.w);
+                }
+                if (cnt4 > 2) {
+                    const float4 a = __ldg(c2 + v), b = __ldg(c2 + v + 1);
+                    L2.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w);
+                    L2.add4(xb.x, xb.y, xb.z, xb.w, b.x, b.y, b.z, b.w);
+                }
+                if (cnt4 > 3) {
+                    const float4 a = __ldg(c3 + v), b = __ldg(c3 + v + 1);
+                    L3.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w);
+                    L3.add4(xb.x, xb.y, xb.z, xb.w, b.x, b.y, b.z, b.w);
+                }
+            }
+            for (; v < nv; ++v) {
+                const float4 xa = __ldg(x4 + v);
+                { const float4 a = __ldg(c0 + v); L0.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w); }
+                if (cnt4 > 1) { const float4 a = __ldg(c1 + v); L1.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w); }
+                if (cnt4 > 2) { const float4 a = __ldg(c2 + v); L2.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w); }
+                if (cnt4 > 3) { const float4 a = __ldg(c3 + v); L3.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w); }
+            }
+            am.offer(L0.result(), js[0]);
+            if (cnt4 > 1) am.offer(L1.result(), js[1]);
+            if (cnt4 > 2) am.offer(L2.result(), js[2]);
+            if (cnt4 > 3) am.offer(L3.result(), js[3]);
+        }
+        labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
     }
     verify_stats(my_groups, my_fb, prm);
 }
@@ -2635,15 +2770,20 @@ int screen_prepare_frames(ScreenPlan* p, const float* dX, int64_t n) {
 static int screen_finish_assign(ScreenPlan* p, const float* dX, int64_t n, const float* dC, int32_t* labels,
                                 float* mind, int lloyd) {
     b2k_ctx* ctx = p->ctx;
-    if (ctx->fallback_mode == 1) {  // CTA per frame (first version; 36.7 ms for 8.4e3 frames at cfg4)
+    // queued frames: a handful -> CTA per frame, all 256 threads over the centers (the register-tiled kernel would put one
+    // CTA on a 128-frame tile that holds one frame: 1.1 ms per step at k=5000, d=256); a long queue -> register-tiled exact
+    // tile kernel (the CTA-per-frame scan needed 36.7 ms for 8.4e3 frames at cfg4).  Both are launched, the device-side
+    // count picks one.
+    const unsigned int split = ctx->fallback_mode == 1 ? 0xffffffffu : (ctx->fallback_mode == 2 ? 0u : 256u);
+    if (split > 0) {
         const size_t fsmem = ((size_t)((p->d + 3) & ~3) + 512) * 4;
-        screen_fallback_kernel<<<ctx->sm_count * 4, 256, fsmem, ctx->stream>>>(dX, p->d, dC, p->k, p->fb_list, p->params,
-                                                                              labels, mind, lloyd);
+        screen_fallback_kernel<<<ctx->sm_count * 2, 256, fsmem, ctx->stream>>>(dX, p->d, dC, p->k, p->fb_list, p->params,
+                                                                              labels, mind, lloyd, split);
         LAUNCH_CHECK();
-    } else {  // register-tiled exact tile kernel over the queued frames
-        B2K_TRY(launch_tile_indexed(ctx, dX, p->d, dC, p->k, p->fb_list, &p->params->fb_count, &p->params->valid, labels,
-                                    mind, lloyd));
     }
+    if (split != 0xffffffffu)
+        B2K_TRY(launch_tile_indexed(ctx, dX, p->d, dC, p->k, p->fb_list, &p->params->fb_count, &p->params->valid, labels,
+                                    mind, lloyd, split));
     return launch_assign_exact_if(ctx, dX, n, p->d, dC, p->k, labels, mind, lloyd, &p->params->valid);
 }
 
@@ -2973,7 +3113,12 @@ int screen_assign_listed(ScreenPlan* p, const float* dX, int64_t n, const float*
         else if (ds == 12) B2K_VTL(12);
         else B2K_VTL(16);
 #undef B2K_VTL
-    } else if (ctx->verify_mode != 2 && p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0 && lcap <= 8192 &&
+    } else if (ctx->verify_mode == 0 && p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0) {
+        // one thread per frame (the default for sorted frames)
+        const unsigned fgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 8));
+        screen_verify_frame_listed_kernel<<<fgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, tlist, lcap,
+                                                                 TILE_M << unit_shift, labels, lloyd, p->params, p->fb_list, p->cg);
+    } else if (ctx->verify_mode == 3 && p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0 && lcap <= 8192 &&
                (size_t)(p->d + 4) * 4 * 8 <= 64 * 1024) {
         // tile verify: the center rows a tile needs are staged once in shared memory
         const int rs = p->d + 4;

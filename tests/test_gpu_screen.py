@@ -153,7 +153,7 @@ def test_screen_list_overflow_goes_to_exact_scan(b2k, oracle, screen_ctx, d, k):
     X = np.zeros((6000, d), np.float32)                      # frames AT the sphere's centre: every center ties
     X[::2] = (Cn[rng.randint(0, k, 3000)] + 0.05 * rng.randn(3000, d)).astype(np.float32)  # ordinary frames
     ref = oracle.assign(X, Cn, n_threads=8)
-    for mode in (0, 1):
+    for mode in (0, 1, 2):   # by queue length / CTA per frame / indexed tile kernel (3000 queued frames: mode 0 takes the tile kernel)
         screen_ctx.set_option("fallback_mode", mode)
         try:
             np.testing.assert_array_equal(b2k.assign(X, Cn), ref, err_msg="fallback_mode=%d" % mode)
