@@ -143,7 +143,7 @@ class ClockSampler:
     process started before the region and read back after it.  Every query -- from a thread of this process, through NVML
     or from a child -- holds up kernel launches on this system for ~0.1 s (measured on the launch-bound cfg1 fit: 10.2 ms
     without sampling, 13.9 / 24.7 ms with 7 / 11 samples in the region), so the launch-bound workload samples once a
-    second and the kernel-bound ones four times."""
+    second and the kernel-bound ones ten times."""
 
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -151,31 +151,49 @@ class ClockSampler:
 
     def __init__(self, index, period_ms=250):
         self.index, self.proc, self.period_ms = index, None, int(period_ms)
+        self.rows, self.reader = [], None   # (arrival time, fields)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
                                           "--format=csv,noheader,nounits", "-lms", str(self.period_ms)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+                                         stderr=subprocess.DEVNULL, text=True, bufsize=1)
         except Exception:
             self.proc = None
+            return
 
-    def stop(self):
-        rows = []
+        def pump():  # only reads the pipe: no driver call from this process
+            for line in self.proc.stdout:
+                if line.strip():
+                    self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+        self.reader = threading.Thread(target=pump, daemon=True)
+        self.reader.start()
+
+    def stop(self, windows):
+        """windows: [(name, t0, t1)] in time.monotonic(); the first one that holds >= 3 samples is reported (the timed
+        region; for very short regions the timed region plus the e2e leg that follows it under the same load)"""
         if self.proc is not None:
             time.sleep(0.05)
             self.proc.terminate()
             try:
-                out, _ = self.proc.communicate(timeout=5)
+                self.proc.wait(timeout=5)
             except Exception:
                 self.proc.kill()
-                out = ""
-            rows = [[c.strip() for c in l.split(",")] for l in out.splitlines() if l.strip()]
+            if self.reader is not None:
+                self.reader.join(timeout=2)
+        rows, used = [], None
+        for name, t0, t1 in windows:
+            rows = [r for (t, r) in self.rows if t0 <= t <= t1]
+            used = name
+            if len(rows) >= 3:
+                break
         sm = sorted(int(r[0]) for r in rows if r[0].isdigit())
         mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         reasons = sorted({self.NAMES[i] for r in rows for i in range(4) if len(r) > 2 + i and r[2 + i] == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(rows), "source": "nvidia-smi -lms %d (child process)" % self.period_ms}
+                "reasons": reasons, "samples": len(rows), "window": used,
+                "source": "nvidia-smi -lms %d (child process)" % self.period_ms}
 
 
 # ---------------------------------------------------------------------------------------------- CPU oracle legs
@@ -569,7 +587,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank, 1000 if W["kind"] == "fit" else 250) if rank == 0 else None
+    sampler = ClockSampler(local_rank, 1000 if W["kind"] == "fit" else 100) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)  # the child is up (and has taken its first sample) before the timed region starts
@@ -579,17 +597,19 @@ def main():
     if W["kind"] == "fit":
         fit_iters.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.monotonic()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     barrier()
+    t_region1 = time.monotonic()
     launches = _lib.launch_count() - l0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if ws > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    clocks = sampler.stop() if sampler else None
+    clocks = None  # read after the e2e leg (a short timed region may hold fewer than three samples)
     if W["kind"] == "fit":
         frames_done = n * sum(fit_iters)
         extra["lloyd_iterations_per_fit"] = sum(fit_iters) / max(len(fit_iters), 1)
@@ -748,6 +768,9 @@ def main():
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
     if ws > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if sampler:
+        clocks = sampler.stop([("timed region", t_region0, t_region1),
+                               ("timed region + e2e leg (same load)", t_region0, time.monotonic())])
     e2e_frames = n * sum(e2e_iters) if W["kind"] == "fit" else n * e2e_steps
     e2e = {"value": e2e_frames * ws / float(dt.item()), "unit": "frames/s",
            "h2d_bytes_per_step": e2e_bytes[0], "d2h_bytes_per_step": e2e_bytes[1], "api": e2e_api,

@@ -611,6 +611,8 @@ struct b2k_lloyd {
     bool prune_wanted = false;
     bool have_labels = false;   // prune_labels() holds the labels of the last step (in the current frame order)
     int64_t steps = 0, next_sort = 1;
+    int64_t last_sort_step = 0;
+    double mean_after_sort = 0, mean_last = 0;  // list length right after the last sort / at the last step
 };
 
 static int ceil_log2_d(double v) {
@@ -738,10 +740,20 @@ B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32
     }
     if (s->plan && s->prune_wanted) {
         // (re)sort by the labels of the previous step when the schedule says so: steps 1, 2, 4, 8, ... or every prune_resort
-        if (s->prune && s->have_labels && s->steps >= s->next_sort) {
+        // Re-sort policy (prune_resort = 0): after iterations 1 and 2 (the labels still change a lot), then whenever the lists
+        // have grown by a quarter since the last sort -- a sort (label sort, row gather, operand rebuild, tile balls) costs
+        // about one and a half iterations, lists 25 % longer cost every iteration about 15 % -- and at iterations 4, 16, 64...
+        // at the latest.  prune_resort = n > 0: every n iterations.
+        bool resort = s->prune && s->have_labels && s->steps >= s->next_sort;
+        if (s->prune && s->have_labels && !resort && ctx->prune_resort == 0 && prune_sorted(s->prune) &&
+            s->steps >= s->last_sort_step + 2 && s->mean_after_sort > 0 && s->mean_last > 1.25 * s->mean_after_sort)
+            resort = true;
+        if (resort) {
             B2K_TRY(prune_sort(s->prune, s->dX, prune_labels(s->prune), dC));
             screen_plan_invalidate_frames(s->plan);
-            s->next_sort = ctx->prune_resort > 0 ? s->steps + ctx->prune_resort : s->steps * 2;
+            s->next_sort = ctx->prune_resort > 0 ? s->steps + ctx->prune_resort : (s->steps < 4 ? s->steps * 2 : s->steps * 4);
+            s->last_sort_step = s->steps;
+            s->mean_after_sort = 0;
             ctx->stat_prune_sorts += 1;
         }
         if (s->prune && prune_sorted(s->prune)) {
@@ -750,6 +762,8 @@ B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32
             int mx = 0, ov = 0;
             B2K_TRY(prune_lists(pr, dC, &mean, &mx, &ov));
             ctx->stat_prune_mean = mean;
+            if (s->mean_after_sort == 0) s->mean_after_sort = mean;
+            s->mean_last = mean;
             // the listed screen drains mean (padded) columns per frame, the full one k rounded up to 256
             if (ov == 0 && (mean <= 0.6 * (double)(cdiv(s->k, 256) * 256) || ctx->prune_mode == 3)) {
                 B2K_TRY(screen_assign_listed(s->plan, prune_frames(pr), s->n, dC, prune_tlist(pr), prune_tcount(pr),

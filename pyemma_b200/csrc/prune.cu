@@ -102,7 +102,7 @@ static void kd_order(const float* C, int d, int* idx, int lo, int hi) {
 // order) and radius of the unit's frames
 __global__ void __launch_bounds__(PT) tile_meta_kernel(const float* __restrict__ Xs, int64_t n, int d, int sshift,
                                                        float* __restrict__ tmean, float* __restrict__ trad) {
-    extern __shared__ float sm[];  // [4][d] partial sums, then [d] mean
+    extern __shared__ __align__(16) float sm[];  // [4][d] partial sums, then [d] mean
     float* part = sm;
     float* mean = sm + 4 * d;
     __shared__ float red[PT / 32];
@@ -115,7 +115,15 @@ __global__ void __launch_bounds__(PT) tile_meta_kernel(const float* __restrict__
     for (int e = lane; e < d; e += 32) {
         float s = 0.f;
         const int r0 = warp * per_warp, r1 = min(rows, r0 + per_warp);
-        for (int r = r0; r < r1; ++r) s += __ldg(Xs + (row0 + r) * d + e);
+        int r = r0;
+        for (; r + 8 <= r1; r += 8) {  // eight independent loads in flight, summed in row order
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(Xs + (row0 + r + u) * d + e);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; r < r1; ++r) s += __ldg(Xs + (row0 + r) * d + e);
         part[warp * d + e] = s;
     }
     __syncthreads();
@@ -126,10 +134,38 @@ __global__ void __launch_bounds__(PT) tile_meta_kernel(const float* __restrict__
     }
     __syncthreads();
     float r2 = 0.f;
+    const bool vec4 = (d & 3) == 0 && (((uintptr_t)Xs) & 15) == 0;
     for (int r = threadIdx.x; r < rows; r += PT) {
         const float* x = Xs + (row0 + r) * d;
-        float q = 0.f;
-        for (int e = 0; e < d; ++e) { const float t = __ldg(x + e) - mean[e]; q = fmaf(t, t, q); }
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+        if (vec4) {
+            const float4* x4 = reinterpret_cast<const float4*>(x);
+            const float4* m4 = reinterpret_cast<const float4*>(mean);
+            int t = 0;
+            for (; t + 4 <= (d >> 2); t += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldg(x4 + t + u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 mm = m4[t + u];
+                    float a = v[u].x - mm.x; q0 = fmaf(a, a, q0);
+                    a = v[u].y - mm.y; q1 = fmaf(a, a, q1);
+                    a = v[u].z - mm.z; q2 = fmaf(a, a, q2);
+                    a = v[u].w - mm.w; q3 = fmaf(a, a, q3);
+                }
+            }
+            for (; t < (d >> 2); ++t) {
+                const float4 vv = __ldg(x4 + t), mm = m4[t];
+                float a = vv.x - mm.x; q0 = fmaf(a, a, q0);
+                a = vv.y - mm.y; q1 = fmaf(a, a, q1);
+                a = vv.z - mm.z; q2 = fmaf(a, a, q2);
+                a = vv.w - mm.w; q3 = fmaf(a, a, q3);
+            }
+        } else {
+            for (int e = 0; e < d; ++e) { const float t = __ldg(x + e) - mean[e]; q0 = fmaf(t, t, q0); }
+        }
+        const float q = (q0 + q1) + (q2 + q3);
         r2 = fmaxf(r2, q);
         if (!(q == q)) r2 = q;  // NaN frame: keep every center (comparisons with NaN are false)
     }
