@@ -433,6 +433,95 @@ __global__ void kmpp_gather_sharded_kernel(const float* __restrict__ X, int d, c
     for (int e = threadIdx.x; e < d; e += blockDim.x) rows[(int64_t)j * d + e] = mine ? X[c * d + e] : 0.f;
 }
 
+// Asynchronous single-GPU rounds: candidate pick (upper tree levels, leaf descent), candidate registration and the gather
+// of the m candidate rows in ONE launch -- the same statements as kmpp_pick_top / pick_leaf / set_cands / gather_sharded,
+// four graph nodes (and their launch latencies on a 100 kB problem) fewer per round.
+__global__ void __launch_bounds__(128) kmpp_pick_fused_kernel(TreeLevels T, int Hs, KmppState* st, const float* __restrict__ U,
+                                                              int m, const unsigned char* __restrict__ taken, int64_t n_local,
+                                                              const float* __restrict__ X, int d, long long* __restrict__ cand_out,
+                                                              float* __restrict__ rows) {
+    __shared__ float root;
+    __shared__ long long cand_s[KMPP_MAX_TRIALS];
+    const float* u = U + (size_t)(st->round - 1) * m;
+    if (threadIdx.x == 0) {
+        root = tree_node_sum(T, nullptr, Hs, 0);
+        st->dist_sum = root;
+        st->n_cand = m;
+    }
+    __syncthreads();
+    const int j = threadIdx.x;
+    if (j < m) {
+        float r = __fmul_rn(root, u[j]);
+        st->rands[j] = r;
+        long long node = 0;
+        for (int h = Hs; h > 10; --h) {
+            const float left = tree_node_sum(T, nullptr, h - 1, 2 * node);
+            if (r <= left) node = 2 * node;
+            else { r = __fsub_rn(r, left); node = 2 * node + 1; }
+        }
+        long long c = -1;
+        if (node >= 0 && node * 1024 < n_local) {
+            for (int h = 10; h > 0; --h) {
+                const float left = tree_node_sum(T, taken, h - 1, 2 * node);
+                if (r <= left) node = 2 * node;
+                else { r = __fsub_rn(r, left); node = 2 * node + 1; }
+            }
+            if (node < n_local && !taken[node]) c = node;
+        }
+        cand_out[j] = c;
+        st->cand[j] = c;
+        cand_s[j] = c;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < m * d; t += blockDim.x) {
+        const int jj = t / d, e = t - jj * d;
+        const long long c = cand_s[jj];
+        rows[t] = (c >= 0 && c < n_local) ? X[c * d + e] : 0.f;
+    }
+}
+
+// ... and potentials -> selection -> commit in one launch (kmpp_tree_roots / select / commit_dev)
+__global__ void __launch_bounds__(128) kmpp_select_commit_kernel(KmppState* st, const float* __restrict__ lv, int64_t stride, int m,
+                                                                 float* __restrict__ pots, int64_t n_local,
+                                                                 const float* __restrict__ rows, int d,
+                                                                 unsigned char* __restrict__ taken, float* __restrict__ centers,
+                                                                 long long* __restrict__ chosen, int* fail, int k) {
+    __shared__ long long s_best;
+    __shared__ int s_jbest, s_found;
+    if (threadIdx.x == 0) {
+        long long best = -1;
+        int jbest = -1;
+        float bp = 3.402823466e+38f;
+        for (int j = 0; j < m; ++j) {
+            const float p = lv[(int64_t)j * stride];
+            pots[j] = p;
+            st->pot[j] = p;
+            if (st->cand[j] >= 0 && p < bp) { bp = p; best = st->cand[j]; jbest = j; }
+        }
+        st->best = best;
+        st->jbest = jbest;
+        s_best = best;
+        s_jbest = jbest;
+        s_found = st->round;
+    }
+    __syncthreads();
+    const long long best = s_best;
+    const int jbest = s_jbest, found = s_found;
+    if (found >= k) return;
+    if (best < 0 || jbest < 0) {
+        if (threadIdx.x == 0) { *fail = 1; st->round = found + 1; }
+        return;
+    }
+    const float* row = rows + (size_t)jbest * d;
+    float* center_out = centers + (size_t)found * d;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) center_out[e] = row[e];
+    if (threadIdx.x == 0) {
+        chosen[found] = best;
+        if (best < n_local) taken[best] = 1;
+        st->round = found + 1;
+    }
+}
+
 // contribution of local frame i to candidate j's potential; candidates are GLOBAL indices
 __global__ void kmpp_contrib_sharded_kernel(float* __restrict__ cd, int64_t n, int m, const float* __restrict__ D,
                                             const unsigned char* __restrict__ taken,
@@ -978,14 +1067,19 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         }
         B2K_TRY(tree_top(bL10g.as<float>(), 1, bL15.as<float>(), bL20.as<float>(), bL25.as<float>(), bL30.as<float>()));
         // ---- candidates ----
-        kmpp_pick_top_kernel<<<1, 32, 0, st>>>(T, Hs, S, ur, m, bNode.as<long long>(), bResid.as<float>(), async_rounds ? 1 : 0);
-        LAUNCH_CHECK();
-        kmpp_pick_leaf_kernel<<<1, 32, 0, st>>>(T, taken, n, node_lo, lo, bNode.as<long long>(), bResid.as<float>(), m, xil);
-        LAUNCH_CHECK();
-        B2K_TRY(exchange(1, m, 1));
-        kmpp_set_cands_kernel<<<1, 32, 0, st>>>(S, xil, m);
-        LAUNCH_CHECK();
-        B2K_TRY(fetch_rows(m));  // reads xil; `rows` valid on every rank afterwards
+        if (async_rounds) {  // (lo = 0, one shard: pick, registration and row gather in one launch)
+            kmpp_pick_fused_kernel<<<1, 128, 0, st>>>(T, Hs, S, bU.as<float>(), m, taken, n, dX, d, xil, rows);
+            LAUNCH_CHECK();
+        } else {
+            kmpp_pick_top_kernel<<<1, 32, 0, st>>>(T, Hs, S, ur, m, bNode.as<long long>(), bResid.as<float>(), 0);
+            LAUNCH_CHECK();
+            kmpp_pick_leaf_kernel<<<1, 32, 0, st>>>(T, taken, n, node_lo, lo, bNode.as<long long>(), bResid.as<float>(), m, xil);
+            LAUNCH_CHECK();
+            B2K_TRY(exchange(1, m, 1));
+            kmpp_set_cands_kernel<<<1, 32, 0, st>>>(S, xil, m);
+            LAUNCH_CHECK();
+            B2K_TRY(fetch_rows(m));  // reads xil; `rows` valid on every rank afterwards
+        }
         // ---- potentials ----
         if (prune && n > 0) {
             // distances of the m candidates to the `found` centers chosen so far, then the pruned distance rows
@@ -1018,15 +1112,17 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         {
             const float* lv = Hs <= 10 ? xf : (Hs <= 20 ? bP20.as<float>() : bP30.as<float>());
             const int64_t stride = Hs <= 10 ? n10g : (Hs <= 20 ? n20g : n30g);
-            kmpp_tree_roots_kernel<<<1, 32, 0, st>>>(lv, stride, m, pots);
+            if (async_rounds) {
+                kmpp_select_commit_kernel<<<1, 128, 0, st>>>(S, lv, stride, m, pots, n, rows, d, taken, dcenters_out,
+                                                             bChosen.as<long long>(), bFail.as<int>(), k);
+            } else {
+                kmpp_tree_roots_kernel<<<1, 32, 0, st>>>(lv, stride, m, pots);
+                LAUNCH_CHECK();
+                kmpp_select_kernel<<<1, 32, 0, st>>>(S, pots, m, taken, n);
+            }
             LAUNCH_CHECK();
         }
-        kmpp_select_kernel<<<1, 32, 0, st>>>(S, pots, m, taken, n);
-        LAUNCH_CHECK();
         if (async_rounds) {
-            kmpp_commit_dev_kernel<<<1, 128, 0, st>>>(S, lo, n, rows, d, taken, dcenters_out, bChosen.as<long long>(),
-                                                      bFail.as<int>(), k);
-            LAUNCH_CHECK();
             // (also after the last pick: the D2 update is then unused, but every round stays the same launch sequence)
             kmpp_update_dev_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(
                 D, taken, n, cd, S, prune ? 1 : 0, prune ? bAssigned.as<int32_t>() : nullptr,
