@@ -465,17 +465,21 @@ def main():
                 dist.all_reduce(acc[:acc_len - 1])
             _lib.check(lib.b2k_dev_lloyd_finalize(sess, C.c_void_p(acc.data_ptr()), C.c_void_p(c.data_ptr()),
                                                   C.c_void_p(nx.data_ptr())))
-            _lib.check(lib.b2k_dev_lloyd_cost(sess, C.c_void_p(nx.data_ptr()), C.c_void_p(labels.data_ptr()),
-                                              C.c_void_p(acc.data_ptr())))
+            _lib.check(lib.b2k_dev_lloyd_cost(sess, C.c_void_p(nx.data_ptr()), step_labels[0], C.c_void_p(acc.data_ptr())))
             if ws > 1:
                 dist.all_reduce(acc[acc_len - 1:])
             # the loop's convergence test needs the cost on the host every iteration
             costs.append(lib.b2k_dev_lloyd_decode_cost(sess, int(acc[acc_len - 1].item())))
             state["cur"], state["nxt"] = nx, c
 
+        # the resident loop does not ask for per-iteration labels in its frame order (deeptime's cluster_loop returns
+        # centers; the session keeps the labels and b2k_dev_lloyd_get_labels hands them out -- read once after the region)
+        step_labels = [None]
+
         def step():
-            _lib.check(lib.b2k_dev_lloyd_assign_accumulate(sess, C.c_void_p(state["cur"].data_ptr()),
-                                                           C.c_void_p(labels.data_ptr()), C.c_void_p(acc.data_ptr())))
+            step_labels[0] = None
+            _lib.check(lib.b2k_dev_lloyd_assign_accumulate(sess, C.c_void_p(state["cur"].data_ptr()), None,
+                                                           C.c_void_p(acc.data_ptr())))
             finish_step()
 
         hx = hl = None
@@ -487,6 +491,7 @@ def main():
             hl = torch.empty(n, dtype=torch.int32, pin_memory=True)
 
         def e2e_step():
+            step_labels[0] = C.c_void_p(labels.data_ptr())
             _lib.check(lib.b2k_stage_lloyd_assign_accumulate(sess, C.c_void_p(hx.data_ptr()),
                                                              C.c_void_p(state["cur"].data_ptr()), C.c_void_p(X.data_ptr()),
                                                              C.c_void_p(labels.data_ptr()), C.c_void_p(hl.data_ptr()),
@@ -605,6 +610,9 @@ def main():
     barrier()
     t_region1 = time.monotonic()
     launches = _lib.launch_count() - l0
+    if W["kind"] == "lloyd":  # the labels of the last timed iteration, in the caller's frame order
+        _lib.check(lib.b2k_dev_lloyd_get_labels(sess, C.c_void_p(labels.data_ptr())))
+        extra["last_labels_sum"] = int(labels.to(torch.int64).sum().item())
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if ws > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

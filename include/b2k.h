@@ -150,8 +150,12 @@ int b2k_dev_lloyd_create(b2k_ctx* ctx, const float* dX, int64_t n_local, int32_t
                          int64_t n_total, float absmax_global, b2k_lloyd** out);
 int b2k_dev_lloyd_destroy(b2k_lloyd* s);
 int64_t b2k_dev_lloyd_acc_len(const b2k_lloyd* s);
-/* labels (n_local) <- argmin vs dcenters (Lloyd tie/NaN semantics); acc <- local sums+counts (cost slot zeroed) */
-int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dcenters, int32_t* dlabels, int64_t* dacc);
+/* labels (n_local) <- argmin vs dcenters (Lloyd tie/NaN semantics); acc <- local sums+counts (cost slot zeroed).
+ * dlabels may be NULL: the loop itself never needs the labels in the caller's frame order (deeptime's cluster_loop returns
+ * centers only, kmeans.py:254-258), the session then keeps them (after its first iteration it works on a copy of the frames
+ * sorted by label) and b2k_dev_lloyd_get_labels hands them out on request. */
+int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dcenters, int32_t* dlabels_or_null, int64_t* dacc);
+int b2k_dev_lloyd_get_labels(b2k_lloyd* s, int32_t* dlabels_out);
 /* the two calls above for frames that are still on the HOST: the shard's frames X (n_local x d, host) are staged chunk
  * by chunk into the session's device array dX_out (the pointer given to b2k_dev_lloyd_create), every chunk is assigned
  * and its member sums are added to acc while the next chunk is on the bus; labels also go to labels_host if given */
@@ -168,8 +172,9 @@ int b2k_stage_lloyd_pass(b2k_lloyd* s, const float* X, const float* dcenters, in
 int b2k_dev_lloyd_accumulate(b2k_lloyd* s, const int32_t* dlabels, int64_t* dacc);
 /* new centers from (all-reduced) acc; count==0 keeps old */
 int b2k_dev_lloyd_finalize(b2k_lloyd* s, const int64_t* dacc, const float* dcenters_old, float* dcenters_new);
-/* acc[k*d+k] <- local fixed-point sum of compute(x_i, new_centers[label_i])^2 */
-int b2k_dev_lloyd_cost(b2k_lloyd* s, const float* dcenters_new, const int32_t* dlabels, int64_t* dacc);
+/* acc[k*d+k] <- local fixed-point sum of compute(x_i, new_centers[label_i])^2, label_i = the labels of the session's last
+ * b2k_dev_lloyd_assign_accumulate (dlabels: that call's label array, or NULL if it was called with NULL) */
+int b2k_dev_lloyd_cost(b2k_lloyd* s, const float* dcenters_new, const int32_t* dlabels_or_null, int64_t* dacc);
 /* host-side decode of the (all-reduced) cost slot */
 double b2k_dev_lloyd_decode_cost(const b2k_lloyd* s, int64_t cost_fixed);
 /* max |x| over a device array (for absmax_global; all-reduce(max) it across ranks) */

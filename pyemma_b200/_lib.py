@@ -34,6 +34,7 @@ SYMBOLS = [
     "b2k_regspace_get_centers", "b2k_regspace_cluster", "b2k_kmpp_exchange_floats",
     "b2k_dev_kmeans_init_centers_kmpp_sharded", "b2k_dev_count_states", "b2k_dev_count_matrix",
     "b2k_stage_lloyd_assign_accumulate", "b2k_dev_project", "b2k_stage_project", "b2k_upload",
+    "b2k_stage_lloyd_pass", "b2k_dev_lloyd_get_labels",
 ]
 
 
@@ -85,6 +86,7 @@ def load():
         L.b2k_dev_lloyd_acc_len.restype = i64
         L.b2k_dev_lloyd_assign_accumulate.argtypes = [vp, vp, vp, vp]
         L.b2k_dev_lloyd_finalize.argtypes = [vp, vp, vp, vp]
+        L.b2k_dev_lloyd_get_labels.argtypes = [vp, vp]
         L.b2k_dev_lloyd_accumulate.argtypes = [vp, vp, vp]
         L.b2k_stage_assign.argtypes = [vp, vp, i64, i32, vp, i32, C.c_int, C.c_int, vp, vp, vp]
         L.b2k_dev_lloyd_cost.argtypes = [vp, vp, vp, vp]

@@ -444,15 +444,14 @@ class KmeansClustering(AbstractClustering):
             inertias = []
             tol = np.float32(self.tolerance)
             while True:
-                _lib.check(lib.b2k_dev_lloyd_assign_accumulate(sess, C.c_void_p(cur.data_ptr()),
-                                                               C.c_void_p(labels.data_ptr()),
+                # (no per-iteration labels in frame order: the session keeps them, kmeans.py:254-258 returns centers only)
+                _lib.check(lib.b2k_dev_lloyd_assign_accumulate(sess, C.c_void_p(cur.data_ptr()), None,
                                                                C.c_void_p(acc.data_ptr())))
                 if ws > 1:
                     dist.all_reduce(acc[:acc_len - 1])
                 _lib.check(lib.b2k_dev_lloyd_finalize(sess, C.c_void_p(acc.data_ptr()), C.c_void_p(cur.data_ptr()),
                                                       C.c_void_p(nxt.data_ptr())))
-                _lib.check(lib.b2k_dev_lloyd_cost(sess, C.c_void_p(nxt.data_ptr()), C.c_void_p(labels.data_ptr()),
-                                                  C.c_void_p(acc.data_ptr())))
+                _lib.check(lib.b2k_dev_lloyd_cost(sess, C.c_void_p(nxt.data_ptr()), None, C.c_void_p(acc.data_ptr())))
                 if ws > 1:
                     dist.all_reduce(acc[acc_len - 1:])
                 cost = np.float32(lib.b2k_dev_lloyd_decode_cost(sess, int(acc[acc_len - 1].item())))
@@ -469,6 +468,8 @@ class KmeansClustering(AbstractClustering):
                 it += 1
                 if not (it < self.max_iter and not converged):
                     break
+            if n_local:
+                _lib.check(lib.b2k_dev_lloyd_get_labels(sess, C.c_void_p(labels.data_ptr())))
             self._dev_last_labels = labels[:n_local]
             return cur, converged, inertias
         finally:

@@ -613,6 +613,10 @@ struct b2k_lloyd {
     int64_t steps = 0, next_sort = 1;
     int64_t last_sort_step = 0;
     double mean_after_sort = 0, mean_last = 0;  // list length right after the last sort / at the last step
+    // labels of the last step when the caller did not ask for them (dlabels == NULL): the loop itself never needs them in
+    // the caller's frame order (deeptime's cluster_loop returns centers only); b2k_dev_lloyd_get_labels hands them out
+    DevMem own_labels;
+    bool labels_in_own = false, labels_in_prune = false;
 };
 
 static int ceil_log2_d(double v) {
@@ -689,6 +693,7 @@ B2K_API int b2k_stage_lloyd_assign_accumulate(b2k_lloyd* s, const float* X, cons
     // the frame array is rewritten: whatever the session derived from its old content (sorted copy, fp16 operand) is stale
     if (s->prune) { prune_destroy(s->prune); s->prune = nullptr; }
     s->have_labels = false;
+    s->labels_in_own = s->labels_in_prune = false;
     s->steps = 0;
     s->next_sort = 1;
     if (s->plan) screen_plan_invalidate_frames(s->plan);
@@ -718,7 +723,13 @@ B2K_API int b2k_stage_lloyd_pass(b2k_lloyd* s, const float* X, const float* dcen
 B2K_API int64_t b2k_dev_lloyd_acc_len(const b2k_lloyd* s) { return s ? (int64_t)s->k * s->d + s->k + 1 : 0; }
 
 B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32_t* dlabels, int64_t* dacc) {
-    if (!s || !dC || !dacc || (s->n > 0 && !dlabels)) return set_error(B2K_ERR_INVALID_ARG, "lloyd step: null argument");
+    if (!s || !dC || !dacc) return set_error(B2K_ERR_INVALID_ARG, "lloyd step: null argument");
+    const bool want_labels = dlabels != nullptr;
+    s->labels_in_own = s->labels_in_prune = false;
+    if (!dlabels && s->n > 0) {  // the caller does not want the labels: keep them here
+        B2K_TRY(s->own_labels.alloc((size_t)s->n * 4));
+        dlabels = s->own_labels.as<int32_t>();
+    }
     if (s->n > 0 && !s->dX) return set_error(B2K_ERR_INVALID_ARG, "lloyd step: out-of-core session (use b2k_stage_lloyd_pass)");
     b2k_ctx* ctx = s->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -778,7 +789,8 @@ B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32
             ctx->stat_pending = true;
             s->have_labels = true;
             s->steps += 1;
-            B2K_TRY(prune_scatter_labels(pr, dlabels));
+            s->labels_in_prune = true;
+            if (want_labels) B2K_TRY(prune_scatter_labels(pr, dlabels));  // back to the caller's frame order
             return launch_accumulate(ctx, prune_frames(pr), s->n, s->d, s->k, prune_labels(pr), s->scale_sum, dacc);
         }
     }
@@ -806,7 +818,21 @@ B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32
         B2K_TRY(s->pc.prepare(ctx, dC, s->k, s->d, s->metric));
         B2K_TRY(assign_any(ctx, s->dX, s->Ga.as<float>(), s->n, s->d, s->pc, s->k, s->metric, dlabels, nullptr, 1));
     }
+    s->labels_in_own = !want_labels;
     return launch_accumulate(ctx, s->dX, s->n, s->d, s->k, dlabels, s->scale_sum, dacc);
+}
+
+// labels of the session's last step in the caller's frame order (for callers that passed dlabels = NULL to the step)
+B2K_API int b2k_dev_lloyd_get_labels(b2k_lloyd* s, int32_t* dlabels_out) {
+    if (!s || (s->n > 0 && !dlabels_out)) return set_error(B2K_ERR_INVALID_ARG, "lloyd get_labels: null argument");
+    if (s->n == 0) return B2K_OK;
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    if (s->labels_in_prune && s->prune) return prune_scatter_labels(s->prune, dlabels_out);
+    if (s->labels_in_own) {
+        CUDA_TRY(cudaMemcpyAsync(dlabels_out, s->own_labels.p, (size_t)s->n * 4, cudaMemcpyDeviceToDevice, s->ctx->stream));
+        return B2K_OK;
+    }
+    return set_error(B2K_ERR_INVALID_ARG, "lloyd get_labels: the last step wrote its labels to the caller's array");
 }
 
 B2K_API int b2k_dev_lloyd_accumulate(b2k_lloyd* s, const int32_t* dlabels, int64_t* dacc) {
@@ -835,6 +861,9 @@ B2K_API int b2k_dev_lloyd_cost(b2k_lloyd* s, const float* dC_new, const int32_t*
     if (s->n == 0) return B2K_OK;
     ProfScope prof(ctx, b2k_ctx::PROF_COST);
     const float* fX = s->dX;
+    if (!dlabels && s->labels_in_own) dlabels = s->own_labels.as<int32_t>();
+    if (!dlabels && !(s->prune && prune_sorted(s->prune) && s->labels_in_prune))
+        return set_error(B2K_ERR_INVALID_ARG, "lloyd cost: no labels (pass them, or run b2k_dev_lloyd_assign_accumulate first)");
     if (s->prune && prune_sorted(s->prune) && s->have_labels) {
         // the session works on its sorted copy of the frames: the labels of the last step are there in the same order
         // (the cost is an exact integer sum, so the order of the frames does not change a bit of it)

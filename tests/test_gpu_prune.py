@@ -91,6 +91,48 @@ def test_pruned_session_is_bit_identical(b2k, oracle, n, d, k, nb, mode, resort)
         assert np.abs(cen1 - rc).max() <= 1e-5 * np.abs(rc).max()
 
 
+def test_session_keeps_labels_when_not_asked(b2k):
+    """dlabels = NULL: the step does not write labels in frame order; cost uses the session's copy and
+    b2k_dev_lloyd_get_labels returns exactly what a step with a label array writes (pruned and unpruned sessions)"""
+    import torch
+    rng = np.random.RandomState(9)
+    X = blobs(rng, 40000, 10, 8)
+    C0 = X[rng.choice(len(X), 90, replace=False)].copy()
+    ref, cen_ref, _ = run_session(b2k, X, C0, 4, {"assign_engine": b2k.ENGINE_SCREEN, "prune_mode": 2})
+    for mode in (2, 0):
+        ctx = b2k.context()
+        dev = torch.device("cuda", ctx.device)
+        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        ctx.set_option("assign_engine", b2k.ENGINE_SCREEN)
+        ctx.set_option("prune_mode", mode)
+        lib = ctx.lib
+        try:
+            dX = torch.from_numpy(X).to(dev)
+            cur = torch.from_numpy(C0).to(dev)
+            nxt = torch.empty_like(cur)
+            sess = C.c_void_p()
+            b2k.check(lib.b2k_dev_lloyd_create(ctx.handle, C.c_void_p(dX.data_ptr()), len(X), 10, 90, 0, len(X),
+                                               C.c_float(float(np.abs(X).max())), C.byref(sess)))
+            acc = torch.zeros(int(lib.b2k_dev_lloyd_acc_len(sess)), dtype=torch.int64, device=dev)
+            lab = torch.empty(len(X), dtype=torch.int32, device=dev)
+            for it in range(4):
+                b2k.check(lib.b2k_dev_lloyd_assign_accumulate(sess, C.c_void_p(cur.data_ptr()), None, C.c_void_p(acc.data_ptr())))
+                sums = acc[:-1].cpu().numpy().copy()
+                b2k.check(lib.b2k_dev_lloyd_finalize(sess, C.c_void_p(acc.data_ptr()), C.c_void_p(cur.data_ptr()),
+                                                     C.c_void_p(nxt.data_ptr())))
+                b2k.check(lib.b2k_dev_lloyd_cost(sess, C.c_void_p(nxt.data_ptr()), None, C.c_void_p(acc.data_ptr())))
+                b2k.check(lib.b2k_dev_lloyd_get_labels(sess, C.c_void_p(lab.data_ptr())))
+                torch.cuda.synchronize()
+                np.testing.assert_array_equal(lab.cpu().numpy(), ref[it][0], err_msg="labels, iteration %d mode %d" % (it, mode))
+                np.testing.assert_array_equal(sums, ref[it][1])
+                assert int(acc[-1].item()) == ref[it][2]
+                cur, nxt = nxt, cur
+            lib.b2k_dev_lloyd_destroy(sess)
+        finally:
+            ctx.set_option("assign_engine", b2k.ENGINE_AUTO)
+            ctx.set_option("prune_mode", 1)
+
+
 def test_pruned_session_unclustered_data(b2k):
     """structureless data: the lists exclude little or nothing; the session must still be exact (it falls back to the
     full screen on the sorted frames whenever the lists would not pay)"""
