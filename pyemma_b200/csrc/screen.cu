@@ -1057,14 +1057,14 @@ screen_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // of the center operand (L2 resident) into the stage with 16-byte cp.async, writing the SWIZZLE_128B K-major layout a
 // tiled TMA load would produce (chunk c of row r at c ^ (r & 7)) and publishing it to the async proxy
 // (fence.proxy.async) before they arrive on the stage's barrier; the MMA thread issues M=128 x N=rows instructions, and
-// the two column halves of the epilogue take alternate 32-column chunks (list lengths are multiples of 64, so both always
-// have work).  A candidate entry's chunk id counts 32-entry chunks of the LIST; the listed verify kernels map list
+// two epilogue teams (four warps each, one accumulator stage each) take alternate tiles: one thread scans every chunk of
+// its frame (list lengths are multiples of 32).  A candidate entry's chunk id counts 32-entry chunks of the LIST; the listed verify kernels map list
 // positions back to center indices.  (gather = 1 fetches the rows with TMA tile::gather4 instead -- four rows per
 // instruction: correct, but measured 1.43 ms against the cp.async gather at 1e7 x 10, k=1000, ~160 listed centers per
 // tile: one gather4 costs the TMA unit ~130 cycles, 40 of them per tile are the whole kernel.)
 struct ListArgs {
-    const uint16_t* tlist;   // [n_tiles][lcap] center ids, ascending, padded with the id of a -inf row
-    const uint32_t* tcount;  // [n_tiles] padded list lengths (multiples of 64, <= lcap)
+    const uint16_t* tlist;   // [n_units][lcap] center ids, ascending, padded with the id of a -inf row
+    const uint32_t* tcount;  // [n_units] padded list lengths (multiples of 32, <= lcap)
     const __half* B;         // center operand [k_rows][Kp]
     int lcap, Kp;
     int ushift;              // list unit of frame tile t: t >> ushift
