@@ -101,7 +101,7 @@ class KmeansClustering(AbstractClustering):
         if self.init_strategy == "kmeans++" and not self._check_resume_iteration():
             # k-means++ scratch next to the frames: m = 2+ln k distance rows, D^2, labels, candidate masks
             need += (total // ws) * 4 * (6 + int(math.log(max(int(self.n_clusters or 1), 1))))
-        free, _tot = torch.cuda.mem_get_info(staging.device())
+        free = staging.free_hbm(need)
         budget = int(os.environ.get("B2K_HBM_BUDGET_BYTES", "0")) or int(free * 0.9)
         self._host_frames = None
         if need > budget:
@@ -229,7 +229,9 @@ class KmeansClustering(AbstractClustering):
                 # the frames the dtrajs are made of are resident right now: one more device pass against the final
                 # centers (3.5 ms per 1e7 x 10 frames) instead of a second trip of every frame over PCIe when
                 # `.dtrajs` is first read (interface.py:101-106 computes them lazily from the host data)
-                self._dtrajs = self._resident_dtrajs(ctx, X, centers, k, metric, lengths, total_length, rank, ws)
+                self._dtrajs = self._resident_dtrajs(ctx, X, centers, k, metric, lengths, total_length, rank, ws,
+                                                     final_labels=getattr(self, "_dev_final_labels", None))
+                self._dev_final_labels = None
                 self._previous_stride = 1
         finally:
             # kmeans.py:269-284: drop the big array unless the user keeps it for a resume
@@ -278,7 +280,7 @@ class KmeansClustering(AbstractClustering):
         else:
             if ws > 1:
                 raise NotImplementedError("out-of-core k-means++ seeding is single-GPU; pass clustercenters or use more GPUs")
-            free, _tot = torch.cuda.mem_get_info(dev)
+            free = staging.free_hbm(n_local * d * 4, ctx)
             budget = int(os.environ.get("B2K_HBM_BUDGET_BYTES", "0")) or int(free * 0.9)
             per_frame = 4 * d + 4 * (6 + int(math.log(max(k, 1))))
             sub = max(1, -(-n_local * per_frame // max(budget, per_frame * k)))
@@ -353,12 +355,15 @@ class KmeansClustering(AbstractClustering):
                                 self.tolerance, self.max_iter)
         return self
 
-    def _resident_dtrajs(self, ctx, X, centers, k, metric, lengths, n_total, rank, ws):
-        """labels of the resident shard against `centers` (b2k_dev_assign), all-gathered over the ranks and split per
-        trajectory: the same values AbstractClustering.assign would produce from the host copy of the frames."""
+    def _resident_dtrajs(self, ctx, X, centers, k, metric, lengths, n_total, rank, ws, final_labels=None):
+        """labels of the resident shard against `centers` (the Lloyd session's own last assignment when given, else
+        b2k_dev_assign), all-gathered over the ranks and split per trajectory: the same values
+        AbstractClustering.assign would produce from the host copy of the frames."""
         n_local, d = X.shape
         lab = torch.empty(max(n_local, 1), dtype=torch.int32, device=X.device)
-        if n_local:
+        if final_labels is not None and final_labels.numel() == n_local:
+            lab[:n_local] = final_labels
+        elif n_local:
             _lib.check(ctx.lib.b2k_dev_assign(ctx.handle, C.c_void_p(X.data_ptr()), n_local, d,
                                               C.c_void_p(centers.data_ptr()), k, metric, C.c_void_p(lab.data_ptr()), None))
         lab = lab[:n_local]
@@ -468,9 +473,13 @@ class KmeansClustering(AbstractClustering):
                 it += 1
                 if not (it < self.max_iter and not converged):
                     break
+            # dtrajs: the assignment to the FINAL centers, taken by the session itself while it is alive (its fp16 operand,
+            # the sorted copy of the frames and the center lists are all in place) instead of a fresh one-shot assign
+            # that would rebuild them; the exact integer sums this call also produces are simply not used
             if n_local:
-                _lib.check(lib.b2k_dev_lloyd_get_labels(sess, C.c_void_p(labels.data_ptr())))
-            self._dev_last_labels = labels[:n_local]
+                _lib.check(lib.b2k_dev_lloyd_assign_accumulate(sess, C.c_void_p(cur.data_ptr()),
+                                                               C.c_void_p(labels.data_ptr()), C.c_void_p(acc.data_ptr())))
+            self._dev_final_labels = labels[:n_local]
             return cur, converged, inertias
         finally:
             lib.b2k_dev_lloyd_destroy(sess)

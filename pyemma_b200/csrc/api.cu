@@ -4,6 +4,9 @@
 #include <cstdarg>
 #include <algorithm>
 #include <thread>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 
 namespace b2k {
 
@@ -18,6 +21,131 @@ int set_error(int code, const char* fmt, ...) {
     va_end(ap);
     g_last_error = buf;
     return code;
+}
+
+// ---- device block cache ----------------------------------------------------------------------
+// cudaFree of the GB-sized working buffers of a Lloyd session (fp16 screen operand, sorted copy of the frames, candidate
+// lists) costs ~0.12 s per GB on these boxes and the next cudaMalloc pays again: a 10-iteration fit of 1e7 x 10 frames
+// spent 270-340 ms in b2k_dev_lloyd_destroy and up to 300 ms in the next session's first step, against 45 ms of
+// kernels.  Freed blocks therefore stay in a per-device free list (same device synchronisation as cudaFree, so a block
+// is never handed out while work that uses it is in flight) and are handed back to the next request of a similar
+// size.  The list is bounded (option "cache_mb", default half of the device memory), released oldest first, released
+// entirely when a cudaMalloc fails, on b2k_ctx_destroy, and on request (option "cache_release") -- e.g. before a
+// caller that allocates with another allocator (torch) needs the room.
+namespace {
+struct CacheBlock { size_t size; int dev; unsigned long long seq; };
+std::mutex g_cache_mu;
+std::unordered_map<void*, CacheBlock> g_live;                       // blocks handed out
+std::map<int, std::multimap<size_t, std::pair<void*, unsigned long long>>> g_free;  // per device: size -> (ptr, age)
+std::map<int, size_t> g_free_bytes;
+std::map<int, long long> g_cache_limit;                             // bytes; absent: default
+unsigned long long g_cache_seq = 0;
+
+size_t cache_round(size_t n) {
+    const size_t g = n < (size_t(1) << 20) ? 4096 : (size_t(2) << 20);
+    return (std::max<size_t>(n, 1) + g - 1) / g * g;
+}
+
+long long cache_limit_locked(int dev) {
+    auto it = g_cache_limit.find(dev);
+    if (it != g_cache_limit.end() && it->second >= 0) return it->second;
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); tot = 0; }
+    const long long lim = (long long)(tot / 2);
+    g_cache_limit[dev] = lim;
+    return lim;
+}
+
+// cudaFree of cached blocks of `dev` (-1: every device), oldest first, until at most `keep` bytes stay
+void cache_shrink_locked(int dev, size_t keep) {
+    for (auto& kv : g_free) {
+        if (dev >= 0 && kv.first != dev) continue;
+        auto& fl = kv.second;
+        size_t& bytes = g_free_bytes[kv.first];
+        while (bytes > keep && !fl.empty()) {
+            auto oldest = fl.begin();
+            for (auto it = fl.begin(); it != fl.end(); ++it)
+                if (it->second.second < oldest->second.second) oldest = it;
+            cudaFree(oldest->second.first);
+            bytes -= oldest->first;
+            fl.erase(oldest);
+        }
+    }
+    cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t dev_alloc_raw(void** p, size_t bytes) {
+    *p = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t want = cache_round(bytes);
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto& fl = g_free[dev];
+    auto it = fl.lower_bound(want);
+    if (it != fl.end() && it->first <= want + want / 4) {
+        *p = it->second.first;
+        g_live[*p] = CacheBlock{it->first, dev, 0};
+        g_free_bytes[dev] -= it->first;
+        fl.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {  // make room: everything this library keeps for later goes back to the driver first
+        cudaGetLastError();
+        cache_shrink_locked(dev, 0);
+        e = cudaMalloc(p, want);
+    }
+    if (e != cudaSuccess) { *p = nullptr; return e; }
+    g_live[*p] = CacheBlock{want, dev, 0};
+    return cudaSuccess;
+}
+
+void dev_free(void* p) {
+    if (!p) return;
+    CacheBlock b;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_live.find(p);
+        if (it == g_live.end()) { cudaFree(p); return; }  // not ours (never happens inside the library)
+        b = it->second;
+        g_live.erase(it);
+    }
+    // what cudaFree guarantees: nothing submitted so far still touches the block
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != b.dev) cudaSetDevice(b.dev);
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    const long long lim = cache_limit_locked(b.dev);
+    if ((long long)b.size > lim) {
+        cudaFree(p);
+    } else {
+        g_free[b.dev].emplace(b.size, std::make_pair(p, ++g_cache_seq));
+        g_free_bytes[b.dev] += b.size;
+        if ((long long)g_free_bytes[b.dev] > lim) cache_shrink_locked(b.dev, (size_t)lim);
+    }
+    if (cur != b.dev) cudaSetDevice(cur);
+}
+
+void dev_cache_release(int dev) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    cache_shrink_locked(dev, 0);
+}
+
+size_t dev_cache_bytes(int dev) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_free_bytes.find(dev);
+    return it == g_free_bytes.end() ? 0 : it->second;
+}
+
+void dev_cache_set_limit(int dev, long long bytes) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (bytes < 0) g_cache_limit.erase(dev);
+    else {
+        g_cache_limit[dev] = bytes;
+        cache_shrink_locked(dev, (size_t)bytes);
+    }
 }
 
 int kmpp_run(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int metric, int64_t seed, int scan_mode,
@@ -139,14 +267,14 @@ int b2k_ctx::slot(int which, size_t bytes, void** out) {
     if (bytes > slot_cap[which]) {
         if (slot_ptr[which]) {
             cudaStreamSynchronize(stream);
-            cudaFree(slot_ptr[which]);
+            b2k::dev_free(slot_ptr[which]);
         }
         slot_ptr[which] = nullptr;
         slot_cap[which] = 0;
         const size_t want = bytes + bytes / 8;  // a little headroom for the next, slightly larger call
-        if (cudaMalloc(&slot_ptr[which], want) != cudaSuccess) {
+        if (b2k::dev_alloc(&slot_ptr[which], want) != cudaSuccess) {
             cudaGetLastError();
-            if (cudaMalloc(&slot_ptr[which], bytes) != cudaSuccess) {
+            if (b2k::dev_alloc(&slot_ptr[which], bytes) != cudaSuccess) {
                 cudaGetLastError();
                 slot_ptr[which] = nullptr;
                 return b2k::set_error(B2K_ERR_NOMEM, "cudaMalloc(%zu bytes) failed", bytes);
@@ -162,20 +290,20 @@ int b2k_ctx::slot(int which, size_t bytes, void** out) {
 
 int b2k_ctx::ensure_scratch(size_t bytes) {
     if (bytes <= scratch_cap) return B2K_OK;
-    if (scratch) cudaFree(scratch);
+    if (scratch) b2k::dev_free(scratch);
     scratch = nullptr;
     scratch_cap = 0;
-    CUDA_TRY(cudaMalloc(&scratch, bytes));
+    CUDA_TRY(b2k::dev_alloc(&scratch, bytes));
     scratch_cap = bytes;
     return B2K_OK;
 }
 
 int b2k_ctx::ensure_scratch2(size_t bytes) {
     if (bytes <= scratch2_cap) return B2K_OK;
-    if (scratch2) cudaFree(scratch2);
+    if (scratch2) b2k::dev_free(scratch2);
     scratch2 = nullptr;
     scratch2_cap = 0;
-    CUDA_TRY(cudaMalloc(&scratch2, bytes));
+    CUDA_TRY(b2k::dev_alloc(&scratch2, bytes));
     scratch2_cap = bytes;
     return B2K_OK;
 }
@@ -231,10 +359,11 @@ B2K_API int b2k_ctx_destroy(b2k_ctx* c) {
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     for (auto& v : c->prof_class) for (cudaEvent_t e : v) cudaEventDestroy(e);
     for (int i = 0; i < b2k_ctx::N_SLOTS; ++i)
-        if (c->slot_ptr[i]) cudaFree(c->slot_ptr[i]);
+        if (c->slot_ptr[i]) dev_free(c->slot_ptr[i]);
     if (c->flags) cudaFree(c->flags);
-    if (c->scratch) cudaFree(c->scratch);
-    if (c->scratch2) cudaFree(c->scratch2);
+    if (c->scratch) dev_free(c->scratch);
+    if (c->scratch2) dev_free(c->scratch2);
+    dev_cache_release(c->device);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return B2K_OK;
@@ -287,6 +416,11 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
         for (auto& v : c->prof_class) { for (cudaEvent_t e : v) cudaEventDestroy(e); v.clear(); }
         c->profile = value != 0;
     }
+    else if (!strcmp(name, "cache_mb")) {  // bound of the device block cache (-1: default, half of the device memory; 0: off)
+        CUDA_TRY(cudaSetDevice(c->device));
+        dev_cache_set_limit(c->device, value < 0 ? -1 : (long long)value << 20);
+    }
+    else if (!strcmp(name, "cache_release")) dev_cache_release(c->device);  // give every cached block back to the driver
     else if (!strcmp(name, "stage_bytes")) c->stage_bytes = (size_t)std::max<int64_t>(value, 1 << 16);
     else if (!strcmp(name, "own_stream")) {
         if (!c->own_stream) {
@@ -346,6 +480,7 @@ B2K_API int b2k_ctx_get_stat(b2k_ctx* c, const char* name, double* value) {
     else if (!strncmp(name, "probe_centers_", 14) && name[14] >= '1' && name[14] <= '3') *value = c->stat_probe_centers[name[14] - '0'];
     else if (!strncmp(name, "probe_fallback_", 15) && name[15] >= '1' && name[15] <= '3') *value = c->stat_probe_fallback[name[15] - '0'];
     else if (!strcmp(name, "sm_count")) *value = c->sm_count;
+    else if (!strcmp(name, "cache_bytes")) *value = (double)dev_cache_bytes(c->device);
     else if (!strcmp(name, "fp32_lane_instr_per_s")) {  // measured now: non-fusable FMUL+FADD chains on every SM
         CUDA_TRY(cudaSetDevice(c->device));
         return measure_fp32_rate(c, value);

@@ -40,16 +40,25 @@ int set_error(int code, const char* fmt, ...);
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// cudaMalloc / cudaFree through the library's device block cache (api.cu): same synchronisation as cudaFree, but the
+// block stays mapped for the next request of a similar size
+cudaError_t dev_alloc_raw(void** p, size_t bytes);
+template <class T> static inline cudaError_t dev_alloc(T** p, size_t bytes) { return dev_alloc_raw((void**)p, bytes); }
+void dev_free(void* p);
+void dev_cache_release(int dev);
+size_t dev_cache_bytes(int dev);
+void dev_cache_set_limit(int dev, long long bytes);
+
 // owning device allocation (freed with the scope)
 struct DevMem {
     void* p = nullptr;
     size_t cap = 0;
-    ~DevMem() { if (p) cudaFree(p); }
+    ~DevMem() { if (p) dev_free(p); }
     int alloc(size_t bytes) {
         if (p && bytes <= cap) return B2K_OK;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        if (p) { dev_free(p); p = nullptr; cap = 0; }
         cap = bytes ? bytes : 16;
-        if (cudaMalloc(&p, cap) != cudaSuccess) {
+        if (dev_alloc(&p, cap) != cudaSuccess) {
             p = nullptr;
             cap = 0;
             cudaGetLastError();

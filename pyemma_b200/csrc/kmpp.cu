@@ -656,12 +656,12 @@ __global__ void kmpp_add_delta_kernel(KmppState* st, const float* __restrict__ s
 // ---- driver ----------------------------------------------------------------------------------
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) dev_free(p); }
     int alloc(size_t bytes) {
-        if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+        if (dev_alloc(&p, bytes ? bytes : 16) != cudaSuccess) {
             p = nullptr;
             cudaGetLastError();
-            return set_error(B2K_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
+            return set_error(B2K_ERR_NOMEM, "dev_alloc(%zu) failed", bytes);
         }
         return B2K_OK;
     }

@@ -122,12 +122,12 @@ struct b2k_regspace {
 
 static int reg_ensure_chunk(b2k_regspace* r, int64_t n) {
     if (n <= r->cap) return B2K_OK;
-    cudaFree(r->mind); cudaFree(r->Ga); cudaFree(r->alive); cudaFree(r->labels);
+    dev_free(r->mind); dev_free(r->Ga); dev_free(r->alive); dev_free(r->labels);
     r->mind = r->Ga = nullptr; r->alive = nullptr; r->labels = nullptr; r->cap = 0;
-    CUDA_TRY(cudaMalloc(&r->mind, n * 4));
-    CUDA_TRY(cudaMalloc(&r->Ga, n * 4));
-    CUDA_TRY(cudaMalloc(&r->alive, n));
-    CUDA_TRY(cudaMalloc(&r->labels, n * 4));
+    CUDA_TRY(dev_alloc(&r->mind, n * 4));
+    CUDA_TRY(dev_alloc(&r->Ga, n * 4));
+    CUDA_TRY(dev_alloc(&r->alive, n));
+    CUDA_TRY(dev_alloc(&r->labels, n * 4));
     r->cap = n;
     return B2K_OK;
 }
@@ -141,15 +141,15 @@ B2K_API int b2k_regspace_create(b2k_ctx* ctx, int32_t d, float dmin, int64_t max
     b2k_regspace* r = new b2k_regspace();
     r->ctx = ctx; r->d = d; r->metric = metric; r->dmin = dmin; r->max_centers = max_centers;
     const size_t cbytes = (size_t)std::max<int64_t>(max_centers, 1) * d * 4;
-    cudaError_t e = cudaMalloc(&r->centers, cbytes);
-    if (e == cudaSuccess) e = cudaMalloc(&r->cur_row, (size_t)d * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&r->st, sizeof(RegState));
-    if (e == cudaSuccess) e = cudaMalloc(&r->frame_idx, (size_t)std::max<int64_t>(max_centers, 1) * 8);
+    cudaError_t e = dev_alloc(&r->centers, cbytes);
+    if (e == cudaSuccess) e = dev_alloc(&r->cur_row, (size_t)d * 4);
+    if (e == cudaSuccess) e = dev_alloc(&r->st, sizeof(RegState));
+    if (e == cudaSuccess) e = dev_alloc(&r->frame_idx, (size_t)std::max<int64_t>(max_centers, 1) * 8);
     if (e == cudaSuccess && metric == B2K_METRIC_MINRMSD) {
-        e = cudaMalloc(&r->centers_c, cbytes);
-        if (e == cudaSuccess) e = cudaMalloc(&r->Gb, (size_t)std::max<int64_t>(max_centers, 1) * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&r->cur_row_c, (size_t)d * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&r->cur_g, 4);
+        e = dev_alloc(&r->centers_c, cbytes);
+        if (e == cudaSuccess) e = dev_alloc(&r->Gb, (size_t)std::max<int64_t>(max_centers, 1) * 4);
+        if (e == cudaSuccess) e = dev_alloc(&r->cur_row_c, (size_t)d * 4);
+        if (e == cudaSuccess) e = dev_alloc(&r->cur_g, 4);
     }
     if (e != cudaSuccess) {
         b2k_regspace_destroy(r);
@@ -164,9 +164,9 @@ B2K_API int b2k_regspace_create(b2k_ctx* ctx, int32_t d, float dmin, int64_t max
 
 B2K_API int b2k_regspace_destroy(b2k_regspace* r) {
     if (!r) return B2K_OK;
-    cudaFree(r->centers); cudaFree(r->centers_c); cudaFree(r->Gb); cudaFree(r->cur_row); cudaFree(r->cur_row_c);
-    cudaFree(r->cur_g); cudaFree(r->st); cudaFree(r->frame_idx); cudaFree(r->mind); cudaFree(r->Ga);
-    cudaFree(r->alive); cudaFree(r->labels);
+    dev_free(r->centers); dev_free(r->centers_c); dev_free(r->Gb); dev_free(r->cur_row); dev_free(r->cur_row_c);
+    dev_free(r->cur_g); dev_free(r->st); dev_free(r->frame_idx); dev_free(r->mind); dev_free(r->Ga);
+    dev_free(r->alive); dev_free(r->labels);
     delete r;
     return B2K_OK;
 }
@@ -264,14 +264,14 @@ B2K_API int b2k_regspace_partial_fit(b2k_regspace* r, const float* X, int64_t n)
     CUDA_TRY(cudaSetDevice(r->ctx->device));
     float* dX = nullptr;
     const size_t bytes = (size_t)n * r->d * 4;
-    if (cudaMalloc(&dX, bytes) != cudaSuccess) {
+    if (dev_alloc(&dX, bytes) != cudaSuccess) {
         cudaGetLastError();
-        return set_error(B2K_ERR_NOMEM, "cudaMalloc(%zu bytes) failed", bytes);
+        return set_error(B2K_ERR_NOMEM, "dev_alloc(%zu bytes) failed", bytes);
     }
     int rc = upload_host(r->ctx, X, dX, bytes);
     if (rc == B2K_OK) rc = b2k_dev_regspace_partial_fit(r, dX, n);
     cudaStreamSynchronize(r->ctx->stream);
-    cudaFree(dX);
+    dev_free(dX);
     return rc;
 }
 

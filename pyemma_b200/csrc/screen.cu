@@ -2610,8 +2610,8 @@ static int screen_default_terms(const b2k_ctx* ctx) {
 void screen_plan_destroy(ScreenPlan* p) {
     if (!p) return;
     cudaStreamSynchronize(p->ctx->stream);
-    cudaFree(p->A); cudaFree(p->B); cudaFree(p->X2); cudaFree(p->XL); cudaFree(p->mu); cudaFree(p->params); cudaFree(p->cand);
-    cudaFree(p->ncand); cudaFree(p->fb_list);
+    dev_free(p->A); dev_free(p->B); dev_free(p->X2); dev_free(p->XL); dev_free(p->mu); dev_free(p->params); dev_free(p->cand);
+    dev_free(p->ncand); dev_free(p->fb_list);
     delete p;
 }
 
@@ -2633,16 +2633,16 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, int terms, Scr
     p->Kc = p->terms * d + 3;
     p->Kp = (int)(cdiv(p->Kc, BLOCK_K) * BLOCK_K);
     p->nk16 = (int)cdiv(p->Kc, 16);
-    cudaError_t e = cudaMalloc(&p->A, (size_t)p->n_pad * p->Kp * 2);
+    cudaError_t e = dev_alloc(&p->A, (size_t)p->n_pad * p->Kp * 2);
     p->k_rows = p->k_pad + 8;
-    if (e == cudaSuccess) e = cudaMalloc(&p->B, (size_t)p->k_rows * p->Kp * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&p->X2, (size_t)p->n_pad * 4);
-    if (e == cudaSuccess && p->terms != 3) e = cudaMalloc(&p->XL, (size_t)p->n_pad * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&p->mu, (size_t)d * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&p->params, sizeof(ScreenParams));
-    if (e == cudaSuccess) e = cudaMalloc(&p->cand, (size_t)p->n_pad * CAND_CAP * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&p->ncand, (size_t)p->n_pad);
-    if (e == cudaSuccess) e = cudaMalloc(&p->fb_list, (size_t)p->n_pad * 4);
+    if (e == cudaSuccess) e = dev_alloc(&p->B, (size_t)p->k_rows * p->Kp * 2);
+    if (e == cudaSuccess) e = dev_alloc(&p->X2, (size_t)p->n_pad * 4);
+    if (e == cudaSuccess && p->terms != 3) e = dev_alloc(&p->XL, (size_t)p->n_pad * 4);
+    if (e == cudaSuccess) e = dev_alloc(&p->mu, (size_t)d * 4);
+    if (e == cudaSuccess) e = dev_alloc(&p->params, sizeof(ScreenParams));
+    if (e == cudaSuccess) e = dev_alloc(&p->cand, (size_t)p->n_pad * CAND_CAP * 4);
+    if (e == cudaSuccess) e = dev_alloc(&p->ncand, (size_t)p->n_pad);
+    if (e == cudaSuccess) e = dev_alloc(&p->fb_list, (size_t)p->n_pad * 4);
     if (e != cudaSuccess) {
         cudaGetLastError();
         screen_plan_destroy(p);

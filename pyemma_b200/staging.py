@@ -32,6 +32,19 @@ def world():
     return 0, 1
 
 
+def free_hbm(need=0, ctx=None):
+    """Free bytes of the context's device.  libb2k keeps the working buffers of finished sessions in a block cache
+    (api.cu, option "cache_mb") that only its own allocations can draw on; when `need` bytes would not fit beside it,
+    the cache goes back to the driver first, so a torch allocation of that size sees the room."""
+    ctx = ctx or _lib.context()
+    dev = device(ctx)
+    free, _tot = torch.cuda.mem_get_info(dev)
+    if need > 0.9 * free and ctx.get_stat("cache_bytes") > 0:
+        ctx.set_option("cache_release", 1)
+        free, _tot = torch.cuda.mem_get_info(dev)
+    return free
+
+
 SHARD_ALIGN = 1024  # frames; a height-10 node of the k-means++ sum tree never straddles two shards
 
 
