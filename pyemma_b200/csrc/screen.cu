@@ -2027,397 +2027,6 @@ __global__ void __launch_bounds__(256, B2K_VF_MINBLOCKS) screen_verify_frame_lis
     verify_stats(my_groups, my_fb, prm);
 }
 
-// ---- listed verify for wide rows, frame rows staged through shared memory (d % 4 == 0) ------------------------------
-// ncu of the kernel above at cfg3: L1/TEX throughput 85 %, DRAM 26 % -- every frame-row load of a warp names 32 rows, i.e.
-// 32 L1 tag lookups per instruction, and that, not HBM, bounds it (2.0 TB/s).  Here a CTA owns tiles of VS_TILE
-// consecutive frames and streams each tile through shared memory in chunks of VS_CH dimensions: all threads copy the
-// chunk with coalesced 16-byte cp.async (16 consecutive threads per 256-byte row piece: 2 L1 lines per row instead of
-// 16 sector lookups), NST chunks in flight per CTA, one barrier per chunk.  A thread still owns one frame and still
-// evaluates every (frame, center) sum alone and in the reference order, four candidates per pass, the accumulators
-// carried from chunk to chunk; its row comes out of shared memory (row stride VS_CH+4 floats: the 8 lanes of a
-// quarter-warp hit 8 different 16-byte bank groups), only the centers' rows go through L1.  Frames with more than four
-// candidate centers (rare with groups of 2) finish the rest from global memory like the kernel above.
-static constexpr int VS_TILE = 128;
-
-struct CandWalk {  // ascending walk over the candidate centers of one frame (entries: chunk id | group mask)
-    uint32_t ent[CAND_CAP];
-    const uint16_t* tl;
-    int nc, t, sub, q, idb, cg, k;
-    uint32_t mask, idm;
-    bool more;
-    unsigned long long groups;
-    __device__ __forceinline__ void start(const uint4 p0, const uint4 p1, int nc_, const uint16_t* tl_, int cg_, int k_) {
-        ent[0] = p0.x; ent[1] = p0.y; ent[2] = p0.z; ent[3] = p0.w;
-        ent[4] = p1.x; ent[5] = p1.y; ent[6] = p1.z; ent[7] = p1.w;
-        tl = tl_; nc = nc_; cg = cg_; k = k_;
-        idb = cand_id_bits(cg_);
-        idm = cand_id_mask(cg_);
-        t = 0; sub = 0; groups = 0;
-        mask = nc > 0 ? ent[0] >> idb : 0u;
-        q = mask ? __ffs(mask) - 1 : 0;
-        more = nc > 0 && mask != 0;
-    }
-    __device__ __forceinline__ uint32_t entry(int which) const {
-        uint32_t e = ent[0];
-#pragma unroll
-        for (int u = 1; u < CAND_CAP; ++u)
-            if (u == which) e = ent[u];
-        return e;
-    }
-    // up to four more centers (ascending); returns how many
-    __device__ __forceinline__ int next4(int (&js)[4]) {
-        int cnt4 = 0;
-        js[0] = js[1] = js[2] = js[3] = 0;
-        while (more && cnt4 < 4) {
-            const int pos = (int)(entry(t) & idm) * CHUNK + q * cg + sub;
-            const int j = (int)__ldg(tl + pos);
-            if (j < k) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (u == cnt4) js[u] = j;
-                ++cnt4;
-            }
-            if (++sub == cg) {  // next group of the entry, next entry
-                sub = 0;
-                groups += 1;
-                mask &= mask - 1;
-                if (mask) {
-                    q = __ffs(mask) - 1;
-                } else {
-                    ++t;
-                    more = false;
-                    while (t < nc) {
-                        mask = entry(t) >> idb;
-                        if (mask) { q = __ffs(mask) - 1; more = true; break; }
-                        ++t;
-                    }
-                }
-            }
-        }
-        return cnt4;
-    }
-};
-
-// vectors [v0, v1) of one frame row against up to four center rows (vector index relative to the row start)
-__device__ __forceinline__ void verify_accum4(const float4* __restrict__ x4, int xoff, const float4* __restrict__ c0,
-                                              const float4* __restrict__ c1, const float4* __restrict__ c2,
-                                              const float4* __restrict__ c3, int cnt4, int v0, int v1, Lanes4& L0,
-                                              Lanes4& L1, Lanes4& L2, Lanes4& L3) {
-    int v = v0;
-    for (; v + 2 <= v1; v += 2) {
-        const float4 xa = x4[v - xoff], xb = x4[v + 1 - xoff];
-        {
-            const float4 a = __ldg(c0 + v), b = __ldg(c0 + v + 1);
-            L0.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w);
-            L0.add4(xb.x, xb.y, xb.z, xb.w, b.x, b.y, b.z, b.w);
-        }
-        if (cnt4 > 1) {
-            const float4 a = __ldg(c1 + v), b = __ldg(c1 + v + 1);
-            L1.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w);
-            L1.add4(xb.x, xb.y, xb.z, xb.w, b.x, b.y, b.z, b.w);
-        }
-        if (cnt4 > 2) {
-            const float4 a = __ldg(c2 + v), b = __ldg(c2 + v + 1);
-            L2.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w);
-            L2.add4(xb.x, xb.y, xb.z, xb.w, b.x, b.y, b.z, b.w);
-        }
-        if (cnt4 > 3) {
-            const float4 a = __ldg(c3 + v), b = __ldg(c3 + v + 1);
-            L3.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w);
-            L3.add4(xb.x, xb.y, xb.z, xb.w, b.x, b.y, b.z, b.w);
-        }
-    }
-    for (; v < v1; ++v) {
-        const float4 xa = x4[v - xoff];
-        { const float4 a = __ldg(c0 + v); L0.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w); }
-        if (cnt4 > 1) { const float4 a = __ldg(c1 + v); L1.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w); }
-        if (cnt4 > 2) { const float4 a = __ldg(c2 + v); L2.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w); }
-        if (cnt4 > 3) { const float4 a = __ldg(c3 + v); L3.add4(xa.x, xa.y, xa.z, xa.w, a.x, a.y, a.z, a.w); }
-    }
-}
-
-// One thread per frame, rows through L1 like screen_verify_frame_listed_kernel, but EIGHT candidate centers per pass over the
-// row: with groups of 2 centers a frame has 2.6 candidates on average, yet in 80-90 % of the warps some lane has more than
-// four, and the whole warp then streams its 32 rows a second time for that lane.
-__device__ __forceinline__ void verify_accum8(const float4* __restrict__ x4, const float4* const (&ca_)[4],
-                                              const float4* const (&cb_)[4], int ca, int cb, int nv, Lanes4 (&A)[4],
-                                              Lanes4 (&B)[4]) {
-    for (int v = 0; v < nv; ++v) {
-        const float4 x = __ldg(x4 + v);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (u < ca) {
-                const float4 a = __ldg(ca_[u] + v);
-                A[u].add4(x.x, x.y, x.z, x.w, a.x, a.y, a.z, a.w);
-            }
-        }
-        if (cb > 0) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (u < cb) {
-                    const float4 a = __ldg(cb_[u] + v);
-                    B[u].add4(x.x, x.y, x.z, x.w, a.x, a.y, a.z, a.w);
-                }
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256, 2) screen_verify_frame8_listed_kernel(
-    const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Cn, int k, const uint32_t* __restrict__ cand,
-    const uint8_t* __restrict__ ncand, const uint16_t* __restrict__ tlist, int lcap, int unit_frames,
-    int32_t* __restrict__ labels, int lloyd, ScreenParams* prm, uint32_t* __restrict__ fb_list, int cg) {
-    if (!prm->valid) return;
-    const int nv = d >> 2;
-    unsigned long long my_groups = 0, my_fb = 0;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        const int nc = ncand[i];
-        if (nc == 255) {
-            fallback_push(prm, fb_list, i);
-            my_fb += 1;
-            continue;
-        }
-        const uint16_t* tl = tlist + (size_t)(i / unit_frames) * lcap;
-        if (nc == NCAND_DECIDED) {
-            const int j = (int)__ldg(tl + cand[i * CAND_CAP]);
-            if (j < k) labels[i] = j;
-            else { fallback_push(prm, fb_list, i); my_fb += 1; }
-            continue;
-        }
-        const uint4* cp = reinterpret_cast<const uint4*>(cand + i * CAND_CAP);
-        const uint4 p0 = __ldg(cp);
-        uint4 p1 = make_uint4(0, 0, 0, 0);
-        if (nc > 4) p1 = __ldg(cp + 1);
-        CandWalk w;
-        w.start(p0, p1, nc, tl, cg, k);
-        const float4* x4 = reinterpret_cast<const float4*>(X + i * d);
-        ArgMin am;
-        am.init();
-        while (w.more) {
-            int ja[4], jb[4];
-            const int ca = w.next4(ja);
-            if (ca == 0) break;
-            const int cb = (ca == 4 && w.more) ? w.next4(jb) : 0;
-            const float4* pa[4];
-            const float4* pb[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                pa[u] = reinterpret_cast<const float4*>(Cn + (int64_t)ja[u] * d);
-                pb[u] = reinterpret_cast<const float4*>(Cn + (int64_t)(cb > 0 ? jb[u] : 0) * d);
-            }
-            Lanes4 A[4], B[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { A[u].init(); B[u].init(); }
-            verify_accum8(x4, pa, pb, ca, cb, nv, A, B);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (u < ca) am.offer(A[u].result(), ja[u]);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (u < cb) am.offer(B[u].result(), jb[u]);
-            if (cb < 4) break;
-        }
-        my_groups += w.groups;
-        labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
-    }
-    verify_stats(my_groups, my_fb, prm);
-}
-
-// the same over NV vectors known at compile time (a full chunk): unrolled, so the loads of a whole chunk can be in flight
-template <int NV>
-__device__ __forceinline__ void verify_accum4_fixed(const float4* __restrict__ x4, const float4* __restrict__ c0,
-                                                    const float4* __restrict__ c1, const float4* __restrict__ c2,
-                                                    const float4* __restrict__ c3, int cnt4, Lanes4& L0, Lanes4& L1,
-                                                    Lanes4& L2, Lanes4& L3) {
-    constexpr int B = 4;  // vectors per batch
-#pragma unroll
-    for (int v = 0; v < NV; v += B) {
-        float4 x[B], a[B];
-#pragma unroll
-        for (int u = 0; u < B; ++u) x[u] = x4[v + u];
-#pragma unroll
-        for (int u = 0; u < B; ++u) a[u] = __ldg(c0 + v + u);
-        if (cnt4 > 1) {
-            float4 b[B];
-#pragma unroll
-            for (int u = 0; u < B; ++u) b[u] = __ldg(c1 + v + u);
-#pragma unroll
-            for (int u = 0; u < B; ++u) L1.add4(x[u].x, x[u].y, x[u].z, x[u].w, b[u].x, b[u].y, b[u].z, b[u].w);
-        }
-        if (cnt4 > 2) {
-            float4 b[B];
-#pragma unroll
-            for (int u = 0; u < B; ++u) b[u] = __ldg(c2 + v + u);
-#pragma unroll
-            for (int u = 0; u < B; ++u) L2.add4(x[u].x, x[u].y, x[u].z, x[u].w, b[u].x, b[u].y, b[u].z, b[u].w);
-        }
-        if (cnt4 > 3) {
-            float4 b[B];
-#pragma unroll
-            for (int u = 0; u < B; ++u) b[u] = __ldg(c3 + v + u);
-#pragma unroll
-            for (int u = 0; u < B; ++u) L3.add4(x[u].x, x[u].y, x[u].z, x[u].w, b[u].x, b[u].y, b[u].z, b[u].w);
-        }
-#pragma unroll
-        for (int u = 0; u < B; ++u) L0.add4(x[u].x, x[u].y, x[u].z, x[u].w, a[u].x, a[u].y, a[u].z, a[u].w);
-    }
-}
-
-template <int NST, int CH>
-__global__ void __launch_bounds__(VS_TILE) screen_verify_staged_listed_kernel(
-    const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Cn, int k, const uint32_t* __restrict__ cand,
-    const uint8_t* __restrict__ ncand, const uint16_t* __restrict__ tlist, int lcap, int unit_frames,
-    int32_t* __restrict__ labels, int lloyd, ScreenParams* prm, uint32_t* __restrict__ fb_list, int cg) {
-    constexpr int RS = CH + 4;            // row stride in shared memory (floats)
-    constexpr int PPR = CH / 4;           // 16-byte pieces per row and chunk
-    constexpr int RPI = VS_TILE / PPR;    // rows copied per iteration of the copy loop
-    extern __shared__ __align__(16) float vs_sm[];  // [NST][VS_TILE][RS]
-    if (!prm->valid) return;
-    const int tid = threadIdx.x;
-    const int nch = (d + CH - 1) / CH;                // chunks per row
-    const int64_t n_tiles = (n + VS_TILE - 1) / VS_TILE;
-    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t steps = my_tiles * nch;
-    unsigned long long my_groups = 0, my_fb = 0;
-    const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(vs_sm);
-
-    // copy of step s (tile s / nch of this CTA, chunk s % nch) into stage s % NST; every thread commits one group per call
-    auto issue = [&](int64_t s) {
-        if (s < steps) {
-            const int64_t tile = blockIdx.x + (s / nch) * (int64_t)gridDim.x;
-            const int c = (int)(s % nch);
-            const int vecs = min(CH, d - c * CH) >> 2;  // 16-byte pieces per row in this chunk
-            const int piece = tid % PPR, r0 = tid / PPR;
-            const uint32_t stage = sm_base + (uint32_t)((s % NST) * VS_TILE * RS * 4);
-            if (piece < vecs) {
-#pragma unroll
-                for (int it = 0; it < PPR; ++it) {
-                    const int r = r0 + it * RPI;
-                    const int64_t row = min(tile * VS_TILE + r, n - 1);
-                    const float* src = X + row * d + c * CH + piece * 4;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage + (uint32_t)((r * RS + piece * 4) * 4)),
-                                 "l"(src) : "memory");
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    // candidate record of this thread's frame in a tile, requested one tile ahead (a dependent chain ncand -> cand ->
-    // list -> center row at every tile start would cost more than the tile's whole copy)
-    int nc_n = 255;
-    uint4 e0_n = make_uint4(0, 0, 0, 0), e1_n = make_uint4(0, 0, 0, 0);
-    auto request = [&](int64_t tile_no) {
-        nc_n = 255;
-        if (tile_no < my_tiles) {
-            const int64_t i2 = (blockIdx.x + tile_no * (int64_t)gridDim.x) * VS_TILE + tid;
-            if (i2 < n) {
-                nc_n = ncand[i2];
-                const uint4* cp = reinterpret_cast<const uint4*>(cand + i2 * CAND_CAP);
-                e0_n = __ldg(cp);
-                e1_n = __ldg(cp + 1);
-            }
-        }
-    };
-
-#pragma unroll
-    for (int s = 0; s < NST - 1; ++s) issue(s);
-    request(0);
-
-    CandWalk w;
-    Lanes4 A0, A1, A2, A3, B0, B1, B2, B3;  // two quads of candidates carried from chunk to chunk
-    int ja[4] = {0, 0, 0, 0}, jb[4] = {0, 0, 0, 0};
-    int ca = 0, cb = 0;
-    int64_t i = 0;
-    bool live = false;
-    for (int64_t s = 0; s < steps; ++s) {
-        const int c = (int)(s % nch);
-        if (c == 0) {  // a new tile: this thread's frame and its first eight candidates
-            const int64_t tile_no = s / nch;
-            i = (blockIdx.x + tile_no * (int64_t)gridDim.x) * VS_TILE + tid;
-            live = false;
-            ca = cb = 0;
-            if (i < n) {
-                const int nc = nc_n;
-                const uint16_t* tl = tlist + (size_t)(i / unit_frames) * lcap;
-                if (nc == 255) {
-                    fallback_push(prm, fb_list, i);
-                    my_fb += 1;
-                } else if (nc == NCAND_DECIDED) {
-                    const int j = (int)__ldg(tl + e0_n.x);
-                    if (j < k) labels[i] = j;
-                    else { fallback_push(prm, fb_list, i); my_fb += 1; }
-                } else {
-                    live = true;
-                    w.start(e0_n, e1_n, nc, tl, cg, k);
-                    ca = w.next4(ja);
-                    if (ca == 4 && w.more) cb = w.next4(jb);
-                    A0.init(); A1.init(); A2.init(); A3.init();
-                    B0.init(); B1.init(); B2.init(); B3.init();
-                }
-            }
-            request(tile_no + 1);
-        }
-        asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");
-        __syncthreads();          // chunk s has landed for every thread; everyone is done with the stage step s-1 used
-        issue(s + NST - 1);       // ... which is the stage this copy overwrites
-        const float4* xs = reinterpret_cast<const float4*>(vs_sm + (size_t)(s % NST) * VS_TILE * RS + (size_t)tid * RS);
-        if (live && ca > 0) {
-            const int v0 = c * PPR, v1 = min(d >> 2, v0 + PPR);
-            {
-                const float4* c0 = reinterpret_cast<const float4*>(Cn + (int64_t)ja[0] * d);
-                const float4* c1 = reinterpret_cast<const float4*>(Cn + (int64_t)ja[1] * d);
-                const float4* c2 = reinterpret_cast<const float4*>(Cn + (int64_t)ja[2] * d);
-                const float4* c3 = reinterpret_cast<const float4*>(Cn + (int64_t)ja[3] * d);
-                if (v1 - v0 == PPR) verify_accum4_fixed<PPR>(xs, c0 + v0, c1 + v0, c2 + v0, c3 + v0, ca, A0, A1, A2, A3);
-                else verify_accum4(xs, v0, c0, c1, c2, c3, ca, v0, v1, A0, A1, A2, A3);
-            }
-            if (cb > 0) {
-                const float4* c0 = reinterpret_cast<const float4*>(Cn + (int64_t)jb[0] * d);
-                const float4* c1 = reinterpret_cast<const float4*>(Cn + (int64_t)jb[1] * d);
-                const float4* c2 = reinterpret_cast<const float4*>(Cn + (int64_t)jb[2] * d);
-                const float4* c3 = reinterpret_cast<const float4*>(Cn + (int64_t)jb[3] * d);
-                if (v1 - v0 == PPR) verify_accum4_fixed<PPR>(xs, c0 + v0, c1 + v0, c2 + v0, c3 + v0, cb, B0, B1, B2, B3);
-                else verify_accum4(xs, v0, c0, c1, c2, c3, cb, v0, v1, B0, B1, B2, B3);
-            }
-        }
-        if (c == nch - 1 && live) {  // the row is complete
-            ArgMin am;
-            am.init();
-            if (ca > 0) am.offer(A0.result(), ja[0]);
-            if (ca > 1) am.offer(A1.result(), ja[1]);
-            if (ca > 2) am.offer(A2.result(), ja[2]);
-            if (ca > 3) am.offer(A3.result(), ja[3]);
-            if (cb > 0) am.offer(B0.result(), jb[0]);
-            if (cb > 1) am.offer(B1.result(), jb[1]);
-            if (cb > 2) am.offer(B2.result(), jb[2]);
-            if (cb > 3) am.offer(B3.result(), jb[3]);
-            // more than eight candidate centers: the rest against the whole row -- still staged when a row is one chunk,
-            // else in global memory (L2)
-            const float4* xrow = nch == 1 ? xs : reinterpret_cast<const float4*>(X + i * d);
-            while (cb == 4 && w.more) {
-                int j2[4];
-                const int c2 = w.next4(j2);
-                if (c2 == 0) break;
-                Lanes4 M0, M1, M2, M3;
-                M0.init(); M1.init(); M2.init(); M3.init();
-                verify_accum4(xrow, 0, reinterpret_cast<const float4*>(Cn + (int64_t)j2[0] * d),
-                              reinterpret_cast<const float4*>(Cn + (int64_t)j2[1] * d),
-                              reinterpret_cast<const float4*>(Cn + (int64_t)j2[2] * d),
-                              reinterpret_cast<const float4*>(Cn + (int64_t)j2[3] * d), c2, 0, d >> 2, M0, M1, M2, M3);
-                am.offer(M0.result(), j2[0]);
-                if (c2 > 1) am.offer(M1.result(), j2[1]);
-                if (c2 > 2) am.offer(M2.result(), j2[2]);
-                if (c2 > 3) am.offer(M3.result(), j2[3]);
-                if (c2 < 4) break;
-            }
-            my_groups += w.groups;
-            labels[i] = (lloyd && am.j < 0) ? 0 : am.j;
-        }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    verify_stats(my_groups, my_fb, prm);
-}
-
 // d <= 16, table too large for shared memory: 8 lanes per frame (4 frames per warp), lane `sub` evaluates center `sub` of every candidate group
 // with the frame in registers; the center table sits in shared memory when it fits (row stride rs = 4 mod 8
 // floats: the 8 rows of a group then cover all 32 banks, so a 16-byte load per lane is conflict free).
@@ -3504,36 +3113,8 @@ int screen_assign_listed(ScreenPlan* p, const float* dX, int64_t n, const float*
         else if (ds == 12) B2K_VTL(12);
         else B2K_VTL(16);
 #undef B2K_VTL
-    } else if (ctx->verify_mode == 7 && p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0) {
-        const unsigned fgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 8));
-        screen_verify_frame8_listed_kernel<<<fgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, tlist, lcap,
-                                                                  TILE_M << unit_shift, labels, lloyd, p->params, p->fb_list, p->cg);
-    } else if ((ctx->verify_mode == 4 || ctx->verify_mode == 5) && p->d % 4 == 0 && p->d >= 32 &&
-               (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0) {
-        // one thread per frame, frame rows staged through shared memory (the default for sorted wide rows)
-        // verify_mode 0: 2 stages of 64 dimensions, 4: 2 stages of 32, 5: 3 stages of 32
-#define B2K_VSL(NST, CH)                                                                                                        \
-    do {                                                                                                                        \
-        const size_t vsm = (size_t)(NST) * VS_TILE * ((CH) + 4) * 4;                                                            \
-        static PerDeviceOnce vattr;                                                                                             \
-        if (vattr.need(ctx->device)) {                                                                                          \
-            CUDA_TRY(cudaFuncSetAttribute(screen_verify_staged_listed_kernel<NST, CH>,                                          \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsm));                              \
-            vattr.done(ctx->device);                                                                                            \
-        }                                                                                                                       \
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(12, (size_t)(220 * 1024) / (vsm + 1024)));                 \
-        const unsigned sgrid =                                                                                                  \
-            (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, VS_TILE), (int64_t)ctx->sm_count * per_sm));               \
-        screen_verify_staged_listed_kernel<NST, CH><<<sgrid, VS_TILE, vsm, st>>>(                                               \
-            dX, n, p->d, dC, p->k, p->cand, p->ncand, tlist, lcap, TILE_M << unit_shift, labels, lloyd, p->params, p->fb_list,  \
-            p->cg);                                                                                                             \
-    } while (0)
-        if (ctx->verify_mode == 4) B2K_VSL(2, 32);
-        else if (ctx->verify_mode == 5) B2K_VSL(3, 32);
-        else B2K_VSL(2, 64);
-#undef B2K_VSL
-    } else if ((ctx->verify_mode == 0 || ctx->verify_mode == 6) && p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0) {
-        // one thread per frame, rows through L1 (rows of 20-28 floats, or on request)
+    } else if (ctx->verify_mode == 0 && p->d % 4 == 0 && (((uintptr_t)dX | (uintptr_t)dC) & 15) == 0) {
+        // one thread per frame (the default for sorted frames)
         const unsigned fgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), (int64_t)ctx->sm_count * 8));
         screen_verify_frame_listed_kernel<<<fgrid, 256, 0, st>>>(dX, n, p->d, dC, p->k, p->cand, p->ncand, tlist, lcap,
                                                                  TILE_M << unit_shift, labels, lloyd, p->params, p->fb_list, p->cg);
