@@ -436,38 +436,78 @@ __global__ void kmpp_gather_sharded_kernel(const float* __restrict__ X, int d, c
 // Asynchronous single-GPU rounds: candidate pick (upper tree levels, leaf descent), candidate registration and the gather
 // of the m candidate rows in ONE launch -- the same statements as kmpp_pick_top / pick_leaf / set_cands / gather_sharded,
 // four graph nodes (and their launch latencies on a 100 kB problem) fewer per round.
-__global__ void __launch_bounds__(128) kmpp_pick_fused_kernel(TreeLevels T, int Hs, KmppState* st, const float* __restrict__ U,
+// One WARP per candidate.  A thread walking the tree alone pays one dependent round trip to L2 per level (and
+// tree_node_sum's 2^r loads per call): 17.8 us per launch at H = 17, the longest node of a cfg1 round.  A stored level
+// holds the 32 descendants of a node five levels up, so the warp loads them with one coalesced request, builds every
+// pairwise partial sum of that block with five shuffle stages -- S[s+1][q] = S[s][q] + S[s][q + 2^s], the very additions
+// tree_node_sum performs, in its order -- and walks five levels out of registers: one round trip per five levels.
+__device__ __forceinline__ float warp_level_entry(const TreeLevels& T, const unsigned char* taken, int b, long long idx) {
+    float v = 0.f;
+    if (idx < T.len[b]) {
+        v = T.lv[b][idx];
+        if (b == 0 && taken && taken[idx]) v = 0.f;
+    }
+    return v;
+}
+
+// tree_node_sum(T, taken, h, t), computed by the whole warp (same additions); every lane returns the sum
+__device__ __forceinline__ float warp_node_sum(const TreeLevels& T, const unsigned char* taken, int h, long long t) {
+    const int lane = threadIdx.x & 31;
+    const int b = h / 5, r = h - 5 * b;
+    float v = lane < (1 << r) ? warp_level_entry(T, taken, b, (t << r) + lane) : 0.f;
+    for (int s = 0; s < r; ++s) v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1 << s));
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
+// walk from `node` at height h_top down to height h_stop (a multiple of 5 below h_top); r is the residual
+__device__ __forceinline__ long long warp_descend(const TreeLevels& T, const unsigned char* taken, int h_top, int h_stop,
+                                                  long long node, float& r) {
+    const int lane = threadIdx.x & 31;
+    int h = h_top;
+    while (h > h_stop) {
+        const int b = (h - 1) / 5, rr = h - 5 * b;  // rr levels inside this block, children stored at level b
+        const long long base = node << rr;
+        float S[6];
+        S[0] = lane < (1 << rr) ? warp_level_entry(T, taken, b, base + lane) : 0.f;
+#pragma unroll
+        for (int sgl = 0; sgl < 5; ++sgl) S[sgl + 1] = __fadd_rn(S[sgl], __shfl_down_sync(0xffffffffu, S[sgl], 1 << sgl));
+        int off = 0;
+#pragma unroll
+        for (int lev = 4; lev >= 0; --lev) {
+            const float left = __shfl_sync(0xffffffffu, S[lev], off);  // the 2^lev entries from `off` on: the left child
+            if (lev < rr) {
+                if (!(r <= left)) { r = __fsub_rn(r, left); off += 1 << lev; }
+            }
+        }
+        node = base + off;
+        h = 5 * b;
+    }
+    return node;
+}
+
+__global__ void __launch_bounds__(32 * KMPP_MAX_TRIALS) kmpp_pick_fused_kernel(TreeLevels T, int Hs, KmppState* st, const float* __restrict__ U,
                                                               int m, const unsigned char* __restrict__ taken, int64_t n_local,
                                                               const float* __restrict__ X, int d, long long* __restrict__ cand_out,
                                                               float* __restrict__ rows) {
-    __shared__ float root;
     __shared__ long long cand_s[KMPP_MAX_TRIALS];
     const float* u = U + (size_t)(st->round - 1) * m;
-    if (threadIdx.x == 0) {
-        root = tree_node_sum(T, nullptr, Hs, 0);
-        st->dist_sum = root;
-        st->n_cand = m;
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;  // blockDim.x = 32 * m
+    const float root = warp_node_sum(T, nullptr, Hs, 0);
+    float r = __fmul_rn(root, u[j]);
+    const float r0 = r;
+    long long node = 0;
+    if (Hs > 10) node = warp_descend(T, nullptr, Hs, 10, 0, r);
+    long long c = -1;
+    if (node >= 0 && node * 1024 < n_local) {
+        node = warp_descend(T, taken, 10, 0, node, r);
+        if (node < n_local && !taken[node]) c = node;
     }
-    __syncthreads();
-    const int j = threadIdx.x;
-    if (j < m) {
-        float r = __fmul_rn(root, u[j]);
-        st->rands[j] = r;
-        long long node = 0;
-        for (int h = Hs; h > 10; --h) {
-            const float left = tree_node_sum(T, nullptr, h - 1, 2 * node);
-            if (r <= left) node = 2 * node;
-            else { r = __fsub_rn(r, left); node = 2 * node + 1; }
+    if (lane == 0) {
+        if (j == 0) {
+            st->dist_sum = root;
+            st->n_cand = m;
         }
-        long long c = -1;
-        if (node >= 0 && node * 1024 < n_local) {
-            for (int h = 10; h > 0; --h) {
-                const float left = tree_node_sum(T, taken, h - 1, 2 * node);
-                if (r <= left) node = 2 * node;
-                else { r = __fsub_rn(r, left); node = 2 * node + 1; }
-            }
-            if (node < n_local && !taken[node]) c = node;
-        }
+        st->rands[j] = r0;
         cand_out[j] = c;
         st->cand[j] = c;
         cand_s[j] = c;
@@ -475,8 +515,8 @@ __global__ void __launch_bounds__(128) kmpp_pick_fused_kernel(TreeLevels T, int 
     __syncthreads();
     for (int t = threadIdx.x; t < m * d; t += blockDim.x) {
         const int jj = t / d, e = t - jj * d;
-        const long long c = cand_s[jj];
-        rows[t] = (c >= 0 && c < n_local) ? X[c * d + e] : 0.f;
+        const long long cc = cand_s[jj];
+        rows[t] = (cc >= 0 && cc < n_local) ? X[cc * d + e] : 0.f;
     }
 }
 
@@ -1068,7 +1108,7 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         B2K_TRY(tree_top(bL10g.as<float>(), 1, bL15.as<float>(), bL20.as<float>(), bL25.as<float>(), bL30.as<float>()));
         // ---- candidates ----
         if (async_rounds) {  // (lo = 0, one shard: pick, registration and row gather in one launch)
-            kmpp_pick_fused_kernel<<<1, 128, 0, st>>>(T, Hs, S, bU.as<float>(), m, taken, n, dX, d, xil, rows);
+            kmpp_pick_fused_kernel<<<1, 32 * m, 0, st>>>(T, Hs, S, bU.as<float>(), m, taken, n, dX, d, xil, rows);
             LAUNCH_CHECK();
         } else {
             kmpp_pick_top_kernel<<<1, 32, 0, st>>>(T, Hs, S, ur, m, bNode.as<long long>(), bResid.as<float>(), 0);
