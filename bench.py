@@ -661,9 +661,13 @@ def main():
         extra["step_breakdown_ms"] = breakdown
         extra["pruning"] = {
             "active": bool(pruned), "mean_centers_per_tile_list": mean_list, "k": K, "sorts": ctx.get_stat("prune_sorts"),
+            "incremental_sum_steps": ctx.get_stat("delta_steps"),
+            "labels_changed_last_step_frac": max(ctx.get_stat("labels_changed"), 0.0) / n,
             "note": ("after its first iteration the session keeps the frames sorted by label; every 128-frame tile is "
                      "screened against the centers the triangle inequality cannot exclude (exact: labels, sums and "
-                     "costs are bit-identical to the unpruned iteration, tests/test_gpu_prune.py); the first (unpruned) "
+                     "costs are bit-identical to the unpruned iteration, tests/test_gpu_prune.py); once at most an eighth of the "
+                     "labels changed in the previous iteration the exact integer member sums are updated from the changed "
+                     "frames only (incremental_sum_steps; same integers as a full pass); the first (unpruned) "
                      "iteration is reported as first_iteration_ms")}
         dominant = max(breakdown, key=lambda c: breakdown[c] if c != "other" else -1.0)
         screen_roof = {"bound": "tensor", "achieved": flops / (gemm_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
@@ -686,7 +690,7 @@ def main():
             kms = breakdown[dominant]
             gbs = n * (4.0 * D + 4) / (kms * 1e-3) / 1e9
             names = {"verify": "exact verify of the screen's candidates (screen_verify_*_kernel + exact fallback)",
-                     "sums": "member sums (seg_* counting sort + seg_sum_kernel)", "cost": "cost (labeled distances + integer sum)",
+                     "sums": "member sums (seg_* counting sort + seg_sum_kernel, or accumulate_delta_kernel)", "cost": "cost (labeled distances + integer sum)",
                      "lists": "per-tile center lists (prune.cu)"}
             roofline = {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
                         "traffic": traffic_by_class.get(dominant), "kernel": names[dominant], "kernel_ms": kms,

@@ -396,6 +396,7 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "kmpp_async")) c->kmpp_async = (int)value;
     else if (!strcmp(name, "prune_mode")) c->prune_mode = (int)value;
     else if (!strcmp(name, "prune_resort")) c->prune_resort = (int)value;
+    else if (!strcmp(name, "delta_sums")) c->delta_sums = (int)value;
     else if (!strcmp(name, "prune_unit_shift")) c->prune_unit_shift = (int)value;
     else if (!strcmp(name, "screen_group")) c->screen_group = (int)value;
     else if (!strcmp(name, "screen_resident_a")) c->screen_resident_a = (int)value;
@@ -477,6 +478,8 @@ B2K_API int b2k_ctx_get_stat(b2k_ctx* c, const char* name, double* value) {
     else if (!strcmp(name, "prune_mean_list")) *value = c->stat_prune_mean;
     else if (!strcmp(name, "prune_steps")) *value = c->stat_prune_steps;
     else if (!strcmp(name, "prune_sorts")) *value = c->stat_prune_sorts;
+    else if (!strcmp(name, "labels_changed")) *value = c->stat_changed;
+    else if (!strcmp(name, "delta_steps")) *value = c->stat_delta_steps;
     else if (!strncmp(name, "probe_centers_", 14) && name[14] >= '1' && name[14] <= '3') *value = c->stat_probe_centers[name[14] - '0'];
     else if (!strncmp(name, "probe_fallback_", 15) && name[15] >= '1' && name[15] <= '3') *value = c->stat_probe_fallback[name[15] - '0'];
     else if (!strcmp(name, "sm_count")) *value = c->sm_count;
@@ -752,6 +755,13 @@ struct b2k_lloyd {
     // the caller's frame order (deeptime's cluster_loop returns centers only); b2k_dev_lloyd_get_labels hands them out
     DevMem own_labels;
     bool labels_in_own = false, labels_in_prune = false;
+    // incremental member sums of the pruned steps (lloyd.cu: accumulate_delta_kernel): the labels of the previous step in
+    // the current frame order, the exact integer sums/counts that belong to them, and the number of frames whose label
+    // changed in the last step (device word copied to a pinned host word; read after the next step's first sync)
+    DevMem prev_labels, acc_state, d_changed;
+    unsigned long long* h_changed = nullptr;  // pinned
+    bool acc_valid = false, changed_known = false;
+    ~b2k_lloyd() { if (h_changed) cudaFreeHost(h_changed); }
 };
 
 static int ceil_log2_d(double v) {
@@ -827,6 +837,7 @@ B2K_API int b2k_stage_lloyd_assign_accumulate(b2k_lloyd* s, const float* X, cons
     if (s->n == 0) return B2K_OK;
     // the frame array is rewritten: whatever the session derived from its old content (sorted copy, fp16 operand) is stale
     if (s->prune) { prune_destroy(s->prune); s->prune = nullptr; }
+    s->acc_valid = s->changed_known = false;
     s->have_labels = false;
     s->labels_in_own = s->labels_in_prune = false;
     s->steps = 0;
@@ -910,6 +921,25 @@ B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32
             ctx->stat_prune_mean = mean;
             if (s->mean_after_sort == 0) s->mean_after_sort = mean;
             s->mean_last = mean;
+            // (prune_lists synchronised the stream: the changed-label count of the previous step has arrived)
+            bool keep_prev = ctx->delta_sums != 0, use_delta = false;
+            if (keep_prev) {
+                if (s->prev_labels.alloc((size_t)s->n * 4) != B2K_OK || s->acc_state.alloc((size_t)b2k_dev_lloyd_acc_len(s) * 8) != B2K_OK ||
+                    s->d_changed.alloc(8) != B2K_OK ||
+                    (!s->h_changed && cudaHostAlloc((void**)&s->h_changed, 64, cudaHostAllocDefault) != cudaSuccess)) {
+                    cudaGetLastError();
+                    keep_prev = false;  // no room: full passes
+                    s->acc_valid = false;
+                }
+            }
+            if (keep_prev) {
+                if (s->changed_known) ctx->stat_changed = (double)*s->h_changed;
+                use_delta = s->acc_valid && (ctx->delta_sums == 2 || (s->changed_known && *s->h_changed * 8 <= (unsigned long long)s->n));
+                // the labels the kept sums belong to, in the current (possibly just re-sorted) frame order
+                CUDA_TRY(cudaMemcpyAsync(s->prev_labels.p, prune_labels(pr), (size_t)s->n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            } else {
+                s->acc_valid = false;
+            }
             // the listed screen drains mean (padded) columns per frame, the full one k rounded up to 256
             if (ov == 0 && (mean <= 0.6 * (double)(cdiv(s->k, 256) * 256) || ctx->prune_mode == 3)) {
                 B2K_TRY(screen_assign_listed(s->plan, prune_frames(pr), s->n, dC, prune_tlist(pr), prune_tcount(pr),
@@ -926,7 +956,26 @@ B2K_API int b2k_dev_lloyd_assign_accumulate(b2k_lloyd* s, const float* dC, int32
             s->steps += 1;
             s->labels_in_prune = true;
             if (want_labels) B2K_TRY(prune_scatter_labels(pr, dlabels));  // back to the caller's frame order
-            return launch_accumulate(ctx, prune_frames(pr), s->n, s->d, s->k, prune_labels(pr), s->scale_sum, dacc);
+            if (!use_delta && !keep_prev)
+                return launch_accumulate(ctx, prune_frames(pr), s->n, s->d, s->k, prune_labels(pr), s->scale_sum, dacc);
+            // member sums: incremental when few labels changed last time, else a full pass whose result is kept
+            const size_t sums_bytes = (size_t)((int64_t)s->k * s->d + s->k) * 8;
+            unsigned long long* dch = s->d_changed.as<unsigned long long>();
+            CUDA_TRY(cudaMemsetAsync(dch, 0, 8, ctx->stream));
+            if (use_delta) {
+                B2K_TRY(launch_accumulate_delta(ctx, prune_frames(pr), s->n, s->d, s->k, s->prev_labels.as<int32_t>(),
+                                                prune_labels(pr), s->scale_sum, s->acc_state.as<int64_t>(), dch));
+                CUDA_TRY(cudaMemcpyAsync(dacc, s->acc_state.p, sums_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+                ctx->stat_delta_steps += 1;
+            } else {
+                B2K_TRY(launch_accumulate(ctx, prune_frames(pr), s->n, s->d, s->k, prune_labels(pr), s->scale_sum, dacc));
+                CUDA_TRY(cudaMemcpyAsync(s->acc_state.p, dacc, sums_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+                B2K_TRY(launch_count_changed(ctx, s->prev_labels.as<int32_t>(), prune_labels(pr), s->n, dch));
+                s->acc_valid = true;
+            }
+            CUDA_TRY(cudaMemcpyAsync(s->h_changed, dch, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            s->changed_known = true;
+            return B2K_OK;
         }
     }
     if (s->plan) {

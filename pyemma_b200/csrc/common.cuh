@@ -129,6 +129,10 @@ struct b2k_ctx {
     int screen_gather = 0;    // listed screen: 0 cp.async gather warps, 1 TMA tile::gather4
     int prune_unit_shift = -1; // 1 << shift consecutive 128-frame tiles share one center list (list kernel cost against list
                               // length: measured at 1e7 x 10, k=1000 step 1.93 / 1.87 / 1.88 / 2.01 ms for shift 0..3); -1: 1 for narrow rows, else 0
+    int delta_sums = 1;       // pruned Lloyd sessions: 1 update the exact integer member sums from the frames whose label changed
+                              // once at most an eighth of them did in the previous iteration, 0 always a full pass,
+                              // 2 always incremental (tests)
+    double stat_changed = -1, stat_delta_steps = 0;  // frames whose label changed in the last counted step; incremental steps
     int prune_resort = 0;     // re-sort schedule: 0 at iterations 1, 2, 4, 8, ... ; n > 0 every n iterations
     double stat_prune_mean = 0, stat_prune_steps = 0, stat_prune_sorts = 0;  // mean list length of the last pruned step
     int screen_group = 0;     // centers per candidate group of the screen (0: automatic; 8, 4, 2)

@@ -56,6 +56,10 @@ int launch_cost_reduce(b2k_ctx* ctx, const float* l, int64_t n, double scale, in
 int launch_cost_fused(b2k_ctx* ctx, const float* X, int64_t n, int d, const float* C, int k, const int32_t* labels,
                       double scale, int64_t* acc_slot, int* done);
 // counting sort of the frame indices by label (labels outside [0, k) are left out; seg[k] = frames sorted)
+// incremental member sums (exact integers): acc under old_l -> acc under new_l, reading only the frames whose label changed
+int launch_accumulate_delta(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, const int32_t* old_l, const int32_t* new_l,
+                            double scale, int64_t* acc, unsigned long long* changed);
+int launch_count_changed(b2k_ctx* ctx, const int32_t* old_l, const int32_t* new_l, int64_t n, unsigned long long* changed);
 int launch_label_sort(b2k_ctx* ctx, const int32_t* labels, int64_t n, int k, uint32_t* seg /* k+1 */, uint32_t* perm /* n */);
 int measure_fp32_rate(b2k_ctx* ctx, double* lane_instr_per_s);
 int launch_absmax(b2k_ctx* ctx, const float* X, int64_t count, float* d_out /* device, 1 float, pre-zeroed */);

@@ -633,6 +633,76 @@ int launch_accumulate(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, con
     return B2K_OK;
 }
 
+// ---- incremental member sums ------------------------------------------------------------------------------------
+// The sums are exact integers (fixed point), so they can be UPDATED instead of recomputed: a frame whose label did not
+// change contributes the same addends to the same center as in the previous iteration.  After the first iterations of a
+// Lloyd run a few per cent of the frames change their label; only those rows are read: -q(x) from the old center's
+// sums, +q(x) to the new one's, counts alike.  The result is the same integer a full pass produces, bit for bit.
+// One warp per 32 frames: lanes compare old and new label, then the warp walks the changed frames, lanes over dimensions.
+__global__ void __launch_bounds__(256) accumulate_delta_kernel(const float* __restrict__ X, int64_t n, int d, int k,
+                                                               const int32_t* __restrict__ old_l,
+                                                               const int32_t* __restrict__ new_l, double scale,
+                                                               unsigned long long* __restrict__ acc,
+                                                               unsigned long long* __restrict__ changed) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * 256) >> 5;
+    unsigned long long mine = 0;
+    for (int64_t base = warp * 32; base < n; base += n_warps * 32) {
+        const int64_t i = base + lane;
+        int32_t o = -1, w = -1;
+        if (i < n) { o = old_l[i]; w = new_l[i]; }
+        unsigned m = __ballot_sync(0xffffffffu, o != w);
+        if (lane == 0) mine += __popc(m);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int32_t oo = __shfl_sync(0xffffffffu, o, src), ww = __shfl_sync(0xffffffffu, w, src);
+            const float* row = X + (base + src) * d;
+            const bool ok_o = oo >= 0 && oo < k, ok_w = ww >= 0 && ww < k;
+            for (int e = lane; e < d; e += 32) {
+                const long long q = __double2ll_rn((double)__ldg(row + e) * scale);
+                if (q != 0) {
+                    if (ok_w) atomicAdd(acc + (int64_t)ww * d + e, (unsigned long long)q);
+                    if (ok_o) atomicAdd(acc + (int64_t)oo * d + e, (unsigned long long)(-q));
+                }
+            }
+            if (lane == 0) {
+                if (ok_w) atomicAdd(acc + (int64_t)k * d + ww, 1ull);
+                if (ok_o) atomicAdd(acc + (int64_t)k * d + oo, (unsigned long long)(-1ll));
+            }
+        }
+    }
+    if (lane == 0 && mine) atomicAdd(changed, mine);
+}
+
+__global__ void __launch_bounds__(256) count_changed_kernel(const int32_t* __restrict__ old_l, const int32_t* __restrict__ new_l,
+                                                            int64_t n, unsigned long long* __restrict__ changed) {
+    unsigned long long mine = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) mine += old_l[i] != new_l[i];
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(changed, mine);
+}
+
+// acc (sums of the frames under old_l) becomes the sums under new_l; *changed += frames whose label differs
+int launch_accumulate_delta(b2k_ctx* ctx, const float* X, int64_t n, int d, int k, const int32_t* old_l, const int32_t* new_l,
+                            double scale, int64_t* acc, unsigned long long* changed) {
+    if (n <= 0) return B2K_OK;
+    ProfScope prof(ctx, b2k_ctx::PROF_SUMS);
+    accumulate_delta_kernel<<<grid_for(ctx, n, 2048), 256, 0, ctx->stream>>>(X, n, d, k, old_l, new_l, scale,
+                                                                            (unsigned long long*)acc, changed);
+    LAUNCH_CHECK();
+    return B2K_OK;
+}
+
+int launch_count_changed(b2k_ctx* ctx, const int32_t* old_l, const int32_t* new_l, int64_t n, unsigned long long* changed) {
+    if (n <= 0) return B2K_OK;
+    ProfScope prof(ctx, b2k_ctx::PROF_SUMS);
+    count_changed_kernel<<<grid_for(ctx, n, 4096), 256, 0, ctx->stream>>>(old_l, new_l, n, changed);
+    LAUNCH_CHECK();
+    return B2K_OK;
+}
+
 // stable counting sort of the frame indices by label: perm[seg[a] .. seg[a+1]) = frames with label a, ascending;
 // frames whose label is outside [0, k) are left out (seg[k] = number of sorted frames)
 int launch_label_sort(b2k_ctx* ctx, const int32_t* labels, int64_t n, int k, uint32_t* seg, uint32_t* perm) {
