@@ -111,6 +111,7 @@ struct b2k_ctx {
     int kmpp_async = 2;       // k-means++ (blocked, one GPU, no callback): 1 rounds are queued without a host round trip each,
                               // 2 (default) additionally replayed from one captured CUDA graph, 0 synchronous loop
     int kmpp_prune = 1;       // k-means++ (blocked, euclidean): skip candidate distances the triangle inequality decides
+                              // (1: unless the frames fit L2 -- n*d <= 4M floats; 2: always; 0: never)
     int operand_kernel = 0;   // frame operand builder: 0 per-input-element tile kernel, 1 per-output-piece kernel
     int fallback_mode = 0;    // frames the screen cannot bound: 0 by queue length (< 256: CTA-per-frame scan, else the indexed
                               // exact tile kernel), 1 always CTA per frame, 2 always the tile kernel

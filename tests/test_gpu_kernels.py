@@ -373,7 +373,7 @@ def test_kmpp_pruning_is_exact(b2k, oracle, n, d, k):
     X[::50] = X[1::50]                                      # exact duplicates: D2 == 0 frames
     ctx = b2k.context()
     picks = []
-    for prune in (1, 0):
+    for prune in (2, 0):                                    # 2: pruned whatever the size (1 = automatic skips small jobs)
         ctx.set_option("kmpp_prune", prune)
         try:
             picks.append(b2k.kmeans_init_centers_kmpp(X, k, 7, scan="blocked", return_indices=True)[1])
