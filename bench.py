@@ -502,7 +502,9 @@ def main():
         e2e_api = ("b2k_stage_lloyd_assign_accumulate (pinned host frames -> HBM chunk by chunk, each chunk assigned and "
                    "summed while the next is on the bus, labels back) + b2k_dev_lloyd_finalize/cost")
         frames_per_step = n
-        # first iteration of a session (no pruning yet; includes building the fp16 operand and the term probe)
+        # first iteration of the first session of the process (no pruning yet; includes building the fp16 operand, the
+        # term probe, the cold cudaMallocs of the working buffers and CUDA's lazy module loading: a later session of the
+        # same shape draws on the library's block cache and takes ~4 ms at cfg2, tools/fit_probe.py)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
