@@ -663,7 +663,7 @@ def main():
         extra["step_breakdown_ms"] = breakdown
         extra["pruning"] = {
             "active": bool(pruned), "mean_centers_per_tile_list": mean_list, "k": K, "sorts": ctx.get_stat("prune_sorts"),
-            "incremental_sum_steps": ctx.get_stat("delta_steps"),
+            "incremental_sum_steps": ctx.get_stat("delta_steps"), "list_reuse_steps": ctx.get_stat("list_reuse_steps"),
             "labels_changed_last_step_frac": max(ctx.get_stat("labels_changed"), 0.0) / n,
             "note": ("after its first iteration the session keeps the frames sorted by label; every 128-frame tile is "
                      "screened against the centers the triangle inequality cannot exclude (exact: labels, sums and "

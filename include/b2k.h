@@ -93,6 +93,9 @@ int b2k_ctx_sync(b2k_ctx* ctx);
  * "delta_sums" (Lloyd sessions with center pruning: 1 = the exact integer member sums are UPDATED from the frames whose
  * label changed once at most an eighth of them did in the previous iteration -- same integers as a full pass; 0 = always a
  * full pass; 2 = always incremental; default 1),
+ * "prune_list_margin" (per mille of the mean tile radius, default 50: the per-tile center lists of a pruned session are
+ * built with that much room for center movement and reused until some center has moved farther from where it was at the
+ * build -- measured by one small kernel per iteration; 0 = lists rebuilt every iteration; exact either way),
  * "cache_mb" (bound, in MiB, of the device block cache: working buffers the library frees -- the fp16 screen operand,
  * the sorted frame copy of a Lloyd session -- stay mapped for the next call of a similar size, because cudaFree /
  * cudaMalloc of GB-sized blocks cost ~0.1 s per GB; -1 = default, half of the device memory; 0 = off),
@@ -107,7 +110,8 @@ int b2k_ctx_set_option(b2k_ctx* ctx, const char* name, int64_t value);
 /* stats: "screen_frames", "screen_cand_chunks" (8-center groups re-evaluated exactly), "screen_fallback_frames"
  * of the last screened assign (host-pointer calls: of its last chunk); "screen_gemm_ms_total" and
  * "screen_gemm_launches" since "profile" was set; "sm_count"; "cache_bytes" (device block cache);
- * "labels_changed" (frames whose label changed in the last counted pruned step), "delta_steps" (incremental-sum steps so far); "fp32_lane_instr_per_s" (measures the fp32 CUDA-core
+ * "labels_changed" (frames whose label changed in the last counted pruned step), "delta_steps" (incremental-sum steps so far),
+ * "list_reuse_steps" (pruned steps that reused the center lists of an earlier step); "fp32_lane_instr_per_s" (measures the fp32 CUDA-core
  * issue rate of non-fusable FMUL/FADD chains on the spot: the denominator quoted for the CUDA-core bound kernels) */
 int b2k_ctx_get_stat(b2k_ctx* ctx, const char* name, double* value);
 

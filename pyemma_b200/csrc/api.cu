@@ -397,6 +397,7 @@ B2K_API int b2k_ctx_set_option(b2k_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "prune_mode")) c->prune_mode = (int)value;
     else if (!strcmp(name, "prune_resort")) c->prune_resort = (int)value;
     else if (!strcmp(name, "delta_sums")) c->delta_sums = (int)value;
+    else if (!strcmp(name, "prune_list_margin")) c->prune_list_margin = (int)std::max<int64_t>(0, value);
     else if (!strcmp(name, "prune_unit_shift")) c->prune_unit_shift = (int)value;
     else if (!strcmp(name, "screen_group")) c->screen_group = (int)value;
     else if (!strcmp(name, "screen_resident_a")) c->screen_resident_a = (int)value;
@@ -480,6 +481,7 @@ B2K_API int b2k_ctx_get_stat(b2k_ctx* c, const char* name, double* value) {
     else if (!strcmp(name, "prune_sorts")) *value = c->stat_prune_sorts;
     else if (!strcmp(name, "labels_changed")) *value = c->stat_changed;
     else if (!strcmp(name, "delta_steps")) *value = c->stat_delta_steps;
+    else if (!strcmp(name, "list_reuse_steps")) *value = c->stat_list_reuse;
     else if (!strncmp(name, "probe_centers_", 14) && name[14] >= '1' && name[14] <= '3') *value = c->stat_probe_centers[name[14] - '0'];
     else if (!strncmp(name, "probe_fallback_", 15) && name[15] >= '1' && name[15] <= '3') *value = c->stat_probe_fallback[name[15] - '0'];
     else if (!strcmp(name, "sm_count")) *value = c->sm_count;

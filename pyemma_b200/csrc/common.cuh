@@ -130,6 +130,10 @@ struct b2k_ctx {
     int screen_gather = 0;    // listed screen: 0 cp.async gather warps, 1 TMA tile::gather4
     int prune_unit_shift = -1; // 1 << shift consecutive 128-frame tiles share one center list (list kernel cost against list
                               // length: measured at 1e7 x 10, k=1000 step 1.93 / 1.87 / 1.88 / 2.01 ms for shift 0..3); -1: 1 for narrow rows, else 0
+    int prune_list_margin = 50;  // per mille of the mean tile radius: the center lists of a pruned session are built with this
+                              // much room for center movement and kept until a center has moved farther (0: rebuilt every
+                              // iteration)
+    double stat_list_reuse = 0;  // pruned steps that reused the lists of an earlier step
     int delta_sums = 1;       // pruned Lloyd sessions: 1 update the exact integer member sums from the frames whose label changed
                               // once at most an eighth of them did in the previous iteration, 0 always a full pass,
                               // 2 always incremental (tests)

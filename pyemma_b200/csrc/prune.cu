@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256, 4) tile_lists_direct_kernel(const float* 
                                                                 const float* __restrict__ tmean,
                                                                 const float* __restrict__ trad, int n_tiles, int lcap,
                                                                 int pad_to, uint16_t dummy, uint16_t* __restrict__ tlist,
-                                                                uint32_t* __restrict__ tcount, PruneStats* st) {
+                                                                uint32_t* __restrict__ tcount, PruneStats* st, float margin) {
     extern __shared__ __align__(16) float ctab[];  // [k][DS]
     for (int t = threadIdx.x; t < k * DS; t += 256) {
         const int r = t / DS, c = t - r * DS;
@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(256, 4) tile_lists_direct_kernel(const float* 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
         // keep unless D_j > thr  <=>  keep unless D_j^2 > thr^2 (both sides >= 0); NaN anywhere keeps the center
-        const float thr = (sqrtf(best) + 2.f * R) * (1.f + PRUNE_SLACK) + 1e-30f;
+        // (+ 2 margin: the list stays valid while no center has moved farther than `margin` from where it is now)
+        const float thr = (sqrtf(best) + 2.f * R + 2.f * margin) * (1.f + PRUNE_SLACK) + 1e-30f;
         const float thr2 = thr * thr;
         uint16_t* out = tlist + (size_t)tile * lcap;
         int count = 0;
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(256) tile_lists_cc_kernel(const float* __restr
                                                             const float* __restrict__ tmean,
                                                             const float* __restrict__ trad, int n_tiles, int lcap,
                                                             int pad_to, uint16_t dummy, uint16_t* __restrict__ tlist,
-                                                            uint32_t* __restrict__ tcount, PruneStats* st) {
+                                                            uint32_t* __restrict__ tcount, PruneStats* st, float margin) {
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5, n_warps = (gridDim.x * 256) >> 5;
     for (int tile = warp_global; tile < n_tiles; tile += n_warps) {
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(256) tile_lists_cc_kernel(const float* __restr
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         const float delta = sqrtf(s) * (1.f + 1e-5f);
-        const float thr = 2.f * (delta + __ldg(trad + tile)) * (1.f + PRUNE_SLACK) + 1e-30f;
+        // (+ 4 margin: c_j and c_a may each move by `margin`, against each other and away from p_t, before the list is stale)
+        const float thr = (2.f * (delta + __ldg(trad + tile)) + 4.f * margin) * (1.f + PRUNE_SLACK) + 1e-30f;
         const float* row = cc + (int64_t)a * k;
         uint16_t* out = tlist + (size_t)tile * lcap;
         int count = 0;
@@ -368,6 +370,27 @@ __global__ void __launch_bounds__(256) tile_lists_cc_kernel(const float* __restr
     }
 }
 
+// max_j |c_j - c0_j| (rounded up), as float bits in *out (non-negative floats order like their bit patterns); NaN -> +inf
+__global__ void __launch_bounds__(256) center_move_kernel(const float* __restrict__ C, const float* __restrict__ C0, int k, int d,
+                                                          unsigned int* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5, n_warps = (gridDim.x * 256) >> 5;
+    float worst = 0.f;
+    for (int j = warp_global; j < k; j += n_warps) {
+        float s = 0.f;
+        for (int e = lane; e < d; e += 32) {
+            const float t = __ldg(C + (int64_t)j * d + e) - __ldg(C0 + (int64_t)j * d + e);
+            s = fmaf(t, t, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        float m = sqrtf(s) * (1.f + 1e-5f);
+        if (!(m >= 0.f)) m = __int_as_float(0x7f800000);
+        worst = fmaxf(worst, m);
+    }
+    if (lane == 0 && worst > 0.f) atomicMax(out, __float_as_uint(worst));
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------
 struct PruneState {
     b2k_ctx* ctx = nullptr;
@@ -378,6 +401,15 @@ struct PruneState {
     std::vector<float> hC;
     std::vector<int> hidx, hrank;
     bool sorted = false;
+    // list reuse: the centers the current lists were built for, the movement they tolerate, the stats of that build
+    DevMem Clist, dmove;
+    float* h_move = nullptr;   // pinned
+    float margin = 0.f;
+    double rmean = 0;          // mean tile radius of the current sort
+    bool lists_valid = false;
+    double c_mean = 0;
+    int c_max = 0, c_ov = 0;
+    ~PruneState() { if (h_move) cudaFreeHost(h_move); }
 };
 
 static unsigned grid_cap(b2k_ctx* ctx, int64_t items, int per_block, int per_sm = 8) {
@@ -484,6 +516,16 @@ int prune_sort(PruneState* p, const float* X, const int32_t* labels, const float
                                                                           p->trad.as<float>());
     LAUNCH_CHECK();
     p->sorted = true;
+    p->lists_valid = false;  // new tiles
+    p->rmean = 0;
+    if (ctx->prune_list_margin > 0) {  // mean tile radius: the scale of the movement margin of the lists
+        p->hC.resize((size_t)p->n_units);
+        CUDA_TRY(cudaMemcpyAsync(p->hC.data(), p->trad.p, (size_t)p->n_units * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        double acc = 0;
+        for (int t = 0; t < p->n_units; ++t) acc += std::isfinite(p->hC[t]) ? (double)p->hC[t] : 0.0;
+        p->rmean = acc / std::max(p->n_units, 1);
+    }
     return B2K_OK;
 }
 
@@ -492,6 +534,38 @@ int prune_sort(PruneState* p, const float* X, const int32_t* labels, const float
 int prune_lists(PruneState* p, const float* dC, double* mean_count, int* max_count, int* overflow_tiles) {
     b2k_ctx* ctx = p->ctx;
     cudaStream_t st = ctx->stream;
+    // List reuse.  A list built for centers c0 with `margin` in its bound excludes j only if j stays strictly farther
+    // than the tile's reference center for EVERY set of centers with |c_j - c0_j| <= margin (triangle inequality, see the
+    // kernels); late Lloyd iterations move the centers by 1e-3 of a tile radius and less, so instead of rebuilding the
+    // lists every iteration (cfg2 0.15 ms, cfg4 1.5 ms) one small kernel measures the movement since the build.
+    if (ctx->prune_list_margin > 0 && (!p->h_move || !p->Clist.p)) {
+        if (p->Clist.alloc((size_t)p->k * p->d * 4) != B2K_OK || p->dmove.alloc(4) != B2K_OK ||
+            (!p->h_move && cudaHostAlloc((void**)&p->h_move, 64, cudaHostAllocDefault) != cudaSuccess)) {
+            cudaGetLastError();
+            p->lists_valid = false;
+            if (p->h_move) { cudaFreeHost(p->h_move); p->h_move = nullptr; }
+        }
+    }
+    const bool can_reuse = ctx->prune_list_margin > 0 && p->h_move && p->Clist.p;
+    if (can_reuse && p->lists_valid && p->margin > 0.f) {
+        ProfScope prof_move(ctx, b2k_ctx::PROF_LISTS);
+        CUDA_TRY(cudaMemsetAsync(p->dmove.p, 0, 4, st));
+        center_move_kernel<<<grid_cap(ctx, p->k, 8), 256, 0, st>>>(dC, p->Clist.as<float>(), p->k, p->d, p->dmove.as<unsigned int>());
+        LAUNCH_CHECK();
+        CUDA_TRY(cudaMemcpyAsync(p->h_move, p->dmove.p, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if ((double)*p->h_move * 1.001 <= (double)p->margin) {
+            *mean_count = p->c_mean;
+            *max_count = p->c_max;
+            *overflow_tiles = p->c_ov;
+            ctx->stat_list_reuse += 1;
+            return B2K_OK;
+        }
+    }
+    p->margin = can_reuse ? (float)(p->rmean * 1e-3 * ctx->prune_list_margin) : 0.f;
+    if (!(p->margin >= 0.f) || !std::isfinite(p->margin)) p->margin = 0.f;
+    const float margin = p->margin;
+    if (can_reuse) CUDA_TRY(cudaMemcpyAsync(p->Clist.p, dC, (size_t)p->k * p->d * 4, cudaMemcpyDeviceToDevice, st));
     PruneStats* ds = p->stats.as<PruneStats>();
     CUDA_TRY(cudaMemsetAsync(ds, 0, sizeof(PruneStats), st));
     ProfScope* prof = new ProfScope(ctx, b2k_ctx::PROF_LISTS);
@@ -512,7 +586,8 @@ int prune_lists(PruneState* p, const float* dC, double* mean_count, int* max_cou
         }                                                                                                             \
         tile_lists_direct_kernel<DS><<<grid, 256, tab, st>>>(dC, p->k, p->d, p->tmean.as<float>(), p->trad.as<float>(), \
                                                              p->n_units, p->lcap, p->pad_to, dummy,                   \
-                                                             p->tlist.as<uint16_t>(), p->tcount.as<uint32_t>(), ds);  \
+                                                             p->tlist.as<uint16_t>(), p->tcount.as<uint32_t>(), ds,   \
+                                                             margin);                                                 \
     } while (0)
         if (ds4 == 4) B2K_TL(4);
         else if (ds4 == 8) B2K_TL(8);
@@ -527,16 +602,18 @@ int prune_lists(PruneState* p, const float* dC, double* mean_count, int* max_cou
         LAUNCH_CHECK();
         tile_lists_cc_kernel<<<grid_cap(ctx, p->n_units, 8, 8), 256, 0, st>>>(
             dC, p->k, p->d, p->cc.as<float>(), p->labels_s.as<int32_t>(), p->n, p->sshift, p->tmean.as<float>(),
-            p->trad.as<float>(), p->n_units, p->lcap, p->pad_to, dummy, p->tlist.as<uint16_t>(), p->tcount.as<uint32_t>(), ds);
+            p->trad.as<float>(), p->n_units, p->lcap, p->pad_to, dummy, p->tlist.as<uint16_t>(), p->tcount.as<uint32_t>(), ds,
+            margin);
         LAUNCH_CHECK();
     }
     delete prof;
     PruneStats h;
     CUDA_TRY(cudaMemcpyAsync(&h, ds, sizeof(h), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    *mean_count = (double)h.total / (double)std::max(p->n_units, 1);
-    *max_count = (int)h.max_count;
-    *overflow_tiles = (int)h.overflow;
+    *mean_count = p->c_mean = (double)h.total / (double)std::max(p->n_units, 1);
+    *max_count = p->c_max = (int)h.max_count;
+    *overflow_tiles = p->c_ov = (int)h.overflow;
+    p->lists_valid = can_reuse;
     return B2K_OK;
 }
 

@@ -49,11 +49,13 @@ def run_session(b2k, X, C0, steps, options):
             torch.cuda.synchronize()
             out.append((lab.cpu().numpy().copy(), sums, int(acc[-1].item()), used))
             cur, nxt = nxt, cur
-        stats = {s: ctx.get_stat(s) for s in ("prune_steps", "prune_sorts", "prune_mean_list", "delta_steps", "labels_changed")}
+        stats = {s: ctx.get_stat(s) for s in ("prune_steps", "prune_sorts", "prune_mean_list", "delta_steps", "labels_changed",
+                                                 "list_reuse_steps")}
     finally:
         lib.b2k_dev_lloyd_destroy(sess)
         for name in options:
-            ctx.set_option(name, {"prune_mode": 1, "assign_engine": b2k.ENGINE_AUTO, "delta_sums": 1}.get(name, 0))
+            ctx.set_option(name, {"prune_mode": 1, "assign_engine": b2k.ENGINE_AUTO, "delta_sums": 1,
+                                  "prune_list_margin": 50}.get(name, 0))
     return out, cur.cpu().numpy(), stats
 
 
@@ -65,8 +67,11 @@ SHAPES = [(60000, 10, 100, 12, 2), (30000, 10, 500, 12, 3), (40000, 2, 100, 5, 2
 
 
 @pytest.mark.parametrize("n,d,k,nb,mode", SHAPES)
-@pytest.mark.parametrize("resort,delta", [(0, 1), (1, 1), (0, 2), (1, 0)])
-def test_pruned_session_is_bit_identical(b2k, oracle, n, d, k, nb, mode, resort, delta):
+@pytest.mark.parametrize("resort,delta,margin", [(0, 1, 50), (1, 1, 50), (0, 2, 2000), (1, 0, 0)])
+def test_pruned_session_is_bit_identical(b2k, oracle, n, d, k, nb, mode, resort, delta, margin):
+    # margin: per mille of the mean tile radius the center lists tolerate as center movement before they are rebuilt
+    # (50 default; 2000: lists twice a tile radius wider, reused from one iteration to the next even this early; 0: rebuilt
+    # every iteration)
     # delta: member sums of the pruned steps -- 1 incremental once few labels change (default), 2 always incremental
     # (from the second pruned step on, every re-sort in between included), 0 always a full pass
     rng = np.random.RandomState(n + d + k)
@@ -76,12 +81,18 @@ def test_pruned_session_is_bit_identical(b2k, oracle, n, d, k, nb, mode, resort,
     base, cen0, _ = run_session(b2k, X, C0, steps, {"assign_engine": b2k.ENGINE_SCREEN, "prune_mode": 0})
     before = b2k.context().get_stat("prune_steps")
     before_delta = b2k.context().get_stat("delta_steps")
+    before_reuse = b2k.context().get_stat("list_reuse_steps")
     got, cen1, stats = run_session(b2k, X, C0, steps, {"assign_engine": b2k.ENGINE_SCREEN, "prune_mode": mode,
-                                                       "prune_resort": resort, "delta_sums": delta})
+                                                       "prune_resort": resort, "delta_sums": delta,
+                                                       "prune_list_margin": margin})
     if delta == 2:
         assert stats["delta_steps"] - before_delta >= steps - 3, stats   # every pruned step after the first one
     if delta == 0:
         assert stats["delta_steps"] == before_delta
+    if margin == 2000 and k <= 8192:
+        assert stats["list_reuse_steps"] - before_reuse >= 1, stats      # an iteration without a re-sort kept its lists
+    if margin == 0:
+        assert stats["list_reuse_steps"] == before_reuse
     if k <= 8192:   # (lists longer than the 8192-entry capacity: the session uses the full screen on the sorted frames)
         assert stats["prune_steps"] - before >= steps - 2, stats     # iterations 2.. ran on per-tile center lists
     if mode == 2:
