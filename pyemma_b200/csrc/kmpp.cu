@@ -441,6 +441,29 @@ __global__ void kmpp_gather_sharded_kernel(const float* __restrict__ X, int d, c
 // holds the 32 descendants of a node five levels up, so the warp loads them with one coalesced request, builds every
 // pairwise partial sum of that block with five shuffle stages -- S[s+1][q] = S[s][q] + S[s][q + 2^s], the very additions
 // tree_node_sum performs, in its order -- and walks five levels out of registers: one round trip per five levels.
+// tree_up_kernel's two upper levels (heights 15 and 20) of ONE tree with at most 1024 height-10 sums, by the calling CTA:
+// the same butterflies over the same aligned blocks of 32, so the same bits.  l15: room for ceil(n10/32) <= 32 sums
+// (global or shared memory).
+__device__ __forceinline__ void cta_tree_top(const float* l10, long long n10, float* l15, float* l20) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int n15 = (int)((n10 + 31) / 32);
+    for (int t5 = w; t5 < n15; t5 += nw) {  // (n15 <= 32)
+        const long long i = (long long)t5 * 32 + lane;
+        float v = i < n10 ? l10[i] : 0.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) l15[t5] = v;
+    }
+    __syncthreads();
+    if (w == 0) {
+        float sum = lane < n15 ? l15[lane] : 0.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+        if (lane == 0) l20[0] = sum;
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ float warp_level_entry(const TreeLevels& T, const unsigned char* taken, int b, long long idx) {
     float v = 0.f;
     if (idx < T.len[b]) {
@@ -488,8 +511,11 @@ __device__ __forceinline__ long long warp_descend(const TreeLevels& T, const uns
 __global__ void __launch_bounds__(32 * KMPP_MAX_TRIALS) kmpp_pick_fused_kernel(TreeLevels T, int Hs, KmppState* st, const float* __restrict__ U,
                                                               int m, const unsigned char* __restrict__ taken, int64_t n_local,
                                                               const float* __restrict__ X, int d, long long* __restrict__ cand_out,
-                                                              float* __restrict__ rows) {
+                                                              float* __restrict__ rows, float* top15, float* top20) {
     __shared__ long long cand_s[KMPP_MAX_TRIALS];
+    // small trees (at most 1024 height-10 sums): the upper levels of the D^2 tree are built here instead of by a launch of
+    // their own (top15 = T.lv[3] has room for 32 sums, top20 = T.lv[4])
+    if (top15) cta_tree_top(T.lv[2], T.len[2], top15, top20);
     const float* u = U + (size_t)(st->round - 1) * m;
     const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;  // blockDim.x = 32 * m
     const float root = warp_node_sum(T, nullptr, Hs, 0);
@@ -525,9 +551,15 @@ __global__ void __launch_bounds__(128) kmpp_select_commit_kernel(KmppState* st, 
                                                                  float* __restrict__ pots, int64_t n_local,
                                                                  const float* __restrict__ rows, int d,
                                                                  unsigned char* __restrict__ taken, float* __restrict__ centers,
-                                                                 long long* __restrict__ chosen, int* fail, int k) {
+                                                                 long long* __restrict__ chosen, int* fail, int k,
+                                                                 const float* pot10, long long n10, float* pot20) {
     __shared__ long long s_best;
     __shared__ int s_jbest, s_found;
+    __shared__ float s15[32];
+    // small trees: the roots of the m potential trees (height 20) from their height-10 sums, here instead of in a launch of
+    // their own; lv == pot20, stride 1
+    if (pot10)
+        for (int j = 0; j < m; ++j) cta_tree_top(pot10 + (long long)j * n10, n10, s15, pot20 + j);
     if (threadIdx.x == 0) {
         long long best = -1;
         int jbest = -1;
@@ -1108,10 +1140,14 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
             B2K_TRY(exchange(0, n10g, 0));
             CUDA_TRY(cudaMemcpyAsync(bL10g.p, xf, (size_t)n10g * 4, cudaMemcpyDeviceToDevice, st));
         }
-        B2K_TRY(tree_top(bL10g.as<float>(), 1, bL15.as<float>(), bL20.as<float>(), bL25.as<float>(), bL30.as<float>()));
+        // (small trees on the asynchronous path: built inside the pick / select kernels, two launches per round fewer)
+        const bool fuse_top = async_rounds && Hs > 10 && Hs <= 20 && n10g <= 1024 && n20g == 1;
+        if (!fuse_top)
+            B2K_TRY(tree_top(bL10g.as<float>(), 1, bL15.as<float>(), bL20.as<float>(), bL25.as<float>(), bL30.as<float>()));
         // ---- candidates ----
         if (async_rounds) {  // (lo = 0, one shard: pick, registration and row gather in one launch)
-            kmpp_pick_fused_kernel<<<1, 32 * m, 0, st>>>(T, Hs, S, bU.as<float>(), m, taken, n, dX, d, xil, rows);
+            kmpp_pick_fused_kernel<<<1, 32 * m, 0, st>>>(T, Hs, S, bU.as<float>(), m, taken, n, dX, d, xil, rows,
+                                                         fuse_top ? bL15.as<float>() : nullptr, bL20.as<float>());
             LAUNCH_CHECK();
         } else {
             kmpp_pick_top_kernel<<<1, 32, 0, st>>>(T, Hs, S, ur, m, bNode.as<long long>(), bResid.as<float>(), 0);
@@ -1151,13 +1187,14 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
             LAUNCH_CHECK();
         }
         B2K_TRY(exchange(0, (int64_t)m * n10g, 0));
-        B2K_TRY(tree_top(xf, m, nullptr, bP20.as<float>(), nullptr, bP30.as<float>()));
+        if (!fuse_top) B2K_TRY(tree_top(xf, m, nullptr, bP20.as<float>(), nullptr, bP30.as<float>()));
         {
             const float* lv = Hs <= 10 ? xf : (Hs <= 20 ? bP20.as<float>() : bP30.as<float>());
             const int64_t stride = Hs <= 10 ? n10g : (Hs <= 20 ? n20g : n30g);
             if (async_rounds) {
                 kmpp_select_commit_kernel<<<1, 128, 0, st>>>(S, lv, stride, m, pots, n, rows, d, taken, dcenters_out,
-                                                             bChosen.as<long long>(), bFail.as<int>(), k);
+                                                             bChosen.as<long long>(), bFail.as<int>(), k,
+                                                             fuse_top ? xf : nullptr, n10g, bP20.as<float>());
             } else {
                 kmpp_tree_roots_kernel<<<1, 32, 0, st>>>(lv, stride, m, pots);
                 LAUNCH_CHECK();
