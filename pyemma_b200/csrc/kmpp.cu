@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(1024) kmpp_pot_tree_kernel(const float* __rest
     const bool in = i < n;
     const bool tk = in ? taken[i] != 0 : true;
     const float di = in ? D[i] : 0.f;
-    const unsigned mask = in ? framemask[i] : 0u;
+    const unsigned mask = in ? (framemask ? (unsigned)framemask[i] : 0xffffu) : 0u;  // no mask: every pair is evaluated
     for (int j0 = 0; j0 < m; j0 += 4) {
         float v[4];
 #pragma unroll
@@ -1176,9 +1176,12 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
             B2K_TRY(dist_rows(rows, m, cd));
         }
         if (ex) CUDA_TRY(cudaMemsetAsync(xf, 0, (size_t)m * n10g * 4, st));
-        if (n > 0 && prune) {
-            kmpp_pot_tree_kernel<<<(unsigned)n10, 1024, 0, st>>>(cd, n, m, D, taken, bFrameMask.as<uint16_t>(), S->cand, lo,
-                                                                 xf + node_lo, n10g);
+        // (asynchronous unpruned rounds use the same kernel without a mask: the contributions are never written, one launch
+        // instead of two; the D2 update then squares the distance row itself)
+        const bool pot_direct = prune || (async_rounds && m <= 16);
+        if (n > 0 && pot_direct) {
+            kmpp_pot_tree_kernel<<<(unsigned)n10, 1024, 0, st>>>(cd, n, m, D, taken, prune ? bFrameMask.as<uint16_t>() : nullptr,
+                                                                 S->cand, lo, xf + node_lo, n10g);
             LAUNCH_CHECK();
         } else if (n > 0) {
             kmpp_contrib_sharded_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cd, n, m, D, taken, S->cand, lo);
@@ -1205,7 +1208,7 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         if (async_rounds) {
             // (also after the last pick: the D2 update is then unused, but every round stays the same launch sequence)
             kmpp_update_dev_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(
-                D, taken, n, cd, S, prune ? 1 : 0, prune ? bAssigned.as<int32_t>() : nullptr,
+                D, taken, n, cd, S, pot_direct ? 1 : 0, prune ? bAssigned.as<int32_t>() : nullptr,
                 prune ? bFrameMask.as<uint16_t>() : nullptr, bFail.as<int>());
             LAUNCH_CHECK();
             if (capturing) {
