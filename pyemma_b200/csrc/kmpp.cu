@@ -145,25 +145,48 @@ __global__ void kmpp_update_kernel(float* __restrict__ D, const unsigned char* _
 
 // The same update with the accepted candidate read from the device state: the host does not wait for the round's result
 // (kmpp_run_blocked, asynchronous rounds).  *fail != 0: an earlier round found no candidate -> the run is repeated with
-// the synchronous loop, whatever happens here is discarded.
-__global__ void kmpp_update_dev_kernel(float* __restrict__ D, const unsigned char* __restrict__ taken, int64_t n,
-                                       const float* __restrict__ cd, const KmppState* __restrict__ st, int src_is_sqrt,
-                                       int32_t* __restrict__ assigned, const uint16_t* __restrict__ framemask,
-                                       const int* __restrict__ fail) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || *fail) return;
-    const int32_t center_index = st->round - 1;  // the commit kernel before this one advanced the counter
-    const int jbit = st->jbest;
-    if (jbit < 0) return;
-    const float* src = cd + (size_t)jbit * n;
-    if (!taken[i] && (!framemask || ((framemask[i] >> jbit) & 1u))) {
-        float dd = src[i];
-        if (src_is_sqrt) dd = __fmul_rn(dd, dd);
-        const float old = D[i];
-        if (dd < old) {
-            D[i] = dd;
-            if (assigned) assigned[i] = center_index;
+// the synchronous loop, whatever happens here is discarded.  It shares its launch with the tree_up_kernel pass over the
+// updated D2 (heights 5 and 10) the NEXT round starts from: a thread updates its frame and feeds the value straight into
+// the butterflies (same statements, same order).
+__global__ void __launch_bounds__(1024) kmpp_update_tree_kernel(float* __restrict__ D, const unsigned char* __restrict__ taken,
+                                                                int64_t n, const float* __restrict__ cd,
+                                                                const KmppState* __restrict__ st, int src_is_sqrt,
+                                                                int32_t* __restrict__ assigned,
+                                                                const uint16_t* __restrict__ framemask,
+                                                                const int* __restrict__ fail, float* __restrict__ out5,
+                                                                float* __restrict__ out10) {
+    __shared__ float ws[32];
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    float v = 0.f;
+    if (i < n) {
+        const bool tk = taken[i] != 0;
+        float cur = D[i];
+        const int jbit = st->jbest;
+        if (!*fail && jbit >= 0 && !tk && (!framemask || ((framemask[i] >> jbit) & 1u))) {
+            float dd = cd[(size_t)jbit * n + i];
+            if (src_is_sqrt) dd = __fmul_rn(dd, dd);
+            if (dd < cur) {
+                D[i] = dd;
+                cur = dd;
+                if (assigned) assigned[i] = st->round - 1;
+            }
         }
+        v = tk ? 0.f : cur;
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        ws[w] = v;
+        const int64_t t5 = (int64_t)blockIdx.x * 32 + w;
+        if (t5 * 32 < n) out5[t5] = v;
+    }
+    __syncthreads();
+    if (w == 0) {
+        float s = ws[threadIdx.x];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+        if (threadIdx.x == 0) out10[blockIdx.x] = s;
     }
 }
 
@@ -1132,7 +1155,7 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         // ---- tree over D: local heights 5 and 10, [sum] height 10, replicated upper levels ----
         float* l10 = ex ? xf : bL10g.as<float>();
         if (ex) CUDA_TRY(cudaMemsetAsync(xf, 0, (size_t)n10g * 4, st));
-        if (n > 0) {
+        if (n > 0 && !(async_rounds && found > 1)) {  // (asynchronous rounds: the previous round's update built it already)
             tree_up_kernel<<<dim3((unsigned)n10, 1), 1024, 0, st>>>(D, n, n, taken, bL5.as<float>(), n5, l10 + node_lo, n10g);
             LAUNCH_CHECK();
         }
@@ -1207,9 +1230,10 @@ int kmpp_run_blocked(b2k_ctx* ctx, const float* dX, int64_t n, int d, int k, int
         }
         if (async_rounds) {
             // (also after the last pick: the D2 update is then unused, but every round stays the same launch sequence)
-            kmpp_update_dev_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(
+            // ... fused with the next round's tree over the updated D2 (heights 5 and 10)
+            kmpp_update_tree_kernel<<<(unsigned)n10, 1024, 0, st>>>(
                 D, taken, n, cd, S, pot_direct ? 1 : 0, prune ? bAssigned.as<int32_t>() : nullptr,
-                prune ? bFrameMask.as<uint16_t>() : nullptr, bFail.as<int>());
+                prune ? bFrameMask.as<uint16_t>() : nullptr, bFail.as<int>(), bL5.as<float>(), bL10g.as<float>());
             LAUNCH_CHECK();
             if (capturing) {
                 capturing = false;
