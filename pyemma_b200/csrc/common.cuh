@@ -129,7 +129,8 @@ struct b2k_ctx {
                               // 1.10 ms at cfg2) than the verify saves (0.36 -> ~0.1 ms)
     int screen_gather = 0;    // listed screen: 0 cp.async gather warps, 1 TMA tile::gather4
     int prune_unit_shift = -1; // 1 << shift consecutive 128-frame tiles share one center list (list kernel cost against list
-                              // length: measured at 1e7 x 10, k=1000 step 1.93 / 1.87 / 1.88 / 2.01 ms for shift 0..3); -1: 1 for narrow rows, else 0
+                              // length: measured at 1e7 x 10, k=1000 step 1.93 / 1.87 / 1.88 / 2.01 ms for shift 0..3 when the lists were rebuilt every
+                              // iteration; with kept lists 1.40 / 1.45 for shift 0 / 1); -1: 0
     int prune_list_margin = 50;  // per mille of the mean tile radius: the center lists of a pruned session are built with this
                               // much room for center movement and kept until a center has moved farther (0: rebuilt every
                               // iteration)
