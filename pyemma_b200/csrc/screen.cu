@@ -2624,11 +2624,12 @@ int screen_plan_create(b2k_ctx* ctx, int64_t n_cap, int d, int k, int terms, Scr
     p->k = k;
     p->k_pad = (int)(cdiv(k, TILE_N) * TILE_N);
     p->terms = (terms >= 1 && terms <= 3) ? terms : screen_default_terms(ctx);
-    // candidate group size: narrow rows (d <= 16) leave the TMEM-read-bound epilogue no slack (measured at 1e7 x 10,
-    // k=1000: screen kernel 2.32 / 2.44 / 2.90 ms for groups of 8 / 4 / 2, step time 3.40 / 3.36 / 3.75 ms) -> 8; wide
+    // candidate group size: narrow rows (d <= 16) leave the TMEM-read-bound epilogue little slack (measured at 1e7 x 10,
+    // k=1000, all centers: screen kernel 2.32 / 2.44 / 2.90 ms for groups of 8 / 4 / 2, step time 3.40 / 3.36 / 3.75 ms;
+    // pruned session: screen 0.752 / 0.764 / 0.792, verify 0.342 / 0.283 / 0.252, step 1.398 / 1.351 / 1.355 ms) -> 4; wide
     // rows are MMA bound and their verify pays 4*d bytes of L2 traffic per candidate center -> 2 (16-bit chunk ids)
     p->cg = (ctx->screen_group == 8 || ctx->screen_group == 4 || ctx->screen_group == 2) ? ctx->screen_group
-                                                                                          : (d > 16 ? 2 : 8);
+                                                                                          : (d > 16 ? 2 : 4);
     if (p->cg == 2 && p->k_pad / CHUNK > (1 << 16)) p->cg = 4;
     p->Kc = p->terms * d + 3;
     p->Kp = (int)(cdiv(p->Kc, BLOCK_K) * BLOCK_K);
